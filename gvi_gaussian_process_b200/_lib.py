@@ -1,0 +1,103 @@
+"""ctypes binding of libgvigp.so (the C ABI declared in include/gvigp.h).
+
+There is NO fallback: if the CUDA library is missing or a call fails, an exception is raised.
+torch is used only for device memory, streams and (elsewhere) torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+import torch  # noqa: F401  (loads libcudart so the .so shares torch's CUDA runtime)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgvigp.so")
+
+# symbol -> (restype, argtypes); must list every symbol of include/gvigp.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "gvi_abi_version": (c_int, []),
+    "gvi_last_error_string": (c_char_p, []),
+    "gvi_ard_gram_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_int64, c_void_p]),
+    "gvi_ard_gram_diag_f64": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
+    "gvi_add_diagonal_regulariser_f64": (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_void_p]),
+    "gvi_chol_factor_f64": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "gvi_gp_factor_bytes": (c_size_t, [c_int, c_int]),
+    "gvi_gp_factor_workspace_bytes": (c_size_t, [c_int]),
+    "gvi_gp_factor_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_gp_predict_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "gvi_risk_workspace_bytes": (c_size_t, [c_int64]),
+    "gvi_risk_f64": (c_int, [c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                             c_void_p, c_void_p]),
+    "gvi_fused_step_workspace_bytes": (c_size_t, [c_int64]),
+    "gvi_fused_step_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "gvi_cond_var_select_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_select_record_len": (c_int64, [c_int, c_int]),
+    "gvi_select_init_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_double, c_void_p,
+                                    c_void_p, c_void_p]),
+    "gvi_select_resolve_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "gvi_select_update_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+REG_KINDS = {
+    "none": 0,
+    "bhattacharyya": 1,
+    "gaussian_wasserstein": 2,
+    "hellinger": 3,
+    "kl": 4,
+    "renyi": 5,
+    "gwi_no_eig": 6,
+    "squared_difference": 7,
+}
+
+
+class GviError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libgvigp.so and bind every symbol; raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GviError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().gvi_last_error_string().decode()
+        raise GviError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "libgvigp takes device pointers; got a CPU tensor"
+    assert t.is_contiguous(), "libgvigp takes C-contiguous arrays"
+    return t.data_ptr()
+
+
+def current_stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,400 @@
+// chol.cu - per-step M x M work for one GP: A = K_ZZ + jitter I (+ noise I), blocked Cholesky, L^-1,
+// fragment-order packing of L^-1 for the DMMA predict kernel, alpha = A^-1 y.
+// Reference: src/utils/matrix_operations.py:7-28 (a4); cho_factor call sites sparse_posterior_kernel.py:68-74 and
+// src/gps/base/base.py:516-521 (a5/a7).  M <= a few thousand: O(M^3) here is <2% of the O(N M^2) predict pass.
+#include "common.cuh"
+
+int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                        const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                        cudaStream_t st);
+
+namespace {
+constexpr int NB = 32;
+
+// ---- a4: trace-relative (or absolute) diagonal regulariser, single CTA, fixed-order trace --------------------
+__global__ void __launch_bounds__(1024) add_diag_kernel(double* __restrict__ A, int M, int64_t ld, double reg,
+                                                        int is_abs, const double* __restrict__ log_noise,
+                                                        double* __restrict__ jitter_out) {
+  __shared__ double part[32];
+  __shared__ double add_s;
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  if (!is_abs)
+    for (int i = tid; i < M; i += 1024) s += A[(int64_t)i * ld + i];
+  s = warp_sum(s);
+  if ((tid & 31) == 0) part[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tr = 0.0;
+    for (int w = 0; w < 32; w++) tr += part[w];
+    double jit = is_abs ? reg : reg * tr / (double)M;
+    if (jitter_out) *jitter_out = jit;
+    add_s = jit + (log_noise ? exp(log_noise[0]) : 0.0);
+  }
+  __syncthreads();
+  const double add = add_s;
+  for (int i = tid; i < M; i += 1024) A[(int64_t)i * ld + i] += add;
+}
+
+// identity padding of rows/cols [M, Mp) so that the padded factor is block-diagonal with I
+__global__ void pad_identity_kernel(double* __restrict__ A, int M, int Mp) {
+  int64_t total = (int64_t)Mp * Mp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(idx / Mp), c = (int)(idx % Mp);
+    if (r >= M || c >= M) A[idx] = (r == c) ? 1.0 : 0.0;
+  }
+}
+
+__device__ __forceinline__ double ld_guard(const double* A, int64_t ld, int M, int r, int c) {
+  return (r < M && c < M) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
+}
+
+// ---- blocked left-looking Cholesky: launch t handles the 32-wide block column jb = t ---------------------------
+// Panel CTA (ib > jb): S_d = A[jb,jb] - L[jb,:] L[jb,:]^T (recomputed by every CTA, cheap),
+// S_r = A[ib,jb] - L[ib,:] L[jb,:]^T, L_d = chol(S_d) in registers of warp 0, L[ib,jb] = S_r L_d^-T.
+// The diagonal block L_d itself is written one launch LATER (CTA 0 of launch t+1 recomputes and stores block t),
+// because panel CTAs of launch t still read the original A[jb,jb] while they run.
+__global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A, int M, int64_t ld, int t,
+                                                         int has_diag, int* __restrict__ info) {
+  __shared__ double Li[NB][NB + 1];
+  __shared__ double Lj[NB][NB + 1];
+  __shared__ double Sd[NB][NB + 1];
+  __shared__ double Sr[NB][NB + 1];
+  const int tid = threadIdx.x;
+  const bool diag_cta = has_diag && blockIdx.x == 0;
+  const int jb = diag_cta ? t - 1 : t;
+  const int ib = diag_cta ? jb : t + 1 + (int)blockIdx.x - has_diag;
+  const int tx = tid & 15, ty = tid >> 4;
+  double accd[2][2] = {{0, 0}, {0, 0}}, accr[2][2] = {{0, 0}, {0, 0}};
+  for (int k0 = 0; k0 < jb * NB; k0 += NB) {
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 5, c = idx & 31;
+      Lj[r][c] = ld_guard(A, ld, M, jb * NB + r, k0 + c);
+      if (!diag_cta) Li[r][c] = ld_guard(A, ld, M, ib * NB + r, k0 + c);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) {
+      double j0 = Lj[2 * tx][k], j1 = Lj[2 * tx + 1][k];
+      double d0 = Lj[2 * ty][k], d1 = Lj[2 * ty + 1][k];
+      accd[0][0] = fma(d0, j0, accd[0][0]);
+      accd[0][1] = fma(d0, j1, accd[0][1]);
+      accd[1][0] = fma(d1, j0, accd[1][0]);
+      accd[1][1] = fma(d1, j1, accd[1][1]);
+      if (!diag_cta) {
+        double i0 = Li[2 * ty][k], i1 = Li[2 * ty + 1][k];
+        accr[0][0] = fma(i0, j0, accr[0][0]);
+        accr[0][1] = fma(i0, j1, accr[0][1]);
+        accr[1][0] = fma(i1, j0, accr[1][0]);
+        accr[1][1] = fma(i1, j1, accr[1][1]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      int r = 2 * ty + a, c = 2 * tx + b;
+      Sd[r][c] = ld_guard(A, ld, M, jb * NB + r, jb * NB + c) - accd[a][b];
+      if (!diag_cta) Sr[r][c] = ld_guard(A, ld, M, ib * NB + r, jb * NB + c) - accr[a][b];
+    }
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    double row[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) row[c] = Sd[lane][c];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      double djj = __shfl_sync(0xffffffffu, row[j], j);
+      if (lane == j && !(djj > 0.0) && diag_cta && info) atomicMin(info, jb * NB + j + 1);
+      double s = sqrt(djj);
+      row[j] = (lane == j) ? s : row[j] / s;
+#pragma unroll
+      for (int k = j + 1; k < NB; k++) {
+        double lkj = __shfl_sync(0xffffffffu, row[j], k);
+        if (lane >= k) row[k] = fma(-row[j], lkj, row[k]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++) Sd[lane][c] = (c <= lane) ? row[c] : 0.0;
+    __syncwarp();
+    if (diag_cta) {
+      int r = jb * NB + lane;
+      if (r < M)
+        for (int c = 0; c <= lane; c++) A[(int64_t)r * ld + jb * NB + c] = Sd[lane][c];
+    } else {
+      // X L_d^T = S_r, lane owns one row of X
+      double x[NB];
+#pragma unroll
+      for (int c = 0; c < NB; c++) x[c] = Sr[lane][c];
+#pragma unroll
+      for (int c = 0; c < NB; c++) {
+        double v = x[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) v = fma(-x[k], Sd[c][k], v);
+        x[c] = v / Sd[c][c];
+      }
+      int r = ib * NB + lane;
+      if (r < M) {
+#pragma unroll
+        for (int c = 0; c < NB; c++)
+          if (jb * NB + c < M) A[(int64_t)r * ld + jb * NB + c] = x[c];
+      }
+    }
+  }
+}
+
+// ---- L^-1: (1) invert the 32x32 diagonal blocks, (2) one CTA per block column sweeps downwards ----------------
+__global__ void __launch_bounds__(32) diag_inverse_kernel(const double* __restrict__ L, int64_t ld,
+                                                          double* __restrict__ X, int64_t ldx) {
+  __shared__ double Ls[NB][NB + 1];
+  const int b = blockIdx.x, lane = threadIdx.x;
+  for (int r = 0; r < NB; r++) Ls[r][lane] = L[(int64_t)(b * NB + r) * ld + b * NB + lane];
+  __syncwarp();
+  // lane j owns column j of the inverse: x[i] = (delta_ij - sum_{k=j}^{i-1} L[i][k] x[k]) / L[i][i]
+  double x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; i++) {
+    double v = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; k++) v = fma(-Ls[i][k], (k >= lane) ? x[k] : 0.0, v);
+    x[i] = (i >= lane) ? v / Ls[i][i] : 0.0;
+  }
+#pragma unroll
+  for (int i = 0; i < NB; i++) X[(int64_t)(b * NB + i) * ldx + b * NB + lane] = x[i];
+}
+
+__global__ void __launch_bounds__(256) linv_sweep_kernel(const double* __restrict__ L, int64_t ld,
+                                                         double* __restrict__ X, int64_t ldx, int G) {
+  __shared__ double As[NB][NB + 1];
+  __shared__ double Bs[NB][NB + 1];
+  __shared__ double Ts[NB][NB + 1];
+  const int jb = blockIdx.x, tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  for (int ib = jb + 1; ib < G; ib++) {
+    double acc[2][2] = {{0, 0}, {0, 0}};
+    for (int kb = jb; kb < ib; kb++) {
+      __syncthreads();
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        int r = idx >> 5, c = idx & 31;
+        As[r][c] = L[(int64_t)(ib * NB + r) * ld + kb * NB + c];
+        Bs[r][c] = X[(int64_t)(kb * NB + r) * ldx + jb * NB + c];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < NB; k++) {
+        double a0 = As[2 * ty][k], a1 = As[2 * ty + 1][k];
+        double b0 = Bs[k][2 * tx], b1 = Bs[k][2 * tx + 1];
+        acc[0][0] = fma(a0, b0, acc[0][0]);
+        acc[0][1] = fma(a0, b1, acc[0][1]);
+        acc[1][0] = fma(a1, b0, acc[1][0]);
+        acc[1][1] = fma(a1, b1, acc[1][1]);
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 5, c = idx & 31;
+      As[r][c] = X[(int64_t)(ib * NB + r) * ldx + ib * NB + c];  // Dinv[ib]
+    }
+    Ts[2 * ty][2 * tx] = acc[0][0];
+    Ts[2 * ty][2 * tx + 1] = acc[0][1];
+    Ts[2 * ty + 1][2 * tx] = acc[1][0];
+    Ts[2 * ty + 1][2 * tx + 1] = acc[1][1];
+    __syncthreads();
+    double o[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll 8
+    for (int k = 0; k < NB; k++) {
+      double a0 = As[2 * ty][k], a1 = As[2 * ty + 1][k];
+      double b0 = Ts[k][2 * tx], b1 = Ts[k][2 * tx + 1];
+      o[0][0] = fma(a0, b0, o[0][0]);
+      o[0][1] = fma(a0, b1, o[0][1]);
+      o[1][0] = fma(a1, b0, o[1][0]);
+      o[1][1] = fma(a1, b1, o[1][1]);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+        X[(int64_t)(ib * NB + 2 * ty + a) * ldx + jb * NB + 2 * tx + b] = -o[a][b];
+    __syncthreads();  // X[ib,jb] visible to the whole CTA before the next row block reads it
+  }
+}
+
+// ---- header, scaled inducing points -----------------------------------------------------------------------------
+__global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, const double* __restrict__ Z,
+                                     const double* __restrict__ log_scaling, const double* __restrict__ log_ls,
+                                     int ls_len) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    double amp = exp(log_scaling[0]);
+    F[0] = amp * amp;
+    F[1] = amp * amp;
+    F[4] = F[5] = F[6] = F[7] = 0.0;
+  }
+  if (tid < f.D) F[f.sqrtw_off + tid] = sqrt(exp(log_ls[ls_len == 1 ? 0 : tid]));
+  for (int64_t idx = tid; idx < (int64_t)f.Mp * f.D; idx += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(idx / f.D), d = (int)(idx % f.D);
+    F[f.zs_off + idx] = (r < f.M) ? Z[idx] * sqrt(exp(log_ls[ls_len == 1 ? 0 : d])) : 0.0;
+  }
+}
+
+// ---- pack L^-1 in fragment order: group g (rows 32g..32g+31), kp (cols 8kp..8kp+7), mt (8-row tile), lane, e ----
+// element = Linv[32g + 8mt + lane/4][8kp + 4e + lane%4]; zero above the diagonal and in the padding.
+__global__ void pack_linv_kernel(const double* __restrict__ X, int Mp, int M, int G, double* __restrict__ W) {
+  const int64_t total = 256LL * G * (G + 1);  // number of double2 items
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (int64_t)gridDim.x * blockDim.x) {
+    // find group: items before group g = 256*g*(g+1)
+    int g = (int)((sqrt(1.0 + (double)it / 64.0) - 1.0) * 0.5);
+    while (256LL * (g + 1) * (g + 2) <= it) g++;
+    while (256LL * g * (g + 1) > it) g--;
+    int64_t local = it - 256LL * g * (g + 1);
+    int lane = (int)(local & 31);
+    int mt = (int)((local >> 5) & 3);
+    int kp = (int)(local >> 7);
+    int c = 32 * g + 8 * mt + (lane >> 2);
+    double2 v;
+    int j0 = 8 * kp + (lane & 3), j1 = j0 + 4;
+    v.x = (c < M && j0 <= c) ? X[(int64_t)c * Mp + j0] : 0.0;
+    v.y = (c < M && j1 <= c) ? X[(int64_t)c * Mp + j1] : 0.0;
+    reinterpret_cast<double2*>(W)[it] = v;
+  }
+}
+
+// ---- alpha = L^-T (L^-1 y): two triangular matvecs with the explicit inverse, fixed summation order ------------
+__global__ void __launch_bounds__(256) linv_matvec_kernel(const double* __restrict__ X, int Mp, int M,
+                                                          const double* __restrict__ y, double* __restrict__ t) {
+  // warp per row c: t[c] = sum_{j<=c} X[c][j] y[j]
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Mp) return;
+  double s = 0.0;
+  if (warp < M)
+    for (int j = lane; j <= warp; j += 32) s = fma(X[(int64_t)warp * Mp + j], y[j], s);
+  s = warp_sum(s);
+  if (lane == 0) t[warp] = s;
+}
+__global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ X, int Mp, int M,
+                                                           const double* __restrict__ t, double* __restrict__ a) {
+  // thread per column j: a[j] = sum_{c>=j} X[c][j] t[c]   (coalesced across j)
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= Mp) return;
+  double s = 0.0;
+  if (j < M)
+    for (int c = j; c < M; c++) s = fma(X[(int64_t)c * Mp + j], t[c], s);
+  a[j] = s;
+}
+__global__ void zero_kernel(double* p, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = 0.0;
+}
+__global__ void info_to_header_kernel(double* F, const int* info, int Mp) {
+  int v = *info;
+  F[3] = (v > Mp) ? 0.0 : (double)v;
+}
+__global__ void info_init_kernel(int* info) { *info = 0x7fffffff; }
+__global__ void info_final_kernel(int* info) {
+  if (*info == 0x7fffffff) *info = 0;
+}
+}  // namespace
+
+static int launch_chol(double* A, int M, int64_t ld, int* info, cudaStream_t st) {
+  const int G = (M + NB - 1) / NB;
+  for (int t = 0; t <= G; t++) {
+    const int has_diag = t > 0 ? 1 : 0;
+    const int ctas = has_diag + (t < G ? G - t - 1 : 0);
+    if (ctas == 0) continue;
+    chol_panel_kernel<<<ctas, 256, 0, st>>>(A, M, ld, t, has_diag, info);
+    GVI_CHECK_LAUNCH("chol_panel_kernel");
+  }
+  return GVI_OK;
+}
+
+extern "C" int gvi_add_diagonal_regulariser_f64(double* A, int M, int64_t ld, double reg, int is_abs, void* stream) {
+  GVI_CHECK_ARG(A && M >= 1 && ld >= M, "matrix");
+  add_diag_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(A, M, ld, reg, is_abs, nullptr, nullptr);
+  GVI_CHECK_LAUNCH("add_diag_kernel");
+  return GVI_OK;
+}
+
+extern "C" int gvi_chol_factor_f64(double* A, int M, int64_t ld, int* info, void* stream) {
+  GVI_CHECK_ARG(A && M >= 1 && ld >= M, "matrix");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (info) {
+    info_init_kernel<<<1, 1, 0, st>>>(info);
+    GVI_CHECK_LAUNCH("info_init_kernel");
+  }
+  int rc = launch_chol(A, M, ld, info, st);
+  if (rc) return rc;
+  if (info) {
+    info_final_kernel<<<1, 1, 0, st>>>(info);
+    GVI_CHECK_LAUNCH("info_final_kernel");
+  }
+  return GVI_OK;
+}
+
+extern "C" size_t gvi_gp_factor_bytes(int M, int D) {
+  if (M < 1 || D < 1) return 0;
+  return (size_t)factor_layout(M, D).total * sizeof(double);
+}
+extern "C" size_t gvi_gp_factor_workspace_bytes(int M) {
+  if (M < 1) return 0;
+  size_t Mp = (size_t)(M + 31) / 32 * 32;
+  return (2 * Mp * Mp + 2 * Mp + 8) * sizeof(double);
+}
+
+extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, const double* log_ls,
+                                 int ls_len, double reg, int is_abs, const double* log_noise, const double* y_z,
+                                 void* factor_out, void* workspace, int* info, void* stream) {
+  GVI_CHECK_ARG(Z && log_scaling && log_ls && factor_out && workspace, "null pointer");
+  GVI_CHECK_ARG(M >= 1 && D >= 1, "sizes");
+  GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FactorLayout f = factor_layout(M, D);
+  double* F = (double*)factor_out;
+  double* A = (double*)workspace;
+  double* X = A + (size_t)f.Mp * f.Mp;
+  double* tvec = X + (size_t)f.Mp * f.Mp;
+  int* winfo = (int*)(tvec + 2 * f.Mp);
+  int rc;
+  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len);
+  GVI_CHECK_LAUNCH("factor_header_kernel");
+  if ((rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st))) return rc;
+  add_diag_kernel<<<1, 1024, 0, st>>>(A, M, f.Mp, reg, is_abs, log_noise, F + 2);
+  GVI_CHECK_LAUNCH("add_diag_kernel");
+  if (f.Mp != M) {
+    pad_identity_kernel<<<148, 256, 0, st>>>(A, M, f.Mp);
+    GVI_CHECK_LAUNCH("pad_identity_kernel");
+  }
+  info_init_kernel<<<1, 1, 0, st>>>(winfo);
+  if ((rc = launch_chol(A, f.Mp, f.Mp, winfo, st))) return rc;
+  info_final_kernel<<<1, 1, 0, st>>>(winfo);
+  info_to_header_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp);
+  GVI_CHECK_LAUNCH("info kernels");
+  if (info) GVI_CUDA(cudaMemcpyAsync(info, winfo, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  zero_kernel<<<148 * 4, 256, 0, st>>>(X, (int64_t)f.Mp * f.Mp);
+  diag_inverse_kernel<<<f.G, 32, 0, st>>>(A, f.Mp, X, f.Mp);
+  GVI_CHECK_LAUNCH("diag_inverse_kernel");
+  if (f.G > 1) {
+    linv_sweep_kernel<<<f.G - 1, 256, 0, st>>>(A, f.Mp, X, f.Mp, f.G);
+    GVI_CHECK_LAUNCH("linv_sweep_kernel");
+  }
+  {
+    int64_t items = 256LL * f.G * (f.G + 1);
+    int blocks = (int)((items + 255) / 256 < 148 * 8 ? (items + 255) / 256 : 148 * 8);
+    pack_linv_kernel<<<blocks, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpack_off);
+    GVI_CHECK_LAUNCH("pack_linv_kernel");
+  }
+  if (y_z) {
+    linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, f.Mp, M, y_z, tvec);
+    linvT_matvec_kernel<<<(f.Mp + 255) / 256, 256, 0, st>>>(X, f.Mp, M, tvec, F + f.alpha_off);
+    GVI_CHECK_LAUNCH("alpha kernels");
+  } else {
+    zero_kernel<<<4, 256, 0, st>>>(F + f.alpha_off, f.Mp);
+    GVI_CHECK_LAUNCH("zero_kernel");
+  }
+  return GVI_OK;
+}

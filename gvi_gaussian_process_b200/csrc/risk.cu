@@ -1,0 +1,123 @@
+// risk.cu - standalone pointwise risk / regulariser reductions (a9-a11): HBM-bound single pass, 8 B per operand
+// per point, vectorised double2 loads, warp-shuffle tree + fixed-order two-stage reduction (run-to-run reproducible).
+// Reference: negative_log_likelihood.py:41-55; regularisations/projected/base.py:44-92 and the five D0 bodies;
+// gaussian_wasserstein_regularisation.py:143-160; gaussian_squared_difference_regularisation.py:48-86.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstring>
+
+namespace {
+constexpr int RTHREADS = 256;
+constexpr int RBLOCKS = GVI_NUM_SMS * 4;
+
+__global__ void __launch_bounds__(RTHREADS) risk_kernel(int kind, double alpha, const double* __restrict__ y,
+                                                        const double* __restrict__ mq, const double* __restrict__ vq,
+                                                        const double* __restrict__ mp, const double* __restrict__ vp,
+                                                        int64_t N, double* __restrict__ partials) {
+  __shared__ double sa[RTHREADS / 32], sb[RTHREADS / 32];
+  const int tid = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  const int64_t npairs = N >> 1;
+  const bool has_reg = (kind != GVI_REG_NONE);
+  // every operand pointer comes from a 16-byte aligned allocation in practice; fall back to scalar loads otherwise
+  const bool aligned = (((uintptr_t)mq | (uintptr_t)vq | (uintptr_t)(y ? y : mq) | (uintptr_t)(has_reg ? mp : mq) |
+                         (uintptr_t)(has_reg ? vp : mq)) & 15) == 0;
+  if (aligned) {
+    for (int64_t p = (int64_t)blockIdx.x * RTHREADS + tid; p < npairs; p += (int64_t)gridDim.x * RTHREADS) {
+      double2 m2 = reinterpret_cast<const double2*>(mq)[p];
+      double2 v2 = reinterpret_cast<const double2*>(vq)[p];
+      if (y) {
+        double2 y2 = reinterpret_cast<const double2*>(y)[p];
+        a += gvi_nll_term(y2.x, m2.x, v2.x);
+        a += gvi_nll_term(y2.y, m2.y, v2.y);
+      }
+      if (has_reg) {
+        double2 pm = reinterpret_cast<const double2*>(mp)[p];
+        double2 pv = reinterpret_cast<const double2*>(vp)[p];
+        b += gvi_reg_term(kind, alpha, pm.x, pv.x, m2.x, v2.x);
+        b += gvi_reg_term(kind, alpha, pm.y, pv.y, m2.y, v2.y);
+      }
+    }
+  }
+  const int64_t tail0 = aligned ? (npairs << 1) : 0;
+  for (int64_t i = tail0 + (int64_t)blockIdx.x * RTHREADS + tid; i < N; i += (int64_t)gridDim.x * RTHREADS) {
+    if (y) a += gvi_nll_term(y[i], mq[i], vq[i]);
+    if (has_reg) b += gvi_reg_term(kind, alpha, mp[i], vp[i], mq[i], vq[i]);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((tid & 31) == 0) {
+    sa[tid >> 5] = a;
+    sb[tid >> 5] = b;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < RTHREADS / 32; w++) {
+      ta += sa[w];
+      tb += sb[w];
+    }
+    partials[2 * blockIdx.x] = ta;
+    partials[2 * blockIdx.x + 1] = tb;
+  }
+}
+
+__global__ void __launch_bounds__(256) risk_finish_kernel(const double* __restrict__ partials, int nblocks, int64_t N,
+                                                          double* __restrict__ out3) {
+  __shared__ double sa[256], sb[256];
+  const int tid = threadIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = tid; i < nblocks; i += 256) {
+    a += partials[2 * i];
+    b += partials[2 * i + 1];
+  }
+  sa[tid] = a;
+  sb[tid] = b;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+      sa[tid] += sa[tid + s];
+      sb[tid] += sb[tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out3[0] = sa[0];
+    out3[1] = sb[0];
+    out3[2] = (double)N;
+  }
+}
+}  // namespace
+
+extern "C" size_t gvi_risk_workspace_bytes(int64_t N) {
+  (void)N;
+  return (size_t)RBLOCKS * 2 * sizeof(double);
+}
+
+extern "C" int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, const double* m_q, const double* v_q,
+                            const double* m_p, const double* v_p, int64_t N, double* out3, void* workspace,
+                            void* stream) {
+  GVI_CHECK_ARG(N >= 1, "N");
+  GVI_CHECK_ARG(m_q && v_q && out3 && workspace, "null pointer");
+  GVI_CHECK_ARG(reg_kind >= GVI_REG_NONE && reg_kind <= GVI_REG_SQUARED_DIFFERENCE, "reg_kind");
+  GVI_CHECK_ARG(reg_kind == GVI_REG_NONE || (m_p && v_p), "regulariser needs m_p and v_p");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t want = (N / 2 + RTHREADS - 1) / RTHREADS;
+  int blocks = (int)(want < 1 ? 1 : (want > RBLOCKS ? RBLOCKS : want));
+  risk_kernel<<<blocks, RTHREADS, 0, st>>>(reg_kind, renyi_alpha, y, m_q, v_q, m_p, v_p, N, (double*)workspace);
+  GVI_CHECK_LAUNCH("risk_kernel");
+  risk_finish_kernel<<<1, 256, 0, st>>>((const double*)workspace, blocks, N, out3);
+  GVI_CHECK_LAUNCH("risk_finish_kernel");
+  return GVI_OK;
+}
+
+// ---- error plumbing ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "no error";
+void gvi_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* gvi_last_error_string(void) { return g_err; }
+extern "C" int gvi_abi_version(void) { return 1; }

@@ -1,0 +1,132 @@
+/*
+ * gvigp.h - C ABI of libgvigp.so: the B200 (sm_100a) implementation of the data-parallel GP hot path of
+ * jswu18/gvi-gaussian-process.  The reference has no native/FFI layer (it is pure Python on JAX); each entry
+ * point below names the reference *Python* override point it replaces (paths relative to the reference repo).
+ *
+ * Conventions
+ *   - every function returns 0 on success and a negative GVI_E* code on failure; gvi_last_error_string()
+ *     describes the last failure of the calling thread.  Nothing throws across the ABI.
+ *   - all pointers are DEVICE pointers unless the name ends in _h; all arrays are float64, C-contiguous,
+ *     row-major; indices are int64.
+ *   - kernel hyper-parameters (log_scaling, log_lengthscales, log_observation_noise) are passed as device
+ *     pointers so a training loop never has to synchronise to read them.
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*); no hidden synchronisation
+ *     and no allocation: the caller owns outputs and workspaces (sizes from the *_bytes queries).
+ */
+#ifndef GVIGP_H
+#define GVIGP_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GVI_OK 0
+#define GVI_EINVAL (-1)   /* bad argument (shape/size/null) - the Python shim raises AssertionError first */
+#define GVI_ECUDA (-2)    /* CUDA runtime error, see gvi_last_error_string() */
+#define GVI_EUNSUPPORTED (-3) /* size outside what this build supports */
+
+/* regulariser kinds for gvi_risk_f64 / gvi_fused_step_f64 (src/regularisations/...) */
+#define GVI_REG_NONE 0
+#define GVI_REG_PROJ_BHATTACHARYYA 1 /* projected/projected_bhattacharyya_regularisation.py:34-36 */
+#define GVI_REG_PROJ_GAUSSIAN_WASSERSTEIN 2 /* projected/projected_gaussian_wasserstein_regularisation.py:34 */
+#define GVI_REG_PROJ_HELLINGER 3 /* projected/projected_hellinger_regularisation.py:34-45 */
+#define GVI_REG_PROJ_KL 4 /* projected/projected_kl_regularisation.py:34-38 */
+#define GVI_REG_PROJ_RENYI 5 /* projected/projected_renyi_regularisation.py:36-45 */
+#define GVI_REG_GWI_NO_EIG 6 /* gaussian_wasserstein_regularisation.py:143-160 (include_eigendecomposition=False) */
+#define GVI_REG_SQUARED_DIFFERENCE 7 /* gaussian_squared_difference_regularisation.py:48-86 (full_covariance=False) */
+
+int gvi_abi_version(void);
+const char* gvi_last_error_string(void);
+
+/* ---- a1-a3: ARDKernel._calculate_gram (src/kernels/standard/base.py:73-103, ard_kernel.py:58-66) ----------
+ * out[i*ld_out + j] = exp(log_scaling)^2 * exp(-0.5 * sum_d exp(log_ls[d]) * (x1[i,d]-x2[j,d])^2).
+ * ls_len is D, or 1 (a scalar lengthscale broadcast over D, README.md:92-94). */
+int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                     const double* log_scaling, const double* log_ls, int ls_len,
+                     double* out, int64_t ld_out, void* stream);
+/* full_covariance=False path of KernelBase.calculate_gram (src/kernels/base.py:132-147): out[i] = k(x_i,x_i). */
+int gvi_ard_gram_diag_f64(int64_t n, const double* log_scaling, double* out, void* stream);
+
+/* ---- a4: add_diagonal_regulariser (src/utils/matrix_operations.py:7-28), in place on A[M,M] (ld doubles) -- */
+int gvi_add_diagonal_regulariser_f64(double* A, int M, int64_t ld, double diagonal_regularisation,
+                                     int is_absolute, void* stream);
+/* ---- cho_factor call sites (sparse_posterior_kernel.py:68-74, src/gps/base/base.py:516-518): blocked
+ * lower Cholesky in place (strict upper triangle left untouched); *info = 0 or 1+first non-PD column. ------- */
+int gvi_chol_factor_f64(double* A, int M, int64_t ld, int* info, void* stream);
+
+/* ---- a5/a7: factorisation state of one GP over the inducing set Z ------------------------------------------
+ * Builds A = K_ZZ + jitter*I (+ exp(log_noise) I), its Cholesky L, L^-1 packed in DMMA-fragment order, and
+ * alpha = A^-1 y_Z.  Replaces the per-call cho_factor of SparsePosteriorKernel._calculate_gram
+ * (sparse_posterior_kernel.py:63-74) and GPBase.calculate_posterior_matrices_of_kernel (base.py:516-521).
+ *   diagonal_regularisation/is_absolute : a4 semantics (pass 0.0 for the exact GP)
+ *   log_noise : device scalar or NULL (adds exp(log_noise) to the diagonal; exact GP, base.py:473-476)
+ *   y_z       : [M] or NULL (alpha = 0)                                                                     */
+size_t gvi_gp_factor_bytes(int M, int D);
+size_t gvi_gp_factor_workspace_bytes(int M);
+int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, const double* log_ls,
+                      int ls_len, double diagonal_regularisation, int is_absolute, const double* log_noise,
+                      const double* y_z, void* factor_out, void* workspace, int* info, void* stream);
+
+/* ---- a5-a7: predictive mean / variance without any N x M intermediate in HBM -------------------------------
+ * var[i]  = k(x_i,x_i) - || L^-1 k(Z,x_i) ||^2 (+ exp(log_noise_add) if given)   (sparse_posterior_kernel.py:90-96
+ *           in diagonal mode; base.py:522-525 for the exact GP; base.py:205-211 for the added noise)
+ * mean[i] = k(x_i,Z) alpha + prior_mean[i]                                    (base.py:519-521, 492)
+ * mean_out / prior_mean / log_noise_add may be NULL.                                                        */
+int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
+                       const double* prior_mean, const double* log_noise_add,
+                       double* mean_out, double* var_out, void* stream);
+
+/* ---- a9-a11: risk and regulariser sums ----------------------------------------------------------------------
+ * out[0] = sum_i NLL_i  (negative_log_likelihood.py:41-55), out[1] = sum_i D0_i (regulariser `kind`),
+ * out[2] = N as double.  Sums, not means, so shards can be all-reduced; deterministic two-stage tree.
+ * workspace: gvi_risk_workspace_bytes(N).  y/m_p/v_p may be NULL when the corresponding term is unused.     */
+size_t gvi_risk_workspace_bytes(int64_t N);
+int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, const double* m_q, const double* v_q,
+                 const double* m_p, const double* v_p, int64_t N, double* out3, void* workspace, void* stream);
+
+/* ---- a12: fused Gram + predict(q) + predict(p) + NLL + regulariser for one shard of points ---------------
+ * (GeneralisedVariationalInference._calculate_loss, src/generalised_variational_inference.py:73-94.)
+ * One launch: per tile of points builds K(x,Z) for q and p in shared memory, runs both triangular products on
+ * the FP64 tensor pipe and reduces the pointwise loss terms; only O(N) data crosses HBM.
+ * factor_p may be NULL with reg_kind == GVI_REG_NONE.  prior-mode regulariser: pass factor_p = NULL and
+ * m_p/v_p arrays instead.  out3 as in gvi_risk_f64.  var_q_out/mean_p_out/var_p_out optional (may be NULL). */
+size_t gvi_fused_step_workspace_bytes(int64_t N);
+int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                       const double* y, const double* m_q, const double* prior_mean_p,
+                       const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha,
+                       double* out3, double* var_q_out, double* mean_p_out, double* var_p_out,
+                       void* workspace, void* stream);
+
+/* ---- a13: ConditionalVarianceInducingPointsSelector.compute_inducing_points
+ * (src/inducing_points_selection.py:113-176) on ALREADY PERMUTED inputs x_perm[N,D] (the permutation is the
+ * host's job).  Writes pivot positions into x_perm to idx_out[M_sel] (int64) and
+ * tr(K-Q) after every step to trace_out[M_sel-1] (NULL ok) for the threshold test (lines 167-172).
+ * workspace: gvi_select_workspace_bytes(N, M_sel) = the C matrix [(M_sel-1), N] + d[N] + scratch.
+ * Multi-GPU use: each rank owns a contiguous slice; see the *_step_* entry points.                           */
+size_t gvi_select_workspace_bytes(int64_t N, int M_sel, int D);
+int gvi_cond_var_select_f64(const double* x_perm, int64_t N, int D, int M_sel, const double* log_scaling,
+                            const double* log_ls, int ls_len, double jitter, int64_t* idx_out,
+                            double* trace_out, void* workspace, void* stream);
+/* Sharded selector, one call per pivot step and rank (N_local points starting at global offset `offset`):
+ *   init    : d = diag + jitter, local first candidate record
+ *   update  : given the winning record (global idx, x_j[D], c_j[m]) applies step m to the local slice and
+ *             writes the next local candidate record
+ *   resolve : picks the winner among R gathered records with the reference tie rule (max d, then max index)
+ * Record layout (doubles): [0]=d value, [1]=global index (as double, exact < 2^53), [2..2+D)=x_j,
+ * [2+D .. 2+D+M_sel-1) = c_j (column of C), so record_len = gvi_select_record_len(D, M_sel).                 */
+int64_t gvi_select_record_len(int D, int M_sel);
+int gvi_select_init_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                        const double* log_scaling, double jitter, double* record_out, void* workspace,
+                        void* stream);
+int gvi_select_resolve_f64(const double* records, int R, int D, int M_sel, int first, double* winner_out,
+                           int64_t* idx_out_m, void* stream);
+int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
+                          const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
+                          double jitter, double* record_out, double* trace_partial_out, void* workspace,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GVIGP_H */
