@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json's metric on its config #3 (synthetic UCI-shaped regression: N=1e6 points per GPU,
+D=8, M=1024 inducing points, ARD kernel, Gaussian NLL + projected Renyi(0.5) regulariser against the exact GP
+posterior): fp64 points/s through the fused "Gram + predict + pGVI risk" step.
+
+One step = everything the reference recomputes per objective evaluation (src/generalised_variational_inference.py
+:73-94 under jit): the tanh-FCN mean on the host framework, the q and p factorisations (K_ZZ, Cholesky, L^-1),
+and one fused launch over all points of the shard (both K(x,Z) tiles, both triangular products on the FP64 tensor
+pipe, NLL + D0 reduction); N>1 adds one 3-double all-reduce.  Weak scaling: every rank owns 1e6 points.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  torchrun ... bench.py --gpus N ...           (one rank per GPU, NCCL)
+
+Prints ONE JSON line on rank 0.  `--impl reference` times the CPU restatement of the reference (the NumPy/SciPy
+oracle - the JAX reference itself is not installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1_000_000
+D = 8
+M = 1024
+LAMBDA = 1e-5
+RENYI_ALPHA = 0.5
+CPU_SAMPLE_ROWS = 50_000  # the reference's own batch size (experiments/regression/base_configs/train_approximate/base.yaml)
+METRIC = "fp64 Gram+predict+pGVI risk points/sec"
+UNIT = "points/s"
+# measured on this pool's B200 (profiles/fp64_peak_r01.txt): DMMA m8n8k4 issue rate 37.1 TFLOP/s, cuBLAS DGEMM
+# 8192^3 35.4 TFLOP/s.  MEASURED_PEAKS.json carries no FP64 entry, so the harder (DMMA) number is the denominator.
+FP64_PEAK_TFLOPS = 37.1
+
+
+def algorithmic_flops_per_point(m: int, d: int) -> float:
+    """per point, q and p together: 2*[M^2 (triangular product) + 2*M*D (Gram)] + 2*M."""
+    return 2.0 * (m * m + 2.0 * m * d) + 2.0 * m
+
+
+def make_inputs(rank: int, n: int, seed: int):
+    """Seeded synthetic shard: X ~ N(0, I_8), y = sin(X w) + 0.1 eps."""
+    rng = np.random.default_rng(1000 * seed + rank)
+    x = rng.standard_normal((n, D))
+    w = np.random.default_rng(12345).standard_normal(D)
+    y = np.sin(x @ w) + 0.1 * rng.standard_normal(n)
+    return x, y
+
+
+def make_replicated(seed: int = 7):
+    """Z (first M rows of a seeded draw), y_Z, hyper-parameters and the tanh-FCN mean weights: same on all ranks."""
+    rng = np.random.default_rng(seed)
+    z = rng.standard_normal((M, D))
+    w = np.random.default_rng(12345).standard_normal(D)
+    yz = np.sin(z @ w) + 0.1 * rng.standard_normal(M)
+    fcn = dict(w1=rng.standard_normal((D, 10)) / np.sqrt(D), b1=0.1 * rng.standard_normal(10),
+               w2=rng.standard_normal((10, 1)) / np.sqrt(10), b2=np.zeros(1))
+    theta = dict(ls_q=0.0, ll_q=np.full(D, np.log(1.0 / D)), ls_p=0.0, ll_p=np.full(D, np.log(1.0 / D)), log_noise=0.0)
+    return z, yz, fcn, theta
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a port of the reference arithmetic) on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_step(x, y, z, yz, fcn, theta):
+    from oracle import gp_oracle as O
+
+    gq = lambda a, b: O.ard_gram(theta["ls_q"], theta["ll_q"], a, b)
+    dq = lambda a: O.ard_gram_diag(theta["ls_q"], theta["ll_q"], a)
+    gp = lambda a, b: O.ard_gram(theta["ls_p"], theta["ll_p"], a, b)
+    dp = lambda a: O.ard_gram_diag(theta["ls_p"], theta["ll_p"], a)
+    m_q = (np.tanh(x @ fcn["w1"] + fcn["b1"]) @ fcn["w2"] + fcn["b2"]).reshape(-1)
+    v_q = O.sparse_posterior_diag(gq, dq, z, x, LAMBDA, False)
+    m_p, v_p = O.exact_gp_posterior(gp, dp, np.zeros(x.shape[0]), z, yz, theta["log_noise"], x)
+    return O.gaussian_nll(y, m_q, v_q) + O.projected_regularisation("renyi", m_p, v_p, m_q, v_q, RENYI_ALPHA)
+
+
+def time_cpu(steps: int, warmup: int):
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+
+        limiter = threadpool_limits(limits=cores)
+    except Exception:  # pragma: no cover
+        limiter = None
+    z, yz, fcn, theta = make_replicated()
+    x, y = make_inputs(0, CPU_SAMPLE_ROWS, seed=1)
+    for _ in range(warmup):
+        cpu_step(x, y, z, yz, fcn, theta)
+    times = []
+    loss = None
+    for _ in range(steps):
+        t = time.perf_counter()
+        loss = cpu_step(x, y, z, yz, fcn, theta)
+        times.append(time.perf_counter() - t)
+    del limiter
+    sec = float(np.mean(times))
+    return dict(value=CPU_SAMPLE_ROWS / sec, unit=UNIT, cores=cores, kind="port",
+                sample=f"{CPU_SAMPLE_ROWS} rows x M={M} (the reference's batch size), mean of {steps} step(s), "
+                       f"NumPy/SciPy restatement of the reference (not JAX), loss={loss:.6f}"), sec
+
+
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {
+                pynvml.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                pynvml.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                pynvml.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop.is_set():
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.reasons.add(f"sampler_error:{type(e).__name__}")
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thread.join(timeout=2)
+
+    def summary(self):
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from gvi_gaussian_process_b200 import _lib, distributed
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
+    from gvi_gaussian_process_b200.src.regularisations.projected import ProjectedRenyiRegularisation
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    z, yz, fcn, theta = make_replicated()
+    # two rotating input batches: 2 x (64 + 8) MB > 126 MB of L2 together with the factor workspaces
+    host_batches = [make_inputs(rank, N_PER_GPU, seed=s) for s in (1, 2)]
+    pinned = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()) for x, y in host_batches]
+    dev_batches = [(x.to(dev), y.to(dev)) for x, y in pinned]
+    fcn_d = {k: torch.as_tensor(v, dtype=torch.float64, device=dev) for k, v in fcn.items()}
+
+    def fcn_mean(params, x):  # 1-hidden-layer tanh FCN of width 10 (experiments/*/base_configs/train_approximate/mean)
+        return torch.addmm(params["b2"], torch.tanh(torch.addmm(params["b1"], x, params["w1"])), params["w2"])
+
+    kernel = ARDKernel(number_of_dimensions=D)
+    approx_mean = CustomMean(mean_function=fcn_mean)
+    sparse = SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=LAMBDA)
+    approx_gp = ApproximateGPRegression(mean=approx_mean, kernel=sparse)
+    to_d = lambda v: torch.as_tensor(np.atleast_1d(v), dtype=torch.float64, device=dev)
+    approx_params = approx_gp.Parameters.construct(
+        mean=approx_mean.Parameters.construct(custom=fcn_d),
+        kernel=sparse.Parameters.construct(base_kernel=kernel.Parameters.construct(
+            log_scaling=to_d(theta["ls_q"]), log_lengthscales=to_d(theta["ll_q"]))))
+    const_mean = ConstantMean()
+    exact_gp = GPRegression(mean=const_mean, kernel=kernel, x=z, y=yz)
+    exact_params = exact_gp.Parameters.construct(
+        log_observation_noise=to_d(theta["log_noise"]), mean=const_mean.Parameters.construct(constant=to_d(0.0)),
+        kernel=kernel.Parameters.construct(log_scaling=to_d(theta["ls_p"]), log_lengthscales=to_d(theta["ll_p"])))
+    risk = NegativeLogLikelihood(gp=approx_gp)
+    reg = ProjectedRenyiRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
+                                       mode="posterior", alpha=RENYI_ALPHA)
+    gvi = GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+
+    def step(x, y):
+        out3 = gvi.loss_sums(approx_params, x, y)
+        distributed.allreduce_loss_sums(out3)
+        return distributed.loss_from_sums(out3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------------------
+    for i in range(args.warmup):
+        loss = step(*dev_batches[i % 2])
+    barrier()
+    launches0 = lib.gvi_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            loss = step(*dev_batches[i % 2])
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.gvi_launch_count() - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    loss_value = float(loss.item())
+
+    # ---- the dominant kernel alone (roofline): events around the fused launch only, factors prepared before ------
+    from gvi_gaussian_process_b200.src import _lib_proxy as L
+
+    f_q = sparse.factorise(approx_params.kernel)
+    f_p = exact_gp.factorise(exact_params)
+    kt = []
+    for i in range(max(3, min(args.steps, 10))):
+        x, y = dev_batches[i % 2]
+        m_q = approx_mean.predict(approx_params.mean, x).contiguous()
+        pm = const_mean.predict(exact_params.mean, x).contiguous()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        L.fused_step(f_q, f_p, x, y, m_q, pm, None, None, L.REG_KINDS["renyi"], RENYI_ALPHA)
+        k1.record()
+        torch.cuda.synchronize()
+        kt.append(k0.elapsed_time(k1))
+    kernel_ms = float(np.mean(kt[1:]))
+    flops = algorithmic_flops_per_point(M, D) * N_PER_GPU
+    achieved = flops / (kernel_ms * 1e-3) / 1e12
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------------------------
+    e2e_steps = max(2, min(args.steps, 5))
+    barrier()
+    for i in range(2):
+        float(step(*pinned[i % 2]).item())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        loss_e2e = float(step(*pinned[i % 2]).item())  # H2D of x, y inside; D2H of the loss
+    torch.cuda.synchronize()
+    e2e_sec = time.perf_counter() - t0
+    t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_sec = float(t.item()) / e2e_steps
+
+    result = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, _ = time_cpu(steps=2, warmup=1)
+            cpu["cpu_model"] = cpu_model()
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get("gp_step_kernel_dram_bytes_per_launch")
+        result = {
+            "metric": METRIC, "value": N_PER_GPU * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: synthetic UCI-shaped regression N={N_PER_GPU} per GPU, D={D}, "
+                                   f"M={M}, ARD, Gaussian NLL + projected Renyi(0.5) vs exact-GP posterior, "
+                                   f"forward step incl. both factorisations",
+                       "n_per_gpu": N_PER_GPU, "d": D, "m": M, "jitter": LAMBDA,
+                       "l2_policy": "2 rotating input batches (2 x 72 MB) plus factor state > 126 MB L2",
+                       "parallelism": f"points sharded over {world} rank(s), Z and theta replicated"},
+            "loss": loss_value, "gpu_launches": int(launches),
+            "e2e": {"value": N_PER_GPU * world / e2e_sec, "unit": UNIT,
+                    "h2d_bytes_per_step": int(N_PER_GPU * (D + 1) * 8), "d2h_bytes_per_step": 8,
+                    "steps": e2e_steps, "loss": loss_e2e},
+            "roofline": {"bound": "tensor", "kernel": "gp_step_kernel<3,8> (FP64 DMMA m8n8k4)",
+                         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic, "kernel_ms": kernel_ms,
+                         "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D),
+                         "peak_source": "measured FP64 DMMA issue rate on this pool's B200 (profiles/fp64_peak_r01.txt; "
+                                        "cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry"},
+            "clocks": clocks.summary(),
+        }
+        if cpu is not None:
+            result["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cpu, sec = time_cpu(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    cpu["cpu_model"] = cpu_model()
+    return {
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[2]: synthetic UCI-shaped regression, D={D}, M={M}, ARD, Gaussian NLL + "
+                               f"projected Renyi(0.5) vs exact-GP posterior; each step = a {CPU_SAMPLE_ROWS}-row "
+                               f"sample of the workload on the host cores",
+                   "d": D, "m": M, "jitter": LAMBDA},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference (NumPy/SciPy float64 oracle), not JAX: jax==0.4.13 is not "
+                "installable in this image (SURVEY.md F4)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    result = run_reference(args) if args.impl == "reference" else run_gpu(args)
+    if result is not None:
+        print(json.dumps(result), flush=True)
+
+
+if __name__ == "__main__":
+    main()

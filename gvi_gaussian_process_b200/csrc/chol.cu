@@ -370,12 +370,15 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
     GVI_CHECK_LAUNCH("pad_identity_kernel");
   }
   info_init_kernel<<<1, 1, 0, st>>>(winfo);
+  GVI_CHECK_LAUNCH("info_init_kernel");
   if ((rc = launch_chol(A, f.Mp, f.Mp, winfo, st))) return rc;
   info_final_kernel<<<1, 1, 0, st>>>(winfo);
+  GVI_CHECK_LAUNCH("info_final_kernel");
   info_to_header_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp);
-  GVI_CHECK_LAUNCH("info kernels");
+  GVI_CHECK_LAUNCH("info_to_header_kernel");
   if (info) GVI_CUDA(cudaMemcpyAsync(info, winfo, sizeof(int), cudaMemcpyDeviceToDevice, st));
   zero_kernel<<<148 * 4, 256, 0, st>>>(X, (int64_t)f.Mp * f.Mp);
+  GVI_CHECK_LAUNCH("zero_kernel");
   diag_inverse_kernel<<<f.G, 32, 0, st>>>(A, f.Mp, X, f.Mp);
   GVI_CHECK_LAUNCH("diag_inverse_kernel");
   if (f.G > 1) {
@@ -390,8 +393,9 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   }
   if (y_z) {
     linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, f.Mp, M, y_z, tvec);
+    GVI_CHECK_LAUNCH("linv_matvec_kernel");
     linvT_matvec_kernel<<<(f.Mp + 255) / 256, 256, 0, st>>>(X, f.Mp, M, tvec, F + f.alpha_off);
-    GVI_CHECK_LAUNCH("alpha kernels");
+    GVI_CHECK_LAUNCH("linvT_matvec_kernel");
   } else {
     zero_kernel<<<4, 256, 0, st>>>(F + f.alpha_off, f.Mp);
     GVI_CHECK_LAUNCH("zero_kernel");

@@ -10,6 +10,7 @@
 #endif
 
 void gvi_set_error(const char* fmt, ...);
+void gvi_count_launch();
 
 #define GVI_CHECK_ARG(cond, msg)                                  \
   do {                                                            \
@@ -21,6 +22,7 @@ void gvi_set_error(const char* fmt, ...);
 
 #define GVI_CHECK_LAUNCH(name)                                                        \
   do {                                                                                \
+    gvi_count_launch();                                                               \
     cudaError_t e__ = cudaGetLastError();                                             \
     if (e__ != cudaSuccess) {                                                         \
       gvi_set_error("CUDA error launching %s: %s", name, cudaGetErrorString(e__));    \

@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   double* Ksm = reinterpret_cast<double*>(smem_raw);            // [Mp*T] fragment order
   double* xs = Ksm + (size_t)P.Mp * T;                            // [T][DR] scaled x tile
   double* redm = xs + T * DR;                                     // [WARPS][T]
-  double* reds = redm + WARPS * T;                                // [WARPS][T]
-  double* res = reds + WARPS * T;                                 // [2 passes][T][2] (mean, var)
+  double* reds = redm + WARPS * T;                                // [G][T] squared norms per 32-row group
+  double* res = reds + (size_t)P.G * T;                           // [2 passes][T][2] (mean, var)
   int* counter = reinterpret_cast<int*>(res + 2 * T * 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,9 +106,6 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       __syncthreads();
       // ---- phase 2: b = L^-1 k on the tensor pipe, accumulate ||b||^2 ----------------------------------
       {
-        double ss[NT][2];
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++) ss[nt][0] = ss[nt][1] = 0.0;
         const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
         const double* __restrict__ W = F + f.wpack_off;
         while (true) {
@@ -146,35 +143,29 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
 #pragma unroll
             for (int mt = 0; mt < 4; mt++) a_cur[mt] = a_nxt[mt];
           }
+          // squared norms of this group's 32 rows: lanes with equal lane%4 hold the same two points of every
+          // n-tile.  Stored per GROUP (not per warp) so the final sum has a fixed order whatever warp ran the group.
 #pragma unroll
-          for (int mt = 0; mt < 4; mt++)
+          for (int nt = 0; nt < NT; nt++)
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++) {
-              ss[nt][0] = fma(acc[mt][nt][0], acc[mt][nt][0], ss[nt][0]);
-              ss[nt][1] = fma(acc[mt][nt][1], acc[mt][nt][1], ss[nt][1]);
+            for (int e = 0; e < 2; e++) {
+              double v = 0.0;
+#pragma unroll
+              for (int mt = 0; mt < 4; mt++) v = fma(acc[mt][nt][e], acc[mt][nt][e], v);
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (lane < 4) reds[g * T + nt * 8 + lane * 2 + e] = v;
             }
         }
-        // lanes with equal lane%4 hold the same two points of every n-tile
-#pragma unroll
-        for (int nt = 0; nt < NT; nt++)
-#pragma unroll
-          for (int e = 0; e < 2; e++) {
-            double v = ss[nt][e];
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 16);
-            if (lane < 4) reds[warp * T + nt * 8 + lane * 2 + e] = v;
-          }
       }
       __syncthreads();
       // ---- tile epilogue: variance and mean of this pass --------------------------------------------
       if (tid < T) {
         double q = 0.0, mu = 0.0;
+        for (int g = 0; g < P.G; g++) q += reds[g * T + tid];
 #pragma unroll
-        for (int w = 0; w < WARPS; w++) {
-          q += reds[w * T + tid];
-          mu += redm[w * T + tid];
-        }
+        for (int w = 0; w < WARPS; w++) mu += redm[w * T + tid];
         double var = F[1] - q;
         if (pd.noise_add) var += exp(pd.noise_add[0]);
         const int64_t r = row0 + tid;
@@ -249,7 +240,7 @@ __global__ void __launch_bounds__(256) finish_partials_kernel(const double* __re
 template <int NT, int DR>
 size_t step_smem_bytes(int Mp) {
   constexpr int T = 8 * NT;
-  return ((size_t)Mp * T + T * DR + 2 * WARPS * T + 4 * T) * sizeof(double) + 16;
+  return ((size_t)Mp * T + T * DR + WARPS * T + (size_t)(Mp / 32) * T + 4 * T) * sizeof(double) + 16;
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;

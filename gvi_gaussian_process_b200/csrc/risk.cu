@@ -121,3 +121,9 @@ void gvi_set_error(const char* fmt, ...) {
 }
 extern "C" const char* gvi_last_error_string(void) { return g_err; }
 extern "C" int gvi_abi_version(void) { return 1; }
+
+// number of kernel-launch sites passed since load (bench.py reports it as gpu_launches)
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void gvi_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t gvi_launch_count(void) { return (int64_t)g_launches.load(); }

@@ -1,0 +1,126 @@
+"""Torch-tensor front end of the C ABI (include/gvigp.h).  Every function enqueues on torch's current stream and
+never synchronises.  No CPU fallback: a missing library or a failed call raises."""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib
+from .utils.device import device, empty
+
+REG_KINDS = _lib.REG_KINDS
+
+
+def _L():
+    return _lib.load()
+
+
+def ard_gram(x1, x2, log_scaling, log_ls, out):
+    rc = _L().gvi_ard_gram_f64(_lib.ptr(x1), x1.shape[0], _lib.ptr(x2), x2.shape[0], x1.shape[1],
+                               _lib.ptr(log_scaling), _lib.ptr(log_ls), log_ls.numel(), _lib.ptr(out),
+                               out.stride(0) if out.ndim == 2 else x2.shape[0], _lib.current_stream())
+    _lib.check(rc, "gvi_ard_gram_f64")
+
+
+def ard_gram_diag(n, log_scaling, out):
+    _lib.check(_L().gvi_ard_gram_diag_f64(n, _lib.ptr(log_scaling), _lib.ptr(out), _lib.current_stream()),
+               "gvi_ard_gram_diag_f64")
+
+
+def add_diagonal_regulariser(a, diagonal_regularisation, is_absolute):
+    _lib.check(_L().gvi_add_diagonal_regulariser_f64(_lib.ptr(a), a.shape[0], a.stride(0),
+                                                     float(diagonal_regularisation), int(bool(is_absolute)),
+                                                     _lib.current_stream()), "gvi_add_diagonal_regulariser_f64")
+
+
+def chol_factor(a):
+    info = torch.zeros(1, dtype=torch.int32, device=a.device)
+    _lib.check(_L().gvi_chol_factor_f64(_lib.ptr(a), a.shape[0], a.stride(0), _lib.ptr(info),
+                                        _lib.current_stream()), "gvi_chol_factor_f64")
+    return info
+
+
+class GpFactor:
+    """Device-resident factorisation state of one GP over an inducing set (see gvi_gp_factor_f64)."""
+
+    def __init__(self, m: int, d: int):
+        self.m, self.d = m, d
+        self.mp = (m + 31) // 32 * 32
+        self.buf = empty(_L().gvi_gp_factor_bytes(m, d) // 8)
+        self.ws = empty(_L().gvi_gp_factor_workspace_bytes(m) // 8)
+        self.info = torch.zeros(1, dtype=torch.int32, device=device())
+
+    def factor(self, z, log_scaling, log_ls, diagonal_regularisation, is_absolute, log_noise=None, y_z=None):
+        rc = _L().gvi_gp_factor_f64(_lib.ptr(z), self.m, self.d, _lib.ptr(log_scaling), _lib.ptr(log_ls),
+                                    log_ls.numel(), float(diagonal_regularisation), int(bool(is_absolute)),
+                                    _lib.ptr(log_noise), _lib.ptr(y_z), _lib.ptr(self.buf), _lib.ptr(self.ws),
+                                    _lib.ptr(self.info), _lib.current_stream())
+        _lib.check(rc, "gvi_gp_factor_f64")
+        return self
+
+    # views into the workspace (valid until the next factor() call) -- used by the full-covariance API only
+    def cholesky(self):
+        return self.ws[: self.mp * self.mp].view(self.mp, self.mp)[: self.m, : self.m]
+
+    def inverse_cholesky(self):
+        return self.ws[self.mp * self.mp: 2 * self.mp * self.mp].view(self.mp, self.mp)[: self.m, : self.m]
+
+
+def gp_predict(factor: GpFactor, x, prior_mean=None, log_noise_add=None, want_mean=True):
+    n = x.shape[0]
+    mean = empty(n) if want_mean else None
+    var = empty(n)
+    rc = _L().gvi_gp_predict_f64(_lib.ptr(factor.buf), factor.m, factor.d, _lib.ptr(x), n, _lib.ptr(prior_mean),
+                                 _lib.ptr(log_noise_add), _lib.ptr(mean), _lib.ptr(var), _lib.current_stream())
+    _lib.check(rc, "gvi_gp_predict_f64")
+    return mean, var
+
+
+_risk_ws = {}
+
+
+def _workspace(key, nbytes):
+    dev = device()
+    buf = _risk_ws.get((key, dev))
+    if buf is None or buf.numel() * 8 < nbytes:
+        buf = empty((nbytes + 7) // 8)
+        _risk_ws[(key, dev)] = buf
+    return buf
+
+
+def risk(reg_kind, alpha, y, m_q, v_q, m_p, v_p):
+    """Returns out3 = [sum nll, sum reg, N] (device tensor)."""
+    n = m_q.numel()
+    out3 = empty(3)
+    ws = _workspace("risk", _L().gvi_risk_workspace_bytes(n))
+    rc = _L().gvi_risk_f64(int(reg_kind), float(alpha), _lib.ptr(y), _lib.ptr(m_q), _lib.ptr(v_q), _lib.ptr(m_p),
+                           _lib.ptr(v_p), n, _lib.ptr(out3), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_risk_f64")
+    return out3
+
+
+def fused_step(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_p_in, reg_kind, alpha,
+               out3=None, var_q_out=None, mean_p_out=None, var_p_out=None):
+    n = x.shape[0]
+    if out3 is None:
+        out3 = empty(3)
+    ws = _workspace("step", _L().gvi_fused_step_workspace_bytes(n))
+    rc = _L().gvi_fused_step_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
+                                 factor_q.m, factor_q.d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q),
+                                 _lib.ptr(prior_mean_p), _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind),
+                                 float(alpha), _lib.ptr(out3), _lib.ptr(var_q_out), _lib.ptr(mean_p_out),
+                                 _lib.ptr(var_p_out), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_fused_step_f64")
+    return out3
+
+
+def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):
+    n, d = x_perm.shape
+    idx = torch.empty(m_sel, dtype=torch.int64, device=x_perm.device)
+    trace = empty(m_sel - 1)
+    nbytes = _L().gvi_select_workspace_bytes(n, m_sel, d)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_perm.device)
+    rc = _L().gvi_cond_var_select_f64(_lib.ptr(x_perm), n, d, m_sel, _lib.ptr(log_scaling), _lib.ptr(log_ls),
+                                      log_ls.numel(), float(jitter), _lib.ptr(idx), _lib.ptr(trace), _lib.ptr(ws),
+                                      _lib.current_stream())
+    _lib.check(rc, "gvi_cond_var_select_f64")
+    return idx, trace

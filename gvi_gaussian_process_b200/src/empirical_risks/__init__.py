@@ -1,0 +1,2 @@
+from .base import EmpiricalRiskBase  # noqa: F401
+from .negative_log_likelihood import NegativeLogLikelihood  # noqa: F401

@@ -1,0 +1,92 @@
+"""GeneralisedVariationalInference (reference: src/generalised_variational_inference.py:18-119):
+loss = empirical risk + regularisation (no weighting).
+
+When the objective is the hot-path configuration - Gaussian NLL of an ApproximateGPRegression over a
+SparsePosteriorKernel(ARD) plus a pointwise regulariser against an exact GPRegression(ARD) (posterior mode) or any
+GP prior (prior mode) on the same GP - the whole step runs as ONE fused CUDA launch (gvi_fused_step_f64): K(x,Z)
+tiles are built in shared memory for q and p, both triangular products run on the FP64 tensor pipe and the
+pointwise loss terms are reduced in the epilogue.  Otherwise the two terms are evaluated separately (still CUDA).
+"""
+from __future__ import annotations
+
+from . import _lib_proxy as L
+from .empirical_risks.base import EmpiricalRiskBase
+from .empirical_risks.negative_log_likelihood import NegativeLogLikelihood
+from .gps.approximate_gp_regression import ApproximateGPRegression
+from .gps.gp_regression import GPRegression
+from .kernels.approximate.sparse_posterior_kernel import SparsePosteriorKernel
+from .regularisations.base import RegularisationBase
+from .regularisations.schemas import RegularisationMode
+from .utils.device import as_2d, as_device
+
+
+class GeneralisedVariationalInference:
+    def __init__(self, regularisation: RegularisationBase, empirical_risk: EmpiricalRiskBase):
+        self._regularisation = regularisation
+        self._empirical_risk = empirical_risk
+
+    @property
+    def regularisation(self):
+        return self._regularisation
+
+    @regularisation.setter
+    def regularisation(self, regularisation):
+        self._regularisation = regularisation
+
+    @property
+    def empirical_risk(self):
+        return self._empirical_risk
+
+    @empirical_risk.setter
+    def empirical_risk(self, empirical_risk):
+        self._empirical_risk = empirical_risk
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _fusable(self) -> bool:
+        er, rg = self._empirical_risk, self._regularisation
+        if not isinstance(er, NegativeLogLikelihood) or not isinstance(rg, RegularisationBase):
+            return False
+        gp = er.gp
+        if gp is not rg.gp or not isinstance(gp, ApproximateGPRegression):
+            return False
+        if not isinstance(gp.kernel, SparsePosteriorKernel) or rg.kind == "none":
+            return False
+        if rg.mode == RegularisationMode.posterior:
+            reg = rg.regulariser
+            return (isinstance(reg, GPRegression) and reg.x.shape == gp.kernel.inducing_points.shape
+                    and reg.x.shape[1] <= 32)
+        return gp.kernel.inducing_points.shape[1] <= 32
+
+    def loss_sums(self, parameters, x, y, refactor_regulariser: bool = True):
+        """Shard-local sums [sum NLL_i, sum D0_i, N] of the fused step (device tensor, no host sync).
+        Multi-GPU callers all-reduce this vector and divide (see gvi_gaussian_process_b200.distributed)."""
+        er, rg = self._empirical_risk, self._regularisation
+        gp = er.gp
+        parameters = gp._to_parameters(parameters)
+        x = as_2d(x)
+        x = x.reshape(x.shape[0], -1)
+        y = as_device(y).reshape(-1)
+        assert y.numel() == x.shape[0], f"{y.numel()=} responses for {x.shape[0]=} points"
+        m_q = gp.mean.predict(parameters.mean, x).contiguous()
+        f_q = gp.kernel.factorise(parameters.kernel)
+        kind = L.REG_KINDS[rg.kind]
+        if rg.mode == RegularisationMode.posterior:
+            reg = rg.regulariser
+            reg_parameters = reg._to_parameters(rg.regulariser_parameters)
+            f_p = reg.factorise(reg_parameters) if (refactor_regulariser or reg._factor is None) else reg._factor
+            prior_mean_p = reg.mean.predict(reg_parameters.mean, x).contiguous()
+            return L.fused_step(f_q, f_p, x, y, m_q, prior_mean_p, None, None, kind, rg.alpha)
+        m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
+        return L.fused_step(f_q, None, x, y, m_q, None, m_p.reshape(-1).contiguous(),
+                            c_p.reshape(-1).contiguous(), kind, rg.alpha)
+
+    def _calculate_loss(self, parameters, x, y):
+        if self._fusable():
+            out3 = self.loss_sums(parameters, x, y)
+            return (out3[0] + out3[1]) / out3[2]
+        return (self._empirical_risk.calculate_empirical_risk(parameters, x, y)
+                + self._regularisation.calculate_regularisation(parameters, x))
+
+    def calculate_loss(self, parameters, x, y):
+        """reference: src/generalised_variational_inference.py:96-119."""
+        return self._calculate_loss(parameters, x, y)

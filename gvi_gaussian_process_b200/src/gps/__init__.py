@@ -1,0 +1,3 @@
+from .base import GPBase, GPBaseParameters  # noqa: F401
+from .gp_regression import GPRegression  # noqa: F401
+from .approximate_gp_regression import ApproximateGPRegression  # noqa: F401

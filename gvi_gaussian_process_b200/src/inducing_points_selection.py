@@ -1,0 +1,63 @@
+"""Inducing-point selectors (reference: src/inducing_points_selection.py:15-176)."""
+from __future__ import annotations
+
+import warnings
+from abc import ABC, abstractmethod
+
+import numpy as np
+import torch
+
+from . import _lib_proxy as L
+from .kernels.standard.ard_kernel import ARDKernel
+from .utils import jax_prng
+from .utils.device import as_device
+
+
+class InducingPointsSelectorBase(ABC):
+    @abstractmethod
+    def compute_inducing_points(self, key, training_inputs, number_of_inducing_points, kernel=None,
+                                kernel_parameters=None):
+        raise NotImplementedError
+
+
+class RandomInducingPointsSelector(InducingPointsSelectorBase):
+    """reference lines 31-46: jax.random.choice over the row indices (with replacement)."""
+
+    def compute_inducing_points(self, key, training_inputs, number_of_inducing_points, kernel=None,
+                                kernel_parameters=None):
+        x = as_device(training_inputs)
+        idx = jax_prng.choice(np.asarray(key), x.shape[0], number_of_inducing_points)
+        idx_d = torch.as_tensor(idx, device=x.device)
+        return x[idx_d], idx_d
+
+
+class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
+    """Greedy conditional-variance selection (reference lines 49-176) as a GPU pivoted Cholesky.
+
+    The PRNG permutation is reproduced on the host (utils/jax_prng.py), the permuted inputs are gathered on the
+    device and the whole M-step loop runs in CUDA (gvi_cond_var_select_f64) with the C matrix resident in HBM."""
+
+    def __init__(self, threshold: float = 0.0):
+        self.threshold = threshold
+
+    def compute_inducing_points(self, key, training_inputs, number_of_inducing_points, kernel=None,
+                                kernel_parameters=None, jitter: float = 1e-12):
+        assert number_of_inducing_points > 1, "Must have at least 2 inducing points"
+        if not isinstance(kernel, ARDKernel):
+            raise NotImplementedError("the B200 selector implements ARDKernel only (SURVEY.md section 8, a13)")
+        x = as_device(training_inputs)
+        n = x.shape[0]
+        _, subkey = jax_prng.split(np.asarray(key))
+        perm = torch.as_tensor(jax_prng.permutation(subkey, n), device=x.device)
+        x_perm = x[perm].contiguous()
+        kernel_parameters = kernel._to_parameters(kernel_parameters)
+        ls, ll = ARDKernel.device_parameters(kernel_parameters)
+        idx, trace = L.cond_var_select(x_perm.reshape(n, -1), number_of_inducing_points, ls, ll, jitter)
+        if self.threshold > 0.0:
+            # reference lines 167-172: the first step m whose tr(K - Q) < threshold truncates to indices[:m]
+            below = torch.nonzero(trace < self.threshold)
+            if below.numel() > 0:
+                m = int(below[0, 0].item())
+                idx = idx[:m]
+                warnings.warn("ConditionalVariance: Terminating selection of inducing points early.")
+        return x_perm[idx], perm[idx]

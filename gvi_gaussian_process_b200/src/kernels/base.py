@@ -1,0 +1,47 @@
+"""KernelBase (reference: src/kernels/base.py:38-147)."""
+from __future__ import annotations
+
+from ..module import Module, ModuleParameters
+from ..utils.checks import check_matching_dimensions, check_maximum_dimension
+from ..utils.device import as_2d
+
+
+class KernelBaseParameters(ModuleParameters):
+    pass
+
+
+class KernelBase(Module):
+    Parameters = KernelBaseParameters
+    number_output_dimensions = 1
+
+    def __init__(self, preprocess_function=None):
+        self.preprocess_function = preprocess_function if preprocess_function is not None else (lambda x: x)
+
+    def preprocess_inputs(self, x, y=None):
+        # reference: src/kernels/base.py:45-63
+        y = x if y is None else y
+        return as_2d(self.preprocess_function(x)), as_2d(self.preprocess_function(y))
+
+    @staticmethod
+    def check_inputs(x, y) -> None:
+        # reference: src/kernels/base.py:65-80
+        check_matching_dimensions(x, y)
+        check_maximum_dimension(x, maximum_dimensionality=2)
+        check_maximum_dimension(y, maximum_dimensionality=2)
+
+    def _calculate_gram(self, parameters, x1, x2):
+        raise NotImplementedError
+
+    def _calculate_gram_diagonal(self, parameters, x):
+        raise NotImplementedError
+
+    def calculate_gram(self, parameters, x1, x2=None, full_covariance: bool = True):
+        """reference: src/kernels/base.py:104-147 (same argument order and assertion behaviour)."""
+        x1, x2 = self.preprocess_inputs(x1, x2)
+        self.check_inputs(x1, x2)
+        parameters = self._to_parameters(parameters)
+        if full_covariance:
+            return self._calculate_gram(parameters, x1, x2)
+        assert x1.shape[0] == x2.shape[0], (
+            f"{x1.shape[0]=} must be equal to {x2.shape[0]=} for diagonal only calculation")
+        return self._calculate_gram_diagonal(parameters, x1)

@@ -1,0 +1,3 @@
+from .base import MeanBase, MeanBaseParameters  # noqa: F401
+from .constant_mean import ConstantMean, ConstantMeanParameters  # noqa: F401
+from .custom_mean import CustomMean, CustomMeanParameters  # noqa: F401

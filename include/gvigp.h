@@ -38,6 +38,8 @@ extern "C" {
 
 int gvi_abi_version(void);
 const char* gvi_last_error_string(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py's gpu_launches) */
+int64_t gvi_launch_count(void);
 
 /* ---- a1-a3: ARDKernel._calculate_gram (src/kernels/standard/base.py:73-103, ard_kernel.py:58-66) ----------
  * out[i*ld_out + j] = exp(log_scaling)^2 * exp(-0.5 * sum_d exp(log_ls[d]) * (x1[i,d]-x2[j,d])^2).

@@ -211,8 +211,9 @@ def gwi_with_eig(m_p, cov_p, m_q, cov_q, gram_batch_train_p, gram_batch_train_q,
     """Single-output full form (gaussian_wasserstein_regularisation.py:106-160, 55-104) - only used to pin the
     reference golden 0.87307723; the O(N^3) eigendecomposition variant is out of scope for the CUDA path."""
     n_b, n_t = gram_batch_train_p.shape
-    prod = gram_batch_train_p.T @ gram_batch_train_q
-    prod = add_diagonal_regulariser(prod, eigenvalue_regularisation, is_absolute) if prod.shape[0] == prod.shape[1] else prod
+    # symmetric branch (lines 80-92): eigenvalues of (q + reg I)(p + reg I) via src/utils/matrix_operations.py:69-102
+    prod = (add_diagonal_regulariser(gram_batch_train_q, eigenvalue_regularisation, is_absolute)
+            @ add_diagonal_regulariser(gram_batch_train_p, eigenvalue_regularisation, is_absolute))
     ev = np.linalg.eigvals(prod)
     ev = np.where(np.real(ev) > 0, np.real(ev), 0.0)
     return float(np.mean((m_p - m_q) ** 2) + np.trace(cov_p) / n_b + np.trace(cov_q) / n_b

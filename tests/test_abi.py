@@ -1,0 +1,67 @@
+"""CPU-only: the C-ABI library builds, loads, and exports every symbol include/gvigp.h declares; argument
+validation that needs no device work returns the documented error codes (no compute calls here)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gvigp.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gvi_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = header_symbols()
+    for must in ("gvi_ard_gram_f64", "gvi_gp_factor_f64", "gvi_gp_predict_f64", "gvi_risk_f64",
+                 "gvi_fused_step_f64", "gvi_cond_var_select_f64", "gvi_select_update_f64"):
+        assert must in syms
+
+
+def test_library_exports_every_header_symbol(lib):
+    from gvi_gaussian_process_b200 import _lib
+
+    syms = header_symbols()
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gvi_[a-z0-9_]+)", out))
+    assert set(syms) <= exported, sorted(set(syms) - exported)
+    for s in syms:
+        assert getattr(lib, s) is not None
+
+
+def test_abi_version_and_size_queries(lib):
+    assert lib.gvi_abi_version() == 1
+    assert lib.gvi_gp_factor_bytes(1024, 8) > 8 * 512 * 32 * 33
+    assert lib.gvi_gp_factor_bytes(0, 8) == 0
+    assert lib.gvi_gp_factor_workspace_bytes(1000) >= 2 * 1024 * 1024 * 8
+    assert lib.gvi_select_record_len(8, 1024) == 2 + 8 + 1023
+    assert lib.gvi_select_workspace_bytes(1000, 10, 3) >= 1000 * 9 * 8
+    assert lib.gvi_select_workspace_bytes(1000, 1, 3) == 0  # fewer than 2 inducing points is invalid
+
+
+def test_argument_validation_without_device(lib):
+    # all rejected before any CUDA call
+    assert lib.gvi_ard_gram_f64(None, -1, None, 4, 3, None, None, 3, None, 4, None) == -1
+    assert b"invalid argument" in lib.gvi_last_error_string()
+    assert lib.gvi_ard_gram_f64(None, 2, None, 4, 3, None, None, 2, None, 4, None) == -1  # ls_len not in {1, D}
+    assert lib.gvi_cond_var_select_f64(None, 10, 3, 1, None, None, 3, 1e-12, None, None, None, None) == -1
+    assert b"at least 2 inducing points" in lib.gvi_last_error_string()
+    assert lib.gvi_risk_f64(99, 0.5, None, None, None, None, None, 10, None, None, None) == -1
+    # empty inputs are a no-op, as in the reference (a 0 x m Gram)
+    assert lib.gvi_ard_gram_f64(None, 0, None, 4, 3, None, None, 3, None, 4, None) == 0
+    assert lib.gvi_gp_predict_f64(None, 4, 3, None, 0, None, None, None, None, None) == 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gvi_gaussian_process_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)

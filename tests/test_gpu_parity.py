@@ -1,0 +1,565 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI / the src-compatible
+shim, against the CPU oracle on the same seeded inputs, against the committed golden fixtures, and - at
+BASELINE.json's full size - through size-independent properties.
+
+Tolerances (BASELINE.json north_star): Gram / mean / variance / risk 1e-10 relative (variance normwise:
+max|delta| / max|ref|), selector indices bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+from oracle import jax_prng as OP
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def S():
+    """The src-compatible shim, imported lazily so collection works without a GPU."""
+    import types
+
+    from gvi_gaussian_process_b200 import _lib, distributed
+    from gvi_gaussian_process_b200.src import _lib_proxy
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.inducing_points_selection import (
+        ConditionalVarianceInducingPointsSelector, RandomInducingPointsSelector)
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
+    from gvi_gaussian_process_b200.src.regularisations import (
+        GaussianSquaredDifferenceRegularisation, GaussianWassersteinRegularisation)
+    from gvi_gaussian_process_b200.src.regularisations import projected
+    from gvi_gaussian_process_b200.src.utils import jax_prng
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.load()  # fails loudly if libgvigp.so is missing
+    return types.SimpleNamespace(**locals())
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_elem(a, ref):
+    return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), 1e-300)))
+
+
+def rel_norm(a, ref):
+    return float(np.max(np.abs(a - ref)) / np.max(np.abs(ref)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a1-a3 Gram
+# ---------------------------------------------------------------------------------------------------------------
+def test_ard_scalar_golden(S):
+    # reference tests/kernels/test_kernels.py:97-142 pins 1.8095777100611745 with ==; CUDA's exp() is not the same
+    # libm, so the GPU value is required to agree to 2 ulp (the oracle reproduces the value exactly on the CPU).
+    k = S.ARDKernel(number_of_dimensions=3)
+    p = k.Parameters.construct(log_scaling=0.5, log_lengthscales=np.array([-0.5, 0.0, 0.5]))
+    g = host(k.calculate_gram(p, np.array([[1.0, 2.0, 3.0]]), np.array([[1.5, 2.5, 3.5]])))
+    assert g.shape == (1, 1)
+    assert abs(g[0, 0] - 1.8095777100611745) <= 2 * np.spacing(1.8095777100611745)
+    k1 = S.ARDKernel(number_of_dimensions=1)
+    p1 = k1.Parameters.construct(log_scaling=np.log(1.0), log_lengthscales=-0.5)
+    assert host(k1.calculate_gram(p1, np.array([[6.0]]), np.array([[6.0]])))[0, 0] == 1.0
+
+
+@pytest.mark.parametrize("m1,m2,d", [(1, 2, 3), (37, 300, 1), (300, 257, 8), (65, 33, 40), (1000, 1, 5)])
+def test_ard_gram_parity(S, m1, m2, d):
+    rng = np.random.default_rng(m1 * 1000 + m2)
+    x1, x2 = rng.standard_normal((m1, d)), rng.standard_normal((m2, d))
+    ls, ll = 0.3, rng.normal(-1.0, 0.5, d)
+    k = S.ARDKernel(number_of_dimensions=d)
+    p = k.Parameters.construct(log_scaling=ls, log_lengthscales=ll)
+    g = host(k.calculate_gram(p, x1, x2))
+    assert g.shape == (m1, m2)
+    assert rel_elem(g, O.ard_gram(ls, ll, x1, x2)) <= TOL
+    # x2=None -> Gram with itself; diagonal mode returns [m1] (src/kernels/base.py:132-147)
+    gs = host(k.calculate_gram(p, x1))
+    assert rel_elem(gs, O.ard_gram(ls, ll, x1, x1)) <= TOL
+    gd = host(k.calculate_gram(p, x1, x1, full_covariance=False))
+    assert gd.shape == (m1,) and rel_elem(gd, O.ard_gram_diag(ls, ll, x1)) <= 1e-15
+
+
+def test_gram_shape_asserts(S):
+    k = S.ARDKernel(number_of_dimensions=3)
+    p = k.Parameters.construct(log_scaling=0.0, log_lengthscales=np.zeros(3))
+    with pytest.raises(AssertionError):
+        k.calculate_gram(p, np.zeros((2, 3)), np.zeros((2, 4)))
+    with pytest.raises(AssertionError):
+        k.calculate_gram(p, np.zeros((2, 3)), np.zeros((3, 3)), full_covariance=False)
+    with pytest.raises(AssertionError):
+        k.calculate_gram({"log_scaling": 0.0, "log_lengthscales": np.zeros(2)}, np.zeros((2, 3)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a4 + Cholesky
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m", [1, 31, 32, 33, 200, 1000])
+def test_add_diag_and_cholesky(S, m):
+    rng = np.random.default_rng(m)
+    b = rng.standard_normal((m, m + 5))
+    a = b @ b.T / m + np.eye(m)
+    for is_abs in (True, False):
+        ad = dev(a)
+        S._lib_proxy.add_diagonal_regulariser(ad, 0.25, is_abs)
+        assert rel_elem(host(ad), O.add_diagonal_regulariser(a, 0.25, is_abs)) <= 1e-14
+    ad = dev(a)
+    info = S._lib_proxy.chol_factor(ad)
+    assert int(info.item()) == 0
+    lref = np.linalg.cholesky(a)
+    assert np.max(np.abs(np.tril(host(ad)) - lref)) <= 1e-12 * np.max(np.abs(lref))
+    # a matrix that is not positive definite reports the failing column (and yields NaN, like the reference)
+    bad = np.eye(m)
+    bad[m // 2, m // 2] = -1.0
+    info = S._lib_proxy.chol_factor(dev(bad))
+    assert int(info.item()) == m // 2 + 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a5-a7 predictive
+# ---------------------------------------------------------------------------------------------------------------
+def make_problem(n, m, d, seed, ll_base=0.0):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d))
+    z = rng.standard_normal((m, d))
+    w = rng.standard_normal(d)
+    y = np.sin(x @ w) + 0.1 * rng.standard_normal(n)
+    yz = np.sin(z @ w) + 0.1 * rng.standard_normal(m)
+    ls_q, ll_q = 0.1, ll_base + 0.1 * rng.standard_normal(d)
+    ls_p, ll_p = -0.2, ll_base + 0.1 * rng.standard_normal(d)
+    m_q = 0.3 * np.tanh(x @ rng.standard_normal(d))
+    return dict(x=x, z=z, y=y, yz=yz, ls_q=ls_q, ll_q=ll_q, ls_p=ls_p, ll_p=ll_p, m_q=m_q)
+
+
+def oracle_predictions(pr, lam=1e-5, prior_const=0.25, log_noise=0.0):
+    gq = lambda a, b: O.ard_gram(pr["ls_q"], pr["ll_q"], a, b)
+    dq = lambda a: O.ard_gram_diag(pr["ls_q"], pr["ll_q"], a)
+    gp = lambda a, b: O.ard_gram(pr["ls_p"], pr["ll_p"], a, b)
+    dp = lambda a: O.ard_gram_diag(pr["ls_p"], pr["ll_p"], a)
+    n = pr["x"].shape[0]
+    v_q = O.sparse_posterior_diag(gq, dq, pr["z"], pr["x"], lam, False)
+    m_p, v_p = O.exact_gp_posterior(gp, dp, np.full(n, prior_const), pr["z"], pr["yz"], log_noise, pr["x"])
+    return v_q, m_p, v_p
+
+
+def build_models(S, pr, lam=1e-5, prior_const=0.25, log_noise=0.0):
+    d = pr["x"].shape[1]
+    kernel = S.ARDKernel(number_of_dimensions=d)
+    mq_table = dev(pr["m_q"])
+    x_dev = dev(pr["x"])
+    # the approximate mean is "any function evaluated by the host framework": here a lookup of precomputed values
+    approx_mean = S.CustomMean(mean_function=lambda params, x: params[: x.shape[0]])
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=pr["z"], diagonal_regularisation=lam)
+    approx_gp = S.ApproximateGPRegression(mean=approx_mean, kernel=sparse)
+    approx_params = approx_gp.Parameters.construct(
+        mean=approx_mean.Parameters.construct(custom=mq_table),
+        kernel=sparse.Parameters.construct(
+            base_kernel=kernel.Parameters.construct(log_scaling=pr["ls_q"], log_lengthscales=pr["ll_q"])))
+    const_mean = S.ConstantMean()
+    exact_gp = S.GPRegression(mean=const_mean, kernel=kernel, x=pr["z"], y=pr["yz"])
+    exact_params = exact_gp.Parameters.construct(
+        log_observation_noise=log_noise, mean=const_mean.Parameters.construct(constant=prior_const),
+        kernel=kernel.Parameters.construct(log_scaling=pr["ls_p"], log_lengthscales=pr["ll_p"]))
+    return approx_gp, approx_params, exact_gp, exact_params, x_dev
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 2, 1), (23, 10, 1), (1000, 100, 3), (2500, 333, 8), (777, 1024, 8),
+                                   (500, 1500, 5), (300, 2048, 16), (200, 64, 32)])
+def test_predictive_parity(S, n, m, d):
+    pr = make_problem(n, m, d, seed=n + m)
+    v_q_ref, m_p_ref, v_p_ref = oracle_predictions(pr)
+    approx_gp, approx_params, exact_gp, exact_params, x_dev = build_models(S, pr)
+    q = approx_gp.predict_probability(approx_params, x_dev)
+    assert q.mean.shape == (n,) and q.covariance.shape == (n,)
+    assert rel_norm(host(q.covariance), v_q_ref) <= TOL
+    assert rel_elem(host(q.mean), pr["m_q"]) <= 1e-15
+    p = exact_gp.predict_probability(exact_params, x_dev)
+    assert p.mean.shape == (1, n) and p.covariance.shape == (n,)  # [1,N] mean quirk, base.py:410-412
+    assert rel_norm(host(p.mean).reshape(-1), m_p_ref) <= TOL
+    assert rel_norm(host(p.covariance), v_p_ref) <= TOL
+    assert np.all(host(q.covariance) > -1e-12) and np.all(host(p.covariance) > 0)
+
+
+def test_unsupported_sizes_fail_loudly(S):
+    pr = make_problem(10, 8, 33, seed=5)
+    approx_gp, approx_params, *_ = build_models(S, pr)
+    with pytest.raises(Exception, match="D <= 32"):
+        approx_gp.predict_probability(approx_params, dev(pr["x"]))
+
+
+def test_sparse_posterior_full_gram_and_identity_golden(S):
+    # reference tests/kernels/test_sparse_posterior_kernels.py:15-64 uses an identity mock kernel: K_ZZ = I,
+    # k(x_i, z_j) = delta_ij -> diag 1 - 1/(1 + 1e-5) = 9.9999e-06, off-diagonal 0.  An ARD kernel with a huge
+    # inverse lengthscale evaluated at x = Z is that identity kernel.
+    z = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    k = S.ARDKernel(number_of_dimensions=3)
+    sp = S.SparsePosteriorKernel(base_kernel=k, inducing_points=z, diagonal_regularisation=1e-5,
+                                 is_diagonal_regularisation_absolute_scale=False)
+    p = sp.generate_parameters({"base_kernel": {"log_scaling": 0.0, "log_lengthscales": np.full(3, 20.0)}})
+    full = host(sp.calculate_gram(p, z, z, full_covariance=True))
+    assert np.allclose(full, np.array([[9.9999e-06, 0.0], [0.0, 9.9999e-06]]), rtol=1e-5, atol=1e-8)
+    diag = host(sp.calculate_gram(p, z, z, full_covariance=False))
+    assert np.allclose(diag, [9.9999e-06, 9.9999e-06], rtol=1e-5, atol=1e-8)
+    # full Gram against the oracle on a random problem
+    pr = make_problem(50, 20, 3, seed=9)
+    sp = S.SparsePosteriorKernel(base_kernel=k, inducing_points=pr["z"])
+    p = sp.generate_parameters({"base_kernel": {"log_scaling": pr["ls_q"], "log_lengthscales": pr["ll_q"]}})
+    x2 = pr["x"][:17]
+    g = host(sp.calculate_gram(p, pr["x"], x2))
+    ref = O.sparse_posterior_gram(lambda a, b: O.ard_gram(pr["ls_q"], pr["ll_q"], a, b), pr["z"], pr["x"], x2)
+    assert rel_norm(g, ref) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference goldens through the real product path: an all-ones Gram is ARD with exp(log_ls) = 0
+# ---------------------------------------------------------------------------------------------------------------
+X_TRAIN = np.array([[1.0, 3.0, 2.0], [1.5, 1.5, 9.5]])
+Y_TRAIN = np.array([1.0, 1.5])
+X2 = np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5]])
+ONES = {"log_scaling": 0.0, "log_lengthscales": np.full(3, -np.inf)}
+
+
+def ones_kernel_models(S):
+    k = S.ARDKernel(number_of_dimensions=3)
+    mean = S.ConstantMean()
+    exact = S.GPRegression(mean=mean, kernel=k, x=X_TRAIN, y=Y_TRAIN)
+    approx = S.ApproximateGPRegression(mean=mean, kernel=k)
+    params = {"log_observation_noise": np.log(1.0), "mean": {"constant": 1.0}, "kernel": ONES}
+    return exact, approx, params
+
+
+def test_reference_goldens_exact_and_approximate_gp(S):
+    exact, approx, params = ones_kernel_models(S)
+    p = exact.predict_probability(params, X2)
+    # tests/gps/test_regression.py:14-56 pins these with array_equal; the GPU inverse-Cholesky route is allowed 2 ulp
+    assert np.allclose(host(p.mean), 1.8333333333333335, rtol=5e-16, atol=0)
+    assert np.allclose(host(p.covariance), 0.33333333333333326, rtol=1e-15, atol=0)
+    q = approx.predict_probability(params, X2)  # noise dropped: tests/gps/test_regression.py:203-249
+    assert np.array_equal(host(q.mean), np.ones(2)) and np.array_equal(host(q.covariance), np.ones(2))
+
+
+def test_reference_goldens_nll(S):
+    exact, approx, params = ones_kernel_models(S)
+    nll = S.NegativeLogLikelihood(gp=exact)
+    assert np.isclose(float(nll.calculate_empirical_risk(params, X2, np.ones(2))), 1.4112988, rtol=1e-5)
+    assert np.isclose(float(nll.calculate_empirical_risk(params, np.tile(X2, (6, 1)), np.ones(12))), 1.4112988,
+                      rtol=1e-5)
+    nll_q = S.NegativeLogLikelihood(gp=approx)
+    assert np.isclose(float(nll_q.calculate_empirical_risk(params, X2, np.array([1.2, 4.2]))), 3.48893853,
+                      rtol=1e-5)
+
+
+REG_CASES = [
+    ("ProjectedBhattacharyyaRegularisation", {}, 0.13702468),
+    ("ProjectedGaussianWassersteinRegularisation", {}, 0.87307724),
+    ("ProjectedHellingerRegularisation", {}, 0.18301035),
+    ("ProjectedKLRegularisation", {}, 0.56319503),
+    ("ProjectedRenyiRegularisation", {"alpha": 0.5}, 0.4042577),
+]
+
+
+@pytest.mark.parametrize("cls,kw,golden", REG_CASES)
+def test_reference_goldens_projected_regularisers(S, cls, kw, golden):
+    # tests/regularisations/projected/test_projected_*.py:120-176: p = (1.8333, 1/3) posterior, q = (1, 1)
+    exact, approx, params = ones_kernel_models(S)
+    reg = getattr(S.projected, cls)(gp=approx, regulariser=exact, regulariser_parameters=params, mode="posterior",
+                                    **kw)
+    assert np.isclose(float(reg.calculate_regularisation(params, X2)), golden, rtol=1e-5)
+    same = getattr(S.projected, cls)(gp=approx, regulariser=approx, regulariser_parameters=params, mode="prior", **kw)
+    assert abs(float(same.calculate_regularisation(params, X2))) <= 1e-12
+
+
+def test_gvi_is_risk_plus_regularisation(S):
+    exact, approx, params = ones_kernel_models(S)
+    risk = S.NegativeLogLikelihood(gp=approx)
+    reg = S.projected.ProjectedKLRegularisation(gp=approx, regulariser=exact, regulariser_parameters=params,
+                                                mode="posterior")
+    gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+    y = np.array([1.2, 4.2])
+    total = float(gvi.calculate_loss(params, X2, y))
+    assert np.isclose(total, 3.48893853 + 0.56319503, rtol=1e-5)
+    assert np.isclose(total, float(risk.calculate_empirical_risk(params, X2, y))
+                      + float(reg.calculate_regularisation(params, X2)), rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a9-a12 risks, regularisers, fused step
+# ---------------------------------------------------------------------------------------------------------------
+ALL_REGS = [("bhattacharyya", "ProjectedBhattacharyyaRegularisation"),
+            ("gaussian_wasserstein", "ProjectedGaussianWassersteinRegularisation"),
+            ("hellinger", "ProjectedHellingerRegularisation"), ("kl", "ProjectedKLRegularisation"),
+            ("renyi", "ProjectedRenyiRegularisation")]
+
+
+def oracle_reg(kind, m_p, v_p, m_q, v_q, alpha=0.5):
+    if kind == "gwi_no_eig":
+        return O.gwi_no_eig(m_p, v_p, m_q, v_q)
+    if kind == "squared_difference":
+        return O.gaussian_squared_difference(m_p, v_p, m_q, v_q)
+    return O.projected_regularisation(kind, m_p, v_p, m_q, v_q, alpha)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 1001, 300000])
+def test_risk_kernel_all_kinds(S, n):
+    rng = np.random.default_rng(n)
+    y, m_q, m_p = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    v_q, v_p = rng.uniform(0.05, 2.0, n), rng.uniform(0.05, 2.0, n)
+    for kind, code in S._lib.REG_KINDS.items():
+        if kind == "none":
+            continue
+        alpha = 0.3 if kind == "renyi" else 0.5
+        out = host(S._lib_proxy.risk(code, alpha, dev(y), dev(m_q), dev(v_q), dev(m_p), dev(v_p)))
+        assert out[2] == n
+        assert abs(out[0] / n - O.gaussian_nll(y, m_q, v_q)) <= TOL * abs(O.gaussian_nll(y, m_q, v_q))
+        ref = oracle_reg(kind, m_p, v_p, m_q, v_q, alpha)
+        assert abs(out[1] / n - ref) <= TOL * abs(ref), kind
+    # unaligned views take the scalar path
+    out = host(S._lib_proxy.risk(4, 0.5, dev(y)[1:].contiguous() if n > 1 else dev(y), *(
+        [t[1:] for t in (dev(m_q), dev(v_q), dev(m_p), dev(v_p))] if n > 1 else
+        [dev(m_q), dev(v_q), dev(m_p), dev(v_p)])))
+    sl = slice(1, None) if n > 1 else slice(None)
+    ref = O.projected_regularisation("kl", m_p[sl], v_p[sl], m_q[sl], v_q[sl])
+    assert abs(out[1] / out[2] - ref) <= TOL * abs(ref)
+
+
+@pytest.mark.parametrize("n,m,d", [(50, 10, 1), (3001, 257, 8)])
+def test_fused_step_matches_oracle_and_unfused(S, n, m, d):
+    pr = make_problem(n, m, d, seed=n)
+    v_q_ref, m_p_ref, v_p_ref = oracle_predictions(pr)
+    approx_gp, approx_params, exact_gp, exact_params, x_dev = build_models(S, pr)
+    nll_ref = O.gaussian_nll(pr["y"], pr["m_q"], v_q_ref)
+    risk = S.NegativeLogLikelihood(gp=approx_gp)
+    y_dev = dev(pr["y"])
+    regs = [(kind, getattr(S.projected, cls)) for kind, cls in ALL_REGS]
+    regs += [("gwi_no_eig", S.GaussianWassersteinRegularisation)]
+    regs += [("squared_difference", lambda **kw: S.GaussianSquaredDifferenceRegularisation(full_covariance=False, **kw))]
+    for mode in ("posterior", "prior"):
+        for kind, ctor in regs:
+            reg = ctor(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params, mode=mode)
+            gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+            assert gvi._fusable()
+            loss = float(gvi.calculate_loss(approx_params, x_dev, y_dev))
+            if mode == "posterior":
+                reg_ref = oracle_reg(kind, m_p_ref, v_p_ref, pr["m_q"], v_q_ref)
+            else:
+                m_pr, v_pr = O.exact_gp_prior(lambda a: O.ard_gram_diag(pr["ls_p"], pr["ll_p"], a), np.full(n, 0.25),
+                                              0.0, pr["x"])
+                reg_ref = oracle_reg(kind, m_pr, v_pr, pr["m_q"], v_q_ref)
+            assert abs(loss - (nll_ref + reg_ref)) <= TOL * abs(nll_ref + reg_ref), (mode, kind)
+            unfused = float(risk.calculate_empirical_risk(approx_params, x_dev, y_dev)) + float(
+                reg.calculate_regularisation(approx_params, x_dev))
+            assert abs(loss - unfused) <= 1e-12 * abs(unfused), (mode, kind)
+
+
+def test_unsupported_variants_raise(S):
+    pr = make_problem(10, 4, 2, seed=1)
+    approx_gp, approx_params, exact_gp, exact_params, _ = build_models(S, pr)
+    with pytest.raises(NotImplementedError):
+        S.GaussianWassersteinRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
+                                            include_eigendecomposition=True)
+    with pytest.raises(NotImplementedError):
+        S.GaussianSquaredDifferenceRegularisation(gp=approx_gp, regulariser=exact_gp,
+                                                  regulariser_parameters=exact_params)
+    with pytest.raises(NotImplementedError):
+        S.SparsePosteriorKernel(base_kernel=object(), inducing_points=pr["z"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden fixtures (configs #1 and #2), end to end through the README-style API
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,m", [("config1_readme", 10), ("config2_toy_curves", 100)])
+def test_golden_fixture_end_to_end(S, name, m):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x, y = g["x"], g["y"]
+    d = x.shape[1]
+    kernel = S.ARDKernel(number_of_dimensions=d)
+    kp = kernel.Parameters.construct(log_scaling=float(g["log_scaling"]), log_lengthscales=g["log_ls"])
+    sel = S.ConditionalVarianceInducingPointsSelector()
+    z, idx = sel.compute_inducing_points(key=S.jax_prng.PRNGKey(0), training_inputs=x,
+                                         number_of_inducing_points=m, kernel=kernel, kernel_parameters=kp)
+    assert np.array_equal(host(idx), g["idx"])          # indices bit-exact
+    assert np.array_equal(host(z), x[g["idx"]])
+    assert rel_elem(host(kernel.calculate_gram(kp, x[:64], z)), g["gram_xz"]) <= TOL
+    yz = y[g["idx"]]
+    mean0 = S.ConstantMean()
+    exact = S.GPRegression(mean=mean0, kernel=kernel, x=z, y=yz)
+    exact_params = exact.Parameters.construct(log_observation_noise=0.0,
+                                              mean=mean0.Parameters.construct(constant=0.0), kernel=kp)
+    p = exact.predict_probability(exact_params, x)
+    assert rel_norm(host(p.mean).reshape(-1), g["m_p"]) <= TOL and rel_norm(host(p.covariance), g["v_p"]) <= TOL
+    mq = dev(g["m_q"])
+    amean = S.CustomMean(mean_function=lambda params, xx: params)
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=float(g["lam"]))
+    approx = S.ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(
+        mean=amean.Parameters.construct(custom=mq),
+        kernel=sparse.Parameters.construct(
+            base_kernel=kernel.Parameters.construct(log_scaling=float(g["ls_q"]), log_lengthscales=g["ll_q"])))
+    q = approx.predict_probability(ap, x)
+    assert rel_norm(host(q.covariance), g["v_q"]) <= TOL
+    risk = S.NegativeLogLikelihood(gp=approx)
+    nll = float(risk.calculate_empirical_risk(ap, x, y))
+    assert abs(nll - float(g["nll"])) <= TOL * abs(float(g["nll"]))
+    for kind, cls in ALL_REGS:
+        reg = getattr(S.projected, cls)(gp=approx, regulariser=exact, regulariser_parameters=exact_params,
+                                        mode="posterior")
+        gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+        ref = float(g["nll"]) + float(g["reg_" + kind])
+        assert abs(float(gvi.calculate_loss(ap, x, y)) - ref) <= TOL * abs(ref), kind
+    gw = S.GaussianWassersteinRegularisation(gp=approx, regulariser=exact, regulariser_parameters=exact_params,
+                                             mode="posterior")
+    assert abs(float(gw.calculate_regularisation(ap, x)) - float(g["reg_gwi_no_eig"])) <= TOL * float(
+        g["reg_gwi_no_eig"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a13 selector
+# ---------------------------------------------------------------------------------------------------------------
+def test_selector_reference_pins(S):
+    # reference tests/test_inducing_points_selection.py:116-182: PRNGKey(0), all-ones Gram -> indices [2, 1]
+    k = S.ARDKernel(number_of_dimensions=3)
+    sel = S.ConditionalVarianceInducingPointsSelector()
+    x4 = np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5], [4.5, 2.5, 3.5], [5.5, 6.5, 7.5]])
+    z, idx = sel.compute_inducing_points(S.jax_prng.PRNGKey(0), x4, 2, k, ONES)
+    assert host(idx).tolist() == [2, 1]
+    assert np.array_equal(host(z), np.array([[4.5, 2.5, 3.5], [1.5, 2.5, 3.5]]))
+    k784 = S.ARDKernel(number_of_dimensions=784)
+    img = np.arange(3 * 784, dtype=float).reshape(3, 28, 28, 1)
+    z, idx = sel.compute_inducing_points(S.jax_prng.PRNGKey(0), img, 2, k784,
+                                         {"log_scaling": 0.0, "log_lengthscales": np.full(784, -np.inf)})
+    assert host(idx).tolist() == [2, 1] and tuple(z.shape) == (2, 28, 28, 1)
+    rnd = S.RandomInducingPointsSelector()
+    assert host(rnd.compute_inducing_points(S.jax_prng.PRNGKey(0), x4, 2)[1]).tolist() == [1, 2]
+    assert host(rnd.compute_inducing_points(S.jax_prng.PRNGKey(0), img, 2)[1]).tolist() == [0, 2]
+
+
+@pytest.mark.parametrize("n,m,d,seed", [(2, 2, 1, 0), (500, 40, 1, 1), (5000, 128, 3, 2), (20000, 200, 8, 3)])
+def test_selector_parity_bit_exact(S, n, m, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d))
+    # Bit-exact pivots are only defined while the residual variances stay far above rounding noise: once
+    # tr(K - Q) ~ 1e-12 the arg-max order is decided by the last bits of exp()/dot and differs between ANY two
+    # implementations (it would between JAX-CPU and JAX-GPU too).  In 1-D a short lengthscale keeps 40 pivots
+    # well-posed.
+    ls, ll = 0.2, rng.normal(4.0 if d == 1 else -0.5, 0.3, d)
+    k = S.ARDKernel(number_of_dimensions=d)
+    kp = k.Parameters.construct(log_scaling=ls, log_lengthscales=ll)
+    key = S.jax_prng.PRNGKey(seed)
+    z, idx = S.ConditionalVarianceInducingPointsSelector().compute_inducing_points(key, x, m, k, kp)
+    _, sub = OP.split(OP.prng_key(seed))
+    perm = OP.permutation(sub, n)
+    piv = O.conditional_variance_select(x[perm], m, lambda a, b: O.ard_gram(ls, ll, a, b),
+                                        lambda a: O.ard_gram_diag(ls, ll, a), use_argsort=(n <= 5000))
+    assert np.array_equal(host(idx), perm[piv])
+    assert np.array_equal(host(z), x[perm[piv]])
+    assert len(set(host(idx).tolist())) == m
+
+
+def test_selector_duplicates_and_threshold(S):
+    # Triplicated rows: the three copies of a point carry bit-identical d, so every pivot is a three-way exact tie
+    # decided by the highest-index rule (reference lines 161-164); picking one copy zeroes the others.  Only the 6
+    # distinct points are well-posed pivots (afterwards every d is rounding noise ~1e-12).
+    rng = np.random.default_rng(4)
+    base = rng.standard_normal((6, 2))
+    x = np.concatenate([base, base, base])
+    k = S.ARDKernel(number_of_dimensions=2)
+    kp = k.Parameters.construct(log_scaling=0.0, log_lengthscales=np.zeros(2))
+    gram = lambda a, b: O.ard_gram(0.0, np.zeros(2), a, b)
+    diag = lambda a: O.ard_gram_diag(0.0, np.zeros(2), a)
+    z, idx = S.ConditionalVarianceInducingPointsSelector().compute_inducing_points(S.jax_prng.PRNGKey(3), x, 6, k, kp)
+    _, sub = OP.split(OP.prng_key(3))
+    perm = OP.permutation(sub, 18)
+    piv = O.conditional_variance_select(x[perm], 6, gram, diag)
+    assert np.array_equal(host(idx), perm[piv])
+    assert sorted((host(idx) % 6).tolist()) == list(range(6))
+    # threshold: tr(K - Q) drops below 1e-3 at step m = 5 (all distinct points used) -> indices[:5], with a warning
+    with pytest.warns(UserWarning, match="Terminating selection"):
+        z, idx_t = S.ConditionalVarianceInducingPointsSelector(threshold=1e-3).compute_inducing_points(
+            S.jax_prng.PRNGKey(3), x, 10, k, kp)
+    import warnings as _w
+    with _w.catch_warnings():
+        _w.simplefilter("ignore")
+        piv_t = O.conditional_variance_select(x[perm], 10, gram, diag, threshold=1e-3)
+    assert len(piv_t) == 5 and np.array_equal(host(idx_t), perm[piv_t])
+    assert tuple(z.shape) == (5, 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json config #3 at full size: size-independent properties + sampled oracle rows
+# ---------------------------------------------------------------------------------------------------------------
+def test_config3_full_size_properties(S):
+    n, m, d = 1_000_000, 1024, 8
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((n, d))
+    w = rng.standard_normal(d)
+    y = np.sin(x @ w) + 0.1 * rng.standard_normal(n)
+    zi = rng.permutation(n)[:m]
+    pr = dict(x=x, z=x[zi], y=y, yz=y[zi], ls_q=0.0, ll_q=np.full(d, np.log(1.0 / d)), ls_p=0.0,
+              ll_p=np.full(d, np.log(1.0 / d)), m_q=0.3 * np.tanh(x @ rng.standard_normal(d)))
+    approx_gp, approx_params, exact_gp, exact_params, x_dev = build_models(S, pr)
+    y_dev = dev(y)
+    risk = S.NegativeLogLikelihood(gp=approx_gp)
+    reg = S.projected.ProjectedRenyiRegularisation(gp=approx_gp, regulariser=exact_gp,
+                                                   regulariser_parameters=exact_params, mode="posterior", alpha=0.5)
+    gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+    full = host(gvi.loss_sums(approx_params, x_dev, y_dev))
+    # (1) shard additivity: the loss sums of two contiguous shards add up to the full-batch sums
+    approx_mean_tbl = approx_params.mean.custom
+    halves = []
+    for lo, hi in ((0, 400_003), (400_003, n)):
+        approx_params.mean.custom = approx_mean_tbl[lo:hi].contiguous()
+        halves.append(host(gvi.loss_sums(approx_params, x_dev[lo:hi], y_dev[lo:hi])))
+    approx_params.mean.custom = approx_mean_tbl
+    both = halves[0] + halves[1]
+    assert both[2] == n == full[2]
+    assert np.all(np.abs(both[:2] - full[:2]) <= 1e-12 * np.abs(full[:2]))
+    # (2) run-to-run reproducibility (fixed-order reductions)
+    assert np.array_equal(full, host(gvi.loss_sums(approx_params, x_dev, y_dev)))
+    # (3) 0 <= var <= k(x,x); homogeneity: with relative jitter var scales exactly with exp(2 log_scaling)
+    q = approx_gp.predict_probability(approx_params, x_dev)
+    v = host(q.covariance)
+    assert v.min() >= -1e-12 and v.max() <= 1.0 + 1e-12
+    approx_params.kernel.base_kernel.log_scaling = np.log(3.0)
+    v3 = host(approx_gp.predict_probability(approx_params, x_dev).covariance)
+    approx_params.kernel.base_kernel.log_scaling = 0.0
+    assert np.max(np.abs(v3 - 9.0 * v)) <= TOL * 9.0 * v.max()
+    # (4) 2000 sampled rows against the oracle (the oracle materialises K(X_s, Z) like the reference)
+    rows = np.sort(rng.permutation(n)[:2000])
+    prs = dict(pr, x=x[rows], y=y[rows], m_q=pr["m_q"][rows])
+    v_q_ref, m_p_ref, v_p_ref = oracle_predictions(prs)
+    p = exact_gp.predict_probability(exact_params, x_dev)
+    assert rel_norm(v[rows], v_q_ref) <= TOL
+    assert rel_norm(host(p.mean).reshape(-1)[rows], m_p_ref) <= TOL
+    assert rel_norm(host(p.covariance)[rows], v_p_ref) <= TOL
+
+
+def test_selector_full_size_properties(S):
+    n, m, d = 1_000_000, 48, 8
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((n, d))
+    ls, ll = 0.0, np.full(d, np.log(1.0 / d))
+    k = S.ARDKernel(number_of_dimensions=d)
+    kp = k.Parameters.construct(log_scaling=ls, log_lengthscales=ll)
+    z, idx = S.ConditionalVarianceInducingPointsSelector().compute_inducing_points(S.jax_prng.PRNGKey(11), x, m, k, kp)
+    idx = host(idx)
+    assert len(set(idx.tolist())) == m and idx.min() >= 0 and idx.max() < n
+    assert np.array_equal(host(z), x[idx])
+    _, sub = OP.split(OP.prng_key(11))
+    perm = OP.permutation(sub, n)
+    piv = O.conditional_variance_select(x[perm], m, lambda a, b: O.ard_gram(ls, ll, a, b),
+                                        lambda a: O.ard_gram_diag(ls, ll, a), use_argsort=False)
+    assert np.array_equal(idx, perm[piv])

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle against every golden vector the reference's own tests hold for the hot path
+(SURVEY.md section 8c).  Values and the reference test locations are cited per case."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as O
+from oracle import jax_prng as P
+
+ones_gram = lambda a, b: np.ones((np.atleast_2d(a).shape[0], np.atleast_2d(b).shape[0]))  # mockers/kernel.py:12-16
+ones_diag = lambda a: np.ones((np.atleast_2d(a).shape[0],))
+
+
+def eye_gram(a, b):  # mockers/kernel.py:19-24
+    n1, n2 = np.atleast_2d(a).shape[0], np.atleast_2d(b).shape[0]
+    return np.eye(max(n1, n2))[:n1, :n2]
+
+
+X_TRAIN = np.array([[1.0, 3.0, 2.0], [1.5, 1.5, 9.5]])
+Y_TRAIN = np.array([1.0, 1.5])
+X = np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5]])
+
+
+def test_ard_scalar_exact():
+    # tests/kernels/test_kernels.py:97-142 (exact ==)
+    assert O.ard_kernel_scalar(0.5, [-0.5, 0.0, 0.5], [1.0, 2.0, 3.0], [1.5, 2.5, 3.5]) == 1.8095777100611745
+    assert O.ard_kernel_scalar(np.log(1.0), -0.5, [6.0], [6.0]) == 1.0
+    assert O.ard_gram(0.5, [-0.5, 0.0, 0.5], [[1.0, 2.0, 3.0]], [[1.5, 2.5, 3.5]])[0, 0] == pytest.approx(
+        1.8095777100611745, rel=1e-15)
+
+
+def test_gram_shapes():
+    # tests/kernels/test_kernels.py:145-211
+    assert O.ard_gram(0.0, [0.0, 0.0, 0.0], [[1.0, 2.0, 3.0]], X).shape == (1, 2)
+    assert O.ard_gram_diag(0.0, [0.0, 0.0, 0.0], X).shape == (2,)
+
+
+def test_add_diagonal_regulariser():
+    # tests/test_matrix_operations.py:95-145
+    m = np.array([[1.0, 0.5], [0.5, 3.0]])
+    np.testing.assert_allclose(O.add_diagonal_regulariser(m, 0.1, True), m + 0.1 * np.eye(2))
+    np.testing.assert_allclose(O.add_diagonal_regulariser(m, 0.1, False), m + 0.1 * 2.0 * np.eye(2))
+
+
+def test_sparse_posterior_gram_identity_kernel():
+    # tests/kernels/test_sparse_posterior_kernels.py:15-64: diag 9.9999e-06, off-diagonal 0
+    z = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    x = np.array([[5.3, 5.0, 6.0], [2.5, 4.5, 2.5]])
+    r = O.sparse_posterior_gram(eye_gram, z, x, x, 1e-5, False)
+    np.testing.assert_allclose(r, np.array([[9.9999e-06, 0.0], [0.0, 9.9999e-06]]), atol=1e-10)
+    d = O.sparse_posterior_diag(eye_gram, ones_diag, z, x, 1e-5, False)
+    np.testing.assert_allclose(d, [9.9999e-06, 9.9999e-06], atol=1e-10)
+
+
+def test_exact_gp_posterior_goldens():
+    # tests/gps/test_regression.py:14-56,100-200 (array_equal)
+    mean, var = O.exact_gp_posterior(ones_gram, ones_diag, np.ones(2), X_TRAIN, Y_TRAIN, np.log(1.0), X)
+    assert np.array_equal(mean, np.array([1.8333333333333335, 1.8333333333333335]))
+    assert np.array_equal(var, np.array([0.33333333333333326, 0.33333333333333326]))
+
+
+def test_approximate_gp_drops_noise():
+    # tests/gps/test_regression.py:58-97,203-249: mean 1, var 1 although log_observation_noise = log 1 is passed
+    mean, var = O.approximate_gp_predict(np.ones(2), ones_diag(X))
+    assert np.array_equal(mean, np.ones(2)) and np.array_equal(var, np.ones(2))
+
+
+def test_gaussian_nll_goldens():
+    # tests/test_empirical_risks.py:20-144.  That module never enables x64, so its goldens are float32 values
+    # compared with jnp.isclose (rtol 1e-5); the same tolerance is used here (hand value: 1.4112990555).
+    mean, var = O.exact_gp_posterior(ones_gram, ones_diag, np.ones(2), X_TRAIN, Y_TRAIN, np.log(1.0), X)
+    assert O.gaussian_nll(np.ones(2), mean, var) == pytest.approx(1.4112988, rel=1e-5)
+    x12 = np.tile(X, (6, 1))
+    mean, var = O.exact_gp_posterior(ones_gram, ones_diag, np.ones(12), X_TRAIN, Y_TRAIN, np.log(1.0), x12)
+    assert O.gaussian_nll(np.ones(12), mean, var) == pytest.approx(1.4112988, rel=1e-5)
+    assert O.gaussian_nll(np.array([1.2, 4.2]), np.ones(2), np.ones(2)) == pytest.approx(3.48893853, rel=1e-5)
+
+
+REG_GOLDENS = {  # tests/regularisations/projected/test_projected_*.py:120-176
+    "bhattacharyya": 0.13702468,
+    "gaussian_wasserstein": 0.87307724,
+    "hellinger": 0.18301035,
+    "kl": 0.56319503,
+    "renyi": 0.4042577,
+}
+
+
+@pytest.mark.parametrize("kind", sorted(REG_GOLDENS))
+def test_projected_regulariser_goldens(kind):
+    m_p, c_p = O.exact_gp_posterior(ones_gram, ones_diag, np.ones(2), X_TRAIN, Y_TRAIN, np.log(1.0), X)
+    m_q, c_q = O.approximate_gp_predict(np.ones(2), ones_diag(X))
+    assert O.projected_regularisation(kind, m_p, c_p, m_q, c_q, 0.5) == pytest.approx(REG_GOLDENS[kind], rel=1e-5)
+    # "same GP => 0" cases
+    assert O.projected_regularisation(kind, m_p, c_p, m_p, c_p, 0.5) == pytest.approx(0.0, abs=1e-12)
+
+
+def test_gwi_and_squared_difference_goldens():
+    m_p, c_p = O.exact_gp_posterior(ones_gram, ones_diag, np.ones(2), X_TRAIN, Y_TRAIN, np.log(1.0), X)
+    m_q, c_q = np.ones(2), np.ones(2)
+    # tests/regularisations/test_gaussian_squared_difference.py:120-176 uses the default full covariances:
+    # posterior cov of the ones-kernel GP is 1/3 everywhere, q's "prior" cov is 1 everywhere
+    full_p, full_q = np.full((1, 2, 2), 1.0 / 3.0), np.ones((1, 2, 2))
+    assert O.gaussian_squared_difference(m_p, full_p, m_q, full_q) == pytest.approx(1.13888889, rel=1e-5)
+    # tests/regularisations/test_gaussian_wasserstein.py:124-181 (with eigendecomposition): 0.87307723
+    val = O.gwi_with_eig(m_p, full_p[0], m_q, full_q[0], full_p[0], full_q[0], 1e-8, False)
+    assert val == pytest.approx(0.87307723, rel=1e-5)
+    # the partial (no-eig) form is what the CUDA path implements; it differs by the cross term only
+    assert O.gwi_no_eig(m_p, c_p, m_q, c_q) == pytest.approx(np.mean((m_p - m_q) ** 2) + 1.0 / 3.0 + 1.0)
+
+
+def test_gvi_sum():
+    assert O.gvi_loss(2.3, 1.2) == 3.5  # tests/test_generalised_variational_inference.py
+
+
+def test_prng_pins():
+    # tests/test_inducing_points_selection.py:128,139 (greedy) and :151,162 (random choice)
+    key = P.prng_key(0)
+    _, sub = P.split(key)
+    assert list(P.permutation(sub, 4)) == [2, 3, 0, 1]
+    assert list(P.permutation(sub, 3)) == [2, 0, 1]
+    assert list(P.choice_with_replacement(key, 4, 2)) == [1, 2]
+    assert list(P.choice_with_replacement(key, 3, 2)) == [0, 2]
+
+
+@pytest.mark.parametrize("use_argsort", [True, False])
+def test_selector_goldens(use_argsort):
+    # tests/test_inducing_points_selection.py:116-182: PRNGKey(0), all-ones Gram, M=2 -> indices [2, 1]
+    key = P.prng_key(0)
+    _, sub = P.split(key)
+    x4 = np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5], [4.5, 2.5, 3.5], [5.5, 6.5, 7.5]])
+    for x in (x4, np.arange(3 * 784, dtype=float).reshape(3, 784)):
+        n = x.shape[0]
+        perm = P.permutation(sub, n)
+        piv = O.conditional_variance_select(x[perm], 2, ones_gram, ones_diag, 1e-12, 0.0, use_argsort)
+        assert list(perm[piv]) == [2, 1]
+    perm = P.permutation(sub, 4)
+    piv = O.conditional_variance_select(x4[perm], 2, ones_gram, ones_diag)
+    np.testing.assert_array_equal(x4[perm][piv], np.array([[4.5, 2.5, 3.5], [1.5, 2.5, 3.5]]))
+
+
+def test_selector_argsort_and_maxrule_agree_on_real_kernel():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((300, 2))
+    g = lambda a, b: O.ard_gram(0.1, [0.3, -0.2], a, b)
+    d = lambda a: O.ard_gram_diag(0.1, [0.3, -0.2], a)
+    a = O.conditional_variance_select(x, 12, g, d, use_argsort=True)
+    b = O.conditional_variance_select(x, 12, g, d, use_argsort=False)
+    assert np.array_equal(a, b) and len(set(a.tolist())) == 12
