@@ -224,6 +224,21 @@ def run_gpu(args):
         distributed.allreduce_loss_sums(out3)
         return distributed.loss_from_sums(out3)
 
+    def grad_step(x, y):
+        """value and gradient (what jax.grad of calculate_loss gives the reference's trainer): loss,
+        d/dlog_scaling, d/dlog_lengthscales[D] all-reduced as one packed (D+4)-vector; d/dm_q back-propagated
+        through the tanh-FCN mean by the host framework (torch autograd), its parameter grads all-reduced."""
+        out, dm, m_q = gvi.loss_and_grad_sums(approx_params, x, y)
+        distributed.allreduce_loss_sums(out)
+        m_q.backward(dm / out[2])
+        if world > 1:
+            for p_ in fcn_d.values():
+                dist.all_reduce(p_.grad)
+        g = torch.cat([out[3:] / out[2]] + [p_.grad.reshape(-1) for p_ in fcn_d.values()])
+        for p_ in fcn_d.values():
+            p_.grad = None
+        return (out[0] + out[1]) / out[2], g
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -244,6 +259,26 @@ def run_gpu(args):
         barrier()
     ms_total = e0.elapsed_time(e1)
     launches = lib.gvi_launch_count() - launches0
+    # ---- forward + gradient step (reported beside the forward number) -----------------------------------------
+    for p_ in fcn_d.values():
+        p_.requires_grad_(True)
+    for i in range(3):
+        grad_step(*dev_batches[i % 2])
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    grad_steps = max(2, min(args.steps, 5))
+    g0.record()
+    for i in range(grad_steps):
+        gl, gvec = grad_step(*dev_batches[i % 2])
+    g1.record()
+    barrier()
+    tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    grad_ms = float(tg.item()) / grad_steps
+    grad_norm = float(gvec.norm().item())
+    for p_ in fcn_d.values():
+        p_.requires_grad_(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,6 +342,13 @@ def run_gpu(args):
                        "l2_policy": "2 rotating input batches (2 x 72 MB) plus factor state > 126 MB L2",
                        "parallelism": f"points sharded over {world} rank(s), Z and theta replicated"},
             "loss": loss_value, "gpu_launches": int(launches),
+            "forward_plus_gradient": {"value": N_PER_GPU * world / (grad_ms * 1e-3), "unit": UNIT,
+                                      "ms_per_step": grad_ms, "steps": grad_steps, "grad_norm": grad_norm,
+                                      "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D)
+                                      + 2.0 * M * M + 2.0 * M * D,
+                                      "note": "value and gradient w.r.t. log_scaling, log_lengthscales[D] and the "
+                                              "tanh-FCN mean parameters (autograd through the mean on the host "
+                                              "framework), factorisations included"},
             "e2e": {"value": N_PER_GPU * world / e2e_sec, "unit": UNIT,
                     "h2d_bytes_per_step": int(N_PER_GPU * (D + 1) * 8), "d2h_bytes_per_step": 8,
                     "steps": e2e_steps, "loss": loss_e2e},

@@ -227,13 +227,14 @@ __global__ void __launch_bounds__(256) linv_sweep_kernel(const double* __restric
 // ---- header, scaled inducing points -----------------------------------------------------------------------------
 __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, const double* __restrict__ Z,
                                      const double* __restrict__ log_scaling, const double* __restrict__ log_ls,
-                                     int ls_len) {
+                                     int ls_len, double abs_jitter) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) {
     double amp = exp(log_scaling[0]);
     F[0] = amp * amp;
     F[1] = amp * amp;
-    F[4] = F[5] = F[6] = F[7] = 0.0;
+    F[4] = abs_jitter;
+    F[5] = F[6] = F[7] = 0.0;
   }
   if (tid < f.D) F[f.sqrtw_off + tid] = sqrt(exp(log_ls[ls_len == 1 ? 0 : tid]));
   for (int64_t idx = tid; idx < (int64_t)f.Mp * f.D; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -262,6 +263,32 @@ __global__ void pack_linv_kernel(const double* __restrict__ X, int Mp, int M, in
     v.x = (c < M && j0 <= c) ? X[(int64_t)c * Mp + j0] : 0.0;
     v.y = (c < M && j1 <= c) ? X[(int64_t)c * Mp + j1] : 0.0;
     reinterpret_cast<double2*>(W)[it] = v;
+  }
+}
+
+// L^-T in the same fragment order: group g holds rows j in [32g, 32g+32) and the k-range c in [32g, Mp):
+// element = Linv[c = 8kp + 4e + lane%4][j = 32g + 8mt + lane/4] for kp >= 4g.  One CTA per group.
+__global__ void __launch_bounds__(256) pack_linvT_kernel(const double* __restrict__ X, int Mp, int M, int G,
+                                                         double* __restrict__ W) {
+  const int g = blockIdx.x;
+  double2* out = reinterpret_cast<double2*>(W + wpackT_group_off(g, G));
+  const int items = 512 * (G - g);
+  for (int it = threadIdx.x; it < items; it += 256) {
+    int lane = it & 31, mt = (it >> 5) & 3, kpl = it >> 7;
+    int j = 32 * g + 8 * mt + (lane >> 2);
+    int c0 = 8 * (4 * g + kpl) + (lane & 3), c1 = c0 + 4;
+    double2 v;
+    v.x = (j < M && c0 < M && c0 >= j) ? X[(int64_t)c0 * Mp + j] : 0.0;
+    v.y = (j < M && c1 < M && c1 >= j) ? X[(int64_t)c1 * Mp + j] : 0.0;
+    out[it] = v;
+  }
+}
+__global__ void copy_linv_kernel(const double* __restrict__ X, int Mp, int M, double* __restrict__ out) {
+  const int64_t total = (int64_t)Mp * Mp;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(idx / Mp), c = (int)(idx % Mp);
+    out[idx] = (r < M && c <= r) ? X[idx] : 0.0;
   }
 }
 
@@ -360,7 +387,7 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   double* tvec = X + (size_t)f.Mp * f.Mp;
   int* winfo = (int*)(tvec + 2 * f.Mp);
   int rc;
-  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len);
+  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0);
   GVI_CHECK_LAUNCH("factor_header_kernel");
   if ((rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st))) return rc;
   add_diag_kernel<<<1, 1024, 0, st>>>(A, M, f.Mp, reg, is_abs, log_noise, F + 2);
@@ -390,6 +417,10 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
     int blocks = (int)((items + 255) / 256 < 148 * 8 ? (items + 255) / 256 : 148 * 8);
     pack_linv_kernel<<<blocks, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpack_off);
     GVI_CHECK_LAUNCH("pack_linv_kernel");
+    pack_linvT_kernel<<<f.G, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpackT_off);
+    GVI_CHECK_LAUNCH("pack_linvT_kernel");
+    copy_linv_kernel<<<148 * 4, 256, 0, st>>>(X, f.Mp, M, F + f.linv_off);
+    GVI_CHECK_LAUNCH("copy_linv_kernel");
   }
   if (y_z) {
     linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, f.Mp, M, y_z, tvec);

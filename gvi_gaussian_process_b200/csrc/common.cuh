@@ -42,14 +42,17 @@ void gvi_count_launch();
 constexpr int GVI_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 
 // ---- factor buffer layout (doubles) ---------------------------------------------------------------------------
-// [0] amp2 = exp(log_scaling)^2   [1] k(x,x)   [2] jitter actually added   [3] chol info (as double)  [4..7] rsvd
+// [0] amp2 = exp(log_scaling)^2   [1] k(x,x)   [2] jitter actually added   [3] chol info (as double)
+// [4] absolute jitter (0 when the regulariser is trace-relative; used by d var / d log_scaling)   [5..7] rsvd
 // [8, 8+D)            sqrtw[d] = sqrt(exp(log_ls[d]))
 // [zs_off, +Mp*D)     Z pre-scaled by sqrtw (rows >= M are zero)
 // [alpha_off, +Mp)    alpha = A^-1 y_Z (zero padded)
 // [wpack_off, ...)    L^-1 packed per 32-row group in DMMA m8n8k4 fragment order (see pack_linv_kernel)
+// [wpackT_off, ...)   L^-T packed the same way (rows j, k-range c >= 32g): a = L^-T b in the backward pass
+// [linv_off, +Mp*Mp)  dense row-major L^-1 (S = A^-1 C A^-1 in the backward pass; full-covariance API)
 struct FactorLayout {
   int M, Mp, D, G;
-  int64_t sqrtw_off, zs_off, alpha_off, wpack_off, total;
+  int64_t sqrtw_off, zs_off, alpha_off, wpack_off, wpackT_off, linv_off, total;
 };
 __host__ __device__ inline FactorLayout factor_layout(int M, int D) {
   FactorLayout f;
@@ -68,9 +71,15 @@ __host__ __device__ inline FactorLayout factor_layout(int M, int D) {
   o = (o + 1) / 2 * 2;
   f.wpack_off = o;
   o += 512LL * f.G * (f.G + 1);
+  f.wpackT_off = o;
+  o += 512LL * f.G * (f.G + 1);
+  f.linv_off = o;
+  o += (int64_t)f.Mp * f.Mp;
   f.total = o;
   return f;
 }
+// offset (doubles) of 32-row group g inside wpackT: sum_{g'<g} 1024*(G-g')
+__host__ __device__ inline int64_t wpackT_group_off(int g, int G) { return 1024LL * ((int64_t)g * G - (int64_t)g * (g - 1) / 2); }
 // offset (doubles) of 32-row group g inside wpack: sum_{g'<g} 1024*(g'+1)
 __host__ __device__ inline int64_t wpack_group_off(int g) { return 512LL * g * (g + 1); }
 
@@ -78,9 +87,41 @@ __host__ __device__ inline int64_t wpack_group_off(int g) { return 512LL * g * (
 // A 8x4 row-major: lane holds A[lane/4][lane%4]; B 4x8 col: lane holds B[lane%4][lane/4];
 // C 8x8: lane holds C[lane/4][(lane%4)*2 + {0,1}].
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+  // not volatile: the data dependences through the accumulators order the MMAs; everything else may be scheduled
+  // between them (FP64-pipe work fills the issue slots the DMMA cadence leaves free)
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
+}
+
+// Branch-free exp for the kernel exponents (x = -0.5 * squared distance <= 0; valid for any x < 709): Cody-Waite
+// reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (remainder < 5e-18 relative), scaling by an
+// integer add into the exponent field; exactly 0 below -708 (k < 1e-307).  <= 1 ulp like CUDA's exp(), but without
+// the slow-path branches, so independent evaluations interleave on the FP64 pipe and between DMMA issue slots.
+__device__ __forceinline__ double gvi_exp(double x) {
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the low word of (y + SHIFT) is rint(y)
+  const double xc = fmax(x, -708.0);
+  const double t = fma(xc, 1.4426950408889634074, SHIFT);
+  const int n = __double2loint(t);
+  const double nf = t - SHIFT;
+  double r = fma(nf, -6.93147180369123816490e-01, xc);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = 1.6059043836821613e-10;             // 1/13!
+  p = fma(p, r, 2.08767569878681e-09);           // 1/12!
+  p = fma(p, r, 2.505210838544172e-08);          // 1/11!
+  p = fma(p, r, 2.755731922398589e-07);          // 1/10!
+  p = fma(p, r, 2.7557319223985893e-06);         // 1/9!
+  p = fma(p, r, 2.48015873015873e-05);           // 1/8!
+  p = fma(p, r, 1.984126984126984e-04);          // 1/7!
+  p = fma(p, r, 1.3888888888888889e-03);         // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);          // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  return x < -708.0 ? 0.0 : res;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -96,6 +137,55 @@ __device__ __forceinline__ double gvi_nll_term(double y, double m, double v) {
   double sd = sqrt(v);
   double z = (y - m) / sd;
   return 0.5 * z * z + log(sd) + half_log_2pi;
+}
+// d nll / d m and d nll / d v
+__device__ __forceinline__ void gvi_nll_grad(double y, double m, double v, double& dm, double& dv) {
+  double r = y - m;
+  dm = -r / v;
+  dv = 0.5 / v - 0.5 * r * r / (v * v);
+}
+// d D0 / d m_q and d D0 / d c_q (p is the fixed regulariser GP)
+__device__ __forceinline__ void gvi_reg_grad(int kind, double alpha, double mp, double cp, double mq, double cq,
+                                             double& dmq, double& dcq) {
+  const double dm = mp - mq;
+  const double s = cp + cq;
+  switch (kind) {
+    case GVI_REG_PROJ_BHATTACHARYYA:
+      dmq = -0.25 * dm / s;
+      dcq = -0.125 * dm * dm / (s * s) + 0.5 / s - 0.25 / cq;
+      break;
+    case GVI_REG_PROJ_GAUSSIAN_WASSERSTEIN:
+      dmq = -2.0 * dm;
+      dcq = 1.0 - sqrt(cp / cq);
+      break;
+    case GVI_REG_PROJ_HELLINGER: {
+      double be = sqrt((2.0 * sqrt(cp) * sqrt(cq)) / s) * exp(-0.25 * dm * dm / s);
+      dmq = -be * (0.5 * dm / s);
+      dcq = -be * (0.25 / cq - 0.5 / s + 0.25 * dm * dm / (s * s));
+      break;
+    }
+    case GVI_REG_PROJ_KL:
+      dmq = -dm / cq;
+      dcq = 0.5 / cq - (cp + dm * dm) / (2.0 * cq * cq);
+      break;
+    case GVI_REG_PROJ_RENYI: {
+      double mix = alpha * cp + (1.0 - alpha) * cq;
+      dmq = -alpha * dm / mix;
+      dcq = -0.5 / cq + 0.5 / mix - 0.5 * alpha * (1.0 - alpha) * dm * dm / (mix * mix);
+      break;
+    }
+    case GVI_REG_GWI_NO_EIG:
+      dmq = -2.0 * dm;
+      dcq = 1.0;
+      break;
+    case GVI_REG_SQUARED_DIFFERENCE:
+      dmq = -2.0 * dm;
+      dcq = -2.0 * (cp - cq);
+      break;
+    default:
+      dmq = 0.0;
+      dcq = 0.0;
+  }
 }
 __device__ __forceinline__ double gvi_reg_term(int kind, double alpha, double mp, double cp, double mq, double cq) {
   double dm = mp - mq;

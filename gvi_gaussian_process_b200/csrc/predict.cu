@@ -2,44 +2,57 @@
 // packed L^-1 on the FP64 tensor pipe (DMMA m8n8k4), and reduce the squared row norms -> predictive variance;
 // the same K tile gives the mean (K alpha).  Up to two GPs (q = approximate GP, p = exact regulariser GP) are
 // processed per tile and the Gaussian NLL + pGVI/GWI terms are reduced in the epilogue, so one launch is the whole
-// "Gram + predict + risk" step and only O(N) bytes cross HBM.
+// "Gram + predict + risk" step and only O(N) bytes cross HBM.  In gradient mode the same launch also produces
+// dR/dm_q[N], g_i = dR/dv_q,i [N] and the point-sized parts of dR/dlog_lengthscales (a_i = L^-T b_i by a second
+// triangular product per tile); the M x M part is finished in grad.cu.
 //
 // Reference arithmetic: sparse_posterior_kernel.py:63-96 in diagonal mode (src/kernels/base.py:132-147),
-// src/gps/base/base.py:495-526 (exact posterior), negative_log_likelihood.py:41-55, regularisations/projected/*.
+// src/gps/base/base.py:495-526 (exact posterior), negative_log_likelihood.py:41-55, regularisations/projected/*;
+// the gradient is jax.grad of generalised_variational_inference.py:73-94 (experiments/shared/trainer.py:83-89).
 // Algebra: v = k(x,x) - k^T A^-1 k = k(x,x) - ||L^-1 k||^2 with A = L L^T;  b = L^-1 k is a dependency-free
 // triangular GEMM against the explicit inverse (validated against cho_solve in tests; see DESIGN.md numerics).
-#include "common.cuh"
+#include "predict.cuh"
 
 namespace {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 
-struct PassDesc {
-  const double* F;          // factor buffer
-  const double* prior_mean; // [N] or null, added to K alpha
-  const double* noise_add;  // device scalar log-noise or null: var += exp(*noise_add)
-  double* mean_out;         // [N] or null
-  double* var_out;          // [N] or null
-};
+// One 32-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
+// acc[mt][nt] += sum_{kp in [kp0, kp0+nkp)} A(group rows 8mt.., cols 8kp..) * Ktile(cols 8kp.., points 8nt..).
+// A fragments come from L2 as one LDG.128 per lane per (kp, mt) (two k-steps), prefetched one kp ahead.
+template <int NT>
+__device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
+                                          const double2* __restrict__ Ks2, int lane, double (&acc)[4][NT][2]) {
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+  double2 a_cur[4], a_nxt[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
+#pragma unroll 1
+  for (int k = 0; k < nkp; k++) {
+    const int kn = (k + 1 < nkp) ? k + 1 : k;
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) a_nxt[mt] = __ldcg(Ag + (kn * 4 + mt) * 32);
+    double2 b[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b[nt].x);
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b[nt].y);
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++) a_cur[mt] = a_nxt[mt];
+  }
+}
 
-struct StepParams {
-  PassDesc pass[2];
-  int npass;
-  int M, Mp, D, G;
-  const double* X;
-  int64_t N;
-  // fused risk epilogue (enabled when partials != null)
-  const double* y;      // [N] or null (no NLL term)
-  const double* m_q;    // [N] mean of q (host framework evaluates the mean function)
-  const double* m_p_in; // [N] regulariser mean when there is no pass 1 (prior mode)
-  const double* v_p_in; // [N]
-  int reg_kind;
-  double renyi_alpha;
-  double* partials;     // [gridDim.x][2]
-};
-
-template <int NT, int DR>
+template <int NT, int DR, bool GRAD>
 __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P) {
   constexpr int T = 8 * NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -47,20 +60,27 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   double* xs = Ksm + (size_t)P.Mp * T;                            // [T][DR] scaled x tile
   double* redm = xs + T * DR;                                     // [WARPS][T]
   double* reds = redm + WARPS * T;                                // [G][T] squared norms per 32-row group
-  double* res = reds + (size_t)P.G * T;                           // [2 passes][T][2] (mean, var)
-  int* counter = reinterpret_cast<int*>(res + 2 * T * 2);
+  double* res = reds + (size_t)P.G * T;                           // [2 GPs][T][2] (mean, var)
+  double* gs = res + 2 * T * 2;                                   // [T] g_i = dR/dv_q,i of the tile
+  double* gpart = gs + T;                                         // [G][DR+1] per-group gradient partials
+  int* counter = reinterpret_cast<int*>(gpart + (size_t)P.G * (DR + 1));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ntiles = (P.N + T - 1) / T;
-  double part_nll = 0.0, part_reg = 0.0;
+  const FactorLayout f = factor_layout(P.M, P.D);
+  double part_nll = 0.0, part_reg = 0.0, part_gv = 0.0;  // threads < T
+  double part_grad = 0.0;                                  // thread d <= DR: d < DR -> T2_d, d == DR -> sum g |a|^2
+  double* bscr = GRAD ? P.bscratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t row0 = tile * T;
-    for (int ps = 0; ps < P.npass; ps++) {
+    for (int pi = 0; pi < P.npass; pi++) {
+      // gradient mode runs p first so that q's tile (and b = L^-1 k of q) is the one left in shared memory
+      const int ps = GRAD ? P.npass - 1 - pi : pi;
       const PassDesc& pd = P.pass[ps];
-      const FactorLayout f = factor_layout(P.M, P.D);
       const double* __restrict__ F = pd.F;
       const double amp2 = F[0];
+      const bool keep_b = GRAD && ps == 0;
       // ---- stage the scaled x tile -------------------------------------------------------------------
       for (int idx = tid; idx < T * DR; idx += THREADS) {
         int i = idx / DR, d = idx % DR;
@@ -92,7 +112,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
               double diff = xs[i * DR + d] - z[d];
               s = fma(diff, diff, s);
             }
-            double k = scale * exp(-0.5 * s);
+            double k = scale * gvi_exp(-0.5 * s);
             kcol[(i >> 3) * 64 + (i & 7) * 8] = k;
             macc[i] = fma(k, aj, macc[i]);
           }
@@ -114,35 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
           gi = __shfl_sync(0xffffffffu, gi, 0);
           if (gi >= P.G) break;
           const int g = P.G - 1 - gi;  // largest groups first
-          const double2* __restrict__ Ag = reinterpret_cast<const double2*>(W + wpack_group_off(g)) + lane;
-          const int nkp = 4 * (g + 1);
           double acc[4][NT][2];
-#pragma unroll
-          for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-          double2 a_cur[4], a_nxt[4];
-#pragma unroll
-          for (int mt = 0; mt < 4; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
-#pragma unroll 1
-          for (int kp = 0; kp < nkp; kp++) {
-            const int kn = (kp + 1 < nkp) ? kp + 1 : kp;
-#pragma unroll
-            for (int mt = 0; mt < 4; mt++) a_nxt[mt] = __ldcg(Ag + (kn * 4 + mt) * 32);
-            double2 b[NT];
-#pragma unroll
-            for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[(kp * NT + nt) * 32 + lane];
-#pragma unroll
-            for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-              for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b[nt].x);
-#pragma unroll
-            for (int mt = 0; mt < 4; mt++)
-#pragma unroll
-              for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b[nt].y);
-#pragma unroll
-            for (int mt = 0; mt < 4; mt++) a_cur[mt] = a_nxt[mt];
-          }
+          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + lane, 0, 4 * (g + 1), Ks2, lane,
+                        acc);
           // squared norms of this group's 32 rows: lanes with equal lane%4 hold the same two points of every
           // n-tile.  Stored per GROUP (not per warp) so the final sum has a fixed order whatever warp ran the group.
 #pragma unroll
@@ -157,6 +151,21 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
               v += __shfl_xor_sync(0xffffffffu, v, 16);
               if (lane < 4) reds[g * T + nt * 8 + lane * 2 + e] = v;
             }
+          if (keep_b) {
+            // b[c][i] goes to the per-CTA scratch (L2 resident) in the K-tile fragment order at "column" c
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+              const int c = 32 * g + 8 * mt + (lane >> 2);
+              double* bcol = bscr + (size_t)(c >> 3) * (NT * 64) + ((c >> 2) & 1) + 2 * (c & 3);
+#pragma unroll
+              for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                  const int il = (lane & 3) * 2 + e;  // point inside the n-tile
+                  __stcg(bcol + nt * 64 + il * 8, acc[mt][nt][e]);
+                }
+            }
+          }
         }
       }
       __syncthreads();
@@ -179,13 +188,23 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       }
       __syncthreads();
     }  // passes
-    // ---- fused risk epilogue -------------------------------------------------------------------------
+    // ---- fused risk epilogue (+ pointwise derivatives in gradient mode) --------------------------------
     if (P.partials && tid < T) {
       const int64_t r = row0 + tid;
+      double g_i = 0.0;
       if (r < P.N) {
         const double vq = res[(0 * T + tid) * 2 + 1];
         const double mq = P.m_q ? P.m_q[r] : res[(0 * T + tid) * 2 + 0];
-        if (P.y) part_nll += gvi_nll_term(P.y[r], mq, vq);
+        double h_i = 0.0;
+        if (P.y) {
+          part_nll += gvi_nll_term(P.y[r], mq, vq);
+          if (GRAD) {
+            double dm, dv;
+            gvi_nll_grad(P.y[r], mq, vq, dm, dv);
+            h_i += dm;
+            g_i += dv;
+          }
+        }
         if (P.reg_kind != GVI_REG_NONE) {
           double mp, vp;
           if (P.npass > 1) {
@@ -196,70 +215,158 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
             vp = P.v_p_in[r];
           }
           part_reg += gvi_reg_term(P.reg_kind, P.renyi_alpha, mp, vp, mq, vq);
+          if (GRAD) {
+            double dm, dv;
+            gvi_reg_grad(P.reg_kind, P.renyi_alpha, mp, vp, mq, vq, dm, dv);
+            h_i += dm;
+            g_i += dv;
+          }
+        }
+        if (GRAD) {
+          part_gv = fma(g_i, vq, part_gv);
+          P.dm_out[r] = h_i;
+          P.g_out[r] = g_i;
         }
       }
+      if (GRAD) gs[tid] = g_i;
+    }
+    // ---- gradient phase 3: a = L^-T b for q, then sum_i g_i a_ij k_ij (x~_id - z~_jd)^2 and sum_i g_i |a_i|^2 ----
+    if (GRAD) {
+      const double* __restrict__ F = P.pass[0].F;
+      const double amp2 = F[0];
+      double2* Ks2w = reinterpret_cast<double2*>(Ksm);
+      const double2* scr2 = reinterpret_cast<const double2*>(bscr);
+      for (int idx = tid; idx < P.Mp * T / 2; idx += THREADS) Ks2w[idx] = __ldcg(scr2 + idx);  // b tile replaces K tile
+      if (tid == 0) *counter = 0;
+      __syncthreads();
+      const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
+      const double* __restrict__ WT = F + f.wpackT_off;
+      const double* __restrict__ Zs = F + f.zs_off;
+      while (true) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(counter, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);  // ascending g = largest k-range first
+        if (g >= P.G) break;
+        double acc[4][NT][2];
+        group_mma<NT>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, 4 * g, 4 * (P.G - g),
+                      Ks2, lane, acc);
+        double t2[DR], na2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < DR; d++) t2[d] = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+          const int j = 32 * g + 8 * mt + (lane >> 2);
+          double z[DR];
+#pragma unroll
+          for (int d = 0; d < DR; d++) z[d] = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const int i = nt * 8 + (lane & 3) * 2 + e;
+              const double a = acc[mt][nt][e];
+              const double gi = gs[i];
+              double diff2[DR], s = 0.0;
+#pragma unroll
+              for (int d = 0; d < DR; d++) {
+                double diff = xs[i * DR + d] - z[d];
+                diff2[d] = diff * diff;
+                s += diff2[d];
+              }
+              const double coef = gi * a * amp2 * gvi_exp(-0.5 * s);
+#pragma unroll
+              for (int d = 0; d < DR; d++) t2[d] = fma(coef, diff2[d], t2[d]);
+              na2 = fma(gi * a, a, na2);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < DR; d++) {
+          double v = warp_sum(t2[d]);
+          if (lane == 0) gpart[g * (DR + 1) + d] = v;
+        }
+        na2 = warp_sum(na2);
+        if (lane == 0) gpart[g * (DR + 1) + DR] = na2;
+      }
+      __syncthreads();
+      if (tid <= DR) {
+        double v = 0.0;
+        for (int g = 0; g < P.G; g++) v += gpart[g * (DR + 1) + tid];
+        part_grad += v;
+      }
+      __syncthreads();
     }
   }  // tiles
-  if (P.partials && warp == 0) {
-    // T <= 24 < 32: threads >= T hold zeros
-    double a = warp_sum(part_nll), b = warp_sum(part_reg);
-    if (lane == 0) {
-      P.partials[2 * blockIdx.x + 0] = a;
-      P.partials[2 * blockIdx.x + 1] = b;
+  if (P.partials) {
+    double* out = P.partials + (size_t)blockIdx.x * STEP_PARTIAL_STRIDE;
+    if (warp == 0) {
+      // T <= 24 < 32: threads >= T hold zeros
+      double a = warp_sum(part_nll), b = warp_sum(part_reg), c = warp_sum(part_gv);
+      if (lane == 0) {
+        out[0] = a;
+        out[1] = b;
+        out[2] = c;
+      }
+    }
+    if (GRAD) {
+      if (tid < DR) out[4 + tid] = part_grad;
+      if (tid == DR) out[3] = part_grad;
+      for (int d = DR + tid; d < 32; d += THREADS) out[4 + d] = 0.0;
+    } else if (tid < 33) {
+      out[3 + tid] = 0.0;
     }
   }
 }
 
-// fixed-order final reduction of per-CTA partial sums -> out3 = {sum nll, sum reg, N}
-__global__ void __launch_bounds__(256) finish_partials_kernel(const double* __restrict__ partials, int nblocks,
-                                                              int64_t N, double* __restrict__ out3) {
-  __shared__ double sa[256], sb[256];
+// fixed-order final reduction of per-CTA partial sums.
+// out[0..2] = {sum nll, sum reg, N}; gradient mode additionally
+// out[3] = sum_i g_i dv_i/dlog_scaling = 2 sum g v - 2 jitter_abs sum g |a|^2,  out[4+d] = T2_d (point part of d/dlog_ls[d])
+__global__ void __launch_bounds__(64) finish_partials_kernel(const double* __restrict__ partials, int nblocks,
+                                                             int64_t N, int grad, int D, const double* __restrict__ Fq,
+                                                             double* __restrict__ out) {
   const int tid = threadIdx.x;
-  double a = 0.0, b = 0.0;
-  for (int i = tid; i < nblocks; i += 256) {
-    a += partials[2 * i];
-    b += partials[2 * i + 1];
-  }
-  sa[tid] = a;
-  sb[tid] = b;
+  if (tid >= STEP_PARTIAL_STRIDE) return;
+  double a = 0.0;
+  for (int i = 0; i < nblocks; i++) a += partials[(size_t)i * STEP_PARTIAL_STRIDE + tid];
+  __shared__ double tot[STEP_PARTIAL_STRIDE];
+  tot[tid] = a;
   __syncthreads();
-  for (int s = 128; s > 0; s >>= 1) {
-    if (tid < s) {
-      sa[tid] += sa[tid + s];
-      sb[tid] += sb[tid + s];
-    }
-    __syncthreads();
-  }
   if (tid == 0) {
-    out3[0] = sa[0];
-    out3[1] = sb[0];
-    out3[2] = (double)N;
+    out[0] = tot[0];
+    out[1] = tot[1];
+    out[2] = (double)N;
+    if (grad) out[3] = 2.0 * tot[2] - 2.0 * Fq[4] * tot[3];
   }
+  if (grad && tid < D) out[4 + tid] = tot[4 + tid];
 }
 
 template <int NT, int DR>
 size_t step_smem_bytes(int Mp) {
   constexpr int T = 8 * NT;
-  return ((size_t)Mp * T + T * DR + WARPS * T + (size_t)(Mp / 32) * T + 4 * T) * sizeof(double) + 16;
+  const size_t G = Mp / 32;
+  return ((size_t)Mp * T + T * DR + WARPS * T + G * T + 4 * T + T + G * (DR + 1)) * sizeof(double) + 16;
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
-template <int NT, int DR>
-int launch_step_inst(const StepParams& P, int grid_cap, cudaStream_t st) {
+template <int NT, int DR, bool GRAD>
+int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
   constexpr int T = 8 * NT;
   size_t smem = step_smem_bytes<NT, DR>(P.Mp);
   static bool configured = false;  // per instantiation
   if (!configured) {
-    GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)SMEM_LIMIT));
     configured = true;
   }
   int64_t ntiles = (P.N + T - 1) / T;
   int grid = (int)(ntiles < grid_cap ? ntiles : grid_cap);
-  gp_step_kernel<NT, DR><<<grid, THREADS, smem, st>>>(P);
+  gp_step_kernel<NT, DR, GRAD><<<grid, THREADS, smem, st>>>(P);
   GVI_CHECK_LAUNCH("gp_step_kernel");
   return grid;
+}
+template <int NT, int DR>
+int launch_step_inst(const StepParams& P, int grid_cap, cudaStream_t st) {
+  return P.grad ? launch_step_inst2<NT, DR, true>(P, grid_cap, st) : launch_step_inst2<NT, DR, false>(P, grid_cap, st);
 }
 
 template <int NT>
@@ -270,23 +377,38 @@ int launch_step_nt(const StepParams& P, int grid_cap, cudaStream_t st) {
   if (P.D <= 16) return launch_step_inst<NT, 16>(P, grid_cap, st);
   return launch_step_inst<NT, 32>(P, grid_cap, st);
 }
+}  // namespace
+
+int gvi_step_tile_points(int Mp) {
+  if (step_smem_bytes<3, 32>(Mp) <= SMEM_LIMIT) return 24;
+  if (step_smem_bytes<2, 32>(Mp) <= SMEM_LIMIT) return 16;
+  if (step_smem_bytes<1, 32>(Mp) <= SMEM_LIMIT) return 8;
+  return 0;
+}
 
 // returns grid size (>0) or a negative error code
-int launch_step(const StepParams& P, cudaStream_t st) {
+int gvi_launch_step(const StepParams& P, cudaStream_t st) {
   if (P.D > 32) {
     gvi_set_error("fused predict supports D <= 32 in this build (got D=%d)", P.D);
     return GVI_EUNSUPPORTED;
   }
-  const int DRmax = 32;
-  (void)DRmax;
   const int grid_cap = GVI_NUM_SMS;
-  if (step_smem_bytes<3, 32>(P.Mp) <= SMEM_LIMIT) return launch_step_nt<3>(P, grid_cap, st);
-  if (step_smem_bytes<2, 32>(P.Mp) <= SMEM_LIMIT) return launch_step_nt<2>(P, grid_cap, st);
-  if (step_smem_bytes<1, 32>(P.Mp) <= SMEM_LIMIT) return launch_step_nt<1>(P, grid_cap, st);
-  gvi_set_error("fused predict supports M <= 3584 in this build (got M=%d)", P.M);
-  return GVI_EUNSUPPORTED;
+  switch (gvi_step_tile_points(P.Mp)) {
+    case 24: return launch_step_nt<3>(P, grid_cap, st);
+    case 16: return launch_step_nt<2>(P, grid_cap, st);
+    case 8: return launch_step_nt<1>(P, grid_cap, st);
+    default:
+      gvi_set_error("fused predict supports M <= 3456 in this build (got M=%d)", P.M);
+      return GVI_EUNSUPPORTED;
+  }
 }
-}  // namespace
+
+int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
+                      cudaStream_t st) {
+  finish_partials_kernel<<<1, 64, 0, st>>>(partials, nblocks, N, grad, D, Fq, out);
+  GVI_CHECK_LAUNCH("finish_partials_kernel");
+  return GVI_OK;
+}
 
 extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
                                   const double* prior_mean, const double* log_noise_add, double* mean_out,
@@ -301,27 +423,24 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;
   P.X = X; P.N = N;
   P.partials = nullptr;
-  int rc = launch_step(P, (cudaStream_t)stream);
+  int rc = gvi_launch_step(P, (cudaStream_t)stream);
   return rc < 0 ? rc : GVI_OK;
 }
 
 extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N) {
   (void)N;
-  return (size_t)GVI_NUM_SMS * 2 * sizeof(double);
+  return (size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE * sizeof(double);
 }
 
-extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
-                                  const double* y, const double* m_q, const double* prior_mean_p,
-                                  const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind,
-                                  double renyi_alpha, double* out3, double* var_q_out, double* mean_p_out,
-                                  double* var_p_out, void* workspace, void* stream) {
+int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                         const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
+                         const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, double* var_q_out,
+                         double* mean_p_out, double* var_p_out) {
   GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 1, "sizes");
-  GVI_CHECK_ARG(factor_q && X && m_q && out3 && workspace, "null pointer");
+  GVI_CHECK_ARG(factor_q && X && m_q, "null pointer");
   GVI_CHECK_ARG(reg_kind >= GVI_REG_NONE && reg_kind <= GVI_REG_SQUARED_DIFFERENCE, "reg_kind");
   GVI_CHECK_ARG(reg_kind == GVI_REG_NONE || factor_p || (m_p_in && v_p_in),
                 "regulariser needs factor_p or (m_p_in, v_p_in)");
-  cudaStream_t st = (cudaStream_t)stream;
-  StepParams P{};
   const FactorLayout f = factor_layout(M, D);
   P.pass[0] = PassDesc{(const double*)factor_q, nullptr, nullptr, nullptr, var_q_out};
   P.npass = 1;
@@ -333,10 +452,22 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
   P.X = X; P.N = N;
   P.y = y; P.m_q = m_q; P.m_p_in = m_p_in; P.v_p_in = v_p_in;
   P.reg_kind = reg_kind; P.renyi_alpha = renyi_alpha;
-  P.partials = (double*)workspace;
-  int grid = launch_step(P, st);
-  if (grid < 0) return grid;
-  finish_partials_kernel<<<1, 256, 0, st>>>(P.partials, grid, N, out3);
-  GVI_CHECK_LAUNCH("finish_partials_kernel");
   return GVI_OK;
+}
+
+extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                                  const double* y, const double* m_q, const double* prior_mean_p,
+                                  const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind,
+                                  double renyi_alpha, double* out3, double* var_q_out, double* mean_p_out,
+                                  double* var_p_out, void* workspace, void* stream) {
+  GVI_CHECK_ARG(out3 && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  StepParams P{};
+  int rc = gvi_fill_step_params(P, factor_q, factor_p, M, D, X, y, m_q, prior_mean_p, m_p_in, v_p_in, N, reg_kind,
+                                renyi_alpha, var_q_out, mean_p_out, var_p_out);
+  if (rc) return rc;
+  P.partials = (double*)workspace;
+  int grid = gvi_launch_step(P, st);
+  if (grid < 0) return grid;
+  return gvi_launch_finish(P.partials, grid, N, 0, D, (const double*)factor_q, out3, st);
 }

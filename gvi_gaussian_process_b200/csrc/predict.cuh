@@ -1,0 +1,44 @@
+// predict.cuh - parameter block of the fused tile kernel, shared between predict.cu and grad.cu
+#pragma once
+#include "common.cuh"
+
+struct PassDesc {
+  const double* F;          // factor buffer
+  const double* prior_mean; // [N] or null, added to K alpha
+  const double* noise_add;  // device scalar log-noise or null: var += exp(*noise_add)
+  double* mean_out;         // [N] or null
+  double* var_out;          // [N] or null
+};
+
+// per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d
+constexpr int STEP_PARTIAL_STRIDE = 36;
+
+struct StepParams {
+  PassDesc pass[2];     // [0] = q (approximate GP), [1] = p (regulariser GP)
+  int npass;
+  int M, Mp, D, G;
+  const double* X;
+  int64_t N;
+  // fused risk epilogue (enabled when partials != null)
+  const double* y;      // [N] or null (no NLL term)
+  const double* m_q;    // [N] mean of q (host framework evaluates the mean function)
+  const double* m_p_in; // [N] regulariser mean when there is no pass 1 (prior mode)
+  const double* v_p_in; // [N]
+  int reg_kind;
+  double renyi_alpha;
+  double* partials;     // [gridDim.x][STEP_PARTIAL_STRIDE]
+  // gradient mode
+  int grad;
+  double* g_out;        // [N] dR/dv_q
+  double* dm_out;       // [N] dR/dm_q
+  double* bscratch;     // [gridDim.x][Mp*T] per-CTA b tile (L2 resident)
+};
+
+int gvi_step_tile_points(int Mp);
+int gvi_launch_step(const StepParams& P, cudaStream_t st);
+int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
+                      cudaStream_t st);
+int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                         const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
+                         const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, double* var_q_out,
+                         double* mean_p_out, double* var_p_out);

@@ -113,6 +113,21 @@ def fused_step(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_
     return out3
 
 
+def fused_step_grad(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_p_in, reg_kind, alpha):
+    """Returns (out[4+D] = [sum nll, sum reg, N, d/dlog_scaling, d/dlog_ls[0..D)], dm[N]) in sum form."""
+    n, d = x.shape
+    out = empty(4 + d)
+    dm = empty(n)
+    ws = _workspace("grad", _L().gvi_fused_step_grad_workspace_bytes(n, factor_q.m, d))
+    rc = _L().gvi_fused_step_grad_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
+                                      factor_q.m, d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q), _lib.ptr(prior_mean_p),
+                                      _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind), float(alpha),
+                                      _lib.ptr(out), _lib.ptr(dm), None, None, None, _lib.ptr(ws),
+                                      _lib.current_stream())
+    _lib.check(rc, "gvi_fused_step_grad_f64")
+    return out, dm
+
+
 def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):
     n, d = x_perm.shape
     idx = torch.empty(m_sel, dtype=torch.int64, device=x_perm.device)

@@ -80,6 +80,54 @@ class GeneralisedVariationalInference:
         return L.fused_step(f_q, None, x, y, m_q, None, m_p.reshape(-1).contiguous(),
                             c_p.reshape(-1).contiguous(), kind, rg.alpha)
 
+    # ---- gradient (what the reference obtains with jax.grad of calculate_loss, trainer.py:83-89) ----------------
+    def loss_and_grad_sums(self, parameters, x, y, refactor_regulariser: bool = True):
+        """Shard-local, SUM-form value and gradient of the fused step (device tensors, no host sync):
+        returns (out, dm, m_q) with out = [sum NLL, sum D0, N, d/dlog_scaling, d/dlog_lengthscales[0..D)],
+        dm[i] = d(sum loss)/dm_q[i] and m_q the mean-function output (so the host framework can back-propagate
+        dm through it).  Multi-GPU: all-reduce `out`, keep dm sharded, divide both by out[2]."""
+        assert self._fusable(), "gradients are implemented for the fused hot-path configuration only"
+        er, rg = self._empirical_risk, self._regularisation
+        gp = er.gp
+        parameters = gp._to_parameters(parameters)
+        x = as_2d(x)
+        x = x.reshape(x.shape[0], -1)
+        y = as_device(y).reshape(-1)
+        assert y.numel() == x.shape[0], f"{y.numel()=} responses for {x.shape[0]=} points"
+        m_q = gp.mean.predict(parameters.mean, x)
+        m_q_c = m_q.detach().contiguous()
+        f_q = gp.kernel.factorise(parameters.kernel)
+        kind = L.REG_KINDS[rg.kind]
+        if rg.mode == RegularisationMode.posterior:
+            reg = rg.regulariser
+            reg_parameters = reg._to_parameters(rg.regulariser_parameters)
+            f_p = reg.factorise(reg_parameters) if (refactor_regulariser or reg._factor is None) else reg._factor
+            prior_mean_p = reg.mean.predict(reg_parameters.mean, x).detach().contiguous()
+            out, dm = L.fused_step_grad(f_q, f_p, x, y, m_q_c, prior_mean_p, None, None, kind, rg.alpha)
+        else:
+            m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
+            out, dm = L.fused_step_grad(f_q, None, x, y, m_q_c, None, m_p.detach().reshape(-1).contiguous(),
+                                        c_p.detach().reshape(-1).contiguous(), kind, rg.alpha)
+        return out, dm, m_q
+
+    def calculate_loss_and_gradients(self, parameters, x, y, allreduce=None):
+        """loss and d loss / d {kernel.base_kernel.log_scaling, kernel.base_kernel.log_lengthscales, m_q}.
+        Returns (loss, grads) with grads = {"log_scaling": 0-d, "log_lengthscales": same shape as the parameter,
+        "mean_output": [N] = d loss / d m_q (feed to autograd of the mean function)}.
+        `allreduce` (e.g. distributed.allreduce_loss_sums) sums the packed vector over ranks before normalising."""
+        gp = self._empirical_risk.gp
+        parameters = gp._to_parameters(parameters)
+        out, dm, _ = self.loss_and_grad_sums(parameters, x, y)
+        if allreduce is not None:
+            out = allreduce(out)
+        n = out[2]
+        ll_shape = as_device(parameters.kernel.base_kernel.log_lengthscales).shape
+        dll = out[4:] / n
+        if as_device(parameters.kernel.base_kernel.log_lengthscales).numel() == 1:
+            dll = dll.sum()  # a scalar lengthscale is broadcast over the D dimensions
+        grads = {"log_scaling": out[3] / n, "log_lengthscales": dll.reshape(ll_shape), "mean_output": dm / n}
+        return (out[0] + out[1]) / n, grads
+
     def _calculate_loss(self, parameters, x, y):
         if self._fusable():
             out3 = self.loss_sums(parameters, x, y)

@@ -100,6 +100,22 @@ int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D,
                        double* out3, double* var_q_out, double* mean_p_out, double* var_p_out,
                        void* workspace, void* stream);
 
+/* ---- gradient of a12 (jax.grad of calculate_loss, experiments/shared/trainer.py:83-89) ---------------------------
+ * Same inputs as gvi_fused_step_f64.  out[0..2] as out3; out[3] = d(sum_i loss_i)/dlog_scaling of q;
+ * out[4+d] = d(sum_i loss_i)/dlog_lengthscales[d] of q (d < D); dm_out[i] = d(sum loss)/dm_q[i].  All in SUM form
+ * (divide by the global N after the all-reduce); the regulariser GP p is constant.  The point-sized work
+ * (a_i = L^-T L^-1 k_i per tile, weighted Gram C = sum_i g_i k_i k_i^T) runs on the FP64 tensor pipe; the M^3
+ * products S = A^-1 C A^-1 are plain cuBLAS DGEMMs.  out has 4 + D doubles.                                    */
+size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D);
+int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                            const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
+                            const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, double* out,
+                            double* dm_out, double* var_q_out, double* mean_p_out, double* var_p_out,
+                            void* workspace, void* stream);
+
+/* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
+int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
+
 /* ---- a13: ConditionalVarianceInducingPointsSelector.compute_inducing_points
  * (src/inducing_points_selection.py:113-176) on ALREADY PERMUTED inputs x_perm[N,D] (the permutation is the
  * host's job).  Writes pivot positions into x_perm to idx_out[M_sel] (int64) and
