@@ -61,7 +61,7 @@ class ShardedSelector:
         dev = x_local.device
         ws = torch.empty(lib.gvi_select_workspace_bytes(n_local, m_sel, d), dtype=torch.uint8, device=dev)
         record = torch.zeros(rl, dtype=torch.float64, device=dev)
-        gathered = torch.zeros(world, rl, dtype=torch.float64, device=dev)
+        gathered = torch.zeros(world * rl, dtype=torch.float64, device=dev)  # flat: accepted by nccl and gloo
         winner = torch.zeros(rl, dtype=torch.float64, device=dev)
         idx = torch.zeros(m_sel, dtype=torch.int64, device=dev)
         trace_local = torch.zeros(m_sel - 1, dtype=torch.float64, device=dev)

@@ -1,0 +1,66 @@
+"""Multi-GPU check, launched by torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/run_multigpu.py
+Every rank owns a contiguous shard of the points; the sharded results must equal the single-GPU results that
+rank 0 computes on the full data: selector pivots bit-exact, loss and packed gradient to 1e-12."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gvi_gaussian_process_b200 import distributed  # noqa: E402
+from gvi_gaussian_process_b200.src import _lib_proxy as L  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+    rng = np.random.default_rng(0)
+    n, d, m = 200_003, 8, 96
+    x = rng.standard_normal((n, d))
+    y = np.sin(x @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    mq = 0.3 * rng.standard_normal(n)
+    ls, ll = t([0.0]), t(np.full(d, np.log(1.0 / d)))
+    lo, hi = distributed.shard_bounds(n, rank, world)
+    # ---- selector ------------------------------------------------------------------------------------------
+    idx, trace = distributed.ShardedSelector().select(t(x[lo:hi]), lo, m, ls, ll)
+    ok = True
+    if rank == 0:
+        ref_idx, ref_trace = L.cond_var_select(t(x), m, ls, ll, 1e-12)
+        same = bool(torch.equal(idx, ref_idx))
+        tr_err = float((trace - ref_trace).abs().max() / ref_trace.abs().max())
+        print(f"[multigpu] world={world} selector pivots identical: {same}; trace rel err {tr_err:.2e}")
+        ok &= same and tr_err < 1e-12
+    # ---- fused step value + gradient -------------------------------------------------------------------------
+    z = t(x[idx.cpu().numpy()])
+    yz = t(y[idx.cpu().numpy()])
+    fq = L.GpFactor(m, d).factor(z, ls, ll, 1e-5, False)
+    fp = L.GpFactor(m, d).factor(z, ls, ll, 0.0, True, log_noise=t([0.0]), y_z=yz)
+    pm = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
+    out, dm = L.fused_step_grad(fq, fp, t(x[lo:hi]), t(y[lo:hi]), t(mq[lo:hi]), pm, None, None, 5, 0.5)
+    distributed.allreduce_loss_sums(out)
+    if rank == 0:
+        pm_full = torch.zeros(n, dtype=torch.float64, device=dev)
+        ref, dm_ref = L.fused_step_grad(fq, fp, t(x), t(y), t(mq), pm_full, None, None, 5, 0.5)
+        err = float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max())
+        dm_err = float((dm - dm_ref[lo:hi]).abs().max() / dm_ref.abs().max())
+        print(f"[multigpu] loss/grad vector rel err vs single GPU {err:.2e}; dm shard err {dm_err:.2e}; "
+              f"loss {float(distributed.loss_from_sums(out)):.12f}")
+        ok &= err < 1e-11 and dm_err < 1e-13
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.broadcast(flag, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+    if flag.item() != 1.0:
+        sys.exit(1)
+    if rank == 0:
+        print("[multigpu] OK")
+
+
+if __name__ == "__main__":
+    main()

@@ -666,3 +666,18 @@ def test_branch_free_exp_is_within_one_ulp(S):
     ulps = np.abs(got[keep] - ref[keep]) / np.spacing(ref[keep])
     assert ulps.max() <= 1.0, ulps.max()
     assert np.all(got[~keep] == 0.0) and got[np.flatnonzero(x == 0.0)[0]] == 1.0
+
+
+def test_multi_gpu_sharding_when_two_gpus_are_visible(S):
+    """Runs tests/run_multigpu.py under torchrun on 2 GPUs (skipped on a 1-GPU box; the N>1 host logic is also
+    covered on CPU by tests/test_distributed_gloo.py)."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        os.path.join(root, "tests", "run_multigpu.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "[multigpu] OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
