@@ -47,11 +47,14 @@ def main():
     if rank == 0:
         pm_full = torch.zeros(n, dtype=torch.float64, device=dev)
         ref, dm_ref = L.fused_step_grad(fq, fp, t(x), t(y), t(mq), pm_full, None, None, 5, 0.5)
-        err = float(((out - ref).abs() / ref.abs().clamp_min(1e-300)).max())
+        rel = (out - ref).abs() / ref.abs().clamp_min(1e-300)
+        err_sums, err_grad = float(rel[:3].max()), float(rel[3:].max())
         dm_err = float((dm - dm_ref[lo:hi]).abs().max() / dm_ref.abs().max())
-        print(f"[multigpu] loss/grad vector rel err vs single GPU {err:.2e}; dm shard err {dm_err:.2e}; "
-              f"loss {float(distributed.loss_from_sums(out)):.12f}")
-        ok &= err < 1e-11 and dm_err < 1e-13
+        print(f"[multigpu] loss sums rel err vs single GPU {err_sums:.2e}; packed gradient rel err {err_grad:.2e}; "
+              f"dm shard err {dm_err:.2e}; loss {float(distributed.loss_from_sums(out)):.12f}")
+        # sums re-associate only (1e-12); the gradient passes through S = A^-1 C A^-1 whose rounding depends on
+        # the order C was accumulated in (cond(A)^2 * eps), tolerance = the gradient parity tolerance
+        ok &= err_sums < 1e-12 and err_grad < 1e-8 and dm_err < 1e-13
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
