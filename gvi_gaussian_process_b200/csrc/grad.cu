@@ -17,127 +17,173 @@ constexpr int CB = 128;  // C tile edge
 constexpr int PC = 32;   // points per chunk
 constexpr int STHREADS = 256;
 
-// Stage buffer: [kp (4)][tile (16)][lane (32)][2] doubles = the DMMA fragments of 128 columns x 32 points; each
-// kp block is padded by 4 doubles so that the 32 lanes of a generating warp (lane = point) hit 16 distinct banks.
+// K block = the DMMA fragments of 128 columns x 32 points: [kp (4)][tile (16)][lane (32)][2] doubles, each kp
+// block padded by 4 doubles (bank spread for the generating warps), followed by the 32 weights g_i of the points.
 constexpr int KPSTRIDE = 16 * 32 * 2 + 4;
 constexpr int STAGE = 4 * KPSTRIDE;
+constexpr int BLK = STAGE + PC;               // doubles per (column block, point group)
+constexpr uint32_t BLK_BYTES = BLK * 8;       // 33152, a multiple of 16 (cp.async.bulk granularity)
+constexpr int NSTAGE = 3;
 __device__ __forceinline__ int frag_index(int c, int i) {
   return (i >> 3) * KPSTRIDE + (((c >> 3) * 32) + ((c & 7) * 4 + (i & 3))) * 2 + ((i >> 2) & 1);
 }
 
-struct SyrkParams {
-  const double* F;   // factor of q
-  const double* X;
-  const double* g;   // [N]
-  int64_t N;
-  int M, Mp, D;
-  int nsplit;
-  double* Cpart;     // [nsplit][Mp*Mp]
-};
-
-// One CTA = one 128x128 tile of C (lower triangle) x one slice of the points.  Per 32-point chunk every warp issues
-// 256 DMMAs (its 32x64 sub-tile) and, in the same instruction stream, generates its share of the NEXT chunk's
-// k(x_i, z_c) values on the FP64 pipe (lane = point, 32 columns per warp), so the two pipes overlap.
+// ---- stage 1: K(x_chunk, Z) once per chunk into an L2-sized ring, already in fragment order ------------------------
+// One CTA per 32-point group: lane = point, warp w takes columns w, w+8, ... four at a time (independent exp chains).
 template <int DR>
-__global__ void __launch_bounds__(STHREADS, 1) syrk_kernel(const SyrkParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* KA = reinterpret_cast<double*>(smem_raw);   // [2][STAGE] weighted (g_i k_ij), A-fragment order
-  double* KB = KA + 2 * STAGE;                         // [2][STAGE] k_il, B-fragment order
-  double* zsm = KB + 2 * STAGE;                        // [256][DR] scaled inducing points of the two column blocks
+__global__ void __launch_bounds__(STHREADS) kgen_kernel(const double* __restrict__ F, const double* __restrict__ X,
+                                                        const double* __restrict__ g, int64_t N, int64_t row0,
+                                                        int npg, int M, int Mp, int D, double* __restrict__ Kc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // lower-triangular tile (bj >= bl) from the linear block index
-  int bj = 0, rem = blockIdx.x;
-  while (rem > bj) { rem -= bj + 1; bj++; }
-  const int bl = rem;
-  const FactorLayout f = factor_layout(P.M, P.D);
-  const double amp2 = P.F[0];
-  const double* __restrict__ sqrtw = P.F + f.sqrtw_off;
-  const double* __restrict__ Zs = P.F + f.zs_off;
-  for (int idx = tid; idx < 256 * DR; idx += STHREADS) {
-    int c = idx / DR, d = idx % DR;
-    int zc = (c < CB ? bj : bl) * CB + (c & (CB - 1));
-    zsm[idx] = (d < P.D && zc < P.Mp) ? Zs[(int64_t)zc * P.D + d] : 0.0;
-  }
-  // generating role: warps 0-3 -> A block (weighted by g_i), warps 4-7 -> B block; 32 columns per warp
-  const int which = warp >> 2;
-  const int gcol0 = (warp & 3) * 32;  // first column (inside the 128-wide block) this warp generates
-  double* mine = which == 0 ? KA : KB;
-
-  const int64_t nchunks = (P.N + PC - 1) / PC;
-  const int64_t c_begin = nchunks * blockIdx.y / P.nsplit, c_end = nchunks * (blockIdx.y + 1) / P.nsplit;
-
-  double xr[DR], wr = 0.0;  // this lane's point of the chunk being generated (scaled) and its weight
-  auto load_point = [&](int64_t chunk) {
-    const int64_t r = chunk * PC + lane;
+  const int pg = blockIdx.x;
+  const FactorLayout f = factor_layout(M, D);
+  const double amp2 = F[0];
+  const double* __restrict__ sqrtw = F + f.sqrtw_off;
+  const double* __restrict__ Zs = F + f.zs_off;
+  const int64_t r = row0 + (int64_t)pg * PC + lane;
+  double xr[DR];
 #pragma unroll
-    for (int d = 0; d < DR; d++) xr[d] = (d < P.D && r < P.N) ? P.X[r * P.D + d] * sqrtw[d] : 0.0;
-    wr = (r < P.N) ? (which == 0 ? P.g[r] : 1.0) : 0.0;
-  };
-  // four columns at once: all loads first, then four independent exp chains (ILP), then the stores
-  auto gen4 = [&](int buf, int cc0) {
+  for (int d = 0; d < DR; d++) xr[d] = (d < D && r < N) ? X[r * D + d] * sqrtw[d] : 0.0;
+  const double live = (r < N) ? amp2 : 0.0;
+  const int ncb = (Mp + CB - 1) / CB;
+  if (warp == 0) {
+    const double gv = (r < N) ? g[r] : 0.0;
+    for (int cb = 0; cb < ncb; cb++) Kc[((size_t)cb * npg + pg) * BLK + STAGE + lane] = gv;
+  }
+  for (int c0 = warp * 4; c0 < ncb * CB; c0 += 32) {
     double s4[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const double* zc = zsm + (which * CB + gcol0 + cc0 + q) * DR;
+      const int c = c0 + q;
       double s = 0.0;
 #pragma unroll
       for (int d = 0; d < DR; d++) {
-        double diff = xr[d] - zc[d];
+        double z = (d < D && c < Mp) ? Zs[(int64_t)c * D + d] : 0.0;
+        double diff = xr[d] - z;
         s = fma(diff, diff, s);
       }
       s4[q] = s;
     }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      const int c = gcol0 + cc0 + q;
-      const int zglob = (which == 0 ? bj : bl) * CB + c;
-      s4[q] = (zglob < P.M ? amp2 : 0.0) * wr * gvi_exp(-0.5 * s4[q]);
+      const int c = c0 + q;
+      const double k = (c < M ? live : 0.0) * gvi_exp(-0.5 * s4[q]);
+      Kc[((size_t)(c / CB) * npg + pg) * BLK + frag_index(c % CB, lane)] = k;
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++) mine[buf * STAGE + frag_index(gcol0 + cc0 + q, lane)] = s4[q];
-  };
+  }
+}
 
-  double acc[4][8][2];
-#pragma unroll
-  for (int a = 0; a < 4; a++)
-#pragma unroll
-    for (int b = 0; b < 8; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+// ---- mbarrier / bulk-copy (TMA 1-D) helpers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+struct SyrkParams {
+  const double* Kc;  // [ncb][npg][BLK]
+  int npg;           // point groups in this chunk
+  int Mp;
+  int nsplit;
+  int first;         // first chunk: accumulators start at zero, otherwise they are reloaded from Cpart
+  double* Cpart;     // [nsplit][Mp*Mp]
+};
+
+// ---- stage 2: C tile += (G K_j)^T K_l over the chunk.  One CTA = one 128x128 lower-triangular tile of C x one slice of
+// the chunk's point groups.  K blocks arrive by cp.async.bulk (TMA 1-D) into a 3-stage shared-memory ring, completion
+// on mbarriers; every warp issues 256 DMMAs per 32-point group for its 32x64 sub-tile; accumulators stay in registers.
+__global__ void __launch_bounds__(STHREADS, 1) syrk_kernel(const SyrkParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);                       // [NSTAGE][2][BLK]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)NSTAGE * 2 * BLK);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int bj = 0, rem = blockIdx.x;
+  while (rem > bj) { rem -= bj + 1; bj++; }
+  const int bl = rem;
+  const bool diag = (bj == bl);
+  const int pg_begin = (int)((int64_t)P.npg * blockIdx.y / P.nsplit);
+  const int pg_end = (int)((int64_t)P.npg * (blockIdx.y + 1) / P.nsplit);
+  const int niter = pg_end - pg_begin;
   const int wj = warp >> 1, wl = warp & 1;
 
-  __syncthreads();  // zsm ready
-  if (c_begin < c_end) {
-    load_point(c_begin);
-#pragma unroll
-    for (int cc = 0; cc < 32; cc += 4) gen4(0, cc);
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; s++) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int64_t chunk = c_begin; chunk < c_end; chunk++) {
-    const int cur = (int)((chunk - c_begin) & 1), nxt = cur ^ 1;
-    __syncthreads();  // stage `cur` complete; every warp has finished reading stage `nxt` (previous iteration)
-    load_point(chunk + 1);  // past the slice end this yields weight 0 / harmless values in the unused stage
-    const double2* A2 = reinterpret_cast<const double2*>(KA + cur * STAGE);
-    const double2* B2 = reinterpret_cast<const double2*>(KB + cur * STAGE);
+  __syncthreads();
+  auto issue = [&](int it) {  // thread 0 only
+    const int s = it % NSTAGE;
+    double* dstA = ring + (size_t)s * 2 * BLK;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&full[s], diag ? BLK_BYTES : 2 * BLK_BYTES);
+    bulk_g2s(dstA, P.Kc + ((size_t)bj * P.npg + pg_begin + it) * BLK, BLK_BYTES, &full[s]);
+    if (!diag) bulk_g2s(dstA + BLK, P.Kc + ((size_t)bl * P.npg + pg_begin + it) * BLK, BLK_BYTES, &full[s]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < NSTAGE && it < niter; it++) issue(it);
+
+  double acc[4][8][2];
+  double* Cout = P.Cpart + (size_t)blockIdx.y * P.Mp * P.Mp;
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int r = bj * CB + (4 * wj + mt) * 8 + (lane >> 2);
+        int c = bl * CB + (8 * wl + nt) * 8 + (lane & 3) * 2 + e;
+        acc[mt][nt][e] = (!P.first && r < P.Mp && c < P.Mp) ? Cout[(size_t)r * P.Mp + c] : 0.0;
+      }
+
+  for (int it = 0; it < niter; it++) {
+    const int s = it % NSTAGE;
+    mbar_wait(&full[s], (it / NSTAGE) & 1);
+    const double* Ab = ring + (size_t)s * 2 * BLK;
+    const double* Bb = diag ? Ab : Ab + BLK;
+    const double2* A2 = reinterpret_cast<const double2*>(Ab);
+    const double2* B2 = reinterpret_cast<const double2*>(Bb);
 #pragma unroll
     for (int kp = 0; kp < PC / 8; kp++) {
+      const double g0 = Ab[STAGE + kp * 8 + (lane & 3)], g1 = Ab[STAGE + kp * 8 + 4 + (lane & 3)];
       double2 a[4], b[8];
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++) a[mt] = A2[kp * (KPSTRIDE / 2) + (4 * wj + mt) * 32 + lane];
+      for (int mt = 0; mt < 4; mt++) {
+        a[mt] = A2[kp * (KPSTRIDE / 2) + (4 * wj + mt) * 32 + lane];
+        a[mt].x *= g0;  // the weight g_i rides on the A operand: (G K_j)^T K_l
+        a[mt].y *= g1;
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) b[nt] = B2[kp * (KPSTRIDE / 2) + (8 * wl + nt) * 32 + lane];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++)
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
-      // generation of the next chunk rides between the DMMA blocks (FP64 pipe || tensor pipe)
-      gen4(nxt, kp * 8);
 #pragma unroll
       for (int mt = 0; mt < 4; mt++)
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
-      gen4(nxt, kp * 8 + 4);
     }
+    __syncthreads();  // every warp is done with stage s before it is refilled
+    if (tid == 0 && it + NSTAGE < niter) issue(it + NSTAGE);
   }
-  // write the partial tile: lane holds C[row = lane/4][col = (lane%4)*2 + e] of each 8x8 tile
-  double* Cout = P.Cpart + (size_t)blockIdx.y * P.Mp * P.Mp;
 #pragma unroll
   for (int mt = 0; mt < 4; mt++)
 #pragma unroll
@@ -234,21 +280,28 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const doubl
 }
 
 template <int DR>
+int launch_kgen(const double* F, const double* X, const double* g, int64_t N, int64_t row0, int npg, int M, int Mp,
+                int D, double* Kc, cudaStream_t st) {
+  kgen_kernel<DR><<<npg, STHREADS, 0, st>>>(F, X, g, N, row0, npg, M, Mp, D, Kc);
+  GVI_CHECK_LAUNCH("kgen_kernel");
+  return GVI_OK;
+}
+
 int launch_syrk(const SyrkParams& P, int ntri, cudaStream_t st) {
-  size_t smem = ((size_t)4 * STAGE + 256 * DR) * sizeof(double);
+  size_t smem = (size_t)NSTAGE * 2 * BLK * sizeof(double) + NSTAGE * sizeof(uint64_t) + 64;
   static bool configured = false;
   if (!configured) {
-    GVI_CUDA(cudaFuncSetAttribute(syrk_kernel<DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    GVI_CUDA(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  syrk_kernel<DR><<<dim3(ntri, P.nsplit), STHREADS, smem, st>>>(P);
+  syrk_kernel<<<dim3(ntri, P.nsplit), STHREADS, smem, st>>>(P);
   GVI_CHECK_LAUNCH("syrk_kernel");
   return GVI_OK;
 }
 
 struct GradWs {
-  double *partials, *g, *bscratch, *Cpart, *C, *T1, *T2, *rowpart;
-  int nsplit, ntri;
+  double *partials, *g, *bscratch, *Cpart, *C, *T1, *T2, *rowpart, *Kc;
+  int nsplit, ntri, ncb, chunk_pg;  // chunk_pg = point groups (of 32 points) per K chunk
 };
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
@@ -270,6 +323,15 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   w.T1 = take((size_t)f.Mp * f.Mp * 8);
   w.T2 = take((size_t)f.Mp * f.Mp * 8);
   w.rowpart = take((size_t)f.Mp * 32 * 8);
+  // K ring: ~48 MB so that a chunk written by kgen_kernel is still L2-resident when syrk_kernel streams it
+  w.ncb = Gc;
+  int64_t pgs = (48LL << 20) / ((int64_t)Gc * BLK * 8);
+  pgs = pgs / w.nsplit * w.nsplit;
+  if (pgs < w.nsplit) pgs = w.nsplit;
+  const int64_t need = (N + PC - 1) / PC;
+  if (pgs > need) pgs = need;
+  w.chunk_pg = (int)pgs;
+  w.Kc = take((size_t)Gc * pgs * BLK * 8);
   if (total) *total = o;
   return w;
 }
@@ -317,14 +379,20 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
-  // C = sum_i g_i k_i k_i^T
-  SyrkParams sp{Fq, X, w.g, N, M, f.Mp, D, w.nsplit, w.Cpart};
-  if (D <= 1) rc = launch_syrk<1>(sp, w.ntri, st);
-  else if (D <= 4) rc = launch_syrk<4>(sp, w.ntri, st);
-  else if (D <= 8) rc = launch_syrk<8>(sp, w.ntri, st);
-  else if (D <= 16) rc = launch_syrk<16>(sp, w.ntri, st);
-  else rc = launch_syrk<32>(sp, w.ntri, st);
-  if (rc) return rc;
+  // C = sum_i g_i k_i k_i^T, chunk by chunk through the L2-sized K ring
+  const int64_t total_pg = (N + PC - 1) / PC;
+  for (int64_t pg0 = 0; pg0 < total_pg; pg0 += w.chunk_pg) {
+    const int npg = (int)(total_pg - pg0 < w.chunk_pg ? total_pg - pg0 : w.chunk_pg);
+    const int64_t row0 = pg0 * PC;
+    if (D <= 1) rc = launch_kgen<1>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 4) rc = launch_kgen<4>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 8) rc = launch_kgen<8>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 16) rc = launch_kgen<16>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else rc = launch_kgen<32>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    if (rc) return rc;
+    SyrkParams sp{w.Kc, npg, f.Mp, w.nsplit, pg0 == 0 ? 1 : 0, w.Cpart};
+    if ((rc = launch_syrk(sp, w.ntri, st))) return rc;
+  }
   syrk_reduce_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.Cpart, w.nsplit, f.Mp, w.C);
   GVI_CHECK_LAUNCH("syrk_reduce_kernel");
   // S = L^-T (L^-1 C L^-T) L^-1  (plain library GEMMs)
