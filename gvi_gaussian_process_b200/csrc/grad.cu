@@ -29,13 +29,14 @@ __device__ __forceinline__ int frag_index(int c, int i) {
 }
 
 // ---- stage 1: K(x_chunk, Z) once per chunk into an L2-sized ring, already in fragment order ------------------------
-// One CTA per 32-point group: lane = point, warp w takes columns w, w+8, ... four at a time (independent exp chains).
+// One CTA per (32-point group, 128-column block): lane = point, warp w takes 16 columns, four at a time (independent
+// exp chains); 48 registers -> several CTAs per SM keep the FP64 pipe busy.
 template <int DR>
 __global__ void __launch_bounds__(STHREADS) kgen_kernel(const double* __restrict__ F, const double* __restrict__ X,
                                                         const double* __restrict__ g, int64_t N, int64_t row0,
                                                         int npg, int M, int Mp, int D, double* __restrict__ Kc) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pg = blockIdx.x;
+  const int pg = blockIdx.x, cb = blockIdx.y;
   const FactorLayout f = factor_layout(M, D);
   const double amp2 = F[0];
   const double* __restrict__ sqrtw = F + f.sqrtw_off;
@@ -45,12 +46,9 @@ __global__ void __launch_bounds__(STHREADS) kgen_kernel(const double* __restrict
 #pragma unroll
   for (int d = 0; d < DR; d++) xr[d] = (d < D && r < N) ? X[r * D + d] * sqrtw[d] : 0.0;
   const double live = (r < N) ? amp2 : 0.0;
-  const int ncb = (Mp + CB - 1) / CB;
-  if (warp == 0) {
-    const double gv = (r < N) ? g[r] : 0.0;
-    for (int cb = 0; cb < ncb; cb++) Kc[((size_t)cb * npg + pg) * BLK + STAGE + lane] = gv;
-  }
-  for (int c0 = warp * 4; c0 < ncb * CB; c0 += 32) {
+  double* blk = Kc + ((size_t)cb * npg + pg) * BLK;
+  if (warp == 0) blk[STAGE + lane] = (r < N) ? g[r] : 0.0;
+  for (int c0 = cb * CB + warp * 16; c0 < cb * CB + warp * 16 + 16; c0 += 4) {
     double s4[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -68,7 +66,7 @@ __global__ void __launch_bounds__(STHREADS) kgen_kernel(const double* __restrict
     for (int q = 0; q < 4; q++) {
       const int c = c0 + q;
       const double k = (c < M ? live : 0.0) * gvi_exp(-0.5 * s4[q]);
-      Kc[((size_t)(c / CB) * npg + pg) * BLK + frag_index(c % CB, lane)] = k;
+      blk[frag_index(c % CB, lane)] = k;
     }
   }
 }
@@ -282,7 +280,7 @@ int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const doubl
 template <int DR>
 int launch_kgen(const double* F, const double* X, const double* g, int64_t N, int64_t row0, int npg, int M, int Mp,
                 int D, double* Kc, cudaStream_t st) {
-  kgen_kernel<DR><<<npg, STHREADS, 0, st>>>(F, X, g, N, row0, npg, M, Mp, D, Kc);
+  kgen_kernel<DR><<<dim3(npg, (Mp + CB - 1) / CB), STHREADS, 0, st>>>(F, X, g, N, row0, npg, M, Mp, D, Kc);
   GVI_CHECK_LAUNCH("kgen_kernel");
   return GVI_OK;
 }

@@ -103,18 +103,42 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
           for (int d = 0; d < DR; d++) z[d] = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
           const double aj = alpha[j];
           const double scale = (j < P.M) ? amp2 : 0.0;
-          double* kcol = Ksm + (size_t)(j >> 3) * (NT * 64) + ((j >> 2) & 1) + 2 * (j & 3);
+          double* __restrict__ kcol = Ksm + (size_t)(j >> 3) * (NT * 64) + ((j >> 2) & 1) + 2 * (j & 3);
+          const double* __restrict__ xr = xs;
+          // four points at a time: all loads first, four independent exp chains, then the stores (the compiler
+          // cannot prove that the K-tile stores do not alias the x tile, so the batching is explicit)
 #pragma unroll
-          for (int i = 0; i < T; i++) {
-            double s = 0.0;
+          for (int i0 = 0; i0 < T; i0 += 4) {
+            double s4[4];
 #pragma unroll
-            for (int d = 0; d < DR; d++) {
-              double diff = xs[i * DR + d] - z[d];
-              s = fma(diff, diff, s);
+            for (int q = 0; q < 4; q++) {
+              double sa = 0.0, sb = 0.0;
+              if constexpr (DR % 2 == 0) {
+                const double2* __restrict__ x2 = reinterpret_cast<const double2*>(xr + (i0 + q) * DR);
+#pragma unroll
+                for (int d = 0; d < DR; d += 2) {
+                  const double2 xv = x2[d / 2];  // LDS.128 broadcast
+                  const double d0 = xv.x - z[d], d1 = xv.y - z[d + 1];
+                  sa = fma(d0, d0, sa);
+                  sb = fma(d1, d1, sb);
+                }
+              } else {
+#pragma unroll
+                for (int d = 0; d < DR; d++) {
+                  const double d0 = xr[(i0 + q) * DR + d] - z[d];
+                  sa = fma(d0, d0, sa);
+                }
+              }
+              s4[q] = sa + sb;
             }
-            double k = scale * gvi_exp(-0.5 * s);
-            kcol[(i >> 3) * 64 + (i & 7) * 8] = k;
-            macc[i] = fma(k, aj, macc[i]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) s4[q] = scale * gvi_exp(-0.5 * s4[q]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int i = i0 + q;
+              kcol[(i >> 3) * 64 + (i & 7) * 8] = s4[q];
+              macc[i] = fma(s4[q], aj, macc[i]);
+            }
           }
         }
 #pragma unroll
