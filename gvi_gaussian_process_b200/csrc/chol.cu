@@ -243,40 +243,37 @@ __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, con
   }
 }
 
-// ---- pack L^-1 in fragment order: group g (rows 32g..32g+31), kp (cols 8kp..8kp+7), mt (8-row tile), lane, e ----
-// element = Linv[32g + 8mt + lane/4][8kp + 4e + lane%4]; zero above the diagonal and in the padding.
-__global__ void pack_linv_kernel(const double* __restrict__ X, int Mp, int M, int G, double* __restrict__ W) {
-  const int64_t total = 256LL * G * (G + 1);  // number of double2 items
-  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
-       it += (int64_t)gridDim.x * blockDim.x) {
-    // find group: items before group g = 256*g*(g+1)
-    int g = (int)((sqrt(1.0 + (double)it / 64.0) - 1.0) * 0.5);
-    while (256LL * (g + 1) * (g + 2) <= it) g++;
-    while (256LL * g * (g + 1) > it) g--;
-    int64_t local = it - 256LL * g * (g + 1);
-    int lane = (int)(local & 31);
-    int mt = (int)((local >> 5) & 3);
-    int kp = (int)(local >> 7);
-    int c = 32 * g + 8 * mt + (lane >> 2);
+// ---- pack L^-1 in fragment order: group g (rows R g .. R g + R - 1, R = GVI_GROUP_ROWS), kp (cols 8kp..8kp+7),
+// mt (8-row tile), lane, e:  element = Linv[R g + 8 mt + lane/4][8 kp + 4 e + lane%4]; zero above the diagonal and in
+// the padding.  One CTA per group.
+__global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict__ X, int Mp, int M, int G,
+                                                        double* __restrict__ W) {
+  const int g = blockIdx.x;
+  double2* out = reinterpret_cast<double2*>(W + wpack_group_off(g));
+  const int items = wpack_nkp(g) * GVI_MT * 32;
+  for (int it = threadIdx.x; it < items; it += 256) {
+    int lane = it & 31, mt = (it >> 5) % GVI_MT, kp = it / (32 * GVI_MT);
+    int c = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
     double2 v;
     int j0 = 8 * kp + (lane & 3), j1 = j0 + 4;
     v.x = (c < M && j0 <= c) ? X[(int64_t)c * Mp + j0] : 0.0;
     v.y = (c < M && j1 <= c) ? X[(int64_t)c * Mp + j1] : 0.0;
-    reinterpret_cast<double2*>(W)[it] = v;
+    out[it] = v;
   }
 }
 
-// L^-T in the same fragment order: group g holds rows j in [32g, 32g+32) and the k-range c in [32g, Mp):
-// element = Linv[c = 8kp + 4e + lane%4][j = 32g + 8mt + lane/4] for kp >= 4g.  One CTA per group.
+// L^-T in the same fragment order: group g holds rows j in [R g, R g + R) and the k-range c in [R g, Mp):
+// element = Linv[c = 8kp + 4e + lane%4][j = R g + 8mt + lane/4] for kp >= R g / 8.  One CTA per group.
 __global__ void __launch_bounds__(256) pack_linvT_kernel(const double* __restrict__ X, int Mp, int M, int G,
                                                          double* __restrict__ W) {
   const int g = blockIdx.x;
   double2* out = reinterpret_cast<double2*>(W + wpackT_group_off(g, G));
-  const int items = 512 * (G - g);
+  const int kp0 = GVI_GROUP_ROWS * g / 8;
+  const int items = (Mp / 8 - kp0) * GVI_MT * 32;
   for (int it = threadIdx.x; it < items; it += 256) {
-    int lane = it & 31, mt = (it >> 5) & 3, kpl = it >> 7;
-    int j = 32 * g + 8 * mt + (lane >> 2);
-    int c0 = 8 * (4 * g + kpl) + (lane & 3), c1 = c0 + 4;
+    int lane = it & 31, mt = (it >> 5) % GVI_MT, kpl = it / (32 * GVI_MT);
+    int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
+    int c0 = 8 * (kp0 + kpl) + (lane & 3), c1 = c0 + 4;
     double2 v;
     v.x = (j < M && c0 < M && c0 >= j) ? X[(int64_t)c0 * Mp + j] : 0.0;
     v.y = (j < M && c1 < M && c1 >= j) ? X[(int64_t)c1 * Mp + j] : 0.0;
@@ -406,16 +403,14 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   if (info) GVI_CUDA(cudaMemcpyAsync(info, winfo, sizeof(int), cudaMemcpyDeviceToDevice, st));
   zero_kernel<<<148 * 4, 256, 0, st>>>(X, (int64_t)f.Mp * f.Mp);
   GVI_CHECK_LAUNCH("zero_kernel");
-  diag_inverse_kernel<<<f.G, 32, 0, st>>>(A, f.Mp, X, f.Mp);
+  diag_inverse_kernel<<<f.Mp / NB, 32, 0, st>>>(A, f.Mp, X, f.Mp);
   GVI_CHECK_LAUNCH("diag_inverse_kernel");
-  if (f.G > 1) {
-    linv_sweep_kernel<<<f.G - 1, 256, 0, st>>>(A, f.Mp, X, f.Mp, f.G);
+  if (f.Mp / NB > 1) {
+    linv_sweep_kernel<<<f.Mp / NB - 1, 256, 0, st>>>(A, f.Mp, X, f.Mp, f.Mp / NB);
     GVI_CHECK_LAUNCH("linv_sweep_kernel");
   }
   {
-    int64_t items = 256LL * f.G * (f.G + 1);
-    int blocks = (int)((items + 255) / 256 < 148 * 8 ? (items + 255) / 256 : 148 * 8);
-    pack_linv_kernel<<<blocks, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpack_off);
+    pack_linv_kernel<<<f.G, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpack_off);
     GVI_CHECK_LAUNCH("pack_linv_kernel");
     pack_linvT_kernel<<<f.G, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpackT_off);
     GVI_CHECK_LAUNCH("pack_linvT_kernel");

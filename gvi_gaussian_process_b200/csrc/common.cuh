@@ -50,16 +50,22 @@ constexpr int GVI_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 // [wpack_off, ...)    L^-1 packed per 32-row group in DMMA m8n8k4 fragment order (see pack_linv_kernel)
 // [wpackT_off, ...)   L^-T packed the same way (rows j, k-range c >= 32g): a = L^-T b in the backward pass
 // [linv_off, +Mp*Mp)  dense row-major L^-1 (S = A^-1 C A^-1 in the backward pass; full-covariance API)
+// rows of L^-1 handled by one warp-level group in the tile kernel = 8 * GVI_MT (m-tiles of the DMMA m8n8k4 shape)
+constexpr int GVI_MT = 2;
+constexpr int GVI_GROUP_ROWS = 8 * GVI_MT;
 struct FactorLayout {
-  int M, Mp, D, G;
+  int M, Mp, D, G;  // G = number of GVI_GROUP_ROWS-row groups
   int64_t sqrtw_off, zs_off, alpha_off, wpack_off, wpackT_off, linv_off, total;
 };
+__host__ __device__ inline int64_t wpack_total(int G) {
+  return (int64_t)GVI_MT * 64 * (GVI_GROUP_ROWS / 8) * ((int64_t)G * (G + 1) / 2);
+}
 __host__ __device__ inline FactorLayout factor_layout(int M, int D) {
   FactorLayout f;
   f.M = M;
   f.Mp = (M + 31) / 32 * 32;
   f.D = D;
-  f.G = f.Mp / 32;
+  f.G = f.Mp / GVI_GROUP_ROWS;
   f.sqrtw_off = 8;
   int64_t o = 8 + D;
   o = (o + 1) / 2 * 2;
@@ -70,18 +76,24 @@ __host__ __device__ inline FactorLayout factor_layout(int M, int D) {
   o += f.Mp;
   o = (o + 1) / 2 * 2;
   f.wpack_off = o;
-  o += 512LL * f.G * (f.G + 1);
+  o += wpack_total(f.G);
   f.wpackT_off = o;
-  o += 512LL * f.G * (f.G + 1);
+  o += wpack_total(f.G);
   f.linv_off = o;
   o += (int64_t)f.Mp * f.Mp;
   f.total = o;
   return f;
 }
-// offset (doubles) of 32-row group g inside wpackT: sum_{g'<g} 1024*(G-g')
-__host__ __device__ inline int64_t wpackT_group_off(int g, int G) { return 1024LL * ((int64_t)g * G - (int64_t)g * (g - 1) / 2); }
-// offset (doubles) of 32-row group g inside wpack: sum_{g'<g} 1024*(g'+1)
-__host__ __device__ inline int64_t wpack_group_off(int g) { return 512LL * g * (g + 1); }
+// transposed pack: group g needs k-pairs kp0(g) = R g / 8 .. Mp/8 - 1, i.e. (R/8) (G - g) of them
+__host__ __device__ inline int64_t wpackT_group_off(int g, int G) {
+  return (int64_t)GVI_MT * 64 * (GVI_GROUP_ROWS / 8) * ((int64_t)g * G - (int64_t)g * (g - 1) / 2);
+}
+// group g (rows [R g, R g + R), R = GVI_GROUP_ROWS) needs k-pairs (8 columns each) 0 .. nkp(g)-1, nkp = R (g+1) / 8;
+// one k-pair of one group = GVI_MT * 64 doubles.
+__host__ __device__ inline int wpack_nkp(int g) { return GVI_GROUP_ROWS * (g + 1) / 8; }
+__host__ __device__ inline int64_t wpack_group_off(int g) {
+  return (int64_t)GVI_MT * 64 * (GVI_GROUP_ROWS / 8) * ((int64_t)g * (g + 1) / 2);
+}
 
 // ---- FP64 tensor-core MMA (legacy warp-level path: SASS DMMA.8x8x4; there is no tcgen05 FP64 kind) -------------
 // A 8x4 row-major: lane holds A[lane/4][lane%4]; B 4x8 col: lane holds B[lane%4][lane/4];

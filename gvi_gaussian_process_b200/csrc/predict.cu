@@ -11,44 +11,47 @@
 // the gradient is jax.grad of generalised_variational_inference.py:73-94 (experiments/shared/trainer.py:83-89).
 // Algebra: v = k(x,x) - k^T A^-1 k = k(x,x) - ||L^-1 k||^2 with A = L L^T;  b = L^-1 k is a dependency-free
 // triangular GEMM against the explicit inverse (validated against cho_solve in tests; see DESIGN.md numerics).
+#include <cstdlib>
+
 #include "predict.cuh"
 
 namespace {
 
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;  // 16 warps = 4 per SM sub-partition: enough to hide DMMA / L2 / FP64 latencies
 constexpr int WARPS = THREADS / 32;
+constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 
-// One 32-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
+// One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
 // acc[mt][nt] += sum_{kp in [kp0, kp0+nkp)} A(group rows 8mt.., cols 8kp..) * Ktile(cols 8kp.., points 8nt..).
 // A fragments come from L2 as one LDG.128 per lane per (kp, mt) (two k-steps), prefetched one kp ahead.
 template <int NT>
 __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
-                                          const double2* __restrict__ Ks2, int lane, double (&acc)[4][NT][2]) {
+                                          const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2]) {
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++)
+  for (int mt = 0; mt < MT; mt++)
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-  double2 a_cur[4], a_nxt[4];
+  double2 a_cur[MT], a_nxt[MT];
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
+  for (int mt = 0; mt < MT; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
 #pragma unroll 1
   for (int k = 0; k < nkp; k++) {
     const int kn = (k + 1 < nkp) ? k + 1 : k;
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) a_nxt[mt] = __ldcg(Ag + (kn * 4 + mt) * 32);
+    for (int mt = 0; mt < MT; mt++) a_nxt[mt] = __ldcg(Ag + (kn * MT + mt) * 32);
     double2 b[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++)
+    for (int mt = 0; mt < MT; mt++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b[nt].x);
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++)
+    for (int mt = 0; mt < MT; mt++)
 #pragma unroll
       for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b[nt].y);
 #pragma unroll
-    for (int mt = 0; mt < 4; mt++) a_cur[mt] = a_nxt[mt];
+    for (int mt = 0; mt < MT; mt++) a_cur[mt] = a_nxt[mt];
   }
 }
 
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   double* Ksm = reinterpret_cast<double*>(smem_raw);            // [Mp*T] fragment order
   double* xs = Ksm + (size_t)P.Mp * T;                            // [T][DR] scaled x tile
   double* redm = xs + T * DR;                                     // [WARPS][T]
-  double* reds = redm + WARPS * T;                                // [G][T] squared norms per 32-row group
+  double* reds = redm + WARPS * T;                                // [G][T] squared norms per row group
   double* res = reds + (size_t)P.G * T;                           // [2 GPs][T][2] (mean, var)
   double* gs = res + 2 * T * 2;                                   // [T] g_i = dR/dv_q,i of the tile
   double* gpart = gs + T;                                         // [G][DR+1] per-group gradient partials
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       if (tid == 0) *counter = 0;
       __syncthreads();
       // ---- phase 1: K tile (T x Mp) into shared memory in B-fragment order; mean partials ------------------
-      {
+      if (!(P.debug_skip & 1)) {
         double macc[T];
 #pragma unroll
         for (int i = 0; i < T; i++) macc[i] = 0.0;
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       }
       __syncthreads();
       // ---- phase 2: b = L^-1 k on the tensor pipe, accumulate ||b||^2 ----------------------------------
-      {
+      if (!(P.debug_skip & 2)) {
         const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
         const double* __restrict__ W = F + f.wpack_off;
         while (true) {
@@ -158,8 +161,8 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
           gi = __shfl_sync(0xffffffffu, gi, 0);
           if (gi >= P.G) break;
           const int g = P.G - 1 - gi;  // largest groups first
-          double acc[4][NT][2];
-          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + lane, 0, 4 * (g + 1), Ks2, lane,
+          double acc[MT][NT][2];
+          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + lane, 0, wpack_nkp(g), Ks2, lane,
                         acc);
           // squared norms of this group's 32 rows: lanes with equal lane%4 hold the same two points of every
           // n-tile.  Stored per GROUP (not per warp) so the final sum has a fixed order whatever warp ran the group.
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
             for (int e = 0; e < 2; e++) {
               double v = 0.0;
 #pragma unroll
-              for (int mt = 0; mt < 4; mt++) v = fma(acc[mt][nt][e], acc[mt][nt][e], v);
+              for (int mt = 0; mt < MT; mt++) v = fma(acc[mt][nt][e], acc[mt][nt][e], v);
               v += __shfl_xor_sync(0xffffffffu, v, 4);
               v += __shfl_xor_sync(0xffffffffu, v, 8);
               v += __shfl_xor_sync(0xffffffffu, v, 16);
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
           if (keep_b) {
             // b[c][i] goes to the per-CTA scratch (L2 resident) in the K-tile fragment order at "column" c
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++) {
-              const int c = 32 * g + 8 * mt + (lane >> 2);
+            for (int mt = 0; mt < MT; mt++) {
+              const int c = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
               double* bcol = bscr + (size_t)(c >> 3) * (NT * 64) + ((c >> 2) & 1) + 2 * (c & 3);
 #pragma unroll
               for (int nt = 0; nt < NT; nt++)
@@ -271,15 +274,16 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
         if (lane == 0) g = atomicAdd(counter, 1);
         g = __shfl_sync(0xffffffffu, g, 0);  // ascending g = largest k-range first
         if (g >= P.G) break;
-        double acc[4][NT][2];
-        group_mma<NT>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, 4 * g, 4 * (P.G - g),
+        double acc[MT][NT][2];
+        const int kp0 = GVI_GROUP_ROWS * g / 8;
+        group_mma<NT>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
                       Ks2, lane, acc);
         double t2[DR], na2 = 0.0;
 #pragma unroll
         for (int d = 0; d < DR; d++) t2[d] = 0.0;
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) {
-          const int j = 32 * g + 8 * mt + (lane >> 2);
+        for (int mt = 0; mt < MT; mt++) {
+          const int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
           double z[DR];
 #pragma unroll
           for (int d = 0; d < DR; d++) z[d] = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __res
 template <int NT, int DR>
 size_t step_smem_bytes(int Mp) {
   constexpr int T = 8 * NT;
-  const size_t G = Mp / 32;
+  const size_t G = Mp / GVI_GROUP_ROWS;
   return ((size_t)Mp * T + T * DR + WARPS * T + G * T + 4 * T + T + G * (DR + 1)) * sizeof(double) + 16;
 }
 
@@ -411,7 +415,10 @@ int gvi_step_tile_points(int Mp) {
 }
 
 // returns grid size (>0) or a negative error code
-int gvi_launch_step(const StepParams& P, cudaStream_t st) {
+int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
+  StepParams P = P_in;
+  static const int debug_skip = getenv("GVI_DEBUG_SKIP") ? atoi(getenv("GVI_DEBUG_SKIP")) : 0;
+  P.debug_skip = debug_skip;
   if (P.D > 32) {
     gvi_set_error("fused predict supports D <= 32 in this build (got D=%d)", P.D);
     return GVI_EUNSUPPORTED;

@@ -32,6 +32,7 @@ struct StepParams {
   double* g_out;        // [N] dR/dv_q
   double* dm_out;       // [N] dR/dm_q
   double* bscratch;     // [gridDim.x][Mp*T] per-CTA b tile (L2 resident)
+  int debug_skip;       // profiling aid (env GVI_DEBUG_SKIP): bit 0 skips phase 1, bit 1 skips phase 2 (results garbage)
 };
 
 int gvi_step_tile_points(int Mp);
