@@ -50,13 +50,131 @@ __device__ __forceinline__ double ld_guard(const double* A, int64_t ld, int M, i
   return (r < M && c < M) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
 }
 
+// 32x32 tile product on the FP64 tensor pipe with the contraction split over warps: this warp takes the k-steps
+// (4 columns each) ks = slice, slice + nslice, ... < nks.  A rows come from Ar[r][k] (k contiguous, row stride lda).
+// BT = true : B given as rows Br[c][k] (k contiguous)  -> acc[r][c] += sum_k Ar[r][k] Br[c][k]   (L_i L_j^T)
+// BT = false: B given as Br[k][c] (c contiguous)       -> acc[r][c] += sum_k Ar[r][k] Br[k][c]   (L X)
+// acc[mt][nt][e] = C[8mt + lane/4][8nt + 2(lane%4) + e].  Loads go straight from global/L2 into fragments.
+template <bool BT>
+__device__ __forceinline__ void tile32_mma(const double* __restrict__ Ar, int64_t lda, const double* __restrict__ Br,
+                                           int64_t ldb, int nks, int slice, int nslice, int lane,
+                                           double (&acc)[4][4][2]) {
+  const int fr = lane >> 2, fk = lane & 3;
+#pragma unroll 2
+  for (int ks = slice; ks < nks; ks += nslice) {
+    const int k0 = ks * 4;
+    double a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      a[t] = Ar[(int64_t)(8 * t + fr) * lda + k0 + fk];
+      b[t] = BT ? Br[(int64_t)(8 * t + fr) * ldb + k0 + fk] : Br[(int64_t)(k0 + fk) * ldb + 8 * t + fr];
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+      for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+  }
+}
+__device__ __forceinline__ void tile32_store(double (*dst)[NB + 1], int lane, const double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) dst[8 * mt + (lane >> 2)][8 * nt + (lane & 3) * 2 + e] = acc[mt][nt][e];
+}
+
 // ---- blocked left-looking Cholesky: launch t handles the 32-wide block column jb = t ---------------------------
 // Panel CTA (ib > jb): S_d = A[jb,jb] - L[jb,:] L[jb,:]^T (recomputed by every CTA, cheap),
-// S_r = A[ib,jb] - L[ib,:] L[jb,:]^T, L_d = chol(S_d) in registers of warp 0, L[ib,jb] = S_r L_d^-T.
+// S_r = A[ib,jb] - L[ib,:] L[jb,:]^T, L_d = chol(S_d), L[ib,jb] = S_r L_d^-T.  The two 32 x 32 x (32 jb) products run
+// on the tensor pipe (DMMA), 4 warps each, contraction split 4 ways, fragments loaded straight from L2.
 // The diagonal block L_d itself is written one launch LATER (CTA 0 of launch t+1 recomputes and stores block t),
 // because panel CTAs of launch t still read the original A[jb,jb] while they run.
+// Requires M % 32 == 0 (gvi_gp_factor_f64 pads; the public gvi_chol_factor_f64 uses chol_panel_guard_kernel).
 __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A, int M, int64_t ld, int t,
                                                          int has_diag, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char chol_smem[];
+  typedef double Tile[NB][NB + 1];
+  Tile* part = reinterpret_cast<Tile*>(chol_smem);  // [4]
+  Tile& Sd = part[4];
+  Tile& Sr = part[5];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool diag_cta = has_diag && blockIdx.x == 0;
+  const int jb = diag_cta ? t - 1 : t;
+  const int ib = diag_cta ? jb : t + 1 + (int)blockIdx.x - has_diag;
+  const double* Lj = A + (int64_t)jb * NB * ld;
+  const double* Li = A + (int64_t)ib * NB * ld;
+  const int nks = jb * NB / 4;
+  // warps 0-3: S_d partials, warps 4-7: S_r partials
+  for (int which = 0; which < 2; which++) {
+    if (which == 1 && diag_cta) break;
+    if ((warp >> 2) == which) {
+      double acc[4][4][2];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+      tile32_mma<true>(which == 0 ? Lj : Li, ld, Lj, ld, nks, warp & 3, 4, lane, acc);
+      tile32_store(part[warp & 3], lane, acc);
+    }
+    __syncthreads();
+    if (which == 0 || !diag_cta) {
+      const double* Ablk = (which == 0 ? Lj : Li) + jb * NB;
+      Tile& dst = which == 0 ? Sd : Sr;
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        int r = idx >> 5, c = idx & 31;
+        dst[r][c] = Ablk[(int64_t)r * ld + c] - (part[0][r][c] + part[1][r][c] + part[2][r][c] + part[3][r][c]);
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0) {
+    // right-looking 32x32 Cholesky in shared memory: lane r owns row r (registers), column j is broadcast from smem
+    double row[NB];
+#pragma unroll
+    for (int c = 0; c < NB; c++) row[c] = Sd[lane][c];
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      const double djj = __shfl_sync(0xffffffffu, row[j], j);
+      if (lane == j && !(djj > 0.0) && diag_cta && info) atomicMin(info, jb * NB + j + 1);
+      const double sq = sqrt(djj);
+      row[j] = (lane == j) ? sq : row[j] / sq;
+      Sd[lane][j] = row[j];  // column j of L (valid for lanes >= j)
+      __syncwarp();
+#pragma unroll
+      for (int k = j + 1; k < NB; k++) {
+        const double lkj = Sd[k][j];  // broadcast
+        if (lane >= k) row[k] = fma(-row[j], lkj, row[k]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB; c++) Sd[lane][c] = (c <= lane) ? row[c] : 0.0;
+    __syncwarp();
+    if (diag_cta) {
+      double* out = A + (int64_t)(jb * NB + lane) * ld + jb * NB;
+      for (int c = 0; c <= lane; c++) out[c] = Sd[lane][c];
+    } else {
+      // X L_d^T = S_r, lane owns one row of X
+      double x[NB];
+#pragma unroll
+      for (int c = 0; c < NB; c++) x[c] = Sr[lane][c];
+#pragma unroll
+      for (int c = 0; c < NB; c++) {
+        double v = x[c];
+#pragma unroll
+        for (int k = 0; k < c; k++) v = fma(-x[k], Sd[c][k], v);
+        x[c] = v / Sd[c][c];
+      }
+      double* out = A + (int64_t)(ib * NB + lane) * ld + jb * NB;
+#pragma unroll
+      for (int c = 0; c < NB; c++) out[c] = x[c];
+    }
+  }
+}
+
+// generic-size variant with bounds guards (public gvi_chol_factor_f64 on matrices whose size is not a multiple of 32)
+__global__ void __launch_bounds__(256) chol_panel_guard_kernel(double* __restrict__ A, int M, int64_t ld, int t,
+                                                               int has_diag, int* __restrict__ info) {
   __shared__ double Li[NB][NB + 1];
   __shared__ double Lj[NB][NB + 1];
   __shared__ double Sd[NB][NB + 1];
@@ -127,7 +245,6 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(double* __restrict__ A,
       if (r < M)
         for (int c = 0; c <= lane; c++) A[(int64_t)r * ld + jb * NB + c] = Sd[lane][c];
     } else {
-      // X L_d^T = S_r, lane owns one row of X
       double x[NB];
 #pragma unroll
       for (int c = 0; c < NB; c++) x[c] = Sr[lane][c];
@@ -168,47 +285,44 @@ __global__ void __launch_bounds__(32) diag_inverse_kernel(const double* __restri
   for (int i = 0; i < NB; i++) X[(int64_t)(b * NB + i) * ldx + b * NB + lane] = x[i];
 }
 
+// One CTA per block column jb sweeps downwards: X[ib,jb] = -Dinv[ib] * sum_{k=jb}^{ib-1} L[ib,k] X[k,jb].  The
+// 32 x 32 x 32(ib-jb) product runs on the tensor pipe, contraction split over the 8 warps.
 __global__ void __launch_bounds__(256) linv_sweep_kernel(const double* __restrict__ L, int64_t ld,
                                                          double* __restrict__ X, int64_t ldx, int G) {
-  __shared__ double As[NB][NB + 1];
-  __shared__ double Bs[NB][NB + 1];
-  __shared__ double Ts[NB][NB + 1];
-  const int jb = blockIdx.x, tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char sweep_smem[];
+  typedef double Tile[NB][NB + 1];
+  Tile* part = reinterpret_cast<Tile*>(sweep_smem);  // [8]
+  Tile& Ts = part[8];
+  Tile& Ds = part[9];
+  const int jb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & 15, ty = tid >> 4;
   for (int ib = jb + 1; ib < G; ib++) {
-    double acc[2][2] = {{0, 0}, {0, 0}};
-    for (int kb = jb; kb < ib; kb++) {
-      __syncthreads();
-      for (int idx = tid; idx < NB * NB; idx += 256) {
-        int r = idx >> 5, c = idx & 31;
-        As[r][c] = L[(int64_t)(ib * NB + r) * ld + kb * NB + c];
-        Bs[r][c] = X[(int64_t)(kb * NB + r) * ldx + jb * NB + c];
-      }
-      __syncthreads();
-#pragma unroll 8
-      for (int k = 0; k < NB; k++) {
-        double a0 = As[2 * ty][k], a1 = As[2 * ty + 1][k];
-        double b0 = Bs[k][2 * tx], b1 = Bs[k][2 * tx + 1];
-        acc[0][0] = fma(a0, b0, acc[0][0]);
-        acc[0][1] = fma(a0, b1, acc[0][1]);
-        acc[1][0] = fma(a1, b0, acc[1][0]);
-        acc[1][1] = fma(a1, b1, acc[1][1]);
-      }
+    double acc[4][4][2];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    // rows of L[ib, jb..ib) and of X[jb..ib, jb]: k runs over 32 (ib - jb) columns starting at column 32 jb
+    tile32_mma<false>(L + (int64_t)ib * NB * ld + jb * NB, ld, X + (int64_t)jb * NB * ldx + jb * NB, ldx,
+                      (ib - jb) * NB / 4, warp, 8, lane, acc);
+    tile32_store(part[warp], lane, acc);
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      int r = idx >> 5, c = idx & 31;
+      Ds[r][c] = X[(int64_t)(ib * NB + r) * ldx + ib * NB + c];  // Dinv[ib]
     }
     __syncthreads();
     for (int idx = tid; idx < NB * NB; idx += 256) {
       int r = idx >> 5, c = idx & 31;
-      As[r][c] = X[(int64_t)(ib * NB + r) * ldx + ib * NB + c];  // Dinv[ib]
+      double v = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) v += part[w][r][c];
+      Ts[r][c] = v;
     }
-    Ts[2 * ty][2 * tx] = acc[0][0];
-    Ts[2 * ty][2 * tx + 1] = acc[0][1];
-    Ts[2 * ty + 1][2 * tx] = acc[1][0];
-    Ts[2 * ty + 1][2 * tx + 1] = acc[1][1];
     __syncthreads();
     double o[2][2] = {{0, 0}, {0, 0}};
 #pragma unroll 8
     for (int k = 0; k < NB; k++) {
-      double a0 = As[2 * ty][k], a1 = As[2 * ty + 1][k];
+      double a0 = Ds[2 * ty][k], a1 = Ds[2 * ty + 1][k];
       double b0 = Ts[k][2 * tx], b1 = Ts[k][2 * tx + 1];
       o[0][0] = fma(a0, b0, o[0][0]);
       o[0][1] = fma(a0, b1, o[0][1]);
@@ -303,13 +417,23 @@ __global__ void __launch_bounds__(256) linv_matvec_kernel(const double* __restri
 }
 __global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ X, int Mp, int M,
                                                            const double* __restrict__ t, double* __restrict__ a) {
-  // thread per column j: a[j] = sum_{c>=j} X[c][j] t[c]   (coalesced across j)
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= Mp) return;
+  // a[j] = sum_{c>=j} X[c][j] t[c]: 32 columns per CTA (coalesced across lanes), rows split over the 8 warps,
+  // fixed-order combination
+  __shared__ double part[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   double s = 0.0;
   if (j < M)
-    for (int c = j; c < M; c++) s = fma(X[(int64_t)c * Mp + j], t[c], s);
-  a[j] = s;
+    for (int c = blockIdx.x * 32 + warp; c < M; c += 8)
+      if (c >= j) s = fma(X[(int64_t)c * Mp + j], t[c], s);
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && j < Mp) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += part[w][lane];
+    a[j] = v;
+  }
 }
 __global__ void zero_kernel(double* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -325,13 +449,29 @@ __global__ void info_final_kernel(int* info) {
 }
 }  // namespace
 
+static int configure_factor_kernels() {
+  static bool done = false;
+  if (!done) {
+    GVI_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(6 * NB * (NB + 1) * sizeof(double))));
+    GVI_CUDA(cudaFuncSetAttribute(linv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(10 * NB * (NB + 1) * sizeof(double))));
+    done = true;
+  }
+  return GVI_OK;
+}
+
 static int launch_chol(double* A, int M, int64_t ld, int* info, cudaStream_t st) {
+  if (int rc = configure_factor_kernels()) return rc;
   const int G = (M + NB - 1) / NB;
   for (int t = 0; t <= G; t++) {
     const int has_diag = t > 0 ? 1 : 0;
     const int ctas = has_diag + (t < G ? G - t - 1 : 0);
     if (ctas == 0) continue;
-    chol_panel_kernel<<<ctas, 256, 0, st>>>(A, M, ld, t, has_diag, info);
+    if (M % NB == 0)
+      chol_panel_kernel<<<ctas, 256, 6 * NB * (NB + 1) * sizeof(double), st>>>(A, M, ld, t, has_diag, info);
+    else
+      chol_panel_guard_kernel<<<ctas, 256, 0, st>>>(A, M, ld, t, has_diag, info);
     GVI_CHECK_LAUNCH("chol_panel_kernel");
   }
   return GVI_OK;
@@ -406,7 +546,7 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   diag_inverse_kernel<<<f.Mp / NB, 32, 0, st>>>(A, f.Mp, X, f.Mp);
   GVI_CHECK_LAUNCH("diag_inverse_kernel");
   if (f.Mp / NB > 1) {
-    linv_sweep_kernel<<<f.Mp / NB - 1, 256, 0, st>>>(A, f.Mp, X, f.Mp, f.Mp / NB);
+    linv_sweep_kernel<<<f.Mp / NB - 1, 256, 10 * NB * (NB + 1) * sizeof(double), st>>>(A, f.Mp, X, f.Mp, f.Mp / NB);
     GVI_CHECK_LAUNCH("linv_sweep_kernel");
   }
   {
@@ -420,7 +560,7 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   if (y_z) {
     linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, f.Mp, M, y_z, tvec);
     GVI_CHECK_LAUNCH("linv_matvec_kernel");
-    linvT_matvec_kernel<<<(f.Mp + 255) / 256, 256, 0, st>>>(X, f.Mp, M, tvec, F + f.alpha_off);
+    linvT_matvec_kernel<<<f.Mp / 32, 256, 0, st>>>(X, f.Mp, M, tvec, F + f.alpha_off);
     GVI_CHECK_LAUNCH("linvT_matvec_kernel");
   } else {
     zero_kernel<<<4, 256, 0, st>>>(F + f.alpha_off, f.Mp);
