@@ -9,6 +9,8 @@ pointwise loss terms are reduced in the epilogue.  Otherwise the two terms are e
 """
 from __future__ import annotations
 
+import torch
+
 from . import _lib_proxy as L
 from .empirical_risks.base import EmpiricalRiskBase
 from .empirical_risks.negative_log_likelihood import NegativeLogLikelihood
@@ -24,6 +26,21 @@ class GeneralisedVariationalInference:
     def __init__(self, regularisation: RegularisationBase, empirical_risk: EmpiricalRiskBase):
         self._regularisation = regularisation
         self._empirical_risk = empirical_risk
+        self._side_stream = None
+
+    def _factorise_regulariser(self, reg, reg_parameters, x, refactor: bool):
+        """The two M x M factorisations (q and p) are latency-bound chains of small kernels that fill a fraction
+        of the GPU, so the regulariser's runs on a side stream concurrently with q's (joined before the fused launch)."""
+        cur = torch.cuda.current_stream()
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream()
+        side = self._side_stream
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            f_p = reg.factorise(reg_parameters) if (refactor or reg._factor is None) else reg._factor
+            prior_mean_p = reg.mean.predict(reg_parameters.mean, x).detach().contiguous()
+        prior_mean_p.record_stream(cur)  # allocated on the side stream, consumed by the fused launch on `cur`
+        return f_p, prior_mean_p, side
 
     @property
     def regularisation(self):
@@ -67,15 +84,17 @@ class GeneralisedVariationalInference:
         x = x.reshape(x.shape[0], -1)
         y = as_device(y).reshape(-1)
         assert y.numel() == x.shape[0], f"{y.numel()=} responses for {x.shape[0]=} points"
-        m_q = gp.mean.predict(parameters.mean, x).contiguous()
-        f_q = gp.kernel.factorise(parameters.kernel)
         kind = L.REG_KINDS[rg.kind]
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
             reg_parameters = reg._to_parameters(rg.regulariser_parameters)
-            f_p = reg.factorise(reg_parameters) if (refactor_regulariser or reg._factor is None) else reg._factor
-            prior_mean_p = reg.mean.predict(reg_parameters.mean, x).contiguous()
+            f_p, prior_mean_p, side = self._factorise_regulariser(reg, reg_parameters, x, refactor_regulariser)
+            m_q = gp.mean.predict(parameters.mean, x).contiguous()
+            f_q = gp.kernel.factorise(parameters.kernel)
+            torch.cuda.current_stream().wait_stream(side)
             return L.fused_step(f_q, f_p, x, y, m_q, prior_mean_p, None, None, kind, rg.alpha)
+        m_q = gp.mean.predict(parameters.mean, x).contiguous()
+        f_q = gp.kernel.factorise(parameters.kernel)
         m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
         return L.fused_step(f_q, None, x, y, m_q, None, m_p.reshape(-1).contiguous(),
                             c_p.reshape(-1).contiguous(), kind, rg.alpha)
@@ -94,15 +113,17 @@ class GeneralisedVariationalInference:
         x = x.reshape(x.shape[0], -1)
         y = as_device(y).reshape(-1)
         assert y.numel() == x.shape[0], f"{y.numel()=} responses for {x.shape[0]=} points"
-        m_q = gp.mean.predict(parameters.mean, x)
-        m_q_c = m_q.detach().contiguous()
-        f_q = gp.kernel.factorise(parameters.kernel)
         kind = L.REG_KINDS[rg.kind]
+        side = None
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
             reg_parameters = reg._to_parameters(rg.regulariser_parameters)
-            f_p = reg.factorise(reg_parameters) if (refactor_regulariser or reg._factor is None) else reg._factor
-            prior_mean_p = reg.mean.predict(reg_parameters.mean, x).detach().contiguous()
+            f_p, prior_mean_p, side = self._factorise_regulariser(reg, reg_parameters, x, refactor_regulariser)
+        m_q = gp.mean.predict(parameters.mean, x)
+        m_q_c = m_q.detach().contiguous()
+        f_q = gp.kernel.factorise(parameters.kernel)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
             out, dm = L.fused_step_grad(f_q, f_p, x, y, m_q_c, prior_mean_p, None, None, kind, rg.alpha)
         else:
             m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
