@@ -28,12 +28,13 @@ SIGNATURES = {
     "gvi_gp_factor_workspace_bytes": (c_size_t, [c_int]),
     "gvi_gp_factor_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_gp_predict_workspace_bytes": (c_size_t, [c_int]),
     "gvi_gp_predict_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
     "gvi_risk_workspace_bytes": (c_size_t, [c_int64]),
     "gvi_risk_f64": (c_int, [c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                              c_void_p, c_void_p]),
-    "gvi_fused_step_workspace_bytes": (c_size_t, [c_int64]),
+    "gvi_fused_step_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "gvi_fused_step_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),

@@ -24,13 +24,11 @@ constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 // One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
 // acc[mt][nt] += sum_{kp in [kp0, kp0+nkp)} A(group rows 8mt.., cols 8kp..) * Ktile(cols 8kp.., points 8nt..).
 // A fragments come from L2 as one LDG.128 per lane per (kp, mt) (two k-steps), prefetched one kp ahead.
+// `Ag` points at the first k-pair to process, `kp0` is the index of that k-pair inside the shared-memory tile;
+// the caller initialises acc (zero, or a parked partial sum in the multi-panel path).
 template <int NT>
 __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
                                           const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2]) {
-#pragma unroll
-  for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-    for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   double2 a_cur[MT], a_nxt[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
@@ -60,13 +58,18 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   constexpr int T = 8 * NT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ksm = reinterpret_cast<double*>(smem_raw);            // [Mp*T] fragment order
-  double* xs = Ksm + (size_t)P.Mp * T;                            // [T][DR] scaled x tile
+  double* xs = Ksm + (size_t)P.Pc * T;                            // [T][DR] scaled x tile
   double* redm = xs + T * DR;                                     // [WARPS][T]
-  double* reds = redm + WARPS * T;                                // [G][T] squared norms per row group
-  double* res = reds + (size_t)P.G * T;                           // [2 GPs][T][2] (mean, var)
+  double* res = redm + WARPS * T;                                 // [2 GPs][T][2] (mean, var)
   double* gs = res + 2 * T * 2;                                   // [T] g_i = dR/dv_q,i of the tile
-  double* gpart = gs + T;                                         // [G][DR+1] per-group gradient partials
-  int* counter = reinterpret_cast<int*>(gpart + (size_t)P.G * (DR + 1));
+  double* tail = gs + T;
+  const bool multi = P.Pc < P.Mp;
+  // [G][T] squared norms per row group: shared memory for a single panel, L2 scratch otherwise
+  double* reds = multi ? P.reds_scratch + (size_t)blockIdx.x * P.G * T : tail;
+  if (!multi) tail += (size_t)P.G * T;
+  double* gpart = tail;                                           // [G][DR+1] per-group gradient partials (GRAD)
+  int* counter = reinterpret_cast<int*>(tail + (GRAD ? (size_t)P.G * (DR + 1) : 0));
+  double* ascr = multi ? P.acc_scratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ntiles = (P.N + T - 1) / T;
@@ -93,20 +96,27 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       }
       if (tid == 0) *counter = 0;
       __syncthreads();
-      // ---- phase 1: K tile (T x Mp) into shared memory in B-fragment order; mean partials ------------------
+      for (int c_lo = 0; c_lo < P.Mp; c_lo += P.Pc) {  // column panels (one iteration unless M is large)
+      const int c_hi = min(c_lo + P.Pc, P.Mp);
+      if (c_lo > 0) {
+        __syncthreads();  // everyone is done with the previous panel's K tile
+        if (tid == 0) *counter = 0;
+      }
+      // ---- phase 1: K panel (T x Pc) into shared memory in B-fragment order; mean partials ------------------
       if (!(P.debug_skip & 1)) {
         double macc[T];
 #pragma unroll
         for (int i = 0; i < T; i++) macc[i] = 0.0;
         const double* __restrict__ Zs = F + f.zs_off;
         const double* __restrict__ alpha = F + f.alpha_off;
-        for (int j = tid; j < P.Mp; j += THREADS) {
+        for (int j = c_lo + tid; j < c_hi; j += THREADS) {
           double z[DR];
 #pragma unroll
           for (int d = 0; d < DR; d++) z[d] = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
           const double aj = alpha[j];
           const double scale = (j < P.M) ? amp2 : 0.0;
-          double* __restrict__ kcol = Ksm + (size_t)(j >> 3) * (NT * 64) + ((j >> 2) & 1) + 2 * (j & 3);
+          const int jl = j - c_lo;
+          double* __restrict__ kcol = Ksm + (size_t)(jl >> 3) * (NT * 64) + ((jl >> 2) & 1) + 2 * (jl & 3);
           const double* __restrict__ xr = xs;
           // four points at a time: all loads first, four independent exp chains, then the stores (the compiler
           // cannot prove that the K-tile stores do not alias the x tile, so the batching is explicit)
@@ -147,7 +157,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
 #pragma unroll
         for (int i = 0; i < T; i++) {
           double v = warp_sum(macc[i]);
-          if (lane == 0) redm[warp * T + i] = v;
+          if (lane == 0) redm[warp * T + i] = (c_lo == 0) ? v : redm[warp * T + i] + v;
         }
       }
       __syncthreads();
@@ -155,16 +165,44 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       if (!(P.debug_skip & 2)) {
         const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
         const double* __restrict__ W = F + f.wpack_off;
+        const int kp_lo = c_lo / 8, kp_hi = c_hi / 8;
+        const int g_lo = c_lo / GVI_GROUP_ROWS;  // groups below g_lo were completed by earlier panels
         while (true) {
           int gi = 0;
           if (lane == 0) gi = atomicAdd(counter, 1);
           gi = __shfl_sync(0xffffffffu, gi, 0);
-          if (gi >= P.G) break;
+          if (gi >= P.G - g_lo) break;
           const int g = P.G - 1 - gi;  // largest groups first
+          const int nkp_g = wpack_nkp(g);
+          const int kp_end = min(kp_hi, nkp_g);
           double acc[MT][NT][2];
-          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + lane, 0, wpack_nkp(g), Ks2, lane,
-                        acc);
-          // squared norms of this group's 32 rows: lanes with equal lane%4 hold the same two points of every
+          if (c_lo == 0) {
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+              for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+          } else {  // partial sums parked by the previous panel
+            const double* src = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+              for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) acc[mt][nt][e] = __ldcg(src + ((mt * NT + nt) * 2 + e) * 32);
+          }
+          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + (size_t)kp_lo * MT * 32 + lane, 0,
+                        kp_end - kp_lo, Ks2, lane, acc);
+          if (kp_end < nkp_g) {  // the group continues in the next panel
+            double* dst = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+              for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) __stcg(dst + ((mt * NT + nt) * 2 + e) * 32, acc[mt][nt][e]);
+            continue;
+          }
+          // squared norms of this group's rows: lanes with equal lane%4 hold the same two points of every
           // n-tile.  Stored per GROUP (not per warp) so the final sum has a fixed order whatever warp ran the group.
 #pragma unroll
           for (int nt = 0; nt < NT; nt++)
@@ -195,11 +233,16 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
           }
         }
       }
+      }  // column panels
       __syncthreads();
       // ---- tile epilogue: variance and mean of this pass --------------------------------------------
       if (tid < T) {
         double q = 0.0, mu = 0.0;
-        for (int g = 0; g < P.G; g++) q += reds[g * T + tid];
+        if (multi) {
+          for (int g = 0; g < P.G; g++) q += __ldcg(reds + g * T + tid);
+        } else {
+          for (int g = 0; g < P.G; g++) q += reds[g * T + tid];
+        }
 #pragma unroll
         for (int w = 0; w < WARPS; w++) mu += redm[w * T + tid];
         double var = F[1] - q;
@@ -275,6 +318,10 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
         g = __shfl_sync(0xffffffffu, g, 0);  // ascending g = largest k-range first
         if (g >= P.G) break;
         double acc[MT][NT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+          for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         const int kp0 = GVI_GROUP_ROWS * g / 8;
         group_mma<NT>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
                       Ks2, lane, acc);
@@ -367,19 +414,24 @@ __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __res
   if (grad && tid < D) out[4 + tid] = tot[4 + tid];
 }
 
+// dynamic shared memory of one CTA: K panel (Pc columns) + x tile + reductions (+ per-group arrays for one panel)
 template <int NT, int DR>
-size_t step_smem_bytes(int Mp) {
+size_t step_smem_bytes(int Mp, int Pc, bool grad) {
   constexpr int T = 8 * NT;
   const size_t G = Mp / GVI_GROUP_ROWS;
-  return ((size_t)Mp * T + T * DR + WARPS * T + G * T + 4 * T + T + G * (DR + 1)) * sizeof(double) + 16;
+  size_t doubles = (size_t)Pc * T + T * DR + WARPS * T + 4 * T + T;
+  if (Pc == Mp) doubles += G * T;
+  if (grad) doubles += G * (DR + 1);
+  return doubles * sizeof(double) + 16;
 }
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr int PANEL_COLS = 1024;  // K panel of the multi-panel path: 1024 x 24 doubles = 192 KB
 
 template <int NT, int DR, bool GRAD>
 int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
   constexpr int T = 8 * NT;
-  size_t smem = step_smem_bytes<NT, DR>(P.Mp);
+  size_t smem = step_smem_bytes<NT, DR>(P.Mp, P.Pc, GRAD);
   static bool configured = false;  // per instantiation
   if (!configured) {
     GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -407,11 +459,17 @@ int launch_step_nt(const StepParams& P, int grid_cap, cudaStream_t st) {
 }
 }  // namespace
 
+// whole-tile (single panel) variants: T = 24, 16 or 8 points per tile; 0 if not even T = 8 fits
 int gvi_step_tile_points(int Mp) {
-  if (step_smem_bytes<3, 32>(Mp) <= SMEM_LIMIT) return 24;
-  if (step_smem_bytes<2, 32>(Mp) <= SMEM_LIMIT) return 16;
-  if (step_smem_bytes<1, 32>(Mp) <= SMEM_LIMIT) return 8;
+  if (step_smem_bytes<3, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 24;
+  if (step_smem_bytes<2, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 16;
+  if (step_smem_bytes<1, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 8;
   return 0;
+}
+int gvi_step_panel_cols(int Mp) { return gvi_step_tile_points(Mp) == 24 ? Mp : PANEL_COLS; }
+size_t gvi_step_scratch_doubles(int Mp) {
+  if (gvi_step_panel_cols(Mp) == Mp) return 0;
+  return (size_t)GVI_NUM_SMS * ((size_t)Mp * 24 + (size_t)(Mp / GVI_GROUP_ROWS) * 24);
 }
 
 // returns grid size (>0) or a negative error code
@@ -424,12 +482,26 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
     return GVI_EUNSUPPORTED;
   }
   const int grid_cap = GVI_NUM_SMS;
+  if (!P.grad) {
+    // forward: always 24-point tiles; K tile in column panels of 1024 when M is large
+    P.Pc = gvi_step_panel_cols(P.Mp);
+    if (P.Pc < P.Mp) {
+      if (!P.acc_scratch) {
+        gvi_set_error("M=%d needs the multi-panel scratch (pass a workspace of gvi_gp_predict_workspace_bytes)", P.M);
+        return GVI_EINVAL;
+      }
+      P.reds_scratch = P.acc_scratch + (size_t)GVI_NUM_SMS * P.Mp * 24;
+    }
+    return launch_step_nt<3>(P, grid_cap, st);
+  }
+  // gradient mode keeps the whole b tile in shared memory
+  P.Pc = P.Mp;
   switch (gvi_step_tile_points(P.Mp)) {
     case 24: return launch_step_nt<3>(P, grid_cap, st);
     case 16: return launch_step_nt<2>(P, grid_cap, st);
     case 8: return launch_step_nt<1>(P, grid_cap, st);
     default:
-      gvi_set_error("fused predict supports M <= 3456 in this build (got M=%d)", P.M);
+      gvi_set_error("the gradient step supports M <= 3456 in this build (got M=%d)", P.M);
       return GVI_EUNSUPPORTED;
   }
 }
@@ -441,9 +513,14 @@ int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, 
   return GVI_OK;
 }
 
+extern "C" size_t gvi_gp_predict_workspace_bytes(int M) {
+  if (M < 1) return 0;
+  return gvi_step_scratch_doubles((M + 31) / 32 * 32) * sizeof(double);
+}
+
 extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
                                   const double* prior_mean, const double* log_noise_add, double* mean_out,
-                                  double* var_out, void* stream) {
+                                  double* var_out, void* workspace, void* stream) {
   GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 0, "sizes");
   if (N == 0) return GVI_OK;
   GVI_CHECK_ARG(factor && X, "null pointer");
@@ -454,13 +531,15 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;
   P.X = X; P.N = N;
   P.partials = nullptr;
+  P.acc_scratch = (double*)workspace;
   int rc = gvi_launch_step(P, (cudaStream_t)stream);
   return rc < 0 ? rc : GVI_OK;
 }
 
-extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N) {
+extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N, int M) {
   (void)N;
-  return (size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE * sizeof(double);
+  const int Mp = (M + 31) / 32 * 32;
+  return ((size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE + gvi_step_scratch_doubles(Mp)) * sizeof(double);
 }
 
 int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
@@ -498,6 +577,7 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
                                 renyi_alpha, var_q_out, mean_p_out, var_p_out);
   if (rc) return rc;
   P.partials = (double*)workspace;
+  P.acc_scratch = P.partials + (size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE;
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   return gvi_launch_finish(P.partials, grid, N, 0, D, (const double*)factor_q, out3, st);

@@ -33,9 +33,18 @@ struct StepParams {
   double* dm_out;       // [N] dR/dm_q
   double* bscratch;     // [gridDim.x][Mp*T] per-CTA b tile (L2 resident)
   int debug_skip;       // profiling aid (env GVI_DEBUG_SKIP): bit 0 skips phase 1, bit 1 skips phase 2 (results garbage)
+  // column panels: the K tile holds Pc columns at a time (Pc == Mp: one panel).  With several panels the accumulators
+  // of the groups that extend past the current panel are parked in `acc_scratch` (L2 resident) between sweeps and the
+  // per-group squared norms go to `reds_scratch` instead of shared memory.
+  int Pc;
+  double* acc_scratch;  // [gridDim.x][Mp*T]  (multi-panel only)
+  double* reds_scratch; // [gridDim.x][G*T]   (multi-panel only)
 };
 
 int gvi_step_tile_points(int Mp);
+// forward-only launches use column panels when the whole K tile does not fit: returns Pc (== Mp: single panel)
+int gvi_step_panel_cols(int Mp);
+size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the multi-panel path (0 for a single panel)
 int gvi_launch_step(const StepParams& P, cudaStream_t st);
 int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
                       cudaStream_t st);

@@ -69,8 +69,11 @@ def gp_predict(factor: GpFactor, x, prior_mean=None, log_noise_add=None, want_me
     n = x.shape[0]
     mean = empty(n) if want_mean else None
     var = empty(n)
+    nbytes = _L().gvi_gp_predict_workspace_bytes(factor.m)
+    ws = _workspace("predict", nbytes) if nbytes else None
     rc = _L().gvi_gp_predict_f64(_lib.ptr(factor.buf), factor.m, factor.d, _lib.ptr(x), n, _lib.ptr(prior_mean),
-                                 _lib.ptr(log_noise_add), _lib.ptr(mean), _lib.ptr(var), _lib.current_stream())
+                                 _lib.ptr(log_noise_add), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(ws),
+                                 _lib.current_stream())
     _lib.check(rc, "gvi_gp_predict_f64")
     return mean, var
 
@@ -103,7 +106,7 @@ def fused_step(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_
     n = x.shape[0]
     if out3 is None:
         out3 = empty(3)
-    ws = _workspace("step", _L().gvi_fused_step_workspace_bytes(n))
+    ws = _workspace("step", _L().gvi_fused_step_workspace_bytes(n, factor_q.m))
     rc = _L().gvi_fused_step_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
                                  factor_q.m, factor_q.d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q),
                                  _lib.ptr(prior_mean_p), _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind),

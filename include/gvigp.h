@@ -74,10 +74,13 @@ int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, 
  * var[i]  = k(x_i,x_i) - || L^-1 k(Z,x_i) ||^2 (+ exp(log_noise_add) if given)   (sparse_posterior_kernel.py:90-96
  *           in diagonal mode; base.py:522-525 for the exact GP; base.py:205-211 for the added noise)
  * mean[i] = k(x_i,Z) alpha + prior_mean[i]                                    (base.py:519-521, 492)
- * mean_out / prior_mean / log_noise_add may be NULL.                                                        */
+ * mean_out / prior_mean / log_noise_add may be NULL; workspace may be NULL when its size query returns 0.
+ * Any M: for M > 1152 the K tile is swept in 1024-column panels and the partial triangular products are parked
+ * in the (L2-resident) workspace between sweeps - still no N x M array in HBM.                               */
+size_t gvi_gp_predict_workspace_bytes(int M);   /* 0 unless M > 1152 (K tile processed in 1024-column panels) */
 int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
                        const double* prior_mean, const double* log_noise_add,
-                       double* mean_out, double* var_out, void* stream);
+                       double* mean_out, double* var_out, void* workspace, void* stream);
 
 /* ---- a9-a11: risk and regulariser sums ----------------------------------------------------------------------
  * out[0] = sum_i NLL_i  (negative_log_likelihood.py:41-55), out[1] = sum_i D0_i (regulariser `kind`),
@@ -93,7 +96,7 @@ int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, const double
  * the FP64 tensor pipe and reduces the pointwise loss terms; only O(N) data crosses HBM.
  * factor_p may be NULL with reg_kind == GVI_REG_NONE.  prior-mode regulariser: pass factor_p = NULL and
  * m_p/v_p arrays instead.  out3 as in gvi_risk_f64.  var_q_out/mean_p_out/var_p_out optional (may be NULL). */
-size_t gvi_fused_step_workspace_bytes(int64_t N);
+size_t gvi_fused_step_workspace_bytes(int64_t N, int M);
 int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                        const double* y, const double* m_q, const double* prior_mean_p,
                        const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha,

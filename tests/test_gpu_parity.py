@@ -178,7 +178,7 @@ def build_models(S, pr, lam=1e-5, prior_const=0.25, log_noise=0.0):
 
 
 @pytest.mark.parametrize("n,m,d", [(1, 2, 1), (23, 10, 1), (1000, 100, 3), (2500, 333, 8), (777, 1024, 8),
-                                   (500, 1500, 5), (300, 2048, 16), (200, 64, 32)])
+                                   (500, 1500, 5), (300, 2048, 16), (200, 64, 32), (260, 4096, 8), (4000, 1153, 2)])
 def test_predictive_parity(S, n, m, d):
     pr = make_problem(n, m, d, seed=n + m)
     v_q_ref, m_p_ref, v_p_ref = oracle_predictions(pr)
