@@ -308,8 +308,7 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   const int Gc = (f.Mp + CB - 1) / CB;
   w.ntri = Gc * (Gc + 1) / 2;
   w.nsplit = GVI_NUM_SMS / w.ntri > 0 ? GVI_NUM_SMS / w.ntri : 1;
-  int T = gvi_step_tile_points(f.Mp);
-  if (T == 0) T = 8;
+  const int T = 24;  // upper bound of the tile height (the b scratch is sized for the largest variant)
   unsigned char* p = (unsigned char*)ws;
   size_t o = 0;
   auto take = [&](size_t bytes) { double* r = (double*)(p + o); o += align256(bytes); return r; };

@@ -460,13 +460,21 @@ int launch_step_nt(const StepParams& P, int grid_cap, cudaStream_t st) {
 }  // namespace
 
 // whole-tile (single panel) variants: T = 24, 16 or 8 points per tile; 0 if not even T = 8 fits
-int gvi_step_tile_points(int Mp) {
-  if (step_smem_bytes<3, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 24;
-  if (step_smem_bytes<2, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 16;
-  if (step_smem_bytes<1, 32>(Mp, Mp, true) <= SMEM_LIMIT) return 8;
+template <int NT>
+static size_t step_smem_bytes_d(int Mp, int D, bool grad) {
+  if (D <= 1) return step_smem_bytes<NT, 1>(Mp, Mp, grad);
+  if (D <= 4) return step_smem_bytes<NT, 4>(Mp, Mp, grad);
+  if (D <= 8) return step_smem_bytes<NT, 8>(Mp, Mp, grad);
+  if (D <= 16) return step_smem_bytes<NT, 16>(Mp, Mp, grad);
+  return step_smem_bytes<NT, 32>(Mp, Mp, grad);
+}
+int gvi_step_tile_points(int Mp, int D, bool grad) {
+  if (step_smem_bytes_d<3>(Mp, D, grad) <= SMEM_LIMIT) return 24;
+  if (step_smem_bytes_d<2>(Mp, D, grad) <= SMEM_LIMIT) return 16;
+  if (step_smem_bytes_d<1>(Mp, D, grad) <= SMEM_LIMIT) return 8;
   return 0;
 }
-int gvi_step_panel_cols(int Mp) { return gvi_step_tile_points(Mp) == 24 ? Mp : PANEL_COLS; }
+int gvi_step_panel_cols(int Mp) { return gvi_step_tile_points(Mp, 32, false) == 24 ? Mp : PANEL_COLS; }
 size_t gvi_step_scratch_doubles(int Mp) {
   if (gvi_step_panel_cols(Mp) == Mp) return 0;
   return (size_t)GVI_NUM_SMS * ((size_t)Mp * 24 + (size_t)(Mp / GVI_GROUP_ROWS) * 24);
@@ -496,7 +504,7 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   }
   // gradient mode keeps the whole b tile in shared memory
   P.Pc = P.Mp;
-  switch (gvi_step_tile_points(P.Mp)) {
+  switch (gvi_step_tile_points(P.Mp, P.D, true)) {
     case 24: return launch_step_nt<3>(P, grid_cap, st);
     case 16: return launch_step_nt<2>(P, grid_cap, st);
     case 8: return launch_step_nt<1>(P, grid_cap, st);

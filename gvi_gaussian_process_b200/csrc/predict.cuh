@@ -41,7 +41,7 @@ struct StepParams {
   double* reds_scratch; // [gridDim.x][G*T]   (multi-panel only)
 };
 
-int gvi_step_tile_points(int Mp);
+int gvi_step_tile_points(int Mp, int D, bool grad);
 // forward-only launches use column panels when the whole K tile does not fit: returns Pc (== Mp: single panel)
 int gvi_step_panel_cols(int Mp);
 size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the multi-panel path (0 for a single panel)
