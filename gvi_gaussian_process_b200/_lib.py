@@ -19,8 +19,9 @@ SIGNATURES = {
     "gvi_abi_version": (c_int, []),
     "gvi_last_error_string": (c_char_p, []),
     "gvi_launch_count": (c_int64, []),
+    "gvi_ard_gram_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "gvi_ard_gram_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p,
-                                 c_int64, c_void_p]),
+                                 c_int64, c_void_p, c_void_p]),
     "gvi_ard_gram_diag_f64": (c_int, [c_int64, c_void_p, c_void_p, c_void_p]),
     "gvi_add_diagonal_regulariser_f64": (c_int, [c_void_p, c_int, c_int64, c_double, c_int, c_void_p]),
     "gvi_chol_factor_f64": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(TC) ard_gram_kernel(const double* __restrict__
   if (col0 + tid < m2) {
 #pragma unroll
     for (int r = 0; r < TR; r++) {
-      if (row0 + r < m1) out[(row0 + r) * ld + col0 + tid] = amp2 * exp(-0.5 * acc[r]);
+      if (row0 + r < m1) out[(row0 + r) * ld + col0 + tid] = amp2 * gvi_exp(-0.5 * acc[r]);
     }
   }
 }
@@ -80,14 +80,30 @@ int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t 
   return GVI_OK;
 }
 
+size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D);
+int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                             const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                             double* workspace, cudaStream_t st);
+
+// wide inputs go through the tensor-pipe contraction (gram_dmma.cu) when the caller supplies the workspace
+constexpr int GVI_GRAM_DMMA_MIN_D = 24;
+
+extern "C" size_t gvi_ard_gram_workspace_bytes(int64_t m1, int64_t m2, int D) {
+  if (m1 < 1 || m2 < 1 || D < GVI_GRAM_DMMA_MIN_D) return 0;
+  return gvi_gram_dmma_workspace_doubles(m1, m2, D) * sizeof(double);
+}
+
 extern "C" int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
                                 const double* log_scaling, const double* log_ls, int ls_len, double* out,
-                                int64_t ld_out, void* stream) {
+                                int64_t ld_out, void* workspace, void* stream) {
   GVI_CHECK_ARG(m1 >= 0 && m2 >= 0 && D >= 1, "sizes");
   GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
   GVI_CHECK_ARG(ld_out >= m2, "ld_out < m2");
   if (m1 == 0 || m2 == 0) return GVI_OK;
   GVI_CHECK_ARG(x1 && x2 && log_scaling && log_ls && out, "null pointer");
+  if (D >= GVI_GRAM_DMMA_MIN_D && workspace)
+    return gvi_launch_ard_gram_dmma(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out,
+                                    (double*)workspace, (cudaStream_t)stream);
   return gvi_launch_ard_gram(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out, (cudaStream_t)stream);
 }
 

@@ -14,10 +14,12 @@ def _L():
     return _lib.load()
 
 
-def ard_gram(x1, x2, log_scaling, log_ls, out):
+def ard_gram(x1, x2, log_scaling, log_ls, out, tensor_pipe: bool = True):
+    nbytes = _L().gvi_ard_gram_workspace_bytes(x1.shape[0], x2.shape[0], x1.shape[1]) if tensor_pipe else 0
+    ws = _workspace("gram", nbytes) if nbytes else None
     rc = _L().gvi_ard_gram_f64(_lib.ptr(x1), x1.shape[0], _lib.ptr(x2), x2.shape[0], x1.shape[1],
                                _lib.ptr(log_scaling), _lib.ptr(log_ls), log_ls.numel(), _lib.ptr(out),
-                               out.stride(0) if out.ndim == 2 else x2.shape[0], _lib.current_stream())
+                               out.stride(0) if out.ndim == 2 else x2.shape[0], _lib.ptr(ws), _lib.current_stream())
     _lib.check(rc, "gvi_ard_gram_f64")
 
 

@@ -44,9 +44,12 @@ int64_t gvi_launch_count(void);
 /* ---- a1-a3: ARDKernel._calculate_gram (src/kernels/standard/base.py:73-103, ard_kernel.py:58-66) ----------
  * out[i*ld_out + j] = exp(log_scaling)^2 * exp(-0.5 * sum_d exp(log_ls[d]) * (x1[i,d]-x2[j,d])^2).
  * ls_len is D, or 1 (a scalar lengthscale broadcast over D, README.md:92-94). */
+/* D >= 24 with a workspace: the x1.x2^T contraction runs on the FP64 tensor pipe (DMMA) with the squared-distance,
+ * lengthscale and exp epilogue fused; otherwise (workspace NULL or small D) direct differences.                  */
+size_t gvi_ard_gram_workspace_bytes(int64_t m1, int64_t m2, int D);
 int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
                      const double* log_scaling, const double* log_ls, int ls_len,
-                     double* out, int64_t ld_out, void* stream);
+                     double* out, int64_t ld_out, void* workspace, void* stream);
 /* full_covariance=False path of KernelBase.calculate_gram (src/kernels/base.py:132-147): out[i] = k(x_i,x_i). */
 int gvi_ard_gram_diag_f64(int64_t n, const double* log_scaling, double* out, void* stream);
 

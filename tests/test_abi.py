@@ -47,15 +47,15 @@ def test_abi_version_and_size_queries(lib):
 
 def test_argument_validation_without_device(lib):
     # all rejected before any CUDA call
-    assert lib.gvi_ard_gram_f64(None, -1, None, 4, 3, None, None, 3, None, 4, None) == -1
+    assert lib.gvi_ard_gram_f64(None, -1, None, 4, 3, None, None, 3, None, 4, None, None) == -1
     assert b"invalid argument" in lib.gvi_last_error_string()
-    assert lib.gvi_ard_gram_f64(None, 2, None, 4, 3, None, None, 2, None, 4, None) == -1  # ls_len not in {1, D}
+    assert lib.gvi_ard_gram_f64(None, 2, None, 4, 3, None, None, 2, None, 4, None, None) == -1  # ls_len not in {1, D}
     assert lib.gvi_cond_var_select_f64(None, 10, 3, 1, None, None, 3, 1e-12, None, None, None, None) == -1
     assert b"at least 2 inducing points" in lib.gvi_last_error_string()
     assert lib.gvi_risk_f64(99, 0.5, None, None, None, None, None, 10, None, None, None) == -1
     # empty inputs are a no-op, as in the reference (a 0 x m Gram)
-    assert lib.gvi_ard_gram_f64(None, 0, None, 4, 3, None, None, 3, None, 4, None) == 0
-    assert lib.gvi_gp_predict_f64(None, 4, 3, None, 0, None, None, None, None, None) == 0
+    assert lib.gvi_ard_gram_f64(None, 0, None, 4, 3, None, None, 3, None, 4, None, None) == 0
+    assert lib.gvi_gp_predict_f64(None, 4, 3, None, 0, None, None, None, None, None, None) == 0
 
 
 def test_product_never_imports_oracle():

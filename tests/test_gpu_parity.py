@@ -94,6 +94,25 @@ def test_ard_gram_parity(S, m1, m2, d):
     assert gd.shape == (m1,) and rel_elem(gd, O.ard_gram_diag(ls, ll, x1)) <= 1e-15
 
 
+@pytest.mark.parametrize("m1,m2,d,offset", [(300, 257, 784, 0.0), (129, 128, 24, 0.0), (200, 130, 100, 1000.0)])
+def test_ard_gram_tensor_pipe_contraction(S, m1, m2, d, offset):
+    """D >= 24: x1.x2^T on the FP64 tensor pipe with the fused distance/exp epilogue (gram_dmma.cu) against the
+    direct-difference oracle, incl. inputs far from the origin (UCI inputs are not standardised) - the common
+    shift keeps the expansion |x|^2 + |z|^2 - 2 x.z from cancelling."""
+    rng = np.random.default_rng(d)
+    x1, x2 = offset + rng.uniform(0, 1, (m1, d)), offset + rng.uniform(0, 1, (m2, d))
+    ls, ll = 0.2, np.log(1.0 / d) + 0.2 * rng.standard_normal(d)
+    k = S.ARDKernel(number_of_dimensions=d)
+    p = k.Parameters.construct(log_scaling=ls, log_lengthscales=ll)
+    g = host(k.calculate_gram(p, x1, x2))
+    ref = O.ard_gram(ls, ll, x1, x2)
+    assert rel_elem(g, ref) <= TOL
+    # and the direct-difference CUDA kernel agrees as well
+    out = torch.empty(m1, m2, dtype=torch.float64, device="cuda")
+    S._lib_proxy.ard_gram(dev(x1), dev(x2), dev([ls]), dev(ll), out, tensor_pipe=False)
+    assert rel_elem(host(out), ref) <= TOL
+
+
 def test_gram_shape_asserts(S):
     k = S.ARDKernel(number_of_dimensions=3)
     p = k.Parameters.construct(log_scaling=0.0, log_lengthscales=np.zeros(3))
