@@ -1,4 +1,4 @@
-// gram_dmma.cu - ARD Gram for wide inputs (D >= 24): k(x,z) = amp^2 exp(-1/2 (|x~|^2 + |z~|^2 - 2 x~.z~)) with the
+// gram_dmma.cu - ARD Gram for wide inputs (D >= 24, caller-supplied workspace; correct for any D): k(x,z) = amp^2 exp(-1/2 (|x~|^2 + |z~|^2 - 2 x~.z~)) with the
 // x~.z~ contraction on the FP64 tensor pipe (DMMA m8n8k4) and the squared-distance / exp epilogue fused.
 // x~ = (x - c) sqrt(w): scaling by the ARD weights and a common shift c (the first row of x2; distances are
 // translation invariant, the shift keeps |x~|^2 of the order of the distances so the expansion does not cancel).
@@ -69,7 +69,7 @@ struct GramParams {
   const double* Bb;   // [nrb2][nchunk][BLKD]
   const double* n1;   // [nchunk][nrb1*128]
   const double* n2;   // [nchunk][nrb2*128]
-  int nrb1, nrb2, nchunk;
+  int nrb1, nrb2, nchunk, D;
   int64_t m1, m2, ld;
   const double* log_scaling;
   double* out;
@@ -119,8 +119,9 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_dmma_kernel(const GramParams
     mbar_wait(&full[s], (it / NSTAGE) & 1);
     const double2* A2 = reinterpret_cast<const double2*>(ring + (size_t)s * 2 * BLKD);
     const double2* B2 = A2 + BLKD / 2;
-#pragma unroll
-    for (int kp = 0; kp < KC / 8; kp++) {
+    const int nkp = min(KC / 8, (P.D - it * KC + 7) / 8);  // k-pairs of this chunk that hold features
+#pragma unroll 1
+    for (int kp = 0; kp < nkp; kp++) {
       double2 a[4], b[8];
 #pragma unroll
       for (int mt = 0; mt < 4; mt++) a[mt] = A2[kp * (KPSTRIDE / 2) + (4 * wj + mt) * 32 + lane];
@@ -138,26 +139,39 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_dmma_kernel(const GramParams
     __syncthreads();
     if (tid == 0 && it + NSTAGE < P.nchunk) issue(it + NSTAGE);
   }
-  // epilogue: squared distance, exp, row-major store (two adjacent columns per lane)
+  // epilogue: squared distance + exp into a shared-memory tile (the ring is free now), then full-row coalesced stores
   const double amp = exp(P.log_scaling[0]);
   const double amp2 = amp * amp;
+  constexpr int OSTRIDE = CB + 2;
+  double* otile = ring;  // [128][130] doubles = 133 KB
 #pragma unroll
   for (int mt = 0; mt < 4; mt++) {
     const int rl = (4 * wj + mt) * 8 + (lane >> 2);
-    const int64_t r = (int64_t)bj * CB + rl;
-    if (r >= P.m1) continue;
     const double nr = n1s[rl];
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++)
+    for (int nt = 0; nt < 8; nt++) {
+      const int cl = (8 * wl + nt) * 8 + (lane & 3) * 2;
+      double2 v;
+      v.x = amp2 * gvi_exp(-0.5 * fmax(nr + n2s[cl] - 2.0 * acc[mt][nt][0], 0.0));
+      v.y = amp2 * gvi_exp(-0.5 * fmax(nr + n2s[cl + 1] - 2.0 * acc[mt][nt][1], 0.0));
+      *reinterpret_cast<double2*>(otile + rl * OSTRIDE + cl) = v;
+    }
+  }
+  __syncthreads();
+  const int64_t c0 = (int64_t)bl * CB;
+  const bool vec_ok = ((P.ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (c0 + CB <= P.m2);
+  for (int rl = warp; rl < CB; rl += GTHREADS / 32) {
+    const int64_t r = (int64_t)bj * CB + rl;
+    if (r >= P.m1) break;
+    double* orow = P.out + r * P.ld + c0;
+    if (vec_ok) {
 #pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int cl = (8 * wl + nt) * 8 + (lane & 3) * 2 + e;
-        const int64_t c = (int64_t)bl * CB + cl;
-        if (c < P.m2) {
-          const double s = fmax(nr + n2s[cl] - 2.0 * acc[mt][nt][e], 0.0);
-          P.out[r * P.ld + c] = amp2 * gvi_exp(-0.5 * s);
-        }
-      }
+      for (int h = 0; h < 2; h++)
+        reinterpret_cast<double2*>(orow)[h * 32 + lane] =
+            *reinterpret_cast<const double2*>(otile + rl * OSTRIDE + (h * 32 + lane) * 2);
+    } else {
+      for (int cl = lane; cl < CB && c0 + cl < P.m2; cl += 32) orow[cl] = otile[rl * OSTRIDE + cl];
+    }
   }
 }
 }  // namespace
@@ -179,7 +193,7 @@ int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int
   GVI_CHECK_LAUNCH("gram_prep_kernel");
   gram_prep_kernel<<<dim3(nrb2, nchunk), GTHREADS, 0, st>>>(x2, m2, D, x2, log_ls, ls_len, nchunk, Bb, n2);
   GVI_CHECK_LAUNCH("gram_prep_kernel");
-  GramParams P{Ab, Bb, n1, n2, nrb1, nrb2, nchunk, m1, m2, ld, log_scaling, out};
+  GramParams P{Ab, Bb, n1, n2, nrb1, nrb2, nchunk, D, m1, m2, ld, log_scaling, out};
   size_t smem = ((size_t)NSTAGE * 2 * BLKD + 2 * CB) * sizeof(double) + NSTAGE * sizeof(uint64_t) + 64;
   static bool configured = false;
   if (!configured) {
