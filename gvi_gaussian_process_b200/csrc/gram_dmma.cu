@@ -44,20 +44,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// sqrtw[d] = sqrt(exp(log_ls[d])), centre_scaled[d] = x2[0][d] * sqrtw[d]
+__global__ void gram_scale_kernel(const double* __restrict__ x2, int D, const double* __restrict__ log_ls, int ls_len,
+                                  double* __restrict__ sqrtw, double* __restrict__ centre_scaled) {
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+    const double s = sqrt(exp(log_ls[ls_len == 1 ? 0 : d]));
+    sqrtw[d] = s;
+    centre_scaled[d] = x2[d] * s;
+  }
+}
+
+// x~ = x * sqrtw - centre_scaled (sqrtw == nullptr: x is already scaled).
 // grid (row blocks, feature chunks): lane = feature inside the chunk, each warp takes 16 rows
 __global__ void __launch_bounds__(GTHREADS) gram_prep_kernel(const double* __restrict__ x, int64_t m, int D,
-                                                             const double* __restrict__ centre,
-                                                             const double* __restrict__ log_ls, int ls_len, int nchunk,
+                                                             const double* __restrict__ sqrtw,
+                                                             const double* __restrict__ centre_scaled, int nchunk,
                                                              double* __restrict__ blocks, double* __restrict__ normpart) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rb = blockIdx.x, ch = blockIdx.y;
   const int d = ch * KC + lane;
-  const double sw = (d < D) ? sqrt(exp(log_ls[ls_len == 1 ? 0 : d])) : 0.0;
-  const double c = (d < D) ? centre[d] : 0.0;
+  const double sw = (d < D) ? (sqrtw ? sqrtw[d] : 1.0) : 0.0;
+  const double c = (d < D) ? centre_scaled[d] : 0.0;
   double* blk = blocks + ((size_t)rb * nchunk + ch) * BLKD;
   for (int rl = warp * 16; rl < warp * 16 + 16; rl++) {
     const int64_t r = (int64_t)rb * CB + rl;
-    const double v = (r < m && d < D) ? (x[r * D + d] - c) * sw : 0.0;
+    const double v = (r < m && d < D) ? fma(x[r * D + d], sw, -c) : 0.0;
     blk[frag_index(rl, lane)] = v;
     const double s = warp_sum(v * v);
     if (lane == 0) normpart[((size_t)ch * gridDim.x + rb) * CB + rl] = s;
@@ -71,7 +82,8 @@ struct GramParams {
   const double* n2;   // [nchunk][nrb2*128]
   int nrb1, nrb2, nchunk, D;
   int64_t m1, m2, ld;
-  const double* log_scaling;
+  const double* log_scaling;  // amplitude = exp(log_scaling)^2 ...
+  const double* amp2_ptr;     // ... or read directly (factor header) when non-null
   double* out;
 };
 
@@ -140,8 +152,13 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_dmma_kernel(const GramParams
     if (tid == 0 && it + NSTAGE < P.nchunk) issue(it + NSTAGE);
   }
   // epilogue: squared distance + exp into a shared-memory tile (the ring is free now), then full-row coalesced stores
-  const double amp = exp(P.log_scaling[0]);
-  const double amp2 = amp * amp;
+  double amp2;
+  if (P.amp2_ptr) {
+    amp2 = P.amp2_ptr[0];
+  } else {
+    const double amp = exp(P.log_scaling[0]);
+    amp2 = amp * amp;
+  }
   constexpr int OSTRIDE = CB + 2;
   double* otile = ring;  // [128][130] doubles = 133 KB
 #pragma unroll
@@ -178,22 +195,24 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_dmma_kernel(const GramParams
 
 size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D) {
   const int64_t nrb1 = (m1 + CB - 1) / CB, nrb2 = (m2 + CB - 1) / CB, nchunk = (D + KC - 1) / KC;
-  return (size_t)((nrb1 + nrb2) * nchunk * (BLKD + CB));
+  return (size_t)((nrb1 + nrb2) * nchunk * (BLKD + CB)) + 2 * (size_t)((D + 1) / 2 * 2);
 }
 
-int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
-                             const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
-                             double* workspace, cudaStream_t st) {
+// scaled-coordinate core: x1 (scaled by sqrtw1 unless null) against x2 (scaled by sqrtw2 unless null), both shifted by
+// centre_scaled; amplitude from log_scaling or amp2_ptr
+static int launch_gram_core(const double* x1, int64_t m1, const double* sqrtw1, const double* x2, int64_t m2,
+                            const double* sqrtw2, const double* centre_scaled, int D, const double* log_scaling,
+                            const double* amp2_ptr, double* out, int64_t ld, double* blocks_ws, cudaStream_t st) {
   const int nrb1 = (int)((m1 + CB - 1) / CB), nrb2 = (int)((m2 + CB - 1) / CB), nchunk = (D + KC - 1) / KC;
-  double* Ab = workspace;
+  double* Ab = blocks_ws;
   double* Bb = Ab + (size_t)nrb1 * nchunk * BLKD;
   double* n1 = Bb + (size_t)nrb2 * nchunk * BLKD;
   double* n2 = n1 + (size_t)nchunk * nrb1 * CB;
-  gram_prep_kernel<<<dim3(nrb1, nchunk), GTHREADS, 0, st>>>(x1, m1, D, x2, log_ls, ls_len, nchunk, Ab, n1);
+  gram_prep_kernel<<<dim3(nrb1, nchunk), GTHREADS, 0, st>>>(x1, m1, D, sqrtw1, centre_scaled, nchunk, Ab, n1);
   GVI_CHECK_LAUNCH("gram_prep_kernel");
-  gram_prep_kernel<<<dim3(nrb2, nchunk), GTHREADS, 0, st>>>(x2, m2, D, x2, log_ls, ls_len, nchunk, Bb, n2);
+  gram_prep_kernel<<<dim3(nrb2, nchunk), GTHREADS, 0, st>>>(x2, m2, D, sqrtw2, centre_scaled, nchunk, Bb, n2);
   GVI_CHECK_LAUNCH("gram_prep_kernel");
-  GramParams P{Ab, Bb, n1, n2, nrb1, nrb2, nchunk, D, m1, m2, ld, log_scaling, out};
+  GramParams P{Ab, Bb, n1, n2, nrb1, nrb2, nchunk, D, m1, m2, ld, log_scaling, amp2_ptr, out};
   size_t smem = ((size_t)NSTAGE * 2 * BLKD + 2 * CB) * sizeof(double) + NSTAGE * sizeof(uint64_t) + 64;
   static bool configured = false;
   if (!configured) {
@@ -203,4 +222,25 @@ int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int
   gram_dmma_kernel<<<dim3(nrb2, nrb1), GTHREADS, smem, st>>>(P);
   GVI_CHECK_LAUNCH("gram_dmma_kernel");
   return GVI_OK;
+}
+
+int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                             const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                             double* workspace, cudaStream_t st) {
+  const int Dp = (D + 1) / 2 * 2;
+  double* sqrtw = workspace;
+  double* centre = workspace + Dp;
+  gram_scale_kernel<<<(D + 255) / 256, 256, 0, st>>>(x2, D, log_ls, ls_len, sqrtw, centre);
+  GVI_CHECK_LAUNCH("gram_scale_kernel");
+  return launch_gram_core(x1, m1, sqrtw, x2, m2, sqrtw, centre, D, log_scaling, nullptr, out, ld, workspace + 2 * Dp,
+                          st);
+}
+
+// K(x_chunk, Z) for the wide-input predictive path: the factor buffer F holds sqrtw, the scaled inducing points Z~
+// (row 0 of which is the common shift) and amp2.  Rows are written with leading dimension Mp.
+int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x, int64_t nr, double* out,
+                         double* workspace, cudaStream_t st) {
+  const int Dp = (f.D + 1) / 2 * 2;
+  return launch_gram_core(x, nr, F + f.sqrtw_off, F + f.zs_off, f.M, nullptr, F + f.zs_off, f.D, nullptr, F, out, f.Mp,
+                          workspace + 2 * Dp, st);
 }

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       for (int idx = tid; idx < T * DR; idx += THREADS) {
         int i = idx / DR, d = idx % DR;
         double v = 0.0;
-        if (d < P.D && row0 + i < P.N) v = P.X[(row0 + i) * P.D + d] * F[f.sqrtw_off + d];
+        if (!pd.Kpre && d < P.D && row0 + i < P.N) v = P.X[(row0 + i) * P.D + d] * F[f.sqrtw_off + d];
         xs[idx] = v;
       }
       if (tid == 0) *counter = 0;
@@ -109,6 +109,21 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
         for (int i = 0; i < T; i++) macc[i] = 0.0;
         const double* __restrict__ Zs = F + f.zs_off;
         const double* __restrict__ alpha = F + f.alpha_off;
+        if (pd.Kpre) {
+          // wide inputs: the K rows of this tile were built by the tensor-pipe Gram kernel; transpose them into the
+          // fragment order (coalesced reads along j)
+          for (int j = c_lo + tid; j < c_hi; j += THREADS) {
+            const double aj = alpha[j];
+            const int jl = j - c_lo;
+            double* __restrict__ kcol = Ksm + (size_t)(jl >> 3) * (NT * 64) + ((jl >> 2) & 1) + 2 * (jl & 3);
+#pragma unroll
+            for (int i = 0; i < T; i++) {
+              const double k = (j < P.M && row0 + i < P.N) ? __ldcg(pd.Kpre + (row0 + i) * pd.ldk + j) : 0.0;
+              kcol[(i >> 3) * 64 + (i & 7) * 8] = k;
+              macc[i] = fma(k, aj, macc[i]);
+            }
+          }
+        } else
         for (int j = c_lo + tid; j < c_hi; j += THREADS) {
           double z[DR];
 #pragma unroll
@@ -451,7 +466,7 @@ int launch_step_inst(const StepParams& P, int grid_cap, cudaStream_t st) {
 
 template <int NT>
 int launch_step_nt(const StepParams& P, int grid_cap, cudaStream_t st) {
-  if (P.D <= 1) return launch_step_inst<NT, 1>(P, grid_cap, st);
+  if (P.D <= 1 || P.pass[0].Kpre) return launch_step_inst<NT, 1>(P, grid_cap, st);
   if (P.D <= 4) return launch_step_inst<NT, 4>(P, grid_cap, st);
   if (P.D <= 8) return launch_step_inst<NT, 8>(P, grid_cap, st);
   if (P.D <= 16) return launch_step_inst<NT, 16>(P, grid_cap, st);
@@ -485,8 +500,10 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   StepParams P = P_in;
   static const int debug_skip = getenv("GVI_DEBUG_SKIP") ? atoi(getenv("GVI_DEBUG_SKIP")) : 0;
   P.debug_skip = debug_skip;
-  if (P.D > 32) {
-    gvi_set_error("fused predict supports D <= 32 in this build (got D=%d)", P.D);
+  const bool pre = P.pass[0].Kpre != nullptr;
+  if (P.D > 32 && !pre) {
+    gvi_set_error("the fused step supports D <= 32 in this build (got D=%d); gvi_gp_predict_f64 handles wider inputs",
+                  P.D);
     return GVI_EUNSUPPORTED;
   }
   const int grid_cap = GVI_NUM_SMS;
@@ -521,9 +538,32 @@ int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, 
   return GVI_OK;
 }
 
-extern "C" size_t gvi_gp_predict_workspace_bytes(int M) {
-  if (M < 1) return 0;
-  return gvi_step_scratch_doubles((M + 31) / 32 * 32) * sizeof(double);
+size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D);
+int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                             const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                             double* workspace, cudaStream_t st);
+
+int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x, int64_t nr, double* out,
+                         double* workspace, cudaStream_t st);
+
+// wide inputs (D > 32): K(x_chunk, Z) is built CHUNK rows at a time by the tensor-pipe Gram kernel into a ring that
+// stays L2 resident, and the tile kernel consumes it (one 24-point tile per CTA and launch)
+constexpr int64_t WIDE_CHUNK = (int64_t)GVI_NUM_SMS * 24;
+static int64_t wide_chunk_rows(int Mp) {
+  int64_t rows = (96LL << 20) / ((int64_t)Mp * 8) / 24 * 24;  // <= 96 MB of K rows
+  if (rows > WIDE_CHUNK) rows = WIDE_CHUNK;
+  return rows < 24 ? 24 : rows;
+}
+
+extern "C" size_t gvi_gp_predict_workspace_bytes(int M, int D) {
+  if (M < 1 || D < 1) return 0;
+  const int Mp = (M + 31) / 32 * 32;
+  size_t doubles = gvi_step_scratch_doubles(Mp);
+  if (D > 32) {
+    const int64_t rows = wide_chunk_rows(Mp);
+    doubles += (size_t)rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D);
+  }
+  return doubles * sizeof(double);
 }
 
 extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
@@ -532,16 +572,36 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 0, "sizes");
   if (N == 0) return GVI_OK;
   GVI_CHECK_ARG(factor && X, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
   StepParams P{};
   const FactorLayout f = factor_layout(M, D);
-  P.pass[0] = PassDesc{(const double*)factor, prior_mean, log_noise_add, mean_out, var_out};
   P.npass = 1;
   P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;
-  P.X = X; P.N = N;
   P.partials = nullptr;
   P.acc_scratch = (double*)workspace;
-  int rc = gvi_launch_step(P, (cudaStream_t)stream);
-  return rc < 0 ? rc : GVI_OK;
+  if (D <= 32) {
+    P.pass[0] = PassDesc{(const double*)factor, prior_mean, log_noise_add, mean_out, var_out, nullptr, 0};
+    P.X = X; P.N = N;
+    int rc = gvi_launch_step(P, st);
+    return rc < 0 ? rc : GVI_OK;
+  }
+  GVI_CHECK_ARG(workspace, "D > 32 needs a workspace of gvi_gp_predict_workspace_bytes(M, D)");
+  const double* F = (const double*)factor;
+  const int64_t rows = wide_chunk_rows(f.Mp);
+  double* ring = (double*)workspace + gvi_step_scratch_doubles(f.Mp);
+  double* gws = ring + (size_t)rows * f.Mp;
+  // the factor buffer carries sqrt(w), the pre-scaled inducing points and amp^2: everything the Gram needs
+  for (int64_t r0 = 0; r0 < N; r0 += rows) {
+    const int64_t nr = N - r0 < rows ? N - r0 : rows;
+    int rc = gvi_launch_wide_gram(F, f, X + r0 * D, nr, ring, gws, st);
+    if (rc) return rc;
+    P.pass[0] = PassDesc{F, prior_mean ? prior_mean + r0 : nullptr, log_noise_add, mean_out ? mean_out + r0 : nullptr,
+                         var_out ? var_out + r0 : nullptr, ring, (int64_t)f.Mp};
+    P.X = nullptr; P.N = nr;
+    rc = gvi_launch_step(P, st);
+    if (rc < 0) return rc;
+  }
+  return GVI_OK;
 }
 
 extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N, int M) {
@@ -560,10 +620,10 @@ int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor
   GVI_CHECK_ARG(reg_kind == GVI_REG_NONE || factor_p || (m_p_in && v_p_in),
                 "regulariser needs factor_p or (m_p_in, v_p_in)");
   const FactorLayout f = factor_layout(M, D);
-  P.pass[0] = PassDesc{(const double*)factor_q, nullptr, nullptr, nullptr, var_q_out};
+  P.pass[0] = PassDesc{(const double*)factor_q, nullptr, nullptr, nullptr, var_q_out, nullptr, 0};
   P.npass = 1;
   if (factor_p) {
-    P.pass[1] = PassDesc{(const double*)factor_p, prior_mean_p, nullptr, mean_p_out, var_p_out};
+    P.pass[1] = PassDesc{(const double*)factor_p, prior_mean_p, nullptr, mean_p_out, var_p_out, nullptr, 0};
     P.npass = 2;
   }
   P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;

@@ -8,6 +8,8 @@ struct PassDesc {
   const double* noise_add;  // device scalar log-noise or null: var += exp(*noise_add)
   double* mean_out;         // [N] or null
   double* var_out;          // [N] or null
+  const double* Kpre;       // optional precomputed K(x, Z) rows [N][ldk] (wide inputs, D > 32: Gram built by the
+  int64_t ldk;              //   tensor-pipe Gram kernel chunk by chunk in an L2-sized ring); null = compute in phase 1
 };
 
 // per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d

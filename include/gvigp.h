@@ -79,8 +79,10 @@ int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, 
  * mean[i] = k(x_i,Z) alpha + prior_mean[i]                                    (base.py:519-521, 492)
  * mean_out / prior_mean / log_noise_add may be NULL; workspace may be NULL when its size query returns 0.
  * Any M: for M > 1152 the K tile is swept in 1024-column panels and the partial triangular products are parked
- * in the (L2-resident) workspace between sweeps - still no N x M array in HBM.                               */
-size_t gvi_gp_predict_workspace_bytes(int M);   /* 0 unless M > 1152 (K tile processed in 1024-column panels) */
+ * in the (L2-resident) workspace between sweeps - still no N x M array in HBM.  Any D: for D > 32 the rows
+ * K(x_chunk, Z) are produced 3552 points at a time by the tensor-pipe Gram kernel into an L2-sized ring inside the
+ * workspace and consumed by the tile kernel (the fused step / gradient entry points support D <= 32).          */
+size_t gvi_gp_predict_workspace_bytes(int M, int D);   /* 0 unless M > 1152 (1024-column K panels) or D > 32 */
 int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
                        const double* prior_mean, const double* log_noise_add,
                        double* mean_out, double* var_out, void* workspace, void* stream);

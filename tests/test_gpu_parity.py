@@ -213,11 +213,29 @@ def test_predictive_parity(S, n, m, d):
     assert np.all(host(q.covariance) > -1e-12) and np.all(host(p.covariance) > 0)
 
 
-def test_unsupported_sizes_fail_loudly(S):
-    pr = make_problem(10, 8, 33, seed=5)
-    approx_gp, approx_params, *_ = build_models(S, pr)
-    with pytest.raises(Exception, match="D <= 32"):
-        approx_gp.predict_probability(approx_params, dev(pr["x"]))
+@pytest.mark.parametrize("n,m,d", [(5000, 300, 33), (700, 1300, 784)])
+def test_predictive_parity_wide_inputs(S, n, m, d):
+    """D > 32 (config #4's MNIST-like width): K(x,Z) rows come from the tensor-pipe Gram kernel in L2-sized chunks."""
+    rng = np.random.default_rng(d)
+    x, z = rng.uniform(0, 1, (n, d)), rng.uniform(0, 1, (m, d))
+    pr = dict(x=x, z=z, y=rng.standard_normal(n), yz=rng.standard_normal(m), ls_q=0.1,
+              ll_q=np.log(40.0 / d) + 0.1 * rng.standard_normal(d), ls_p=-0.2,
+              ll_p=np.log(40.0 / d) + 0.1 * rng.standard_normal(d), m_q=0.3 * rng.standard_normal(n))
+    v_q_ref, m_p_ref, v_p_ref = oracle_predictions(pr)
+    approx_gp, approx_params, exact_gp, exact_params, x_dev = build_models(S, pr)
+    q = approx_gp.predict_probability(approx_params, x_dev)
+    p = exact_gp.predict_probability(exact_params, x_dev)
+    assert rel_norm(host(q.covariance), v_q_ref) <= TOL
+    assert rel_norm(host(p.mean).reshape(-1), m_p_ref) <= TOL and rel_norm(host(p.covariance), v_p_ref) <= TOL
+    # the objective falls back to predict + risk kernels (the single-launch fused step needs D <= 32)
+    risk = S.NegativeLogLikelihood(gp=approx_gp)
+    reg = S.projected.ProjectedKLRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
+                                                mode="posterior")
+    gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+    assert not gvi._fusable()
+    ref = O.gaussian_nll(pr["y"], pr["m_q"], v_q_ref) + O.projected_regularisation("kl", m_p_ref, v_p_ref, pr["m_q"],
+                                                                                  v_q_ref)
+    assert abs(float(gvi.calculate_loss(approx_params, x_dev, dev(pr["y"]))) - ref) <= TOL * abs(ref)
 
 
 def test_sparse_posterior_full_gram_and_identity_golden(S):
