@@ -151,11 +151,72 @@ class GeneralisedVariationalInference:
 
     def _calculate_loss(self, parameters, x, y):
         if self._fusable():
+            if torch.is_grad_enabled() and self._wants_grad(parameters):
+                return _FusedLoss.apply(self, parameters, x, y, *self._grad_leaves(parameters))
             out3 = self.loss_sums(parameters, x, y)
             return (out3[0] + out3[1]) / out3[2]
         return (self._empirical_risk.calculate_empirical_risk(parameters, x, y)
                 + self._regularisation.calculate_regularisation(parameters, x))
 
+    # ---- torch autograd front end: `gvi.calculate_loss(...).backward()` plays the role of jax.grad ------------------
+    def _grad_leaves(self, parameters):
+        """(log_scaling, log_lengthscales) of q's base kernel followed by the tensors of the mean parameters."""
+        parameters = self._empirical_risk.gp._to_parameters(parameters)
+        base = parameters.kernel.base_kernel
+        leaves = [base.log_scaling, base.log_lengthscales]
+        leaves += [t for t in _tensor_leaves(parameters.mean.dict()) if t.requires_grad]
+        return leaves
+
+    def _wants_grad(self, parameters) -> bool:
+        return any(isinstance(t, torch.Tensor) and t.requires_grad for t in self._grad_leaves(parameters))
+
     def calculate_loss(self, parameters, x, y):
-        """reference: src/generalised_variational_inference.py:96-119."""
+        """reference: src/generalised_variational_inference.py:96-119.  When any of q's kernel hyper-parameters or
+        mean parameters is a torch tensor with requires_grad, the returned loss carries a backward that runs the
+        CUDA gradient step (the role jax.grad plays in the reference's trainer)."""
         return self._calculate_loss(parameters, x, y)
+
+
+def _tensor_leaves(obj):
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from _tensor_leaves(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _tensor_leaves(v)
+
+
+class _FusedLoss(torch.autograd.Function):
+    """loss = (sum NLL + sum D0) / N of the fused step; backward = the CUDA gradient step, with dR/dm_q pushed
+    through the (host-framework) mean function by torch autograd."""
+
+    @staticmethod
+    def forward(ctx, gvi, parameters, x, y, log_scaling, log_lengthscales, *mean_leaves):
+        with torch.enable_grad():
+            out, dm, m_q = gvi.loss_and_grad_sums(parameters, x, y)
+        n = out[2]
+        ctx.shapes = (getattr(log_scaling, "shape", ()), getattr(log_lengthscales, "shape", ()))
+        ctx.is_tensor = (isinstance(log_scaling, torch.Tensor), isinstance(log_lengthscales, torch.Tensor))
+        ctx.mean_leaves = mean_leaves
+        ctx.m_q = m_q
+        ctx.save_for_backward((out[3] / n).detach(), (out[4:] / n).detach(), (dm / n).detach())
+        return ((out[0] + out[1]) / n).detach()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        d_ls, d_ll, d_m = ctx.saved_tensors
+        g_ls = (grad_out * d_ls).reshape(ctx.shapes[0]) if ctx.is_tensor[0] else None
+        if ctx.is_tensor[1]:
+            n_ll = 1
+            for s_ in ctx.shapes[1]:
+                n_ll *= s_
+            g_ll = (grad_out * (d_ll.sum() if n_ll == 1 else d_ll)).reshape(ctx.shapes[1])
+        else:
+            g_ll = None
+        mean_grads = [None] * len(ctx.mean_leaves)
+        if ctx.mean_leaves and ctx.m_q.requires_grad:
+            mean_grads = torch.autograd.grad(ctx.m_q, ctx.mean_leaves, grad_outputs=grad_out * d_m,
+                                             allow_unused=True)
+        return (None, None, None, None, g_ls, g_ll, *mean_grads)

@@ -718,3 +718,64 @@ def test_multi_gpu_sharding_when_two_gpus_are_visible(S):
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(root, "tests", "run_multigpu.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "[multigpu] OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_autograd_backward_and_training_loop(S):
+    """README-style training (README.md:336-354 of the reference uses jax.grad + optax): here loss.backward() runs the
+    CUDA gradient step, torch autograd carries dR/dm_q through a tanh-FCN mean, and Adam decreases the objective."""
+    from oracle import torch_twin as TT
+
+    g = np.load(os.path.join(GOLDEN, "config1_readme.npz"))
+    x, y = g["x"], g["y"]
+    xd, yd = dev(x), dev(y)
+    kernel = S.ARDKernel(number_of_dimensions=1)
+    z, yz = x[g["idx"]], y[g["idx"]]
+    torch.manual_seed(0)
+    w1 = (0.5 * torch.randn(1, 10, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    b1 = torch.zeros(10, dtype=torch.float64, device="cuda", requires_grad=True)
+    w2 = (0.3 * torch.randn(10, 1, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    ls = torch.tensor(float(g["ls_q"]), dtype=torch.float64, device="cuda", requires_grad=True)
+    ll = torch.tensor(g["ll_q"], dtype=torch.float64, device="cuda", requires_grad=True)
+    fcn = lambda p, xx: torch.tanh(xx @ p["w1"] + p["b1"]) @ p["w2"]
+    amean = S.CustomMean(mean_function=fcn)
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=z)
+    approx = S.ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(
+        mean=amean.Parameters.construct(custom={"w1": w1, "b1": b1, "w2": w2}),
+        kernel=sparse.Parameters.construct(base_kernel=kernel.Parameters.construct(log_scaling=ls,
+                                                                                   log_lengthscales=ll)))
+    mean0 = S.ConstantMean()
+    exact = S.GPRegression(mean=mean0, kernel=kernel, x=z, y=yz)
+    ep = exact.Parameters.construct(log_observation_noise=0.0, mean=mean0.Parameters.construct(constant=0.0),
+                                    kernel=kernel.Parameters.construct(log_scaling=float(g["log_scaling"]),
+                                                                       log_lengthscales=g["log_ls"]))
+    gvi = S.GeneralisedVariationalInference(
+        regularisation=S.projected.ProjectedRenyiRegularisation(gp=approx, regulariser=exact,
+                                                                regulariser_parameters=ep, mode="posterior"),
+        empirical_risk=S.NegativeLogLikelihood(gp=approx))
+    loss = gvi.calculate_loss(ap, xd, yd)
+    loss.backward()
+    # reference gradients: the torch twin differentiates the same objective end to end (mean included)
+    t = lambda a: torch.tensor(host(a), dtype=torch.float64, requires_grad=True)
+    cw1, cb1, cw2, cls_, cll = t(w1), t(b1), t(w2), t(ls), t(ll)
+    xt, yt, zt = torch.tensor(x), torch.tensor(y), torch.tensor(z)
+    mq = (torch.tanh(xt @ cw1 + cb1) @ cw2).reshape(-1)
+    vq = TT.sparse_posterior_diag(cls_, cll, zt, xt)
+    ref = TT.gaussian_nll(yt, mq, vq) + TT.regulariser("renyi", torch.tensor(g["m_p"]), torch.tensor(g["v_p"]), mq, vq)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= TOL * abs(float(ref))
+    for ours, theirs in ((w1, cw1), (b1, cb1), (w2, cw2), (ls, cls_), (ll, cll)):
+        scale = max(float(theirs.grad.abs().max()), 1e-6)
+        assert float((ours.grad.cpu() - theirs.grad).abs().max()) <= GRAD_TOL * scale
+    # a short Adam run lowers the objective (the reference trains with optax.adabelief the same way)
+    opt = torch.optim.Adam([w1, b1, w2, ls, ll], lr=1e-2)
+    first = float(loss)
+    for _ in range(40):
+        opt.zero_grad()
+        loss = gvi.calculate_loss(ap, xd, yd)
+        loss.backward()
+        opt.step()
+    assert float(loss) < first and np.isfinite(float(loss))
+    # no-grad evaluation takes the forward-only launch and agrees
+    with torch.no_grad():
+        assert abs(float(gvi.calculate_loss(ap, xd, yd)) - float(gvi.calculate_loss(ap, xd, yd))) == 0.0
