@@ -305,6 +305,32 @@ def run_gpu(args):
     flops = algorithmic_flops_per_point(M, D) * N_PER_GPU
     achieved = flops / (kernel_ms * 1e-3) / 1e12
 
+    # ---- greedy conditional-variance selection (the other metric of BASELINE.json: selector points*M/s) ----------
+    sel_m = 512
+    sel = None
+    try:
+        xs_sel = dev_batches[0][0]
+        L.cond_var_select(xs_sel[:4096].contiguous(), 32, to_d(theta["ls_q"]), to_d(theta["ll_q"]), 1e-12)  # warm-up
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        sel_idx, _ = L.cond_var_select(xs_sel, sel_m, to_d(theta["ls_q"]), to_d(theta["ll_q"]), 1e-12)
+        s1.record()
+        torch.cuda.synchronize()
+        sel_ms = s0.elapsed_time(s1)
+        sel_bytes = 4.0 * N_PER_GPU * sel_m * sel_m + 32.0 * N_PER_GPU * sel_m
+        hbm_peak = 6558.1
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp):
+            hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+        sel = {"n": N_PER_GPU, "m": sel_m, "ms": sel_ms, "points_times_m_per_s": N_PER_GPU * sel_m / (sel_ms * 1e-3),
+               "roofline": {"bound": "hbm", "achieved": sel_bytes / (sel_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                            "unit": "GB/s", "frac": sel_bytes / (sel_ms * 1e-3) / 1e9 / hbm_peak,
+                            "algorithmic_bytes": sel_bytes},
+               "unique_pivots": int(torch.unique(sel_idx).numel())}
+    except Exception as e:  # pragma: no cover - reported, never hidden
+        sel = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- end to end through the public API with HOST buffers ---------------------------------------------------
     e2e_steps = max(2, min(args.steps, 5))
     barrier()
@@ -358,6 +384,7 @@ def run_gpu(args):
                          "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D),
                          "peak_source": "measured FP64 DMMA issue rate on this pool's B200 (profiles/fp64_peak_r01.txt; "
                                         "cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry"},
+            "selector": sel,
             "clocks": clocks.summary(),
         }
         if cpu is not None:
