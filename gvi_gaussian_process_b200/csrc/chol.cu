@@ -341,14 +341,15 @@ __global__ void __launch_bounds__(256) linv_sweep_kernel(const double* __restric
 // ---- header, scaled inducing points -----------------------------------------------------------------------------
 __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, const double* __restrict__ Z,
                                      const double* __restrict__ log_scaling, const double* __restrict__ log_ls,
-                                     int ls_len, double abs_jitter) {
+                                     int ls_len, double abs_jitter, int frozen) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid == 0) {
     double amp = exp(log_scaling[0]);
     F[0] = amp * amp;
     F[1] = amp * amp;
     F[4] = abs_jitter;
-    F[5] = F[6] = F[7] = 0.0;
+    F[5] = frozen ? 1.0 : 0.0;
+    F[6] = F[7] = 0.0;
   }
   if (tid < f.D) F[f.sqrtw_off + tid] = sqrt(exp(log_ls[ls_len == 1 ? 0 : tid]));
   for (int64_t idx = tid; idx < (int64_t)f.Mp * f.D; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -360,7 +361,7 @@ __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, con
 // ---- pack L^-1 in fragment order: group g (rows R g .. R g + R - 1, R = GVI_GROUP_ROWS), kp (cols 8kp..8kp+7),
 // mt (8-row tile), lane, e:  element = Linv[R g + 8 mt + lane/4][8 kp + 4 e + lane%4]; zero above the diagonal and in
 // the padding.  One CTA per group.
-__global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict__ X, int Mp, int M, int G,
+__global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict__ X, int64_t Mp, int M, int G,
                                                         double* __restrict__ W) {
   const int g = blockIdx.x;
   double2* out = reinterpret_cast<double2*>(W + wpack_group_off(g));
@@ -510,9 +511,52 @@ extern "C" size_t gvi_gp_factor_workspace_bytes(int M) {
   return (2 * Mp * Mp + 2 * Mp + 8) * sizeof(double);
 }
 
+static int factor_impl(const double* Z, int M, int D, const double* log_scaling, const double* log_ls, int ls_len,
+                       const double* chol_log_scaling, const double* chol_log_ls, int chol_ls_len, double reg,
+                       int is_abs, const double* log_noise, const double* y_z, void* factor_out, void* workspace,
+                       int* info, void* stream);
+
 extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, const double* log_ls,
                                  int ls_len, double reg, int is_abs, const double* log_noise, const double* y_z,
                                  void* factor_out, void* workspace, int* info, void* stream) {
+  return factor_impl(Z, M, D, log_scaling, log_ls, ls_len, nullptr, nullptr, 0, reg, is_abs, log_noise, y_z, factor_out,
+                     workspace, info, stream);
+}
+
+extern "C" int gvi_gp_factor_frozen_f64(const double* Z, int M, int D, const double* log_scaling,
+                                        const double* log_ls, int ls_len, const double* chol_log_scaling,
+                                        const double* chol_log_ls, int chol_ls_len, double reg, int is_abs,
+                                        void* factor_out, void* workspace, int* info, void* stream) {
+  GVI_CHECK_ARG(chol_log_scaling && chol_log_ls, "null pointer");
+  GVI_CHECK_ARG(chol_ls_len == 1 || chol_ls_len == D, "chol log_lengthscales must have 1 or D entries");
+  return factor_impl(Z, M, D, log_scaling, log_ls, ls_len, chol_log_scaling, chol_log_ls, chol_ls_len, reg, is_abs,
+                     nullptr, nullptr, factor_out, workspace, info, stream);
+}
+
+__global__ void set_flag_kernel(double* F, int idx, double v) { F[idx] = v; }
+
+extern "C" int gvi_gp_factor_set_extra_f64(void* factor, int M, int D, const double* E, int64_t ld, void* stream) {
+  GVI_CHECK_ARG(factor && M >= 1 && D >= 1, "factor");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FactorLayout f = factor_layout(M, D);
+  double* F = (double*)factor;
+  if (!E) {
+    set_flag_kernel<<<1, 1, 0, st>>>(F, 6, 0.0);
+    GVI_CHECK_LAUNCH("set_flag_kernel");
+    return GVI_OK;
+  }
+  GVI_CHECK_ARG(ld >= M, "ld < M");
+  pack_linv_kernel<<<f.G, 256, 0, st>>>(E, ld, M, f.G, F + f.wextra_off);
+  GVI_CHECK_LAUNCH("pack_linv_kernel");
+  set_flag_kernel<<<1, 1, 0, st>>>(F, 6, 1.0);
+  GVI_CHECK_LAUNCH("set_flag_kernel");
+  return GVI_OK;
+}
+
+static int factor_impl(const double* Z, int M, int D, const double* log_scaling, const double* log_ls, int ls_len,
+                       const double* chol_log_scaling, const double* chol_log_ls, int chol_ls_len, double reg,
+                       int is_abs, const double* log_noise, const double* y_z, void* factor_out, void* workspace,
+                       int* info, void* stream) {
   GVI_CHECK_ARG(Z && log_scaling && log_ls && factor_out && workspace, "null pointer");
   GVI_CHECK_ARG(M >= 1 && D >= 1, "sizes");
   GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
@@ -524,9 +568,15 @@ extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* lo
   double* tvec = X + (size_t)f.Mp * f.Mp;
   int* winfo = (int*)(tvec + 2 * f.Mp);
   int rc;
-  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0);
+  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0,
+                                           chol_log_scaling != nullptr);
   GVI_CHECK_LAUNCH("factor_header_kernel");
-  if ((rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st))) return rc;
+  // K_ZZ of the Cholesky: the kernel's own parameters, or the frozen (regulariser) parameters
+  if (chol_log_scaling)
+    rc = gvi_launch_ard_gram(Z, M, Z, M, D, chol_log_scaling, chol_log_ls, chol_ls_len, A, f.Mp, st);
+  else
+    rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st);
+  if (rc) return rc;
   add_diag_kernel<<<1, 1024, 0, st>>>(A, M, f.Mp, reg, is_abs, log_noise, F + 2);
   GVI_CHECK_LAUNCH("add_diag_kernel");
   if (f.Mp != M) {

@@ -43,19 +43,22 @@ constexpr int GVI_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 
 // ---- factor buffer layout (doubles) ---------------------------------------------------------------------------
 // [0] amp2 = exp(log_scaling)^2   [1] k(x,x)   [2] jitter actually added   [3] chol info (as double)
-// [4] absolute jitter (0 when the regulariser is trace-relative; used by d var / d log_scaling)   [5..7] rsvd
+// [4] absolute jitter (0 when the regulariser is trace-relative; used by d var / d log_scaling)
+// [5] 1 when the Cholesky factor was built from OTHER (frozen) kernel parameters than the K-tile parameters
+// [6] 1 when the extra packed matrix E is set: var += ||E k||^2 (SVGP family)   [7] rsvd
 // [8, 8+D)            sqrtw[d] = sqrt(exp(log_ls[d]))
 // [zs_off, +Mp*D)     Z pre-scaled by sqrtw (rows >= M are zero)
 // [alpha_off, +Mp)    alpha = A^-1 y_Z (zero padded)
 // [wpack_off, ...)    L^-1 packed per 32-row group in DMMA m8n8k4 fragment order (see pack_linv_kernel)
 // [wpackT_off, ...)   L^-T packed the same way (rows j, k-range c >= 32g): a = L^-T b in the backward pass
 // [linv_off, +Mp*Mp)  dense row-major L^-1 (S = A^-1 C A^-1 in the backward pass; full-covariance API)
+// [wextra_off, ...)   optional extra lower-triangular matrix E packed like L^-1 (gvi_gp_factor_set_extra_f64)
 // rows of L^-1 handled by one warp-level group in the tile kernel = 8 * GVI_MT (m-tiles of the DMMA m8n8k4 shape)
 constexpr int GVI_MT = 2;
 constexpr int GVI_GROUP_ROWS = 8 * GVI_MT;
 struct FactorLayout {
   int M, Mp, D, G;  // G = number of GVI_GROUP_ROWS-row groups
-  int64_t sqrtw_off, zs_off, alpha_off, wpack_off, wpackT_off, linv_off, total;
+  int64_t sqrtw_off, zs_off, alpha_off, wpack_off, wpackT_off, linv_off, wextra_off, total;
 };
 __host__ __device__ inline int64_t wpack_total(int G) {
   return (int64_t)GVI_MT * 64 * (GVI_GROUP_ROWS / 8) * ((int64_t)G * (G + 1) / 2);
@@ -81,6 +84,8 @@ __host__ __device__ inline FactorLayout factor_layout(int M, int D) {
   o += wpack_total(f.G);
   f.linv_off = o;
   o += (int64_t)f.Mp * f.Mp;
+  f.wextra_off = o;
+  o += wpack_total(f.G);
   f.total = o;
   return f;
 }

@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       }
       if (tid == 0) *counter = 0;
       __syncthreads();
+      double qfirst = 0.0;      // ||L^-1 k||^2 of threads < T when a second matrix follows
+      bool have_extra = false;
       for (int c_lo = 0; c_lo < P.Mp; c_lo += P.Pc) {  // column panels (one iteration unless M is large)
       const int c_hi = min(c_lo + P.Pc, P.Mp);
       if (c_lo > 0) {
@@ -177,9 +179,8 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       }
       __syncthreads();
       // ---- phase 2: b = L^-1 k on the tensor pipe, accumulate ||b||^2 ----------------------------------
-      if (!(P.debug_skip & 2)) {
+      auto run_groups = [&](const double* __restrict__ W, const bool store_b) {
         const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
-        const double* __restrict__ W = F + f.wpack_off;
         const int kp_lo = c_lo / 8, kp_hi = c_hi / 8;
         const int g_lo = c_lo / GVI_GROUP_ROWS;  // groups below g_lo were completed by earlier panels
         while (true) {
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
               v += __shfl_xor_sync(0xffffffffu, v, 16);
               if (lane < 4) reds[g * T + nt * 8 + lane * 2 + e] = v;
             }
-          if (keep_b) {
+          if (store_b) {
             // b[c][i] goes to the per-CTA scratch (L2 resident) in the K-tile fragment order at "column" c
 #pragma unroll
             for (int mt = 0; mt < MT; mt++) {
@@ -247,6 +248,20 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
             }
           }
         }
+      };
+      if (!(P.debug_skip & 2)) run_groups(F + f.wpack_off, keep_b);
+      // SVGP family: a second lower-triangular matrix E adds ||E k||^2 to the variance (same K tile, same loop)
+      if (F[6] != 0.0 && !multi) {
+        __syncthreads();
+        if (tid < T) {
+          double q0 = 0.0;
+          for (int g = 0; g < P.G; g++) q0 += reds[g * T + tid];
+          qfirst = q0;
+        }
+        if (tid == 0) *counter = 0;
+        have_extra = true;
+        __syncthreads();
+        run_groups(F + f.wextra_off, false);
       }
       }  // column panels
       __syncthreads();
@@ -260,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
         }
 #pragma unroll
         for (int w = 0; w < WARPS; w++) mu += redm[w * T + tid];
-        double var = F[1] - q;
+        double var = have_extra ? F[1] - qfirst + q : F[1] - q;
         if (pd.noise_add) var += exp(pd.noise_add[0]);
         const int64_t r = row0 + tid;
         if (r < P.N) {

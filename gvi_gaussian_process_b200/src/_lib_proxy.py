@@ -59,6 +59,24 @@ class GpFactor:
         _lib.check(rc, "gvi_gp_factor_f64")
         return self
 
+    def factor_frozen(self, z, log_scaling, log_ls, chol_log_scaling, chol_log_ls, diagonal_regularisation,
+                      is_absolute):
+        rc = _L().gvi_gp_factor_frozen_f64(_lib.ptr(z), self.m, self.d, _lib.ptr(log_scaling), _lib.ptr(log_ls),
+                                           log_ls.numel(), _lib.ptr(chol_log_scaling), _lib.ptr(chol_log_ls),
+                                           chol_log_ls.numel(), float(diagonal_regularisation),
+                                           int(bool(is_absolute)), _lib.ptr(self.buf), _lib.ptr(self.ws),
+                                           _lib.ptr(self.info), _lib.current_stream())
+        _lib.check(rc, "gvi_gp_factor_frozen_f64")
+        return self
+
+    def set_extra(self, e_matrix):
+        """Attach (or detach with None) the lower-triangular E of the SVGP family: var += ||E k||^2."""
+        rc = _L().gvi_gp_factor_set_extra_f64(_lib.ptr(self.buf), self.m, self.d, _lib.ptr(e_matrix),
+                                              e_matrix.stride(0) if e_matrix is not None else 0,
+                                              _lib.current_stream())
+        _lib.check(rc, "gvi_gp_factor_set_extra_f64")
+        return self
+
     # views into the workspace (valid until the next factor() call) -- used by the full-covariance API only
     def cholesky(self):
         return self.ws[: self.mp * self.mp].view(self.mp, self.mp)[: self.m, : self.m]

@@ -66,8 +66,8 @@ class GeneralisedVariationalInference:
         gp = er.gp
         if gp is not rg.gp or not isinstance(gp, ApproximateGPRegression):
             return False
-        if not isinstance(gp.kernel, SparsePosteriorKernel) or rg.kind == "none":
-            return False
+        if not hasattr(gp.kernel, "factorise") or rg.kind == "none":
+            return False  # SparsePosteriorKernel, FixedSparsePosteriorKernel and the SVGP kernels provide factorise()
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
             return (isinstance(reg, GPRegression) and reg.x.shape == gp.kernel.inducing_points.shape
@@ -105,7 +105,8 @@ class GeneralisedVariationalInference:
         returns (out, dm, m_q) with out = [sum NLL, sum D0, N, d/dlog_scaling, d/dlog_lengthscales[0..D)],
         dm[i] = d(sum loss)/dm_q[i] and m_q the mean-function output (so the host framework can back-propagate
         dm through it).  Multi-GPU: all-reduce `out`, keep dm sharded, divide both by out[2]."""
-        assert self._fusable(), "gradients are implemented for the fused hot-path configuration only"
+        assert self._fusable() and isinstance(self._empirical_risk.gp.kernel, SparsePosteriorKernel), (
+            "gradients are implemented for the fused hot-path configuration (SparsePosteriorKernel over ARD) only")
         er, rg = self._empirical_risk, self._regularisation
         gp = er.gp
         parameters = gp._to_parameters(parameters)
@@ -168,6 +169,8 @@ class GeneralisedVariationalInference:
         return leaves
 
     def _wants_grad(self, parameters) -> bool:
+        if not isinstance(self._empirical_risk.gp.kernel, SparsePosteriorKernel):
+            return False
         return any(isinstance(t, torch.Tensor) and t.requires_grad for t in self._grad_leaves(parameters))
 
     def calculate_loss(self, parameters, x, y):

@@ -1,1 +1,2 @@
 from .base import KernelBase, KernelBaseParameters  # noqa: F401
+from .tempered_kernel import TemperedKernel, TemperedKernelParameters  # noqa: F401

@@ -1,0 +1,60 @@
+"""FixedSparsePosteriorKernel (reference: src/kernels/approximate/fixed_sparse_posterior_kernel.py:14-99):
+r(x1,x2) = k_b(x1,x2) - k_b(x1,Z) cho_solve(chol(K_reg(Z,Z) + jitter), k_b(Z,x2)) - the Cholesky factor comes from
+the regulariser kernel with FIXED parameters (computed once), the cross-Grams from the trainable base kernel."""
+from __future__ import annotations
+
+from ... import _lib_proxy as L
+from ...utils.device import as_2d
+from ..base import KernelBase, KernelBaseParameters
+from ..standard.ard_kernel import ARDKernel
+
+
+class FixedSparsePosteriorKernelParameters(KernelBaseParameters):
+    """base_kernel: parameters of the base kernel."""
+
+
+class FixedSparsePosteriorKernel(KernelBase):
+    Parameters = FixedSparsePosteriorKernelParameters
+
+    def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, base_kernel: KernelBase,
+                 inducing_points, diagonal_regularisation: float = 1e-5,
+                 is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
+        if not isinstance(base_kernel, ARDKernel) or not isinstance(regulariser_kernel, ARDKernel):
+            raise NotImplementedError("the B200 path implements FixedSparsePosteriorKernel over ARDKernel only")
+        self.regulariser_kernel = regulariser_kernel
+        self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
+        self.base_kernel = base_kernel
+        self.inducing_points = as_2d(inducing_points)
+        self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
+        self.diagonal_regularisation = diagonal_regularisation
+        self.is_diagonal_regularisation_absolute_scale = is_diagonal_regularisation_absolute_scale
+        self._factor = None
+        super().__init__(preprocess_function=preprocess_function)
+
+    def generate_parameters(self, parameters) -> FixedSparsePosteriorKernelParameters:
+        return FixedSparsePosteriorKernel.Parameters(
+            base_kernel=self.base_kernel._to_parameters(parameters["base_kernel"]))
+
+    def factorise(self, parameters) -> "L.GpFactor":
+        parameters = self._to_parameters(parameters)
+        z = self.inducing_points
+        if self._factor is None:
+            self._factor = L.GpFactor(z.shape[0], z.shape[1])
+        ls, ll = ARDKernel.device_parameters(self.base_kernel._to_parameters(parameters.base_kernel))
+        cls_, cll = ARDKernel.device_parameters(self.regulariser_kernel_parameters)
+        return self._factor.factor_frozen(z, ls, ll, cls_, cll, self.diagonal_regularisation,
+                                          self.is_diagonal_regularisation_absolute_scale)
+
+    def _calculate_gram_diagonal(self, parameters, x):
+        f = self.factorise(parameters)
+        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        return var
+
+    def _calculate_gram(self, parameters, x1, x2):
+        f = self.factorise(parameters)
+        base_parameters = parameters.base_kernel
+        linv = f.inverse_cholesky()
+        k1z = self.base_kernel.calculate_gram(base_parameters, x1, self.inducing_points)
+        k2z = self.base_kernel.calculate_gram(base_parameters, x2, self.inducing_points)
+        k12 = self.base_kernel.calculate_gram(base_parameters, x1, x2)
+        return k12 - (k1z @ linv.T) @ (k2z @ linv.T).T

@@ -1,0 +1,7 @@
+from .svgp_kernels import (  # noqa: F401
+    CholeskySVGPKernel,
+    CholeskySVGPKernelParameters,
+    DiagonalSVGPKernel,
+    DiagonalSVGPKernelParameters,
+    SVGPBaseKernel,
+)

@@ -1,0 +1,129 @@
+"""SVGP-family variational kernels (reference: src/kernels/approximate/svgp/base.py:24-73,
+cholesky_svgp_kernel.py:75-150, diagonal_svgp_kernel.py:63-129).
+
+All Grams use the regulariser kernel with FIXED parameters; the trainable part is Sigma = E^T E:
+    r(x1,x2) = k(x1,x2) - k(x1,Z) (K_ZZ + jitter)^-1 k(Z,x2) + k(x1,Z) Sigma k(Z,x2)
+  Cholesky parameterisation: E = tril(P, -1) + diag(exp(d));   diagonal: Sigma = diag(exp(d)), E = diag(exp(d/2)).
+Diagonal mode (the training hot path) runs in the fused tile kernel: K(x,Z) tile once, two triangular products on
+the FP64 tensor pipe (L^-1 k and E k), var = k(x,x) - ||L^-1 k||^2 + ||E k||^2.  The Cholesky of the fixed K_ZZ is
+factorised once and cached."""
+from __future__ import annotations
+
+import torch
+
+from .... import _lib_proxy as L
+from ....utils.device import as_2d, as_device, scalar
+from ...base import KernelBase, KernelBaseParameters
+from ...standard.ard_kernel import ARDKernel
+
+
+class SVGPBaseKernel(KernelBase):
+    def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, log_observation_noise,
+                 inducing_points, training_points, diagonal_regularisation: float = 1e-5,
+                 is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
+        if not isinstance(regulariser_kernel, ARDKernel):
+            raise NotImplementedError("the B200 path implements the SVGP kernels over ARDKernel only")
+        self.regulariser_kernel = regulariser_kernel
+        self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
+        self.log_observation_noise = log_observation_noise
+        self.inducing_points = as_2d(inducing_points)
+        self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
+        self.training_points = as_2d(training_points)
+        self.training_points = self.training_points.reshape(self.training_points.shape[0], -1)
+        self.number_of_dimensions = self.inducing_points.shape[1]
+        self.diagonal_regularisation = diagonal_regularisation
+        self.is_diagonal_regularisation_absolute_scale = is_diagonal_regularisation_absolute_scale
+        self._factor = None
+        super().__init__(preprocess_function=preprocess_function)
+
+    # ---- one-time state (fixed regulariser kernel): svgp/base.py:57-73 ---------------------------------------
+    def _frozen_factor(self) -> "L.GpFactor":
+        if self._factor is None:
+            z = self.inducing_points
+            ls, ll = ARDKernel.device_parameters(self.regulariser_kernel_parameters)
+            self._factor = L.GpFactor(z.shape[0], z.shape[1]).factor(
+                z, ls, ll, self.diagonal_regularisation, self.is_diagonal_regularisation_absolute_scale)
+        return self._factor
+
+    def _initial_inverse_cholesky(self) -> torch.Tensor:
+        """inv(chol(K_ZZ + exp(-log_noise) K_ZX K_XZ)) - initialisation only, M^3 once (library linear algebra)."""
+        k = self.regulariser_kernel
+        kzz = k.calculate_gram(self.regulariser_kernel_parameters, self.inducing_points, self.inducing_points)
+        kzx = k.calculate_gram(self.regulariser_kernel_parameters, self.inducing_points, self.training_points)
+        precision = 1.0 / scalar(self.log_observation_noise).exp()
+        chol = torch.linalg.cholesky(kzz + precision * (kzx @ kzx.T))
+        return torch.linalg.inv(chol)
+
+    def _el_matrix(self, parameters) -> torch.Tensor:
+        raise NotImplementedError
+
+    def factorise(self, parameters) -> "L.GpFactor":
+        """State for the tile kernel: the cached frozen factor with this step's E attached."""
+        parameters = self._to_parameters(parameters)
+        f = self._frozen_factor()
+        f.set_extra(self._el_matrix(parameters).contiguous())
+        return f
+
+    def _calculate_gram_diagonal(self, parameters, x):
+        f = self.factorise(parameters)
+        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        return var
+
+    def _calculate_gram(self, parameters, x1, x2):
+        f = self._frozen_factor()
+        linv = f.inverse_cholesky()
+        k = self.regulariser_kernel
+        kp = self.regulariser_kernel_parameters
+        k1z = k.calculate_gram(kp, x1, self.inducing_points)
+        k2z = k.calculate_gram(kp, x2, self.inducing_points)
+        k12 = k.calculate_gram(kp, x1, x2)
+        e = self._el_matrix(parameters)
+        return k12 - (k1z @ linv.T) @ (k2z @ linv.T).T + (k1z @ e.T) @ (k2z @ e.T).T
+
+
+class CholeskySVGPKernelParameters(KernelBaseParameters):
+    """el_matrix_lower_triangle [M,M], el_matrix_log_diagonal [M]."""
+
+
+class CholeskySVGPKernel(SVGPBaseKernel):
+    Parameters = CholeskySVGPKernelParameters
+
+    def initialise_el_matrix_parameters(self):
+        """reference: cholesky_svgp_kernel.py:75-100."""
+        inv_chol = self._initial_inverse_cholesky()
+        lower = torch.tril(inv_chol, diagonal=-1)
+        log_diag = torch.log(torch.clamp(torch.diagonal(inv_chol), min=self.diagonal_regularisation))
+        return lower, log_diag
+
+    def generate_parameters(self, parameters=None) -> CholeskySVGPKernelParameters:
+        if parameters is None:
+            lower, log_diag = self.initialise_el_matrix_parameters()
+            return CholeskySVGPKernelParameters(el_matrix_lower_triangle=lower, el_matrix_log_diagonal=log_diag)
+        return CholeskySVGPKernelParameters(el_matrix_lower_triangle=parameters["el_matrix_lower_triangle"],
+                                            el_matrix_log_diagonal=parameters["el_matrix_log_diagonal"])
+
+    def _el_matrix(self, parameters) -> torch.Tensor:
+        lower = torch.tril(as_device(parameters.el_matrix_lower_triangle), diagonal=-1)
+        return lower + torch.diag(torch.exp(as_device(parameters.el_matrix_log_diagonal).reshape(-1)))
+
+
+class DiagonalSVGPKernelParameters(KernelBaseParameters):
+    """log_el_matrix_diagonal [M]."""
+
+
+class DiagonalSVGPKernel(SVGPBaseKernel):
+    Parameters = DiagonalSVGPKernelParameters
+
+    def initialise_diagonal_parameters(self):
+        """reference: diagonal_svgp_kernel.py:63-87 - diag(log(clip(L L^T))), L = inv(chol(...))."""
+        inv_chol = self._initial_inverse_cholesky()
+        sigma = inv_chol @ inv_chol.T
+        return torch.log(torch.clamp(torch.diagonal(sigma), min=self.diagonal_regularisation))
+
+    def generate_parameters(self, parameters=None) -> DiagonalSVGPKernelParameters:
+        if parameters is None:
+            return DiagonalSVGPKernelParameters(log_el_matrix_diagonal=self.initialise_diagonal_parameters())
+        return DiagonalSVGPKernelParameters(log_el_matrix_diagonal=parameters["log_el_matrix_diagonal"])
+
+    def _el_matrix(self, parameters) -> torch.Tensor:
+        return torch.diag(torch.exp(0.5 * as_device(parameters.log_el_matrix_diagonal).reshape(-1)))

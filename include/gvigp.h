@@ -73,6 +73,19 @@ int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, 
                       int ls_len, double diagonal_regularisation, int is_absolute, const double* log_noise,
                       const double* y_z, void* factor_out, void* workspace, int* info, void* stream);
 
+/* Same state with a FROZEN Cholesky: K(x,Z) tiles use (log_scaling, log_ls) but A = K_ZZ(chol_*) + jitter is built
+ * from other, fixed parameters - FixedSparsePosteriorKernel (fixed_sparse_posterior_kernel.py:41-52, 78-99) and the
+ * SVGP family (svgp/base.py:57-73).                                                                           */
+int gvi_gp_factor_frozen_f64(const double* Z, int M, int D, const double* log_scaling, const double* log_ls,
+                             int ls_len, const double* chol_log_scaling, const double* chol_log_ls, int chol_ls_len,
+                             double diagonal_regularisation, int is_absolute, void* factor_out, void* workspace,
+                             int* info, void* stream);
+/* SVGP family: attach (E != NULL) or detach a lower-triangular matrix E [M,M] (row stride ld) to the state; the
+ * predictive variance becomes k(x,x) - ||L^-1 k||^2 + ||E k||^2, i.e. + k(x,Z) (E^T E) k(Z,x)
+ * (svgp/cholesky_svgp_kernel.py:133-150 with E = tril(P,-1) + diag(exp(d)); diagonal_svgp_kernel.py:117-129 with
+ * E = diag(exp(d/2))).  The second triangular product runs in the same tile kernel on the same K tile.        */
+int gvi_gp_factor_set_extra_f64(void* factor, int M, int D, const double* E, int64_t ld, void* stream);
+
 /* ---- a5-a7: predictive mean / variance without any N x M intermediate in HBM -------------------------------
  * var[i]  = k(x_i,x_i) - || L^-1 k(Z,x_i) ||^2 (+ exp(log_noise_add) if given)   (sparse_posterior_kernel.py:90-96
  *           in diagonal mode; base.py:522-525 for the exact GP; base.py:205-211 for the added noise)

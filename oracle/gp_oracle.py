@@ -274,3 +274,53 @@ def conditional_variance_select(x_perm, number_of_inducing_points, gram_fn, diag
             indices = indices[:m]
             break
     return indices.astype(int)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# section 8(f)-1: fixed sparse posterior and SVGP-family kernels
+# --------------------------------------------------------------------------------------------------------------
+def fixed_sparse_posterior_gram(base_gram_fn, regulariser_gram_fn, inducing_points, x1, x2=None,
+                                diagonal_regularisation=1e-5, is_absolute=False) -> np.ndarray:
+    """src/kernels/approximate/fixed_sparse_posterior_kernel.py:41-52, 78-99: Cholesky from the regulariser kernel
+    (fixed), cross-Grams from the base kernel."""
+    x2 = x1 if x2 is None else x2
+    c_and_lower = cho_factor(add_diagonal_regulariser(regulariser_gram_fn(inducing_points, inducing_points),
+                                                      diagonal_regularisation, is_absolute))
+    k1z, k2z = base_gram_fn(x1, inducing_points), base_gram_fn(x2, inducing_points)
+    return base_gram_fn(x1, x2) - k1z @ cho_solve(c_and_lower, k2z.T)
+
+
+def svgp_initial_inverse_cholesky(gram_fn, inducing_points, training_points, log_observation_noise) -> np.ndarray:
+    """svgp/base.py:57-73 + cholesky_svgp_kernel.py:86-95: inv(chol(K_ZZ + exp(-log_noise) K_ZX K_XZ))."""
+    kzz = gram_fn(inducing_points, inducing_points)
+    kzx = gram_fn(inducing_points, training_points)
+    return np.linalg.inv(np.linalg.cholesky(kzz + (1.0 / np.exp(log_observation_noise)) * kzx @ kzx.T))
+
+
+def svgp_cholesky_initial_parameters(gram_fn, inducing_points, training_points, log_observation_noise,
+                                     diagonal_regularisation=1e-5):
+    """cholesky_svgp_kernel.py:75-100."""
+    inv_chol = svgp_initial_inverse_cholesky(gram_fn, inducing_points, training_points, log_observation_noise)
+    return np.tril(inv_chol, k=-1), np.log(np.clip(np.diag(inv_chol), diagonal_regularisation, None))
+
+
+def svgp_diagonal_initial_parameters(gram_fn, inducing_points, training_points, log_observation_noise,
+                                     diagonal_regularisation=1e-5):
+    """diagonal_svgp_kernel.py:63-87."""
+    inv_chol = svgp_initial_inverse_cholesky(gram_fn, inducing_points, training_points, log_observation_noise)
+    return np.diag(np.log(np.clip(inv_chol @ inv_chol.T, diagonal_regularisation, None)))
+
+
+def svgp_gram(gram_fn, inducing_points, sigma_matrix, x1, x2=None, diagonal_regularisation=1e-5,
+              is_absolute=False) -> np.ndarray:
+    """cholesky_svgp_kernel.py:133-150 / diagonal_svgp_kernel.py:117-129 with sigma = el^T el or diag(exp(d))."""
+    x2 = x1 if x2 is None else x2
+    c_and_lower = cho_factor(add_diagonal_regulariser(gram_fn(inducing_points, inducing_points),
+                                                      diagonal_regularisation, is_absolute))
+    k1z, k2z = gram_fn(x1, inducing_points), gram_fn(x2, inducing_points)
+    return gram_fn(x1, x2) - k1z @ cho_solve(c_and_lower, k2z.T) + k1z @ sigma_matrix @ k2z.T
+
+
+def cholesky_sigma(el_matrix_lower_triangle, el_matrix_log_diagonal) -> np.ndarray:
+    el = np.tril(el_matrix_lower_triangle, k=-1) + np.diag(np.exp(el_matrix_log_diagonal))
+    return el.T @ el

@@ -779,3 +779,101 @@ def test_autograd_backward_and_training_loop(S):
     # no-grad evaluation takes the forward-only launch and agrees
     with torch.no_grad():
         assert abs(float(gvi.calculate_loss(ap, xd, yd)) - float(gvi.calculate_loss(ap, xd, yd))) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# section 8(f)-1: fixed sparse posterior, SVGP family, tempered kernel
+# ---------------------------------------------------------------------------------------------------------------
+def test_fixed_sparse_svgp_and_tempered_kernels(S):
+    from gvi_gaussian_process_b200.src.kernels import TemperedKernel
+    from gvi_gaussian_process_b200.src.kernels.approximate import (CholeskySVGPKernel, DiagonalSVGPKernel,
+                                                                   FixedSparsePosteriorKernel)
+
+    rng = np.random.default_rng(11)
+    n, m, d = 3000, 200, 4
+    x, z, xt = rng.standard_normal((n, d)), rng.standard_normal((m, d)), rng.standard_normal((500, d))
+    ls_r, ll_r = 0.1, rng.normal(0.3, 0.1, d)     # regulariser (frozen) kernel
+    ls_b, ll_b = -0.1, rng.normal(0.5, 0.1, d)    # trainable base kernel
+    g_r = lambda a, b: O.ard_gram(ls_r, ll_r, a, b)
+    g_b = lambda a, b: O.ard_gram(ls_b, ll_b, a, b)
+    k = S.ARDKernel(number_of_dimensions=d)
+    p_r = k.Parameters.construct(log_scaling=ls_r, log_lengthscales=ll_r)
+    p_b = k.Parameters.construct(log_scaling=ls_b, log_lengthscales=ll_b)
+    # ---- fixed sparse posterior -------------------------------------------------------------------------------
+    fk = FixedSparsePosteriorKernel(regulariser_kernel=k, regulariser_kernel_parameters=p_r, base_kernel=k,
+                                    inducing_points=z)
+    fp = fk.generate_parameters({"base_kernel": p_b})
+    ref_full = O.fixed_sparse_posterior_gram(g_b, g_r, z, x[:60], x[:40])
+    assert rel_norm(host(fk.calculate_gram(fp, x[:60], x[:40])), ref_full) <= TOL
+    ref_diag = np.diag(O.fixed_sparse_posterior_gram(g_b, g_r, z, x[:400], x[:400]))
+    assert rel_norm(host(fk.calculate_gram(fp, x, x, full_covariance=False))[:400], ref_diag) <= TOL
+    # identity-kernel golden of the reference (9.9999e-06) through ARD with a huge inverse lengthscale at x = Z
+    zz = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    k3 = S.ARDKernel(number_of_dimensions=3)
+    delta = k3.Parameters.construct(log_scaling=0.0, log_lengthscales=np.full(3, 20.0))
+    fk3 = FixedSparsePosteriorKernel(regulariser_kernel=k3, regulariser_kernel_parameters=delta, base_kernel=k3,
+                                     inducing_points=zz)
+    assert np.allclose(host(fk3.calculate_gram({"base_kernel": delta}, zz, zz, full_covariance=False)), 9.9999e-06,
+                       rtol=1e-5)
+    # ---- SVGP, Cholesky and diagonal parameterisations -----------------------------------------------------------
+    ck = CholeskySVGPKernel(regulariser_kernel=k, regulariser_kernel_parameters=p_r, log_observation_noise=np.log(0.5),
+                            inducing_points=z, training_points=xt)
+    cp = ck.generate_parameters()
+    lower_ref, logd_ref = O.svgp_cholesky_initial_parameters(g_r, z, xt, np.log(0.5))
+    assert rel_norm(host(cp.el_matrix_lower_triangle), lower_ref) <= 1e-9
+    assert np.max(np.abs(host(cp.el_matrix_log_diagonal) - logd_ref)) <= 1e-9
+    lower = lower_ref + 0.01 * np.tril(rng.standard_normal((m, m)), k=-1)
+    logd = logd_ref + 0.1 * rng.standard_normal(m)
+    cp = ck.generate_parameters({"el_matrix_lower_triangle": lower, "el_matrix_log_diagonal": logd})
+    sigma = O.cholesky_sigma(lower, logd)
+    ref_diag = np.diag(O.svgp_gram(g_r, z, sigma, x[:400], x[:400]))
+    got = host(ck.calculate_gram(cp, x, x, full_covariance=False))
+    assert got.shape == (n,) and rel_norm(got[:400], ref_diag) <= TOL
+    assert rel_norm(host(ck.calculate_gram(cp, x[:50], x[:30])), O.svgp_gram(g_r, z, sigma, x[:50], x[:30])) <= TOL
+    dk = DiagonalSVGPKernel(regulariser_kernel=k, regulariser_kernel_parameters=p_r, log_observation_noise=np.log(0.5),
+                            inducing_points=z, training_points=xt)
+    dp = dk.generate_parameters()
+    assert np.max(np.abs(host(dp.log_el_matrix_diagonal) - O.svgp_diagonal_initial_parameters(g_r, z, xt, np.log(0.5)))
+                  ) <= 1e-9
+    dlog = host(dp.log_el_matrix_diagonal) + 0.1 * rng.standard_normal(m)
+    ref_diag = np.diag(O.svgp_gram(g_r, z, np.diag(np.exp(dlog)), x[:400], x[:400]))
+    got = host(dk.calculate_gram({"log_el_matrix_diagonal": dlog}, x, x, full_covariance=False))
+    assert rel_norm(got[:400], ref_diag) <= TOL
+    # reference goldens (identity mock kernel): 0.5000099999 and 0.50001 on the diagonal, via ARD-delta at x = Z
+    xtr = np.array([[1.0, 2.0, 3.0], [5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    ck3 = CholeskySVGPKernel(regulariser_kernel=k3, regulariser_kernel_parameters=delta, log_observation_noise=0.0,
+                             inducing_points=zz, training_points=xtr)
+    lo3, ld3 = ck3.initialise_el_matrix_parameters()
+    assert np.allclose(host(ld3), -0.34657359027997275, rtol=1e-12) and np.all(host(lo3) == 0.0)
+    g3 = host(ck3.calculate_gram({"el_matrix_lower_triangle": np.zeros((2, 2)),
+                                  "el_matrix_log_diagonal": np.array([-0.34657359, -0.34657359])}, zz, zz,
+                                 full_covariance=False))
+    assert np.allclose(g3, 0.5000099999000007, rtol=1e-7)
+    # an approximate GP on top of an SVGP kernel goes through predict_probability unchanged
+    gp = S.ApproximateGPRegression(mean=S.ConstantMean(), kernel=ck)
+    pred = gp.predict_probability({"mean": {"constant": 0.3}, "kernel": cp.dict()}, x)
+    assert np.allclose(host(pred.mean), 0.3) and rel_norm(host(pred.covariance)[:400], np.diag(
+        O.svgp_gram(g_r, z, sigma, x[:400], x[:400]))) <= TOL
+    # the fused single-launch objective accepts these kernels too (q = SVGP GP, p = exact GP posterior)
+    y = np.sin(x[:, 0]) + 0.1 * rng.standard_normal(n)
+    yz = np.sin(z[:, 0])
+    exact = S.GPRegression(mean=S.ConstantMean(), kernel=k, x=z, y=yz)
+    ep = {"log_observation_noise": 0.0, "mean": {"constant": 0.0}, "kernel": p_r}
+    qparams = {"mean": {"constant": 0.3}, "kernel": cp.dict()}
+    gvi = S.GeneralisedVariationalInference(
+        regularisation=S.projected.ProjectedKLRegularisation(gp=gp, regulariser=exact, regulariser_parameters=ep,
+                                                             mode="posterior"),
+        empirical_risk=S.NegativeLogLikelihood(gp=gp))
+    assert gvi._fusable()
+    v_q_full = np.diag(O.svgp_gram(g_r, z, sigma, x[:600], x[:600]))
+    m_p, v_p = O.exact_gp_posterior(g_r, lambda a: O.ard_gram_diag(ls_r, ll_r, a), np.zeros(600), z, yz, 0.0, x[:600])
+    ref = O.gaussian_nll(y[:600], np.full(600, 0.3), v_q_full) + O.projected_regularisation(
+        "kl", m_p, v_p, np.full(600, 0.3), v_q_full)
+    assert abs(float(gvi.calculate_loss(qparams, x[:600], y[:600])) - ref) <= TOL * abs(ref)
+    # ---- tempered kernel (reference tests/gps/test_regression.py:252-372: factor 2 doubles the variance) -----------
+    sp = S.SparsePosteriorKernel(base_kernel=k, inducing_points=z)
+    sp_params = sp.generate_parameters({"base_kernel": p_b})
+    tk = TemperedKernel(base_kernel=sp, base_kernel_parameters=sp_params, number_output_dimensions=1)
+    base_var = host(sp.calculate_gram(sp_params, x, x, full_covariance=False))
+    temp_var = host(tk.calculate_gram({"log_tempering_factor": np.log(2.0)}, x, x, full_covariance=False))
+    assert np.allclose(temp_var, 2.0 * base_var, rtol=1e-15)

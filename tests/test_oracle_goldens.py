@@ -145,3 +145,27 @@ def test_selector_argsort_and_maxrule_agree_on_real_kernel():
     a = O.conditional_variance_select(x, 12, g, d, use_argsort=True)
     b = O.conditional_variance_select(x, 12, g, d, use_argsort=False)
     assert np.array_equal(a, b) and len(set(a.tolist())) == 12
+
+
+def test_svgp_goldens():
+    # tests/kernels/test_svgp_kernels.py:20-160 (initial parameters) and :202-300 (Grams), identity mock kernel
+    x_train = np.array([[1.0, 2.0, 3.0], [5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    z = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    x = np.array([[5.3, 5.0, 6.0], [2.5, 4.5, 2.5]])
+    lower, log_diag = O.svgp_cholesky_initial_parameters(eye_gram, z, x_train, np.log(1.0))
+    assert np.array_equal(log_diag, np.array([-0.34657359027997275, -0.34657359027997275]))
+    assert np.array_equal(lower, np.zeros((2, 2)))
+    assert np.allclose(O.svgp_diagonal_initial_parameters(eye_gram, z, x_train, np.log(1.0)), -0.69314724, rtol=1e-6)
+    sigma = O.cholesky_sigma(np.zeros((2, 2)), np.array([-0.34657359, -0.34657359]))
+    g = O.svgp_gram(eye_gram, z, sigma, x, x)
+    assert np.allclose(g, np.array([[0.5000099999000007, 0.0], [0.0, 0.5000099999000007]]))
+    g = O.svgp_gram(eye_gram, z, np.diag(np.exp([-0.69314724, -0.69314724])), x, x)
+    assert np.allclose(g, np.array([[0.50001, 0.0], [0.0, 0.50001]]))
+
+
+def test_fixed_sparse_posterior_golden():
+    # tests/kernels/test_sparse_posterior_kernels.py:66-114 (fixed variant, identity mock for both kernels)
+    z = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    x = np.array([[5.3, 5.0, 6.0], [2.5, 4.5, 2.5]])
+    r = O.fixed_sparse_posterior_gram(eye_gram, eye_gram, z, x, x, 1e-5, False)
+    np.testing.assert_allclose(r, np.array([[9.9999e-06, 0.0], [0.0, 9.9999e-06]]), atol=1e-10)
