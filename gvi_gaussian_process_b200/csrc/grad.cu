@@ -347,6 +347,30 @@ extern "C" int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* s
   return GVI_OK;
 }
 
+// C = sum_i g_i k_i k_i^T (symmetric, full matrix in w.C), chunk by chunk through the L2-sized K ring
+static int gvi_weighted_gram(const double* Fq, const double* X, const double* g, int64_t N, int M, int D,
+                             const GradWs& w, cudaStream_t st) {
+  const FactorLayout f = factor_layout(M, D);
+  int rc = GVI_OK;
+  // C = sum_i g_i k_i k_i^T, chunk by chunk through the L2-sized K ring
+  const int64_t total_pg = (N + PC - 1) / PC;
+  for (int64_t pg0 = 0; pg0 < total_pg; pg0 += w.chunk_pg) {
+    const int npg = (int)(total_pg - pg0 < w.chunk_pg ? total_pg - pg0 : w.chunk_pg);
+    const int64_t row0 = pg0 * PC;
+    if (D <= 1) rc = launch_kgen<1>(Fq, X, g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 4) rc = launch_kgen<4>(Fq, X, g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 8) rc = launch_kgen<8>(Fq, X, g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else if (D <= 16) rc = launch_kgen<16>(Fq, X, g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    else rc = launch_kgen<32>(Fq, X, g, N, row0, npg, M, f.Mp, D, w.Kc, st);
+    if (rc) return rc;
+    SyrkParams sp{w.Kc, npg, f.Mp, w.nsplit, pg0 == 0 ? 1 : 0, w.Cpart};
+    if ((rc = launch_syrk(sp, w.ntri, st))) return rc;
+  }
+  syrk_reduce_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.Cpart, w.nsplit, f.Mp, w.C);
+  GVI_CHECK_LAUNCH("syrk_reduce_kernel");
+  return GVI_OK;
+}
+
 extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
   if (N < 1 || M < 1 || D < 1) return 0;
   size_t total = 0;
@@ -357,8 +381,9 @@ extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
 extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                                        const double* y, const double* m_q, const double* prior_mean_p,
                                        const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind,
-                                       double renyi_alpha, double* out, double* dm_out, double* var_q_out,
-                                       double* mean_p_out, double* var_p_out, void* workspace, void* stream) {
+                                       double renyi_alpha, int frozen_cholesky, double* out, double* dm_out,
+                                       double* var_q_out, double* mean_p_out, double* var_p_out, void* workspace,
+                                       void* stream) {
   GVI_CHECK_ARG(out && dm_out && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   StepParams P{};
@@ -376,22 +401,8 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
-  // C = sum_i g_i k_i k_i^T, chunk by chunk through the L2-sized K ring
-  const int64_t total_pg = (N + PC - 1) / PC;
-  for (int64_t pg0 = 0; pg0 < total_pg; pg0 += w.chunk_pg) {
-    const int npg = (int)(total_pg - pg0 < w.chunk_pg ? total_pg - pg0 : w.chunk_pg);
-    const int64_t row0 = pg0 * PC;
-    if (D <= 1) rc = launch_kgen<1>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
-    else if (D <= 4) rc = launch_kgen<4>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
-    else if (D <= 8) rc = launch_kgen<8>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
-    else if (D <= 16) rc = launch_kgen<16>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
-    else rc = launch_kgen<32>(Fq, X, w.g, N, row0, npg, M, f.Mp, D, w.Kc, st);
-    if (rc) return rc;
-    SyrkParams sp{w.Kc, npg, f.Mp, w.nsplit, pg0 == 0 ? 1 : 0, w.Cpart};
-    if ((rc = launch_syrk(sp, w.ntri, st))) return rc;
-  }
-  syrk_reduce_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.Cpart, w.nsplit, f.Mp, w.C);
-  GVI_CHECK_LAUNCH("syrk_reduce_kernel");
+  if (frozen_cholesky) return GVI_OK;  // A does not depend on the trained parameters: no <dK_ZZ, S> term
+  if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
   // S = L^-T (L^-1 C L^-T) L^-1  (plain library GEMMs)
   if (!g_cublas) {
     if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
@@ -411,5 +422,61 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   GVI_CHECK_LAUNCH("dkzz_contract_kernel");
   grad_finish_kernel<<<1, 32, 0, st>>>(w.rowpart, M, D, out);
   GVI_CHECK_LAUNCH("grad_finish_kernel");
+  return GVI_OK;
+}
+
+
+// ---- SVGP family: value and gradient w.r.t. the extra matrix E (the kernel hyper-parameters are frozen) -------------
+// v_i = k_ii - ||L^-1 k_i||^2 + ||E k_i||^2  =>  dR/dE = 2 E C (lower triangle), C = sum_i g_i k_i k_i^T.
+// out[0..2] as out3; dm_out[N]; dE_out[M*M] row-major (only the lower triangle is meaningful).  E is the dense matrix
+// that was attached with gvi_gp_factor_set_extra_f64.
+namespace {
+__global__ void tril_scale_kernel(double* __restrict__ A, int M, int64_t ld, double scale) {
+  const int64_t total = (int64_t)M * M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(idx / M), c = (int)(idx % M);
+    A[(int64_t)r * ld + c] = (c <= r) ? scale * A[(int64_t)r * ld + c] : 0.0;
+  }
+}
+}  // namespace
+
+extern "C" int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                                      const double* y, const double* m_q, const double* prior_mean_p,
+                                      const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind,
+                                      double renyi_alpha, const double* E, int64_t lde, double* out3, double* dm_out,
+                                      double* dE_out, void* workspace, void* stream) {
+  GVI_CHECK_ARG(out3 && dm_out && dE_out && E && workspace, "null pointer");
+  GVI_CHECK_ARG(lde >= M, "lde < M");
+  cudaStream_t st = (cudaStream_t)stream;
+  StepParams P{};
+  int rc = gvi_fill_step_params(P, factor_q, factor_p, M, D, X, y, m_q, prior_mean_p, m_p_in, v_p_in, N, reg_kind,
+                                renyi_alpha, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  GradWs w = carve_grad(workspace, N, M, D, nullptr);
+  const FactorLayout f = factor_layout(M, D);
+  const double* Fq = (const double*)factor_q;
+  P.partials = w.partials;
+  P.grad = 1;
+  P.grad_pointwise_only = 1;
+  P.g_out = w.g;
+  P.dm_out = dm_out;
+  P.bscratch = w.bscratch;
+  int grid = gvi_launch_step(P, st);
+  if (grid < 0) return grid;
+  if ((rc = gvi_launch_finish(P.partials, grid, N, 0, D, Fq, out3, st))) return rc;
+  if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
+  if (!g_cublas) {
+    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
+      gvi_set_error("cublasCreate failed");
+      return GVI_ECUDA;
+    }
+  }
+  cublasSetStream(g_cublas, st);
+  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
+  // dE = 2 tril(E C): one plain library GEMM on the M x M blocks
+  if ((rc = gemm_rm(g_cublas, false, false, M, M, M, E, (int)lde, w.C, f.Mp, dE_out, M))) return rc;
+  tril_scale_kernel<<<GVI_NUM_SMS * 2, 256, 0, st>>>(dE_out, M, M, 2.0);
+  GVI_CHECK_LAUNCH("tril_scale_kernel");
   return GVI_OK;
 }

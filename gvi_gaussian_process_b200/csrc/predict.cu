@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ntiles = (P.N + T - 1) / T;
   const FactorLayout f = factor_layout(P.M, P.D);
-  double part_nll = 0.0, part_reg = 0.0, part_gv = 0.0;  // threads < T
+  double part_nll = 0.0, part_reg = 0.0, part_gv = 0.0, part_g = 0.0;  // threads < T
   double part_grad = 0.0;                                  // thread d <= DR: d < DR -> T2_d, d == DR -> sum g |a|^2
   double* bscr = GRAD ? P.bscratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
 
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       const PassDesc& pd = P.pass[ps];
       const double* __restrict__ F = pd.F;
       const double amp2 = F[0];
-      const bool keep_b = GRAD && ps == 0;
+      const bool keep_b = GRAD && ps == 0 && !P.grad_pointwise_only;
       // ---- stage the scaled x tile -------------------------------------------------------------------
       for (int idx = tid; idx < T * DR; idx += THREADS) {
         int i = idx / DR, d = idx % DR;
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
         }
         if (GRAD) {
           part_gv = fma(g_i, vq, part_gv);
+          part_g += g_i;
           P.dm_out[r] = h_i;
           P.g_out[r] = g_i;
         }
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       if (GRAD) gs[tid] = g_i;
     }
     // ---- gradient phase 3: a = L^-T b for q, then sum_i g_i a_ij k_ij (x~_id - z~_jd)^2 and sum_i g_i |a_i|^2 ----
-    if (GRAD) {
+    if (GRAD && !P.grad_pointwise_only) {
       const double* __restrict__ F = P.pass[0].F;
       const double amp2 = F[0];
       double2* Ks2w = reinterpret_cast<double2*>(Ksm);
@@ -405,11 +406,13 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
     double* out = P.partials + (size_t)blockIdx.x * STEP_PARTIAL_STRIDE;
     if (warp == 0) {
       // T <= 24 < 32: threads >= T hold zeros
-      double a = warp_sum(part_nll), b = warp_sum(part_reg), c = warp_sum(part_gv);
+      double a = warp_sum(part_nll), b = warp_sum(part_reg), c = warp_sum(part_gv), d = warp_sum(part_g);
       if (lane == 0) {
         out[0] = a;
         out[1] = b;
         out[2] = c;
+        out[36] = d;
+        out[37] = 0.0;
       }
     }
     if (GRAD) {
@@ -424,7 +427,9 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
 
 // fixed-order final reduction of per-CTA partial sums.
 // out[0..2] = {sum nll, sum reg, N}; gradient mode additionally
-// out[3] = sum_i g_i dv_i/dlog_scaling = 2 sum g v - 2 jitter_abs sum g |a|^2,  out[4+d] = T2_d (point part of d/dlog_ls[d])
+// out[3] = sum_i g_i dv_i/dlog_scaling = 2 sum g v - 2 jitter_abs sum g |a|^2   (A built from the same parameters)
+//                                     = 4 sum g v - 2 k(x,x) sum g                (frozen Cholesky, Fq[5] == 1)
+// out[4+d] = T2_d (point part of d/dlog_ls[d])
 __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __restrict__ partials, int nblocks,
                                                              int64_t N, int grad, int D, const double* __restrict__ Fq,
                                                              double* __restrict__ out) {
@@ -439,7 +444,8 @@ __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __res
     out[0] = tot[0];
     out[1] = tot[1];
     out[2] = (double)N;
-    if (grad) out[3] = 2.0 * tot[2] - 2.0 * Fq[4] * tot[3];
+    if (grad)
+      out[3] = (Fq[5] != 0.0) ? 4.0 * tot[2] - 2.0 * Fq[1] * tot[36] : 2.0 * tot[2] - 2.0 * Fq[4] * tot[3];
   }
   if (grad && tid < D) out[4 + tid] = tot[4 + tid];
 }

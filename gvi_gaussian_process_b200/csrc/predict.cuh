@@ -12,8 +12,8 @@ struct PassDesc {
   int64_t ldk;              //   tensor-pipe Gram kernel chunk by chunk in an L2-sized ring); null = compute in phase 1
 };
 
-// per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d
-constexpr int STEP_PARTIAL_STRIDE = 36;
+// per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d, [36] sum g
+constexpr int STEP_PARTIAL_STRIDE = 38;
 
 struct StepParams {
   PassDesc pass[2];     // [0] = q (approximate GP), [1] = p (regulariser GP)
@@ -34,6 +34,7 @@ struct StepParams {
   double* g_out;        // [N] dR/dv_q
   double* dm_out;       // [N] dR/dm_q
   double* bscratch;     // [gridDim.x][Mp*T] per-CTA b tile (L2 resident)
+  int grad_pointwise_only;  // 1: only g_out / dm_out are needed (SVGP step: no a_i, no phase 3)
   int debug_skip;       // profiling aid (env GVI_DEBUG_SKIP): bit 0 skips phase 1, bit 1 skips phase 2 (results garbage)
   // column panels: the K tile holds Pc columns at a time (Pc == Mp: one panel).  With several panels the accumulators
   // of the groups that extend past the current panel are parked in `acc_scratch` (L2 resident) between sweeps and the

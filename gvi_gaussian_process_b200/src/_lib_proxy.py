@@ -136,7 +136,8 @@ def fused_step(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_
     return out3
 
 
-def fused_step_grad(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_p_in, reg_kind, alpha):
+def fused_step_grad(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_p_in, reg_kind, alpha,
+                    frozen_cholesky: bool = False):
     """Returns (out[4+D] = [sum nll, sum reg, N, d/dlog_scaling, d/dlog_ls[0..D)], dm[N]) in sum form."""
     n, d = x.shape
     out = empty(4 + d)
@@ -145,10 +146,25 @@ def fused_step_grad(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_i
     rc = _L().gvi_fused_step_grad_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
                                       factor_q.m, d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q), _lib.ptr(prior_mean_p),
                                       _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind), float(alpha),
-                                      _lib.ptr(out), _lib.ptr(dm), None, None, None, _lib.ptr(ws),
-                                      _lib.current_stream())
+                                      int(bool(frozen_cholesky)), _lib.ptr(out), _lib.ptr(dm), None, None, None,
+                                      _lib.ptr(ws), _lib.current_stream())
     _lib.check(rc, "gvi_fused_step_grad_f64")
     return out, dm
+
+
+def svgp_step_grad(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_p_in, reg_kind, alpha, e_matrix):
+    """SVGP family: returns (out3 = [sum nll, sum reg, N], dm[N], dE[M,M]) in sum form (kernel parameters frozen)."""
+    n, d = x.shape
+    out3, dm = empty(3), empty(n)
+    d_e = empty(factor_q.m, factor_q.m)
+    ws = _workspace("grad", _L().gvi_fused_step_grad_workspace_bytes(n, factor_q.m, d))
+    rc = _L().gvi_svgp_step_grad_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
+                                     factor_q.m, d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q), _lib.ptr(prior_mean_p),
+                                     _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind), float(alpha),
+                                     _lib.ptr(e_matrix), e_matrix.stride(0), _lib.ptr(out3), _lib.ptr(dm),
+                                     _lib.ptr(d_e), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_svgp_step_grad_f64")
+    return out3, dm, d_e
 
 
 def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):

@@ -16,7 +16,9 @@ from .empirical_risks.base import EmpiricalRiskBase
 from .empirical_risks.negative_log_likelihood import NegativeLogLikelihood
 from .gps.approximate_gp_regression import ApproximateGPRegression
 from .gps.gp_regression import GPRegression
+from .kernels.approximate.fixed_sparse_posterior_kernel import FixedSparsePosteriorKernel
 from .kernels.approximate.sparse_posterior_kernel import SparsePosteriorKernel
+from .kernels.approximate.svgp.svgp_kernels import SVGPBaseKernel
 from .regularisations.base import RegularisationBase
 from .regularisations.schemas import RegularisationMode
 from .utils.device import as_2d, as_device
@@ -105,8 +107,11 @@ class GeneralisedVariationalInference:
         returns (out, dm, m_q) with out = [sum NLL, sum D0, N, d/dlog_scaling, d/dlog_lengthscales[0..D)],
         dm[i] = d(sum loss)/dm_q[i] and m_q the mean-function output (so the host framework can back-propagate
         dm through it).  Multi-GPU: all-reduce `out`, keep dm sharded, divide both by out[2]."""
-        assert self._fusable() and isinstance(self._empirical_risk.gp.kernel, SparsePosteriorKernel), (
-            "gradients are implemented for the fused hot-path configuration (SparsePosteriorKernel over ARD) only")
+        assert self._fusable() and isinstance(self._empirical_risk.gp.kernel,
+                                              (SparsePosteriorKernel, FixedSparsePosteriorKernel)), (
+            "loss_and_grad_sums: SparsePosteriorKernel / FixedSparsePosteriorKernel over ARD (SVGP kernels: "
+            "svgp_loss_and_grad_sums)")
+        frozen = isinstance(self._empirical_risk.gp.kernel, FixedSparsePosteriorKernel)
         er, rg = self._empirical_risk, self._regularisation
         gp = er.gp
         parameters = gp._to_parameters(parameters)
@@ -125,12 +130,41 @@ class GeneralisedVariationalInference:
         f_q = gp.kernel.factorise(parameters.kernel)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
-            out, dm = L.fused_step_grad(f_q, f_p, x, y, m_q_c, prior_mean_p, None, None, kind, rg.alpha)
+            out, dm = L.fused_step_grad(f_q, f_p, x, y, m_q_c, prior_mean_p, None, None, kind, rg.alpha, frozen)
         else:
             m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
             out, dm = L.fused_step_grad(f_q, None, x, y, m_q_c, None, m_p.detach().reshape(-1).contiguous(),
-                                        c_p.detach().reshape(-1).contiguous(), kind, rg.alpha)
+                                        c_p.detach().reshape(-1).contiguous(), kind, rg.alpha, frozen)
         return out, dm, m_q
+
+    def svgp_loss_and_grad_sums(self, parameters, x, y, refactor_regulariser: bool = True):
+        """SVGP kernels (hyper-parameters frozen, Sigma = E^T E trained): shard-local SUM-form
+        (out3 = [sum NLL, sum D0, N], dm[N], m_q, dE[M,M]) with dE = 2 tril(E C)."""
+        assert self._fusable() and isinstance(self._empirical_risk.gp.kernel, SVGPBaseKernel)
+        er, rg = self._empirical_risk, self._regularisation
+        gp = er.gp
+        parameters = gp._to_parameters(parameters)
+        x = as_2d(x)
+        x = x.reshape(x.shape[0], -1)
+        y = as_device(y).reshape(-1)
+        kind = L.REG_KINDS[rg.kind]
+        side = None
+        if rg.mode == RegularisationMode.posterior:
+            reg = rg.regulariser
+            reg_parameters = reg._to_parameters(rg.regulariser_parameters)
+            f_p, prior_mean_p, side = self._factorise_regulariser(reg, reg_parameters, x, refactor_regulariser)
+        m_q = gp.mean.predict(parameters.mean, x)
+        m_q_c = m_q.detach().contiguous()
+        e_matrix = gp.kernel._el_matrix(parameters.kernel).detach().contiguous()
+        f_q = gp.kernel.factorise(parameters.kernel)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            out3, dm, d_e = L.svgp_step_grad(f_q, f_p, x, y, m_q_c, prior_mean_p, None, None, kind, rg.alpha, e_matrix)
+        else:
+            m_p, c_p = rg.regulariser.calculate_prior(rg.regulariser_parameters, x, full_covariance=False)
+            out3, dm, d_e = L.svgp_step_grad(f_q, None, x, y, m_q_c, None, m_p.detach().reshape(-1).contiguous(),
+                                             c_p.detach().reshape(-1).contiguous(), kind, rg.alpha, e_matrix)
+        return out3, dm, m_q, d_e
 
     def calculate_loss_and_gradients(self, parameters, x, y, allreduce=None):
         """loss and d loss / d {kernel.base_kernel.log_scaling, kernel.base_kernel.log_lengthscales, m_q}.
@@ -161,15 +195,22 @@ class GeneralisedVariationalInference:
 
     # ---- torch autograd front end: `gvi.calculate_loss(...).backward()` plays the role of jax.grad ------------------
     def _grad_leaves(self, parameters):
-        """(log_scaling, log_lengthscales) of q's base kernel followed by the tensors of the mean parameters."""
-        parameters = self._empirical_risk.gp._to_parameters(parameters)
-        base = parameters.kernel.base_kernel
-        leaves = [base.log_scaling, base.log_lengthscales]
+        """Trainable kernel leaves - (log_scaling, log_lengthscales) of q's base kernel, or the E parameters of an
+        SVGP kernel - followed by the tensors of the mean parameters."""
+        gp = self._empirical_risk.gp
+        parameters = gp._to_parameters(parameters)
+        if isinstance(gp.kernel, SVGPBaseKernel):
+            leaves = list(gp.kernel.grad_leaves(parameters.kernel))
+        else:
+            base = parameters.kernel.base_kernel
+            leaves = [base.log_scaling, base.log_lengthscales]
+        self._n_kernel_leaves = len(leaves)
         leaves += [t for t in _tensor_leaves(parameters.mean.dict()) if t.requires_grad]
         return leaves
 
     def _wants_grad(self, parameters) -> bool:
-        if not isinstance(self._empirical_risk.gp.kernel, SparsePosteriorKernel):
+        if not isinstance(self._empirical_risk.gp.kernel,
+                          (SparsePosteriorKernel, FixedSparsePosteriorKernel, SVGPBaseKernel)):
             return False
         return any(isinstance(t, torch.Tensor) and t.requires_grad for t in self._grad_leaves(parameters))
 
@@ -196,30 +237,37 @@ class _FusedLoss(torch.autograd.Function):
     through the (host-framework) mean function by torch autograd."""
 
     @staticmethod
-    def forward(ctx, gvi, parameters, x, y, log_scaling, log_lengthscales, *mean_leaves):
+    def forward(ctx, gvi, parameters, x, y, *leaves):
+        gp = gvi._empirical_risk.gp
+        nk = gvi._n_kernel_leaves
+        kernel_leaves, mean_leaves = leaves[:nk], leaves[nk:]
         with torch.enable_grad():
-            out, dm, m_q = gvi.loss_and_grad_sums(parameters, x, y)
-        n = out[2]
-        ctx.shapes = (getattr(log_scaling, "shape", ()), getattr(log_lengthscales, "shape", ()))
-        ctx.is_tensor = (isinstance(log_scaling, torch.Tensor), isinstance(log_lengthscales, torch.Tensor))
+            if isinstance(gp.kernel, SVGPBaseKernel):
+                out, dm, m_q, d_e = gvi.svgp_loss_and_grad_sums(parameters, x, y)
+                n = out[2]
+                raw = gp.kernel.parameter_gradients(gp._to_parameters(parameters).kernel, d_e / n)
+            else:
+                out, dm, m_q = gvi.loss_and_grad_sums(parameters, x, y)
+                n = out[2]
+                d_ll = out[4:] / n
+                ll = kernel_leaves[1]
+                n_ll = ll.numel() if isinstance(ll, torch.Tensor) else 1
+                raw = [out[3] / n, d_ll.sum() if n_ll == 1 else d_ll]  # a scalar lengthscale is broadcast over D
+        kernel_grads = []
+        for leaf, g in zip(kernel_leaves, raw):
+            kernel_grads.append(g.detach().reshape(leaf.shape) if isinstance(leaf, torch.Tensor) else None)
+        ctx.kernel_grads = kernel_grads
         ctx.mean_leaves = mean_leaves
         ctx.m_q = m_q
-        ctx.save_for_backward((out[3] / n).detach(), (out[4:] / n).detach(), (dm / n).detach())
+        ctx.save_for_backward((dm / n).detach())
         return ((out[0] + out[1]) / n).detach()
 
     @staticmethod
     def backward(ctx, grad_out):
-        d_ls, d_ll, d_m = ctx.saved_tensors
-        g_ls = (grad_out * d_ls).reshape(ctx.shapes[0]) if ctx.is_tensor[0] else None
-        if ctx.is_tensor[1]:
-            n_ll = 1
-            for s_ in ctx.shapes[1]:
-                n_ll *= s_
-            g_ll = (grad_out * (d_ll.sum() if n_ll == 1 else d_ll)).reshape(ctx.shapes[1])
-        else:
-            g_ll = None
+        (d_m,) = ctx.saved_tensors
+        kernel_grads = [None if g is None else grad_out * g for g in ctx.kernel_grads]
         mean_grads = [None] * len(ctx.mean_leaves)
         if ctx.mean_leaves and ctx.m_q.requires_grad:
             mean_grads = torch.autograd.grad(ctx.m_q, ctx.mean_leaves, grad_outputs=grad_out * d_m,
                                              allow_unused=True)
-        return (None, None, None, None, g_ls, g_ll, *mean_grads)
+        return (None, None, None, None, *kernel_grads, *mean_grads)

@@ -106,6 +106,14 @@ class CholeskySVGPKernel(SVGPBaseKernel):
         lower = torch.tril(as_device(parameters.el_matrix_lower_triangle), diagonal=-1)
         return lower + torch.diag(torch.exp(as_device(parameters.el_matrix_log_diagonal).reshape(-1)))
 
+    # gradient plumbing: E = tril(P,-1) + diag(exp(d))  =>  dP = tril(dE,-1), dd = diag(dE) exp(d)
+    def grad_leaves(self, parameters):
+        return [parameters.el_matrix_lower_triangle, parameters.el_matrix_log_diagonal]
+
+    def parameter_gradients(self, parameters, d_e):
+        d = as_device(parameters.el_matrix_log_diagonal).reshape(-1)
+        return [torch.tril(d_e, diagonal=-1), torch.diagonal(d_e) * torch.exp(d)]
+
 
 class DiagonalSVGPKernelParameters(KernelBaseParameters):
     """log_el_matrix_diagonal [M]."""
@@ -127,3 +135,11 @@ class DiagonalSVGPKernel(SVGPBaseKernel):
 
     def _el_matrix(self, parameters) -> torch.Tensor:
         return torch.diag(torch.exp(0.5 * as_device(parameters.log_el_matrix_diagonal).reshape(-1)))
+
+    # E = diag(exp(d/2))  =>  dd = diag(dE) * exp(d/2) / 2
+    def grad_leaves(self, parameters):
+        return [parameters.log_el_matrix_diagonal]
+
+    def parameter_gradients(self, parameters, d_e):
+        d = as_device(parameters.log_el_matrix_diagonal).reshape(-1)
+        return [torch.diagonal(d_e) * 0.5 * torch.exp(0.5 * d)]

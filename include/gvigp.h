@@ -130,9 +130,19 @@ int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D,
 size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D);
 int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                             const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
-                            const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, double* out,
-                            double* dm_out, double* var_q_out, double* mean_p_out, double* var_p_out,
+                            const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, int frozen_cholesky,
+                            double* out, double* dm_out, double* var_q_out, double* mean_p_out, double* var_p_out,
                             void* workspace, void* stream);
+/* frozen_cholesky = 1 for a state built with gvi_gp_factor_frozen_f64 (FixedSparsePosteriorKernel): A does not depend
+ * on the trained parameters, so the <dK_ZZ, S> term (and the weighted-Gram pass) is skipped.
+ *
+ * SVGP family (state with an extra matrix E attached, kernel hyper-parameters frozen): value, dR/dm_q[N] and
+ * dR/dE = 2 tril(E C), C = sum_i g_i k_i k_i^T from the same weighted-Gram kernel; dE_out is [M,M] row-major.
+ * Workspace: gvi_fused_step_grad_workspace_bytes.                                                              */
+int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
+                           const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
+                           const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, const double* E,
+                           int64_t lde, double* out3, double* dm_out, double* dE_out, void* workspace, void* stream);
 
 /* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
 int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);

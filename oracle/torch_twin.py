@@ -84,3 +84,20 @@ def gvi_loss_and_grads(x, y, z, m_q, ls_q, ll_q, m_p, v_p, kind, alpha=0.5, reg=
     loss = gaussian_nll(y, mq, v_q) + regulariser(kind, m_p, v_p, mq, v_q, alpha)
     loss.backward()
     return float(loss.detach()), float(ls.grad), ll.grad.numpy().copy(), mq.grad.numpy().copy()
+
+
+def fixed_sparse_posterior_diag(ls_b, ll_b, ls_r, ll_r, z, x, reg=1e-5, is_absolute=False):
+    # fixed_sparse_posterior_kernel.py:41-52, 78-99 (Cholesky from the frozen regulariser kernel)
+    a = add_diagonal_regulariser(ard_gram(ls_r, ll_r, z, z), reg, is_absolute)
+    chol = torch.linalg.cholesky(a)
+    kxz = ard_gram(ls_b, ll_b, x, z)
+    return torch.exp(ls_b) ** 2 - (kxz * torch.cholesky_solve(kxz.T, chol).T).sum(-1)
+
+
+def svgp_diag(ls_r, ll_r, z, x, sigma, reg=1e-5, is_absolute=False):
+    # cholesky_svgp_kernel.py:133-150 / diagonal_svgp_kernel.py:117-129 in diagonal mode
+    a = add_diagonal_regulariser(ard_gram(ls_r, ll_r, z, z), reg, is_absolute)
+    chol = torch.linalg.cholesky(a)
+    kxz = ard_gram(ls_r, ll_r, x, z)
+    return (torch.exp(ls_r) ** 2 - (kxz * torch.cholesky_solve(kxz.T, chol).T).sum(-1)
+            + ((kxz @ sigma) * kxz).sum(-1))
