@@ -32,7 +32,7 @@ __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp
   double2 a_cur[MT], a_nxt[MT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
-#pragma unroll 1
+#pragma unroll 2
   for (int k = 0; k < nkp; k++) {
     const int kn = (k + 1 < nkp) ? k + 1 : k;
 #pragma unroll
