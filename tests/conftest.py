@@ -14,6 +14,9 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def lib():
-    from gvi_gaussian_process_b200 import _lib
+    """The C-ABI library; built on demand (nvcc cross-compiles sm_100a without a GPU) if it is not there yet."""
+    from gvi_gaussian_process_b200 import _lib, build
 
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
     return _lib.load()
