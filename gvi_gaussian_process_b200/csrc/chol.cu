@@ -535,11 +535,26 @@ extern "C" int gvi_gp_factor_frozen_f64(const double* Z, int M, int D, const dou
 
 __global__ void set_flag_kernel(double* F, int idx, double v) { F[idx] = v; }
 
+// host-side record of which factor buffers carry an extra matrix (the launcher must keep their K tile in one panel)
+#include <mutex>
+#include <unordered_set>
+static std::mutex g_extra_mutex;
+static std::unordered_set<const void*> g_extra_factors;
+static void note_extra(const void* factor, bool on) {
+  std::lock_guard<std::mutex> lock(g_extra_mutex);
+  if (on) g_extra_factors.insert(factor); else g_extra_factors.erase(factor);
+}
+bool gvi_factor_has_extra(const void* factor) {
+  std::lock_guard<std::mutex> lock(g_extra_mutex);
+  return g_extra_factors.count(factor) != 0;
+}
+
 extern "C" int gvi_gp_factor_set_extra_f64(void* factor, int M, int D, const double* E, int64_t ld, void* stream) {
   GVI_CHECK_ARG(factor && M >= 1 && D >= 1, "factor");
   cudaStream_t st = (cudaStream_t)stream;
   const FactorLayout f = factor_layout(M, D);
   double* F = (double*)factor;
+  note_extra(factor, E != nullptr);
   if (!E) {
     set_flag_kernel<<<1, 1, 0, st>>>(F, 6, 0.0);
     GVI_CHECK_LAUNCH("set_flag_kernel");
@@ -563,6 +578,7 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   cudaStream_t st = (cudaStream_t)stream;
   const FactorLayout f = factor_layout(M, D);
   double* F = (double*)factor_out;
+  note_extra(factor_out, false);  // a fresh factorisation clears the extra-matrix flag (F[6] = 0 in the header kernel)
   double* A = (double*)workspace;
   double* X = A + (size_t)f.Mp * f.Mp;
   double* tvec = X + (size_t)f.Mp * f.Mp;

@@ -17,8 +17,14 @@
 
 namespace {
 
-constexpr int THREADS = 512;  // 16 warps = 4 per SM sub-partition: enough to hide DMMA / L2 / FP64 latencies
-constexpr int WARPS = THREADS / 32;
+// Two launch shapes:
+//   forward, M <= 2048: 8 warps per CTA, TWO CTAs per SM, each sweeping its K tile in column panels of about half the
+//             shared memory (barriers and tile epilogues of one CTA are covered by the other; +1 % at M=1024, +10 %
+//             at M=512).  NB: DFMA and DMMA share one datapath on B200 (tools/fp64_mix.cu: a half/half mix runs at
+//             the SUM of the two times), so phase 1 (FP64) can never hide under phase 2 (DMMA) - the kernel's floor
+//             is DMMA time + phase-1 FP64 time.
+//   forward, larger M and gradient: 16 warps, one CTA per SM (the gradient keeps the whole b tile in shared memory).
+constexpr int MAX_WARPS = 16;
 constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 
 // One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
@@ -53,9 +59,10 @@ __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp
   }
 }
 
-template <int NT, int DR, bool GRAD>
-__global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P) {
+template <int NT, int DR, bool GRAD, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel(const StepParams P) {
   constexpr int T = 8 * NT;
+  constexpr int THREADS = WARPS * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ksm = reinterpret_cast<double*>(smem_raw);            // [Mp*T] fragment order
   double* xs = Ksm + (size_t)P.Pc * T;                            // [T][DR] scaled x tile
@@ -64,9 +71,9 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
   double* gs = res + 2 * T * 2;                                   // [T] g_i = dR/dv_q,i of the tile
   double* tail = gs + T;
   const bool multi = P.Pc < P.Mp;
-  // [G][T] squared norms per row group: shared memory for a single panel, L2 scratch otherwise
-  double* reds = multi ? P.reds_scratch + (size_t)blockIdx.x * P.G * T : tail;
-  if (!multi) tail += (size_t)P.G * T;
+  // [G][T] squared norms per row group: shared memory when it fits, L2 scratch otherwise
+  double* reds = P.reds_in_smem ? tail : P.reds_scratch + (size_t)blockIdx.x * P.G * T;
+  if (P.reds_in_smem) tail += (size_t)P.G * T;
   double* gpart = tail;                                           // [G][DR+1] per-group gradient partials (GRAD)
   int* counter = reinterpret_cast<int*>(tail + (GRAD ? (size_t)P.G * (DR + 1) : 0));
   double* ascr = multi ? P.acc_scratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
@@ -251,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       };
       if (!(P.debug_skip & 2)) run_groups(F + f.wpack_off, keep_b);
       // SVGP family: a second lower-triangular matrix E adds ||E k||^2 to the variance (same K tile, same loop)
-      if (F[6] != 0.0 && !multi) {
+      if (F[6] != 0.0 && !multi) {  // (launches with an extra matrix are forced to a single panel by the host)
         __syncthreads();
         if (tid < T) {
           double q0 = 0.0;
@@ -268,7 +275,7 @@ __global__ void __launch_bounds__(THREADS, 1) gp_step_kernel(const StepParams P)
       // ---- tile epilogue: variance and mean of this pass --------------------------------------------
       if (tid < T) {
         double q = 0.0, mu = 0.0;
-        if (multi) {
+        if (!P.reds_in_smem) {
           for (int g = 0; g < P.G; g++) q += __ldcg(reds + g * T + tid);
         } else {
           for (int g = 0; g < P.G; g++) q += reds[g * T + tid];
@@ -450,39 +457,46 @@ __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __res
   if (grad && tid < D) out[4 + tid] = tot[4 + tid];
 }
 
-// dynamic shared memory of one CTA: K panel (Pc columns) + x tile + reductions (+ per-group arrays for one panel)
+// dynamic shared memory of one CTA: K panel (Pc columns) + x tile + reductions (+ per-group arrays when they fit)
 template <int NT, int DR>
-size_t step_smem_bytes(int Mp, int Pc, bool grad) {
+size_t step_smem_bytes(int Mp, int Pc, bool grad, int warps, bool reds_in_smem) {
   constexpr int T = 8 * NT;
   const size_t G = Mp / GVI_GROUP_ROWS;
-  size_t doubles = (size_t)Pc * T + T * DR + WARPS * T + 4 * T + T;
-  if (Pc == Mp) doubles += G * T;
+  size_t doubles = (size_t)Pc * T + T * DR + (size_t)warps * T + 4 * T + T;
+  if (reds_in_smem) doubles += G * T;
   if (grad) doubles += G * (DR + 1);
   return doubles * sizeof(double) + 16;
 }
 
-constexpr size_t SMEM_LIMIT = 227 * 1024;
-constexpr int PANEL_COLS = 1024;  // K panel of the multi-panel path: 1024 x 24 doubles = 192 KB
+constexpr size_t SMEM_LIMIT = 227 * 1024;          // one CTA per SM
+constexpr size_t SMEM_LIMIT_2CTA = 113 * 1024;     // two CTAs per SM (228 KB - 2 x 1 KB reserved, halved)
 
-template <int NT, int DR, bool GRAD>
+template <int NT, int DR, bool GRAD, int WARPS>
 int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
   constexpr int T = 8 * NT;
-  size_t smem = step_smem_bytes<NT, DR>(P.Mp, P.Pc, GRAD);
+  size_t smem = step_smem_bytes<NT, DR>(P.Mp, P.Pc, GRAD, WARPS, P.reds_in_smem != 0);
   static bool configured = false;  // per instantiation
   if (!configured) {
-    GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)SMEM_LIMIT));
+    GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(WARPS == 8 ? SMEM_LIMIT_2CTA : SMEM_LIMIT)));
+    if (WARPS == 8)
+      GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD, WARPS>,
+                                    cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     configured = true;
   }
   int64_t ntiles = (P.N + T - 1) / T;
   int grid = (int)(ntiles < grid_cap ? ntiles : grid_cap);
-  gp_step_kernel<NT, DR, GRAD><<<grid, THREADS, smem, st>>>(P);
+  gp_step_kernel<NT, DR, GRAD, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
   GVI_CHECK_LAUNCH("gp_step_kernel");
   return grid;
 }
 template <int NT, int DR>
 int launch_step_inst(const StepParams& P, int grid_cap, cudaStream_t st) {
-  return P.grad ? launch_step_inst2<NT, DR, true>(P, grid_cap, st) : launch_step_inst2<NT, DR, false>(P, grid_cap, st);
+  if (P.grad) return launch_step_inst2<NT, DR, true, 16>(P, grid_cap, st);
+  if constexpr (NT == 3) {
+    if (P.two_cta) return launch_step_inst2<NT, DR, false, 8>(P, grid_cap, st);
+  }
+  return launch_step_inst2<NT, DR, false, 16>(P, grid_cap, st);
 }
 
 template <int NT>
@@ -495,31 +509,69 @@ int launch_step_nt(const StepParams& P, int grid_cap, cudaStream_t st) {
 }
 }  // namespace
 
-// whole-tile (single panel) variants: T = 24, 16 or 8 points per tile; 0 if not even T = 8 fits
+// whole-tile (single panel, one CTA per SM) variants: T = 24, 16 or 8 points per tile; 0 if not even T = 8 fits
 template <int NT>
-static size_t step_smem_bytes_d(int Mp, int D, bool grad) {
-  if (D <= 1) return step_smem_bytes<NT, 1>(Mp, Mp, grad);
-  if (D <= 4) return step_smem_bytes<NT, 4>(Mp, Mp, grad);
-  if (D <= 8) return step_smem_bytes<NT, 8>(Mp, Mp, grad);
-  if (D <= 16) return step_smem_bytes<NT, 16>(Mp, Mp, grad);
-  return step_smem_bytes<NT, 32>(Mp, Mp, grad);
+static size_t step_smem_bytes_d(int Mp, int Pc, int D, bool grad, int warps, bool reds_in_smem) {
+  if (D <= 1) return step_smem_bytes<NT, 1>(Mp, Pc, grad, warps, reds_in_smem);
+  if (D <= 4) return step_smem_bytes<NT, 4>(Mp, Pc, grad, warps, reds_in_smem);
+  if (D <= 8) return step_smem_bytes<NT, 8>(Mp, Pc, grad, warps, reds_in_smem);
+  if (D <= 16) return step_smem_bytes<NT, 16>(Mp, Pc, grad, warps, reds_in_smem);
+  return step_smem_bytes<NT, 32>(Mp, Pc, grad, warps, reds_in_smem);
 }
 int gvi_step_tile_points(int Mp, int D, bool grad) {
-  if (step_smem_bytes_d<3>(Mp, D, grad) <= SMEM_LIMIT) return 24;
-  if (step_smem_bytes_d<2>(Mp, D, grad) <= SMEM_LIMIT) return 16;
-  if (step_smem_bytes_d<1>(Mp, D, grad) <= SMEM_LIMIT) return 8;
+  if (step_smem_bytes_d<3>(Mp, Mp, D, grad, 16, true) <= SMEM_LIMIT) return 24;
+  if (step_smem_bytes_d<2>(Mp, Mp, D, grad, 16, true) <= SMEM_LIMIT) return 16;
+  if (step_smem_bytes_d<1>(Mp, Mp, D, grad, 16, true) <= SMEM_LIMIT) return 8;
   return 0;
 }
-int gvi_step_panel_cols(int Mp) { return gvi_step_tile_points(Mp, 32, false) == 24 ? Mp : PANEL_COLS; }
+// scratch (doubles) for launches that sweep the K tile in panels: parked accumulators + per-group norms, per CTA
 size_t gvi_step_scratch_doubles(int Mp) {
-  if (gvi_step_panel_cols(Mp) == Mp) return 0;
-  return (size_t)GVI_NUM_SMS * ((size_t)Mp * 24 + (size_t)(Mp / GVI_GROUP_ROWS) * 24);
+  return (size_t)2 * GVI_NUM_SMS * ((size_t)Mp * 24 + (size_t)(Mp / GVI_GROUP_ROWS) * 24);
 }
+
+// forward launches: pick the panel width and the launch shape.  Returns false if nothing fits.
+static bool plan_forward(StepParams& P, bool allow_two_cta) {
+  const int D = P.pass[0].Kpre ? 1 : P.D;
+  if (allow_two_cta) {
+    // two CTAs per SM: the widest panel (multiple of 64 columns) that leaves room for two CTAs
+    for (int reds_smem = 1; reds_smem >= 0; reds_smem--) {
+      int pc = P.Mp;  // whole tile if it fits, else the widest multiple of 64 columns
+      if (step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) > SMEM_LIMIT_2CTA) {
+        pc = P.Mp / 64 * 64;
+        while (pc > 64 && step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) > SMEM_LIMIT_2CTA) pc -= 64;
+      }
+      if (step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) <= SMEM_LIMIT_2CTA && (pc == P.Mp || pc >= 256)) {
+        P.two_cta = 1;
+        P.Pc = pc;
+        P.reds_in_smem = reds_smem;
+        return true;
+      }
+    }
+  }
+  P.two_cta = 0;
+  for (int reds_smem = 1; reds_smem >= 0; reds_smem--) {
+    if (step_smem_bytes_d<3>(P.Mp, P.Mp, D, false, 16, reds_smem) <= SMEM_LIMIT) {
+      P.Pc = P.Mp;
+      P.reds_in_smem = reds_smem;
+      return true;
+    }
+    if (P.Mp > 1024 && step_smem_bytes_d<3>(P.Mp, 1024, D, false, 16, reds_smem) <= SMEM_LIMIT) {
+      P.Pc = 1024;
+      P.reds_in_smem = reds_smem;
+      return true;
+    }
+  }
+  return false;
+}
+
+bool gvi_factor_has_extra(const void* factor);
 
 // returns grid size (>0) or a negative error code
 int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   StepParams P = P_in;
+  P.has_extra = gvi_factor_has_extra(P.pass[0].F) ? 1 : 0;
   static const int debug_skip = getenv("GVI_DEBUG_SKIP") ? atoi(getenv("GVI_DEBUG_SKIP")) : 0;
+  static const int one_cta = getenv("GVI_ONE_CTA") ? atoi(getenv("GVI_ONE_CTA")) : 0;
   P.debug_skip = debug_skip;
   const bool pre = P.pass[0].Kpre != nullptr;
   if (P.D > 32 && !pre) {
@@ -527,25 +579,28 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
                   P.D);
     return GVI_EUNSUPPORTED;
   }
-  const int grid_cap = GVI_NUM_SMS;
   if (!P.grad) {
-    // forward: always 24-point tiles; K tile in column panels of 1024 when M is large
-    P.Pc = gvi_step_panel_cols(P.Mp);
-    if (P.Pc < P.Mp) {
-      if (!P.acc_scratch) {
-        gvi_set_error("M=%d needs the multi-panel scratch (pass a workspace of gvi_gp_predict_workspace_bytes)", P.M);
-        return GVI_EINVAL;
-      }
-      P.reds_scratch = P.acc_scratch + (size_t)GVI_NUM_SMS * P.Mp * 24;
+    // the SVGP second product needs the whole K tile (single panel); everything else may use two CTAs per SM
+    const bool allow_two = !one_cta && !P.has_extra && P.acc_scratch != nullptr && P.Mp <= 2048;
+    if (!plan_forward(P, allow_two) || (P.has_extra && P.Pc < P.Mp)) {
+      gvi_set_error("no launch shape fits M=%d (extra matrix: %d)", P.M, P.has_extra);
+      return GVI_EUNSUPPORTED;
     }
-    return launch_step_nt<3>(P, grid_cap, st);
+    if ((P.Pc < P.Mp || !P.reds_in_smem) && !P.acc_scratch) {
+      gvi_set_error("M=%d needs the panel scratch (pass a workspace of gvi_gp_predict_workspace_bytes)", P.M);
+      return GVI_EINVAL;
+    }
+    if (P.acc_scratch) P.reds_scratch = P.acc_scratch + (size_t)2 * GVI_NUM_SMS * P.Mp * 24;
+    return launch_step_nt<3>(P, P.two_cta ? 2 * GVI_NUM_SMS : GVI_NUM_SMS, st);
   }
   // gradient mode keeps the whole b tile in shared memory
   P.Pc = P.Mp;
+  P.two_cta = 0;
+  P.reds_in_smem = 1;
   switch (gvi_step_tile_points(P.Mp, P.D, true)) {
-    case 24: return launch_step_nt<3>(P, grid_cap, st);
-    case 16: return launch_step_nt<2>(P, grid_cap, st);
-    case 8: return launch_step_nt<1>(P, grid_cap, st);
+    case 24: return launch_step_nt<3>(P, GVI_NUM_SMS, st);
+    case 16: return launch_step_nt<2>(P, GVI_NUM_SMS, st);
+    case 8: return launch_step_nt<1>(P, GVI_NUM_SMS, st);
     default:
       gvi_set_error("the gradient step supports M <= 3456 in this build (got M=%d)", P.M);
       return GVI_EUNSUPPORTED;
@@ -628,7 +683,7 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
 extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N, int M) {
   (void)N;
   const int Mp = (M + 31) / 32 * 32;
-  return ((size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE + gvi_step_scratch_doubles(Mp)) * sizeof(double);
+  return ((size_t)2 * GVI_NUM_SMS * STEP_PARTIAL_STRIDE + gvi_step_scratch_doubles(Mp)) * sizeof(double);
 }
 
 int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
@@ -666,7 +721,7 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
                                 renyi_alpha, var_q_out, mean_p_out, var_p_out);
   if (rc) return rc;
   P.partials = (double*)workspace;
-  P.acc_scratch = P.partials + (size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE;
+  P.acc_scratch = P.partials + (size_t)2 * GVI_NUM_SMS * STEP_PARTIAL_STRIDE;
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   return gvi_launch_finish(P.partials, grid, N, 0, D, (const double*)factor_q, out3, st);

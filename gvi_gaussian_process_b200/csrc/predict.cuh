@@ -41,13 +41,15 @@ struct StepParams {
   // per-group squared norms go to `reds_scratch` instead of shared memory.
   int Pc;
   double* acc_scratch;  // [gridDim.x][Mp*T]  (multi-panel only)
-  double* reds_scratch; // [gridDim.x][G*T]   (multi-panel only)
+  double* reds_scratch; // [gridDim.x][G*T]   (when the per-group norms do not fit in shared memory)
+  int reds_in_smem;     // set by the launcher
+  int two_cta;          // set by the launcher: 8-warp CTAs, two per SM
+  int has_extra;        // the q factor carries an extra matrix E (SVGP): single panel required
 };
 
 int gvi_step_tile_points(int Mp, int D, bool grad);
 // forward-only launches use column panels when the whole K tile does not fit: returns Pc (== Mp: single panel)
-int gvi_step_panel_cols(int Mp);
-size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the multi-panel path (0 for a single panel)
+size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the panel path
 int gvi_launch_step(const StepParams& P, cudaStream_t st);
 int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
                       cudaStream_t st);
