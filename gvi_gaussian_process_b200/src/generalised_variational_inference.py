@@ -68,7 +68,7 @@ class GeneralisedVariationalInference:
         gp = er.gp
         if gp is not rg.gp or not isinstance(gp, ApproximateGPRegression):
             return False
-        if not hasattr(gp.kernel, "factorise") or rg.kind == "none":
+        if getattr(gp.kernel, "factorise", None) is None or rg.kind == "none":
             return False  # SparsePosteriorKernel, FixedSparsePosteriorKernel and the SVGP kernels provide factorise()
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser

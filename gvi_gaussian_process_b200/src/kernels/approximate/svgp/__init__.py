@@ -3,5 +3,7 @@ from .svgp_kernels import (  # noqa: F401
     CholeskySVGPKernelParameters,
     DiagonalSVGPKernel,
     DiagonalSVGPKernelParameters,
+    KernelisedSVGPKernel,
+    KernelisedSVGPKernelParameters,
     SVGPBaseKernel,
 )

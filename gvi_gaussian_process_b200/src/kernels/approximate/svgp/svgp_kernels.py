@@ -143,3 +143,48 @@ class DiagonalSVGPKernel(SVGPBaseKernel):
     def parameter_gradients(self, parameters, d_e):
         d = as_device(parameters.log_el_matrix_diagonal).reshape(-1)
         return [torch.diagonal(d_e) * 0.5 * torch.exp(0.5 * d)]
+
+
+class KernelisedSVGPKernelParameters(KernelBaseParameters):
+    """base_kernel: parameters of the (trainable) base kernel."""
+
+
+class KernelisedSVGPKernel(SVGPBaseKernel):
+    """reference: src/kernels/approximate/svgp/kernelised_svgp_kernel.py:20-99 -
+    r = k_reg - k_reg(x,Z) (K_ZZ + jitter)^-1 k_reg(Z,x') + k_base(x,x'): the frozen sparse-posterior part comes from
+    the cached factorisation, the trainable base kernel is added on top."""
+
+    Parameters = KernelisedSVGPKernelParameters
+
+    def __init__(self, base_kernel: KernelBase, regulariser_kernel: KernelBase, regulariser_kernel_parameters,
+                 log_observation_noise, inducing_points, training_points, diagonal_regularisation: float = 1e-5,
+                 is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
+        self.base_kernel = base_kernel
+        super().__init__(regulariser_kernel=regulariser_kernel,
+                         regulariser_kernel_parameters=regulariser_kernel_parameters,
+                         log_observation_noise=log_observation_noise, inducing_points=inducing_points,
+                         training_points=training_points, diagonal_regularisation=diagonal_regularisation,
+                         is_diagonal_regularisation_absolute_scale=is_diagonal_regularisation_absolute_scale,
+                         preprocess_function=preprocess_function)
+
+    def generate_parameters(self, parameters) -> KernelisedSVGPKernelParameters:
+        return KernelisedSVGPKernelParameters(base_kernel=self.base_kernel._to_parameters(parameters["base_kernel"]))
+
+    # no extra matrix: the objective goes through the predict + risk kernels (not the single-launch fused step)
+    factorise = None
+
+    def _calculate_gram_diagonal(self, parameters, x):
+        f = self._frozen_factor()
+        f.set_extra(None)
+        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        return var + self.base_kernel.calculate_gram(parameters.base_kernel, x, x, full_covariance=False)
+
+    def _calculate_gram(self, parameters, x1, x2):
+        f = self._frozen_factor()
+        linv = f.inverse_cholesky()
+        k = self.regulariser_kernel
+        kp = self.regulariser_kernel_parameters
+        k1z = k.calculate_gram(kp, x1, self.inducing_points)
+        k2z = k.calculate_gram(kp, x2, self.inducing_points)
+        return (k.calculate_gram(kp, x1, x2) - (k1z @ linv.T) @ (k2z @ linv.T).T
+                + self.base_kernel.calculate_gram(parameters.base_kernel, x1, x2))

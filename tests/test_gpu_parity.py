@@ -854,6 +854,15 @@ def test_fixed_sparse_svgp_and_tempered_kernels(S):
     pred = gp.predict_probability({"mean": {"constant": 0.3}, "kernel": cp.dict()}, x)
     assert np.allclose(host(pred.mean), 0.3) and rel_norm(host(pred.covariance)[:400], np.diag(
         O.svgp_gram(g_r, z, sigma, x[:400], x[:400]))) <= TOL
+    # kernelised SVGP: frozen sparse-posterior part + trainable base kernel (kernelised_svgp_kernel.py:87-99)
+    from gvi_gaussian_process_b200.src.kernels.approximate import KernelisedSVGPKernel
+    kk = KernelisedSVGPKernel(base_kernel=k, regulariser_kernel=k, regulariser_kernel_parameters=p_r,
+                              log_observation_noise=np.log(0.5), inducing_points=z, training_points=xt)
+    kparams = kk.generate_parameters({"base_kernel": p_b})
+    ref_k = O.svgp_gram(g_r, z, np.zeros((m, m)), x[:300], x[:200]) + g_b(x[:300], x[:200])
+    assert rel_norm(host(kk.calculate_gram(kparams, x[:300], x[:200])), ref_k) <= TOL
+    ref_kd = np.diag(O.svgp_gram(g_r, z, np.zeros((m, m)), x[:300], x[:300])) + O.ard_gram_diag(ls_b, ll_b, x[:300])
+    assert rel_norm(host(kk.calculate_gram(kparams, x, x, full_covariance=False))[:300], ref_kd) <= TOL
     # the fused single-launch objective accepts these kernels too (q = SVGP GP, p = exact GP posterior)
     y = np.sin(x[:, 0]) + 0.1 * rng.standard_normal(n)
     yz = np.sin(z[:, 0])
