@@ -18,7 +18,7 @@
 namespace {
 
 // Two launch shapes:
-//   forward, M <= 2048: 8 warps per CTA, TWO CTAs per SM, each sweeping its K tile in column panels of about half the
+//   forward, M <= 1024: 8 warps per CTA, TWO CTAs per SM, each sweeping its K tile in column panels of about half the
 //             shared memory (barriers and tile epilogues of one CTA are covered by the other; +1 % at M=1024, +10 %
 //             at M=512).  NB: DFMA and DMMA share one datapath on B200 (tools/fp64_mix.cu: a half/half mix runs at
 //             the SUM of the two times), so phase 1 (FP64) can never hide under phase 2 (DMMA) - the kernel's floor
@@ -32,30 +32,60 @@ constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 // A fragments come from L2 as one LDG.128 per lane per (kp, mt) (two k-steps), prefetched one kp ahead.
 // `Ag` points at the first k-pair to process, `kp0` is the index of that k-pair inside the shared-memory tile;
 // the caller initialises acc (zero, or a parked partial sum in the multi-panel path).
-template <int NT>
+// PREFETCH_B: also fetch the B fragments (shared memory) one k-pair ahead - pays in the 16-warp one-CTA shape
+// (M=2048: 67.1 -> 65.5 ms, M=4096: 108 -> 101 ms), costs in the 8-warp two-CTA shape (71.6 -> 72.9 ms at M=1024).
+template <int NT, bool PREFETCH_B>
 __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
                                           const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2]) {
-  double2 a_cur[MT], a_nxt[MT];
+  if constexpr (!PREFETCH_B) {
+    double2 a_cur[MT], a_nxt[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
+#pragma unroll 2
+    for (int k = 0; k < nkp; k++) {
+      const int kn = (k + 1 < nkp) ? k + 1 : k;
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) a_nxt[mt] = __ldcg(Ag + (kn * MT + mt) * 32);
+      double2 b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b[nt].y);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) a_cur[mt] = a_nxt[mt];
+    }
+    return;
+  }
+  double2 a_cur[MT], a_nxt[MT], b_cur[NT], b_nxt[NT];
 #pragma unroll
   for (int mt = 0; mt < MT; mt++) a_cur[mt] = __ldcg(Ag + mt * 32);
+#pragma unroll
+  for (int nt = 0; nt < NT; nt++) b_cur[nt] = Ks2[(kp0 * NT + nt) * 32 + lane];
 #pragma unroll 2
   for (int k = 0; k < nkp; k++) {
     const int kn = (k + 1 < nkp) ? k + 1 : k;
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) a_nxt[mt] = __ldcg(Ag + (kn * MT + mt) * 32);
-    double2 b[NT];
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
-#pragma unroll
-    for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b[nt].x);
+    for (int nt = 0; nt < NT; nt++) b_nxt[nt] = Ks2[((kp0 + kn) * NT + nt) * 32 + lane];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b[nt].y);
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].x, b_cur[nt].x);
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a_cur[mt].y, b_cur[nt].y);
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) a_cur[mt] = a_nxt[mt];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) b_cur[nt] = b_nxt[nt];
   }
 }
 
@@ -213,7 +243,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
 #pragma unroll
                 for (int e = 0; e < 2; e++) acc[mt][nt][e] = __ldcg(src + ((mt * NT + nt) * 2 + e) * 32);
           }
-          group_mma<NT>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + (size_t)kp_lo * MT * 32 + lane, 0,
+          group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + (size_t)kp_lo * MT * 32 + lane, 0,
                         kp_end - kp_lo, Ks2, lane, acc);
           if (kp_end < nkp_g) {  // the group continues in the next panel
             double* dst = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
@@ -361,7 +391,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
 #pragma unroll
           for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
         const int kp0 = GVI_GROUP_ROWS * g / 8;
-        group_mma<NT>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
+        group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
                       Ks2, lane, acc);
         double t2[DR], na2 = 0.0;
 #pragma unroll
@@ -581,7 +611,7 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   }
   if (!P.grad) {
     // the SVGP second product needs the whole K tile (single panel); everything else may use two CTAs per SM
-    const bool allow_two = !one_cta && !P.has_extra && P.acc_scratch != nullptr && P.Mp <= 2048;
+    const bool allow_two = !one_cta && !P.has_extra && P.acc_scratch != nullptr && P.Mp <= 1024;
     if (!plan_forward(P, allow_two) || (P.has_extra && P.Pc < P.Mp)) {
       gvi_set_error("no launch shape fits M=%d (extra matrix: %d)", P.M, P.has_extra);
       return GVI_EUNSUPPORTED;
