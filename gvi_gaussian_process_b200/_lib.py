@@ -38,6 +38,8 @@ SIGNATURES = {
     "gvi_risk_workspace_bytes": (c_size_t, [c_int64]),
     "gvi_risk_f64": (c_int, [c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                              c_void_p, c_void_p]),
+    "gvi_risk_grad_f64": (c_int, [c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "gvi_fused_step_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "gvi_fused_step_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p,
@@ -49,6 +51,17 @@ SIGNATURES = {
     "gvi_svgp_step_grad_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_int64, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_gp_predict_grad_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p,
+                                        c_void_p, c_void_p]),
+    "gvi_class_probabilities_f64": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_double,
+                                            c_double, c_void_p, c_void_p]),
+    "gvi_class_probabilities_grad_f64": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int,
+                                                 c_double, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_multinomial_risk_workspace_bytes": (c_size_t, [c_int64]),
+    "gvi_multinomial_risk_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p,
+                                         c_void_p]),
+    "gvi_multinomial_risk_grad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p,
+                                              c_void_p]),
     "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_cond_var_select_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double,

@@ -371,6 +371,31 @@ static int gvi_weighted_gram(const double* Fq, const double* X, const double* g,
   return GVI_OK;
 }
 
+// S = L^-T (L^-1 C L^-T) L^-1 (plain library GEMMs), then out[4+d] += <dK_ZZ/dlog_ls[d], S>
+static int gvi_finish_kzz_term(const double* Fq, const FactorLayout& f, int M, int D, const GradWs& w, double* out,
+                               cudaStream_t st) {
+  int rc;
+  if (!g_cublas) {
+    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
+      gvi_set_error("cublasCreate failed");
+      return GVI_ECUDA;
+    }
+  }
+  cublasSetStream(g_cublas, st);
+  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
+  const double* Linv = Fq + f.linv_off;
+  const int n = f.Mp;
+  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, Linv, n, w.C, n, w.T1, n))) return rc;   // T1 = Linv C
+  if ((rc = gemm_rm(g_cublas, false, true, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;   // T2 = T1 Linv^T
+  if ((rc = gemm_rm(g_cublas, true, false, n, n, n, Linv, n, w.T2, n, w.T1, n))) return rc;   // T1 = Linv^T T2
+  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;  // S = T1 Linv
+  dkzz_contract_kernel<<<M, 256, 0, st>>>(w.T2, Fq, M, f.Mp, D, w.rowpart);
+  GVI_CHECK_LAUNCH("dkzz_contract_kernel");
+  grad_finish_kernel<<<1, 32, 0, st>>>(w.rowpart, M, D, out);
+  GVI_CHECK_LAUNCH("grad_finish_kernel");
+  return GVI_OK;
+}
+
 extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
   if (N < 1 || M < 1 || D < 1) return 0;
   size_t total = 0;
@@ -403,28 +428,44 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
   if (frozen_cholesky) return GVI_OK;  // A does not depend on the trained parameters: no <dK_ZZ, S> term
   if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
-  // S = L^-T (L^-1 C L^-T) L^-1  (plain library GEMMs)
-  if (!g_cublas) {
-    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
-      gvi_set_error("cublasCreate failed");
-      return GVI_ECUDA;
-    }
-  }
-  cublasSetStream(g_cublas, st);
-  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
-  const double* Linv = Fq + f.linv_off;
-  const int n = f.Mp;
-  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, Linv, n, w.C, n, w.T1, n))) return rc;   // T1 = Linv C
-  if ((rc = gemm_rm(g_cublas, false, true, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;   // T2 = T1 Linv^T
-  if ((rc = gemm_rm(g_cublas, true, false, n, n, n, Linv, n, w.T2, n, w.T1, n))) return rc;   // T1 = Linv^T T2
-  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;  // S = T1 Linv
-  dkzz_contract_kernel<<<M, 256, 0, st>>>(w.T2, Fq, M, f.Mp, D, w.rowpart);
-  GVI_CHECK_LAUNCH("dkzz_contract_kernel");
-  grad_finish_kernel<<<1, 32, 0, st>>>(w.rowpart, M, D, out);
-  GVI_CHECK_LAUNCH("grad_finish_kernel");
-  return GVI_OK;
+  return gvi_finish_kzz_term(Fq, f, M, D, w, out, st);
 }
 
+
+// ---- vector-Jacobian product of the predictive variance (gvi_gp_predict_f64) w.r.t. the kernel hyper-parameters ----
+// Given g_i = dLoss/dvar_i for an arbitrary downstream loss (e.g. the classification epilogue of classify.cu, or any
+// host-framework graph), returns out[3] = dLoss/dlog_scaling and out[4+d] = dLoss/dlog_lengthscales[d]; out[0] =
+// out[1] = 0 and out[2] = N so the vector has the layout of gvi_fused_step_grad_f64.  Same kernels as the fused
+// gradient step: the tile kernel in gradient mode (a_i = L^-T L^-1 k_i), the weighted Gram C = sum_i g_i k_i k_i^T,
+// S = A^-1 C A^-1 and <dK_ZZ/dtheta, S>.
+extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N,
+                                       const double* g_var, int frozen_cholesky, double* out, void* workspace,
+                                       void* stream) {
+  GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 1, "sizes");
+  GVI_CHECK_ARG(factor && X && g_var && out && workspace, "null pointer");
+  GVI_CHECK_ARG(D <= 32, "the variance VJP supports D <= 32 in this build");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FactorLayout f = factor_layout(M, D);
+  const double* Fq = (const double*)factor;
+  GradWs w = carve_grad(workspace, N, M, D, nullptr);
+  StepParams P{};
+  P.pass[0] = PassDesc{Fq, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  P.npass = 1;
+  P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;
+  P.X = X; P.N = N;
+  P.reg_kind = GVI_REG_NONE;
+  P.partials = w.partials;
+  P.grad = 1;
+  P.g_in = g_var;
+  P.bscratch = w.bscratch;
+  int grid = gvi_launch_step(P, st);
+  if (grid < 0) return grid;
+  int rc;
+  if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
+  if (frozen_cholesky) return GVI_OK;
+  if ((rc = gvi_weighted_gram(Fq, X, g_var, N, M, D, w, st))) return rc;
+  return gvi_finish_kzz_term(Fq, f, M, D, w, out, st);
+}
 
 // ---- SVGP family: value and gradient w.r.t. the extra matrix E (the kernel hyper-parameters are frozen) -------------
 // v_i = k_ii - ||L^-1 k_i||^2 + ||E k_i||^2  =>  dR/dE = 2 E C (lower triangle), C = sum_i g_i k_i k_i^T.

@@ -329,7 +329,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
     if (P.partials && tid < T) {
       const int64_t r = row0 + tid;
       double g_i = 0.0;
-      if (r < P.N) {
+      if (GRAD && P.g_in) {
+        // vector-Jacobian product of the predictive variance: the caller supplies g_i = dLoss/dvar_i
+        if (r < P.N) {
+          g_i = P.g_in[r];
+          part_gv = fma(g_i, res[(0 * T + tid) * 2 + 1], part_gv);
+          part_g += g_i;
+        }
+      } else if (r < P.N) {
         const double vq = res[(0 * T + tid) * 2 + 1];
         const double mq = P.m_q ? P.m_q[r] : res[(0 * T + tid) * 2 + 0];
         double h_i = 0.0;

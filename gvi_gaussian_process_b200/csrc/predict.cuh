@@ -32,6 +32,7 @@ struct StepParams {
   // gradient mode
   int grad;
   double* g_out;        // [N] dR/dv_q
+  const double* g_in;   // [N] or null: externally supplied dLoss/dvar (gvi_gp_predict_grad_f64); the risk epilogue is skipped
   double* dm_out;       // [N] dR/dm_q
   double* bscratch;     // [gridDim.x][Mp*T] per-CTA b tile (L2 resident)
   int grad_pointwise_only;  // 1: only g_out / dm_out are needed (SVGP step: no a_i, no phase 3)

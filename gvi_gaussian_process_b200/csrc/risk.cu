@@ -111,6 +111,54 @@ extern "C" int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, c
   return GVI_OK;
 }
 
+// ---- pointwise derivatives of the sums above (what jax.grad propagates into the predictive mean / variance) -----
+// dm_out[i] = w[0] dNLL_i/dm_q + w[1] dD0_i/dm_q,  dv_out[i] likewise for v_q (p is constant); w is a device array so
+// the cotangents of the two sums never visit the host.
+namespace {
+__global__ void __launch_bounds__(RTHREADS) risk_grad_kernel(int kind, double alpha, const double* __restrict__ y,
+                                                             const double* __restrict__ mq,
+                                                             const double* __restrict__ vq,
+                                                             const double* __restrict__ mp,
+                                                             const double* __restrict__ vp, int64_t N,
+                                                             const double* __restrict__ w2,
+                                                             double* __restrict__ dm_out,
+                                                             double* __restrict__ dv_out) {
+  const double w_nll = w2[0], w_reg = w2[1];
+  for (int64_t i = (int64_t)blockIdx.x * RTHREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * RTHREADS) {
+    double dm = 0.0, dv = 0.0;
+    if (y) {
+      double a, b;
+      gvi_nll_grad(y[i], mq[i], vq[i], a, b);
+      dm = w_nll * a;
+      dv = w_nll * b;
+    }
+    if (kind != GVI_REG_NONE) {
+      double a, b;
+      gvi_reg_grad(kind, alpha, mp[i], vp[i], mq[i], vq[i], a, b);
+      dm = fma(w_reg, a, dm);
+      dv = fma(w_reg, b, dv);
+    }
+    dm_out[i] = dm;
+    dv_out[i] = dv;
+  }
+}
+}  // namespace
+
+extern "C" int gvi_risk_grad_f64(int reg_kind, double renyi_alpha, const double* y, const double* m_q,
+                                 const double* v_q, const double* m_p, const double* v_p, int64_t N,
+                                 const double* weights2, double* dm_out, double* dv_out, void* stream) {
+  GVI_CHECK_ARG(N >= 1, "N");
+  GVI_CHECK_ARG(m_q && v_q && dm_out && dv_out && weights2, "null pointer");
+  GVI_CHECK_ARG(reg_kind >= GVI_REG_NONE && reg_kind <= GVI_REG_SQUARED_DIFFERENCE, "reg_kind");
+  GVI_CHECK_ARG(reg_kind == GVI_REG_NONE || (m_p && v_p), "regulariser needs m_p and v_p");
+  int64_t want = (N + RTHREADS - 1) / RTHREADS;
+  int blocks = (int)(want > RBLOCKS ? RBLOCKS : want);
+  risk_grad_kernel<<<blocks, RTHREADS, 0, (cudaStream_t)stream>>>(reg_kind, renyi_alpha, y, m_q, v_q, m_p, v_p, N,
+                                                                  weights2, dm_out, dv_out);
+  GVI_CHECK_LAUNCH("risk_grad_kernel");
+  return GVI_OK;
+}
+
 // ---- error plumbing ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "no error";
 void gvi_set_error(const char* fmt, ...) {

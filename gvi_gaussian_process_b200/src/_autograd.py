@@ -1,0 +1,91 @@
+"""torch.autograd front end of the CUDA vector-Jacobian products (the role jax.grad plays in the reference's trainer,
+experiments/shared/trainer.py:83-89).  Every backward here is a CUDA kernel of libgvigp; torch only chains them and
+differentiates the host-framework mean function."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib_proxy as L
+
+
+def wants_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
+
+class PredictVariance(torch.autograd.Function):
+    """var[N] = k(x,x) - ||L^-1 k(Z,x)||^2 of a factorised sparse posterior; differentiable w.r.t. the base kernel's
+    (log_scaling, log_lengthscales).  `refactor()` rebuilds the factor state if another evaluation overwrote it
+    between forward and backward."""
+
+    @staticmethod
+    def forward(ctx, factor, refactor, x, frozen, log_scaling, log_lengthscales):
+        _, var = L.gp_predict(factor, x, want_mean=False)
+        ctx.factor, ctx.refactor, ctx.x, ctx.frozen = factor, refactor, x, frozen
+        ctx.version = factor.version
+        ctx.shapes = (getattr(log_scaling, "shape", None), getattr(log_lengthscales, "shape", None))
+        ctx.n_ll = log_lengthscales.numel() if isinstance(log_lengthscales, torch.Tensor) else 1
+        return var
+
+    @staticmethod
+    def backward(ctx, g_var):
+        factor = ctx.factor
+        if factor.version != ctx.version:
+            factor = ctx.refactor()
+        out = L.gp_predict_grad(factor, ctx.x, g_var.contiguous(), ctx.frozen)
+        d_ls = out[3].reshape(ctx.shapes[0]) if ctx.needs_input_grad[4] else None
+        d_ll = None
+        if ctx.needs_input_grad[5]:
+            d_ll = out[4:].sum() if ctx.n_ll == 1 else out[4:]  # a scalar lengthscale is broadcast over D
+            d_ll = d_ll.reshape(ctx.shapes[1])
+        return None, None, None, None, d_ls, d_ll
+
+
+class PointwiseRisk(torch.autograd.Function):
+    """out3 = [sum NLL_i, sum D0_i, N] of gvi_risk_f64, differentiable w.r.t. (m_q, v_q)."""
+
+    @staticmethod
+    def forward(ctx, kind, alpha, y, m_p, v_p, m_q, v_q):
+        ctx.args = (kind, alpha, y, m_p, v_p)
+        ctx.save_for_backward(m_q, v_q)
+        return L.risk(kind, alpha, y, m_q, v_q, m_p, v_p)
+
+    @staticmethod
+    def backward(ctx, g_out3):
+        kind, alpha, y, m_p, v_p = ctx.args
+        m_q, v_q = ctx.saved_tensors
+        dm, dv = L.risk_grad(kind, alpha, y, m_q, v_q, m_p, v_p, g_out3[:2].contiguous())
+        return None, None, None, None, None, dm, dv
+
+
+class ClassProbabilities(torch.autograd.Function):
+    """probabilities[N,K] from the [K,N] predictive means / variances (gvi_class_probabilities_f64)."""
+
+    @staticmethod
+    def forward(ctx, mean, var, roots, weights, epsilon, cdf_lower_bound):
+        ctx.consts = (roots, weights, epsilon, cdf_lower_bound)
+        ctx.save_for_backward(mean, var)
+        return L.class_probabilities(mean, var, roots, weights, epsilon, cdf_lower_bound)
+
+    @staticmethod
+    def backward(ctx, dprob):
+        roots, weights, epsilon, cdf_lower_bound = ctx.consts
+        mean, var = ctx.saved_tensors
+        dmean, dvar = L.class_probabilities_grad(mean, var, roots, weights, epsilon, cdf_lower_bound,
+                                                 dprob.contiguous())
+        return dmean, dvar, None, None, None, None
+
+
+class MultinomialRisk(torch.autograd.Function):
+    """out4 = [sum NLL, sum Wasserstein, N, sum cross-entropy] of gvi_multinomial_risk_f64, differentiable w.r.t. q."""
+
+    @staticmethod
+    def forward(ctx, prob_q, y, prob_p, power):
+        ctx.args = (y, prob_p, power)
+        ctx.save_for_backward(prob_q)
+        return L.multinomial_risk(prob_q, y, prob_p, power)
+
+    @staticmethod
+    def backward(ctx, g_out4):
+        y, prob_p, power = ctx.args
+        (prob_q,) = ctx.saved_tensors
+        return L.multinomial_risk_grad(prob_q, y, prob_p, power, g_out4.contiguous()), None, None, None

@@ -50,6 +50,7 @@ class GpFactor:
         self.buf = empty(_L().gvi_gp_factor_bytes(m, d) // 8)
         self.ws = empty(_L().gvi_gp_factor_workspace_bytes(m) // 8)
         self.info = torch.zeros(1, dtype=torch.int32, device=device())
+        self.version = 0  # bumped by every (re)factorisation; the autograd wrappers use it to detect stale state
 
     def factor(self, z, log_scaling, log_ls, diagonal_regularisation, is_absolute, log_noise=None, y_z=None):
         rc = _L().gvi_gp_factor_f64(_lib.ptr(z), self.m, self.d, _lib.ptr(log_scaling), _lib.ptr(log_ls),
@@ -57,6 +58,7 @@ class GpFactor:
                                     _lib.ptr(log_noise), _lib.ptr(y_z), _lib.ptr(self.buf), _lib.ptr(self.ws),
                                     _lib.ptr(self.info), _lib.current_stream())
         _lib.check(rc, "gvi_gp_factor_f64")
+        self.version += 1
         return self
 
     def factor_frozen(self, z, log_scaling, log_ls, chol_log_scaling, chol_log_ls, diagonal_regularisation,
@@ -67,6 +69,7 @@ class GpFactor:
                                            int(bool(is_absolute)), _lib.ptr(self.buf), _lib.ptr(self.ws),
                                            _lib.ptr(self.info), _lib.current_stream())
         _lib.check(rc, "gvi_gp_factor_frozen_f64")
+        self.version += 1
         return self
 
     def set_extra(self, e_matrix):
@@ -75,6 +78,7 @@ class GpFactor:
                                               e_matrix.stride(0) if e_matrix is not None else 0,
                                               _lib.current_stream())
         _lib.check(rc, "gvi_gp_factor_set_extra_f64")
+        self.version += 1
         return self
 
     # views into the workspace (valid until the next factor() call) -- used by the full-covariance API only
@@ -178,3 +182,68 @@ def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):
                                       _lib.current_stream())
     _lib.check(rc, "gvi_cond_var_select_f64")
     return idx, trace
+
+
+# ---- vector-Jacobian products and the classification epilogue ---------------------------
+def gp_predict_grad(factor: GpFactor, x, g_var, frozen_cholesky: bool = False):
+    """out[4+D] with out[3] = dLoss/dlog_scaling and out[4:] = dLoss/dlog_lengthscales, given g_var = dLoss/dvar."""
+    n, d = x.shape
+    out = empty(4 + d)
+    ws = _workspace("grad", _L().gvi_fused_step_grad_workspace_bytes(n, factor.m, d))
+    rc = _L().gvi_gp_predict_grad_f64(_lib.ptr(factor.buf), factor.m, d, _lib.ptr(x), n, _lib.ptr(g_var),
+                                      int(bool(frozen_cholesky)), _lib.ptr(out), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_gp_predict_grad_f64")
+    return out
+
+
+def risk_grad(reg_kind, alpha, y, m_q, v_q, m_p, v_p, weights2):
+    """(dm, dv): cotangents of the sums of `risk` pulled back to the approximate GP's mean and variance."""
+    n = m_q.numel()
+    dm, dv = empty(n), empty(n)
+    rc = _L().gvi_risk_grad_f64(int(reg_kind), float(alpha), _lib.ptr(y), _lib.ptr(m_q), _lib.ptr(v_q),
+                                _lib.ptr(m_p), _lib.ptr(v_p), n, _lib.ptr(weights2), _lib.ptr(dm), _lib.ptr(dv),
+                                _lib.current_stream())
+    _lib.check(rc, "gvi_risk_grad_f64")
+    return dm, dv
+
+
+def class_probabilities(mean, var, roots, weights, epsilon, cdf_lower_bound):
+    """mean, var [K,N] -> probabilities [N,K] (gvi_class_probabilities_f64)."""
+    k, n = mean.shape
+    prob = empty(n, k)
+    rc = _L().gvi_class_probabilities_f64(_lib.ptr(mean), _lib.ptr(var), k, n, _lib.ptr(roots), _lib.ptr(weights),
+                                          roots.numel(), float(epsilon), float(cdf_lower_bound), _lib.ptr(prob),
+                                          _lib.current_stream())
+    _lib.check(rc, "gvi_class_probabilities_f64")
+    return prob
+
+
+def class_probabilities_grad(mean, var, roots, weights, epsilon, cdf_lower_bound, dprob):
+    k, n = mean.shape
+    dmean, dvar = empty(k, n), empty(k, n)
+    rc = _L().gvi_class_probabilities_grad_f64(_lib.ptr(mean), _lib.ptr(var), k, n, _lib.ptr(roots),
+                                               _lib.ptr(weights), roots.numel(), float(epsilon),
+                                               float(cdf_lower_bound), _lib.ptr(dprob), _lib.ptr(dmean),
+                                               _lib.ptr(dvar), _lib.current_stream())
+    _lib.check(rc, "gvi_class_probabilities_grad_f64")
+    return dmean, dvar
+
+
+def multinomial_risk(prob_q, y, prob_p, power):
+    """out4 = [sum NLL, sum Wasserstein, N, sum cross-entropy] (device tensor)."""
+    n, k = prob_q.shape
+    out4 = empty(4)
+    ws = _workspace("mrisk", _L().gvi_multinomial_risk_workspace_bytes(n))
+    rc = _L().gvi_multinomial_risk_f64(_lib.ptr(prob_q), _lib.ptr(y), _lib.ptr(prob_p), k, n, int(power),
+                                       _lib.ptr(out4), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_multinomial_risk_f64")
+    return out4
+
+
+def multinomial_risk_grad(prob_q, y, prob_p, power, weights4):
+    n, k = prob_q.shape
+    dprob = empty(n, k)
+    rc = _L().gvi_multinomial_risk_grad_f64(_lib.ptr(prob_q), _lib.ptr(y), _lib.ptr(prob_p), k, n, int(power),
+                                            _lib.ptr(weights4), _lib.ptr(dprob), _lib.current_stream())
+    _lib.check(rc, "gvi_multinomial_risk_grad_f64")
+    return dprob

@@ -1,4 +1,4 @@
-"""Gaussian container (reference: src/distributions.py:14-29)."""
+"""Gaussian / Multinomial containers (reference: src/distributions.py:14-40)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -18,3 +18,11 @@ class Gaussian(Distribution):
     @property
     def full_covariance(self) -> bool:
         return self.covariance.ndim > self.mean.ndim
+
+
+@dataclass
+class Multinomial(Distribution):
+    probabilities: Any
+
+    def dict(self):
+        return {"probabilities": self.probabilities}

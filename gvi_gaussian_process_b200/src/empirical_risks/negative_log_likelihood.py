@@ -1,18 +1,33 @@
-"""Gaussian negative log-likelihood (reference: src/empirical_risks/negative_log_likelihood.py:17-55, 80-91):
-mean_i [ 0.5 log(2 pi) + 0.5 log v_i + (y_i - m_i)^2 / (2 v_i) ] as one vectorised CUDA reduction."""
+"""Negative log-likelihood (reference: src/empirical_risks/negative_log_likelihood.py:17-91).
+Regression: mean_i [ 0.5 log(2 pi) + 0.5 log v_i + (y_i - m_i)^2 / (2 v_i) ] as one vectorised CUDA reduction
+(lines 17-55).  Classification: -sum_i log sum_k p_ik y_ik (lines 57-78; a SUM over points, as in the reference)."""
 from __future__ import annotations
 
 from .. import _lib_proxy as L
+from .._autograd import MultinomialRisk, PointwiseRisk, wants_grad
+from ..gps.classification_base import GPClassificationBase
 from ..utils.device import as_device
 from .base import EmpiricalRiskBase
 
 
 class NegativeLogLikelihood(EmpiricalRiskBase):
+    def _calculate_multinomial_negative_log_likelihood(self, parameters, x, y):
+        probabilities = self._gp.predict_probability(parameters, x).probabilities
+        y = as_device(y).reshape(probabilities.shape)
+        if wants_grad(probabilities):
+            return MultinomialRisk.apply(probabilities, y, None, 2)[0]
+        return L.multinomial_risk(probabilities, y, None, 2)[0]
+
     def _calculate_empirical_risk(self, parameters, x, y):
+        if isinstance(self._gp, GPClassificationBase):
+            return self._calculate_multinomial_negative_log_likelihood(parameters, x, y)
         gaussian = self._gp.predict_probability(parameters, x)
         mean = gaussian.mean.reshape(-1).contiguous()
         variance = gaussian.covariance.reshape(-1).contiguous()
         y = as_device(y).reshape(-1)
         assert y.numel() == mean.numel(), f"{y.numel()=} responses for {mean.numel()=} predictions"
-        out3 = L.risk(L.REG_KINDS["none"], 0.0, y, mean, variance, None, None)
+        if wants_grad(mean, variance):
+            out3 = PointwiseRisk.apply(L.REG_KINDS["none"], 0.0, y, None, None, mean, variance)
+        else:
+            out3 = L.risk(L.REG_KINDS["none"], 0.0, y, mean, variance, None, None)
         return out3[0] / out3[2]

@@ -15,6 +15,7 @@ from . import _lib_proxy as L
 from .empirical_risks.base import EmpiricalRiskBase
 from .empirical_risks.negative_log_likelihood import NegativeLogLikelihood
 from .gps.approximate_gp_regression import ApproximateGPRegression
+from .gps.classification_base import GPClassificationBase
 from .gps.gp_regression import GPRegression
 from .kernels.approximate.fixed_sparse_posterior_kernel import FixedSparsePosteriorKernel
 from .kernels.approximate.sparse_posterior_kernel import SparsePosteriorKernel
@@ -66,8 +67,8 @@ class GeneralisedVariationalInference:
         if not isinstance(er, NegativeLogLikelihood) or not isinstance(rg, RegularisationBase):
             return False
         gp = er.gp
-        if gp is not rg.gp or not isinstance(gp, ApproximateGPRegression):
-            return False
+        if gp is not rg.gp or not isinstance(gp, ApproximateGPRegression) or isinstance(gp, GPClassificationBase):
+            return False  # classification objectives take the general path (K predictives + quadrature epilogue)
         if getattr(gp.kernel, "factorise", None) is None or rg.kind == "none":
             return False  # SparsePosteriorKernel, FixedSparsePosteriorKernel and the SVGP kernels provide factorise()
         if rg.mode == RegularisationMode.posterior:
@@ -190,8 +191,12 @@ class GeneralisedVariationalInference:
                 return _FusedLoss.apply(self, parameters, x, y, *self._grad_leaves(parameters))
             out3 = self.loss_sums(parameters, x, y)
             return (out3[0] + out3[1]) / out3[2]
-        return (self._empirical_risk.calculate_empirical_risk(parameters, x, y)
-                + self._regularisation.calculate_regularisation(parameters, x))
+        gp = self._empirical_risk.gp
+        parameters = gp._to_parameters(parameters)
+        x = as_device(x)  # one device copy, so both terms see the same tensor
+        with gp.memoise():  # one predictive of q for both terms (XLA's CSE does this inside the reference's jit)
+            return (self._empirical_risk.calculate_empirical_risk(parameters, x, y)
+                    + self._regularisation.calculate_regularisation(parameters, x))
 
     # ---- torch autograd front end: `gvi.calculate_loss(...).backward()` plays the role of jax.grad ------------------
     def _grad_leaves(self, parameters):

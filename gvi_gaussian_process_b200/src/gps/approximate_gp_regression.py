@@ -19,8 +19,12 @@ class ApproximateGPRegression(GPBase):
         # observation noise of an approximate GP is dropped even when a Parameters object carries one
         # (pinned by tests/regularisations/projected/test_projected_kl.py: q = (1, 1) with log_noise = log 1).
         if isinstance(parameters, self.Parameters):
+            if getattr(parameters, "_noise_dropped", False):
+                return parameters  # already regenerated: idempotent, so one objective can share a predictive
             parameters = parameters.dict_shallow()
-        return self.generate_parameters(dict(parameters))
+        out = self.generate_parameters(dict(parameters))
+        out._noise_dropped = True
+        return out
 
     def _calculate_prediction_gaussian(self, parameters, x, full_covariance: bool):
         return self.calculate_prior(parameters, x, full_covariance)

@@ -4,6 +4,7 @@ the regulariser kernel with FIXED parameters (computed once), the cross-Grams fr
 from __future__ import annotations
 
 from ... import _lib_proxy as L
+from ..._autograd import PredictVariance, wants_grad
 from ...utils.device import as_2d
 from ..base import KernelBase, KernelBaseParameters
 from ..standard.ard_kernel import ARDKernel
@@ -47,7 +48,13 @@ class FixedSparsePosteriorKernel(KernelBase):
 
     def _calculate_gram_diagonal(self, parameters, x):
         f = self.factorise(parameters)
-        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        x = x.reshape(x.shape[0], -1)
+        base = self.base_kernel._to_parameters(parameters.base_kernel)
+        if wants_grad(base.log_scaling, base.log_lengthscales):
+            # torch autograd front end: backward = gvi_gp_predict_grad_f64 (the variance VJP on the tensor pipe)
+            return PredictVariance.apply(f, lambda: self.factorise(parameters), x, True, base.log_scaling,
+                                         base.log_lengthscales)
+        _, var = L.gp_predict(f, x, want_mean=False)
         return var
 
     def _calculate_gram(self, parameters, x1, x2):

@@ -18,5 +18,7 @@ class ConstantMean(MeanBase):
         return ConstantMean.Parameters(**parameters)
 
     def _predict(self, parameters, x):
+        # jnp.tile(constant, n) (reference line 66): for K > 1 this is [c_0..c_{K-1}, c_0.., ...] and MeanBase.predict
+        # then RESHAPES it to [K, n] (means/base.py:97-100) - reproduced as is, it only matters when the constants differ
         c = as_device(parameters.constant).reshape(-1)
-        return c.repeat_interleave(x.shape[0]) if c.numel() > 1 else c.expand(x.shape[0]).contiguous()
+        return c.repeat(x.shape[0]) if c.numel() > 1 else c.expand(x.shape[0]).contiguous()

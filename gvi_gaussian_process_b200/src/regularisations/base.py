@@ -5,6 +5,7 @@ CUDA side therefore needs only a `kind` code (include/gvigp.h GVI_REG_*) and an 
 from __future__ import annotations
 
 from .. import _lib_proxy as L
+from .._autograd import PointwiseRisk, wants_grad
 from ..distributions import Gaussian
 from ..gps.base import GPBase
 from .schemas import RegularisationMode
@@ -63,13 +64,16 @@ class RegularisationBase:
             parameters=self._regulariser_parameters, x=x, full_covariance=full_covariance)
 
     def _pointwise_sums(self, parameters, x):
-        """out3 = [-, sum_i D0_i, N] through the CUDA reduction (single-output GPs: K = 1)."""
+        """out3 = [-, sum_i D0_i, N] through the CUDA reduction.  K-output GPs give [K, N] arrays; with equal N per
+        output the reference's mean over outputs of per-output means (projected/base.py:75-92) is the mean over K*N."""
         gaussian_p = self._calculate_regulariser_gaussian(x, full_covariance=False)
         gaussian_q = self._gp.calculate_prediction_gaussian(parameters, x, full_covariance=False)
         m_p = gaussian_p.mean.reshape(-1).contiguous()
         c_p = gaussian_p.covariance.reshape(-1).contiguous()
         m_q = gaussian_q.mean.reshape(-1).contiguous()
         c_q = gaussian_q.covariance.reshape(-1).contiguous()
+        if wants_grad(m_q, c_q):
+            return PointwiseRisk.apply(L.REG_KINDS[self.kind], self.alpha, None, m_p.detach(), c_p.detach(), m_q, c_q)
         return L.risk(L.REG_KINDS[self.kind], self.alpha, None, m_q, c_q, m_p, c_p)
 
     def _calculate_regularisation(self, parameters, x):

@@ -108,6 +108,14 @@ size_t gvi_risk_workspace_bytes(int64_t N);
 int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, const double* m_q, const double* v_q,
                  const double* m_p, const double* v_p, int64_t N, double* out3, void* workspace, void* stream);
 
+/* Pointwise derivatives of the sums of gvi_risk_f64 w.r.t. the approximate GP's mean and variance (p constant):
+ * dm_out[i] = w[0] dNLL_i/dm_q,i + w[1] dD0_i/dm_q,i and dv_out[i] likewise for v_q,i - the cotangents that
+ * jax.grad of the reference's risks feeds back into predict_probability.  weights2 is a DEVICE array [2] (the
+ * cotangents of out3[0], out3[1]) so a training step never synchronises.                                       */
+int gvi_risk_grad_f64(int reg_kind, double renyi_alpha, const double* y, const double* m_q, const double* v_q,
+                      const double* m_p, const double* v_p, int64_t N, const double* weights2, double* dm_out,
+                      double* dv_out, void* stream);
+
 /* ---- a12: fused Gram + predict(q) + predict(p) + NLL + regulariser for one shard of points ---------------
  * (GeneralisedVariationalInference._calculate_loss, src/generalised_variational_inference.py:73-94.)
  * One launch: per tile of points builds K(x,Z) for q and p in shared memory, runs both triangular products on
@@ -143,6 +151,42 @@ int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p, int M, in
                            const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
                            const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, const double* E,
                            int64_t lde, double* out3, double* dm_out, double* dE_out, void* workspace, void* stream);
+
+/* Vector-Jacobian product of gvi_gp_predict_f64's variance w.r.t. the kernel hyper-parameters: given
+ * g_var[i] = dLoss/dvar_i of ANY downstream loss, out[3] = dLoss/dlog_scaling, out[4+d] = dLoss/dlog_lengthscales[d]
+ * (out[0] = out[1] = 0, out[2] = N; same layout and workspace as gvi_fused_step_grad_f64).  This is what jax.grad
+ * produces through SparsePosteriorKernel._calculate_gram (sparse_posterior_kernel.py:54-96) for losses that are not
+ * the fused regression objective - e.g. the classification objective of section 8(f)-2.  D <= 32.            */
+int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g_var,
+                            int frozen_cholesky, double* out, void* workspace, void* stream);
+
+/* ---- section 8(f)-2: classification epilogue on [K,N] predictive means / variances ---------------------------
+ * GPClassificationBase._calculate_s_matrix + _predict_probability (src/gps/base/classification_base.py:53-153):
+ *   s[n,j]    = 1/sqrt(pi) sum_h weights[h] prod_{l != j} max(Phi((sqrt2 roots[h] sd[j,n] + mean[j,n] - mean[l,n])
+ *               / sd[l,n]), cdf_lower_bound),   sd = sqrt(var)
+ *   prob[n,j] = (1 - epsilon) s + epsilon / (K - 1) (1 - s)
+ * mean, var are [K,N] row-major; roots/weights are the H Gauss-Hermite nodes (device arrays); prob_out is [N,K].
+ * The _grad entry is the vector-Jacobian product: dprob[N,K] -> dmean_out[K,N], dvar_out[K,N].  2 <= K <= 64. */
+int gvi_class_probabilities_f64(const double* mean, const double* var, int K, int64_t N, const double* roots,
+                                const double* weights, int H, double epsilon, double cdf_lower_bound,
+                                double* prob_out, void* stream);
+int gvi_class_probabilities_grad_f64(const double* mean, const double* var, int K, int64_t N, const double* roots,
+                                     const double* weights, int H, double epsilon, double cdf_lower_bound,
+                                     const double* dprob, double* dmean_out, double* dvar_out, void* stream);
+/* Risks / regularisers on class probabilities ([N,K] row-major), as SUMS over the shard's points:
+ *   out4[0] = sum_i -log sum_k q_ik y_ik                     (negative_log_likelihood.py:57-78; the reference sums)
+ *   out4[1] = sum_i (sum_k |p_ik - q_ik|^power)^(1/power)    (multinomial_wasserstein_regularisation.py:46-76; mean)
+ *   out4[2] = N
+ *   out4[3] = sum_i -sum_k y_ik log_softmax(q_i)_k           (cross_entropy.py:11-30: jax_metrics' Crossentropy takes
+ *                                                             `preds` as logits; pinned by the reference's 1.306689)
+ * y / prob_p may be NULL (their terms are 0).  The _grad entry writes
+ * dprob_out[i,k] = w[0] d out4[0]/dq_ik + w[1] d out4[1]/dq_ik + w[3] d out4[3]/dq_ik, w = weights4, a DEVICE array
+ * [4] (the cotangent of out4).                                                                                 */
+size_t gvi_multinomial_risk_workspace_bytes(int64_t N);
+int gvi_multinomial_risk_f64(const double* prob_q, const double* y, const double* prob_p, int K, int64_t N,
+                             int power, double* out4, void* workspace, void* stream);
+int gvi_multinomial_risk_grad_f64(const double* prob_q, const double* y, const double* prob_p, int K, int64_t N,
+                                  int power, const double* weights4, double* dprob_out, void* stream);
 
 /* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
 int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);

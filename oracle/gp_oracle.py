@@ -324,3 +324,88 @@ def svgp_gram(gram_fn, inducing_points, sigma_matrix, x1, x2=None, diagonal_regu
 def cholesky_sigma(el_matrix_lower_triangle, el_matrix_log_diagonal) -> np.ndarray:
     el = np.tril(el_matrix_lower_triangle, k=-1) + np.diag(np.exp(el_matrix_log_diagonal))
     return el.T @ el
+
+
+# --------------------------------------------------------------------------------------------------------------
+# section 8(f)-2: classification (multi-output GPs + Gauss-Hermite class probabilities)
+# --------------------------------------------------------------------------------------------------------------
+def multi_output_exact_gp_posterior(gram_fns, diag_fns, prior_mean_values, x_train, y_train, log_observation_noise,
+                                    x):
+    """K independent exact posteriors, one per output (src/gps/base/base.py:414-493 vmapped over outputs, 384-412 in
+    diagonal mode): gram_fns[k] / diag_fns[k] are the k-th kernel of a MultiOutputKernel
+    (src/kernels/multi_output_kernel.py:38-70), y_train is [n, K] and is transposed to [K, n] (base.py:480),
+    log_observation_noise is [K] (construct_observation_noise_matrix, base.py:153-171).  Returns [K, N] arrays."""
+    k_out = len(gram_fns)
+    y_t = np.atleast_2d(np.asarray(y_train, dtype=np.float64).T)
+    noise = np.broadcast_to(np.atleast_1d(np.asarray(log_observation_noise, dtype=np.float64)), (k_out,))
+    pm = np.asarray(prior_mean_values, dtype=np.float64).reshape(k_out, -1)
+    means, variances = [], []
+    for k in range(k_out):
+        m, v = exact_gp_posterior(gram_fns[k], diag_fns[k], pm[k], x_train, y_t[k], noise[k], x)
+        means.append(m)
+        variances.append(v)
+    return np.stack(means), np.stack(variances)
+
+
+def multi_output_prior(diag_fns, prior_mean_values, log_observation_noise, x):
+    """ApproximateGPBase._calculate_prediction_gaussian -> calculate_prior (approximate_base.py:31-39,
+    base.py:173-212): covariance [K, N] = diag k_k(x, x) + exp(log_observation_noise)[:, None]."""
+    k_out = len(diag_fns)
+    noise = np.broadcast_to(np.atleast_1d(np.exp(np.asarray(log_observation_noise, dtype=np.float64))), (k_out,))
+    pm = np.asarray(prior_mean_values, dtype=np.float64).reshape(k_out, -1)
+    cov = np.stack([diag_fns[k](x) for k in range(k_out)]) + noise[:, None]
+    return pm.copy(), cov
+
+
+def classification_s_matrix(means, covariance_diagonals, hermite_roots, hermite_weights, cdf_lower_bound):
+    """GPClassificationBase._calculate_s_matrix (src/gps/base/classification_base.py:76-153): [K,N],[K,N] -> [N,K]."""
+    from scipy.stats import norm
+
+    means = np.asarray(means, dtype=np.float64)
+    sd = np.sqrt(np.asarray(covariance_diagonals, dtype=np.float64))
+    r = np.asarray(hermite_roots, dtype=np.float64)
+    w = np.asarray(hermite_weights, dtype=np.float64)
+    # (h, k_j, k_l, n)
+    cdf_input = (np.sqrt(2.0) * r[:, None, None, None] * sd[None, :, None, :] + means[None, :, None, :]
+                 - means[None, None, :, :]) / sd[None, None, :, :]
+    log_cdf = np.log(np.clip(norm.cdf(cdf_input), cdf_lower_bound, None))
+    diag = np.swapaxes(np.diagonal(log_cdf, axis1=1, axis2=2), 1, 2)  # (h, n, k) -> (h, k, n)
+    comp = w[:, None, None] * np.exp(np.sum(log_cdf, axis=2) - diag)
+    return ((1.0 / np.sqrt(np.pi)) * np.sum(comp, axis=0)).T
+
+
+def classification_probabilities(means, covariance_diagonals, epsilon=0.01, hermite_polynomial_order=50,
+                                 cdf_lower_bound=1e-10):
+    """GPClassificationBase._predict_probability (classification_base.py:53-74) with the default constructor
+    arguments of gp_classification.py:38-45 / approximate_gp_classification.py:30-36."""
+    from scipy.special import roots_hermite
+
+    roots, weights = roots_hermite(hermite_polynomial_order)
+    s = classification_s_matrix(means, covariance_diagonals, roots, weights, cdf_lower_bound)
+    k_out = np.asarray(means).shape[0]
+    return (1.0 - epsilon) * s + (epsilon / (k_out - 1)) * (1.0 - s)
+
+
+def multinomial_nll(probabilities, y) -> float:
+    """negative_log_likelihood.py:57-78: -sum_i log sum_k p_ik y_ik  (a SUM over points, not a mean)."""
+    return float(-np.sum(np.log(np.sum(np.asarray(probabilities) * np.asarray(y, dtype=np.float64), axis=1))))
+
+
+def multinomial_wasserstein(probabilities_p, probabilities_q, power=2) -> float:
+    """multinomial_wasserstein_regularisation.py:46-76: mean_i (sum_k |p_ik - q_ik|^power)^(1/power)."""
+    d = np.abs(np.asarray(probabilities_p) - np.asarray(probabilities_q))
+    return float(np.mean(np.power(np.sum(np.power(d, power), axis=1), 1.0 / power)))
+
+
+def tempered_diag(diag_fn, log_tempering_factor):
+    """src/kernels/tempered_kernel.py:72-81: exp(log_tempering_factor) * base Gram (per output)."""
+    return lambda x: np.exp(log_tempering_factor) * diag_fn(x)
+
+
+def cross_entropy_from_probabilities(probabilities, y) -> float:
+    """cross_entropy.py:11-30: jax_metrics.losses.Crossentropy() (third-party, jax_metrics pinned in poetry.lock) is
+    called with preds = the class probabilities and its default from_logits=True, i.e. the probabilities go through a
+    log-softmax; pinned by the reference golden 1.306689 (tests/test_empirical_risks.py:215-269)."""
+    p = np.asarray(probabilities, dtype=np.float64)
+    logp = p - np.log(np.sum(np.exp(p), axis=1, keepdims=True))
+    return float(np.mean(-np.sum(np.asarray(y, dtype=np.float64) * logp, axis=1)))

@@ -101,3 +101,31 @@ def svgp_diag(ls_r, ll_r, z, x, sigma, reg=1e-5, is_absolute=False):
     kxz = ard_gram(ls_r, ll_r, x, z)
     return (torch.exp(ls_r) ** 2 - (kxz * torch.cholesky_solve(kxz.T, chol).T).sum(-1)
             + ((kxz @ sigma) * kxz).sum(-1))
+
+
+# ---- section 8(f)-2: classification ------------------------------------------------------------------------------
+def classification_probabilities(means, variances, roots, weights, epsilon=0.01, cdf_lower_bound=1e-10):
+    """classification_base.py:53-153 with differentiable torch ops: [K,N],[K,N] -> [N,K]."""
+    sd = torch.sqrt(variances)
+    r = torch.as_tensor(roots, dtype=torch.float64)
+    w = torch.as_tensor(weights, dtype=torch.float64)
+    cdf_input = (math.sqrt(2.0) * r[:, None, None, None] * sd[None, :, None, :] + means[None, :, None, :]
+                 - means[None, None, :, :]) / sd[None, None, :, :]
+    log_cdf = torch.log(torch.clamp(torch.special.ndtr(cdf_input), min=cdf_lower_bound))
+    diag = torch.diagonal(log_cdf, dim1=1, dim2=2).permute(0, 2, 1)  # (h, n, k) -> (h, k, n)
+    comp = w[:, None, None] * torch.exp(log_cdf.sum(dim=2) - diag)
+    s = ((1.0 / math.sqrt(math.pi)) * comp.sum(dim=0)).T
+    k = means.shape[0]
+    return (1.0 - epsilon) * s + (epsilon / (k - 1)) * (1.0 - s)
+
+
+def multinomial_nll(prob, y):
+    return -torch.log((prob * y).sum(dim=1)).sum()
+
+
+def multinomial_wasserstein(prob_p, prob_q, power=2):
+    return torch.pow(torch.pow(torch.abs(prob_p - prob_q), power).sum(dim=1), 1.0 / power).mean()
+
+
+def cross_entropy_from_probabilities(prob, y):
+    return (-(y * torch.log_softmax(prob, dim=1)).sum(dim=1)).mean()

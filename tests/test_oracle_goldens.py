@@ -169,3 +169,78 @@ def test_fixed_sparse_posterior_golden():
     x = np.array([[5.3, 5.0, 6.0], [2.5, 4.5, 2.5]])
     r = O.fixed_sparse_posterior_gram(eye_gram, eye_gram, z, x, x, 1e-5, False)
     np.testing.assert_allclose(r, np.array([[9.9999e-06, 0.0], [0.0, 9.9999e-06]]), atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# classification.  The reference's diagonal mode vmaps 1-point posteriors
+# (src/gps/base/base.py:384-412), so position-dependent mock kernels (the identity mock) are evaluated point by point.
+# ---------------------------------------------------------------------------------------------------------------
+K_CLS = 4
+Y_CLS = np.array([[0.5, 0.1, 0.2, 0.2], [0.1, 0.2, 0.3, 0.4]])
+NOISE_A = np.log(np.array([1.0, 0.5, 0.2, 0.9]))
+NOISE_B = np.log(np.array([0.1, 0.2, 0.4, 1.8]))
+eye_diag = ones_diag
+
+
+def pointwise_exact(gram_fns, diag_fns, x_train, y_train, noise, xs):
+    ms, vs = [], []
+    for i in range(xs.shape[0]):
+        m, v = O.multi_output_exact_gp_posterior(gram_fns, diag_fns, np.ones((K_CLS, 1)), x_train, y_train, noise,
+                                                 xs[i : i + 1])
+        ms.append(m)
+        vs.append(v)
+    return np.concatenate(ms, axis=1), np.concatenate(vs, axis=1)
+
+
+def test_classification_prediction_goldens():
+    # tests/gps/test_classification.py:23-88 (array_equal in the reference; LAPACK/libm orderings allow 2 ulp here)
+    m, v = pointwise_exact([ones_gram] * K_CLS, [ones_diag] * K_CLS, X, Y_CLS, NOISE_A, X_TRAIN)
+    p = O.classification_probabilities(m, v)
+    golden = np.array([0.29579238035540445, 0.19449721942556136, 0.2159886961681648, 0.29372170534428094])
+    np.testing.assert_allclose(p, np.tile(golden, (2, 1)), rtol=1e-14)
+    # :91-128 approximate GP, ones kernel -> uniform
+    m, v = O.multi_output_prior([ones_diag] * K_CLS, np.ones((K_CLS, 2)), -np.inf, X_TRAIN)
+    np.testing.assert_allclose(O.classification_probabilities(m, v), 0.25, rtol=1e-12)
+    # :131-206 tempered exact GP on the identity mock
+    temper = np.log(np.array([0.5, 1.0, 3.0, 4.0]))
+    gf = [(lambda a, b, t=t: np.exp(t) * eye_gram(a, b)) for t in temper]
+    df = [O.tempered_diag(eye_diag, t) for t in temper]
+    m, v = pointwise_exact(gf, df, X, Y_CLS, NOISE_A, X_TRAIN)
+    np.testing.assert_allclose(O.classification_probabilities(m, v),
+                               np.tile([0.25269439, 0.19932216, 0.22324345, 0.32474002], (2, 1)), rtol=2e-7)
+    # :209-265 tempered approximate GP: the observation noise passed in is DROPPED (generate_parameters)
+    m, v = O.multi_output_prior([O.tempered_diag(ones_diag, t) for t in temper], np.ones((K_CLS, 2)), -np.inf,
+                                X_TRAIN)
+    np.testing.assert_allclose(O.classification_probabilities(m, v),
+                               np.tile([0.1690632, 0.20674086, 0.29816303, 0.32603688], (2, 1)), rtol=2e-7)
+
+
+def test_classification_risk_goldens():
+    # tests/test_empirical_risks.py:147-212 (exact GP, identity mock): multinomial NLL 2.63190702
+    m, v = pointwise_exact([eye_gram] * K_CLS, [eye_diag] * K_CLS, X_TRAIN, Y_CLS, NOISE_B, X)
+    p = O.classification_probabilities(m, v)
+    assert np.isclose(O.multinomial_nll(p, Y_CLS), 2.63190702, rtol=1e-8)
+    # :215-269 cross entropy 1.306689: jax_metrics treats the probabilities as logits
+    labels = np.array([[0, 0, 0, 1], [1, 0, 0, 0]])
+    assert np.isclose(O.cross_entropy_from_probabilities(p, labels), 1.306689, rtol=1e-6)
+    # :272-316 approximate GP NLL 2.77258869 = 2 log 4; :319-370 cross entropy 1.3862944 = log 4
+    m, v = O.multi_output_prior([ones_diag] * K_CLS, np.ones((K_CLS, 2)), -np.inf, X)
+    q = O.classification_probabilities(m, v)
+    assert np.isclose(O.multinomial_nll(q, Y_CLS), 2.77258869, rtol=1e-8)
+    assert np.isclose(O.cross_entropy_from_probabilities(q, np.array([[0, 0, 0, 1], [0, 1, 0, 0]])), 1.3862944,
+                      rtol=1e-7)
+
+
+def test_classification_regulariser_goldens():
+    # tests/regularisations/**: K = 4 cases (line ~316 of each file); p = exact GP (ones mock), q = approximate GP
+    m_p, v_p = pointwise_exact([ones_gram] * K_CLS, [ones_diag] * K_CLS, X_TRAIN, Y_CLS, NOISE_B, X)
+    m_q, v_q = O.multi_output_prior([ones_diag] * K_CLS, np.ones((K_CLS, 2)), -np.inf, X)
+    for kind, golden in [("bhattacharyya", 0.24135331), ("gaussian_wasserstein", 0.4287477),
+                         ("hellinger", 0.208868), ("kl", 0.61610398), ("renyi", 0.49202457)]:
+        assert np.isclose(O.projected_regularisation(kind, m_p, v_p, m_q, v_q), golden, rtol=2e-6), kind
+    assert np.isclose(O.gaussian_squared_difference(m_p, v_p, m_q, v_q), 0.71837243, rtol=1e-7)
+    # tests/regularisations/test_multinomial_wasserstein.py:130-197
+    p = O.classification_probabilities(m_p, v_p)
+    q = O.classification_probabilities(m_q, v_q)
+    assert np.isclose(O.multinomial_wasserstein(p, q), 0.12691447, rtol=1e-7)
+    assert O.multinomial_wasserstein(q, q, power=4) == 0.0
