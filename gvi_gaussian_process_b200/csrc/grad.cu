@@ -371,6 +371,20 @@ static int gvi_weighted_gram(const double* Fq, const double* X, const double* g,
   return GVI_OK;
 }
 
+// the per-thread cuBLAS handle, bound to `st` (shared with exact.cu)
+int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st) {
+  if (!g_cublas) {
+    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
+      gvi_set_error("cublasCreate failed");
+      return GVI_ECUDA;
+    }
+  }
+  cublasSetStream(g_cublas, st);
+  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
+  *h = g_cublas;
+  return GVI_OK;
+}
+
 // S = L^-T (L^-1 C L^-T) L^-1 (plain library GEMMs), then out[4+d] += <dK_ZZ/dlog_ls[d], S>
 static int gvi_finish_kzz_term(const double* Fq, const FactorLayout& f, int M, int D, const GradWs& w, double* out,
                                cudaStream_t st) {

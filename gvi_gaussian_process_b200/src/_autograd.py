@@ -89,3 +89,37 @@ class MultinomialRisk(torch.autograd.Function):
         y, prob_p, power = ctx.args
         (prob_q,) = ctx.saved_tensors
         return L.multinomial_risk_grad(prob_q, y, prob_p, power, g_out4.contiguous()), None, None, None
+
+
+class ExactPredict(torch.autograd.Function):
+    """(mean[N], var[N]) of an exact GP posterior (gvi_gp_predict_f64 on a state with alpha = A^-1 y), differentiable
+    w.r.t. the prior mean values, log_observation_noise and the ARD kernel's (log_scaling, log_lengthscales):
+    backward = gvi_exact_gp_predict_grad_f64."""
+
+    @staticmethod
+    def forward(ctx, factor, refactor, x, prior_mean, log_noise, log_scaling, log_lengthscales):
+        mean, var = L.gp_predict(factor, x, prior_mean=prior_mean.contiguous())
+        ctx.factor, ctx.refactor, ctx.x = factor, refactor, x
+        ctx.version = factor.version
+        ctx.log_noise = log_noise.detach().reshape(-1)[:1].contiguous()
+        ctx.shapes = (log_noise.shape, getattr(log_scaling, "shape", None), getattr(log_lengthscales, "shape", None))
+        ctx.n_ll = log_lengthscales.numel() if isinstance(log_lengthscales, torch.Tensor) else 1
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, h_mean, g_var):
+        factor = ctx.factor
+        if factor.version != ctx.version:
+            factor = ctx.refactor()
+        d = ctx.x.shape[1]
+        if g_var is None:
+            g_var = torch.zeros_like(h_mean)
+        out = L.exact_gp_predict_grad(factor, ctx.x, g_var.contiguous(),
+                                      None if h_mean is None else h_mean.contiguous(), ctx.log_noise)
+        d_noise = out[4 + d].reshape(ctx.shapes[0]) if ctx.needs_input_grad[4] else None
+        d_ls = out[3].reshape(ctx.shapes[1]) if ctx.needs_input_grad[5] else None
+        d_ll = None
+        if ctx.needs_input_grad[6]:
+            d_ll = out[4:4 + d].sum() if ctx.n_ll == 1 else out[4:4 + d]
+            d_ll = d_ll.reshape(ctx.shapes[2])
+        return None, None, None, h_mean, d_noise, d_ls, d_ll

@@ -247,3 +247,16 @@ def multinomial_risk_grad(prob_q, y, prob_p, power, weights4):
                                             _lib.ptr(weights4), _lib.ptr(dprob), _lib.current_stream())
     _lib.check(rc, "gvi_multinomial_risk_grad_f64")
     return dprob
+
+
+def exact_gp_predict_grad(factor: GpFactor, x, g_var, h_mean, log_noise):
+    """out[5+D]: out[3] = d/dlog_scaling, out[4:4+D] = d/dlog_lengthscales, out[4+D] = d/dlog_observation_noise of an
+    exact-GP predictive (gvi_exact_gp_predict_grad_f64), given the cotangents of its variance and mean."""
+    n, d = x.shape
+    out = empty(5 + d)
+    ws = _workspace("exact_grad", _L().gvi_exact_gp_predict_grad_workspace_bytes(n, factor.m))
+    rc = _L().gvi_exact_gp_predict_grad_f64(_lib.ptr(factor.buf), factor.m, d, _lib.ptr(x), n, _lib.ptr(g_var),
+                                            _lib.ptr(h_mean), _lib.ptr(log_noise), _lib.ptr(out), _lib.ptr(ws),
+                                            _lib.current_stream())
+    _lib.check(rc, "gvi_exact_gp_predict_grad_f64")
+    return out

@@ -9,6 +9,7 @@ The K=1 predictive mean has shape [1,N] as in the reference (only the covariance
 from __future__ import annotations
 
 from .. import _lib_proxy as L
+from .._autograd import ExactPredict, wants_grad
 from ..kernels.standard.ard_kernel import ARDKernel
 from ..utils.device import as_2d, as_device, scalar
 from .base import GPBase
@@ -40,7 +41,14 @@ class GPRegression(GPBase):
         x = x.reshape(x.shape[0], -1)
         f = self.factorise(parameters)
         prior_mean = self.mean.predict(parameters.mean, x).contiguous()
-        mean, var = L.gp_predict(f, x, prior_mean=prior_mean)
+        kp = self.kernel._to_parameters(parameters.kernel)
+        if wants_grad(prior_mean, parameters.log_observation_noise, kp.log_scaling, kp.log_lengthscales):
+            # training the exact GP itself (train_regulariser, experiments/regression/trainers.py:19-85)
+            noise = as_device(parameters.log_observation_noise)
+            mean, var = ExactPredict.apply(f, lambda: self.factorise(parameters), x, prior_mean, noise,
+                                           kp.log_scaling, kp.log_lengthscales)
+        else:
+            mean, var = L.gp_predict(f, x, prior_mean=prior_mean)
         return mean.reshape(1, -1), var
 
     def _calculate_prediction_gaussian(self, parameters, x, full_covariance: bool):

@@ -160,6 +160,19 @@ int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p, int M, in
 int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g_var,
                             int frozen_cholesky, double* out, void* workspace, void* stream);
 
+/* ---- section 8(f)-3: vector-Jacobian product of the EXACT GP predictive (mean AND variance) - the backward pass of
+ * the exact-GP NLL training step on the inducing set (experiments/regression/trainers.py:19-85: jax.grad through
+ * GPRegression.predict_probability, src/gps/base/base.py:384-526).  `factor` is a state built by gvi_gp_factor_f64
+ * with y_z and log_noise (A = K_ZZ + exp(log_noise) I, alpha = A^-1 y_Z).  Given g_var[i] = dLoss/dvar_i and
+ * h_mean[i] = dLoss/dmean_i (NULL = 0):  out[0] = out[1] = 0, out[2] = N, out[3] = dLoss/dlog_scaling,
+ * out[4+d] = dLoss/dlog_lengthscales[d], out[4+D] = dLoss/dlog_observation_noise (5 + D doubles).  The gradient
+ * w.r.t. the prior-mean parameters is the host framework's (dLoss/dm(x_i) = h_mean[i]).  Dense route: K(x,Z) in
+ * row chunks, M^3-shaped products by cuBLAS, hand-written contraction kernels.  D <= 32.                          */
+size_t gvi_exact_gp_predict_grad_workspace_bytes(int64_t N, int M);
+int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g_var,
+                                  const double* h_mean, const double* log_noise, double* out, void* workspace,
+                                  void* stream);
+
 /* ---- section 8(f)-2: classification epilogue on [K,N] predictive means / variances ---------------------------
  * GPClassificationBase._calculate_s_matrix + _predict_probability (src/gps/base/classification_base.py:53-153):
  *   s[n,j]    = 1/sqrt(pi) sum_h weights[h] prod_{l != j} max(Phi((sqrt2 roots[h] sd[j,n] + mean[j,n] - mean[l,n])

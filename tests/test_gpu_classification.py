@@ -393,3 +393,35 @@ def test_classification_wide_inputs_mnist_shaped(S):
     assert np.max(np.abs(got - ref)) <= TOL
     nll = float(S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, x, y))
     assert abs(nll - O.multinomial_nll(ref, y)) <= TOL * abs(nll)
+
+
+# ---- section 8(f)-3: the exact-GP NLL training step on the inducing set, value and gradient -----------------------
+@pytest.mark.parametrize("n,m,d,scalar_ll", [(40, 40, 1, True), (300, 200, 3, False), (5000, 700, 8, False)])
+def test_exact_gp_nll_step_backward_matches_autograd_twin(S, n, m, d, scalar_ll):
+    rng = np.random.default_rng(n + d)
+    z = rng.standard_normal((m, d))
+    wv = rng.standard_normal(d)
+    yz = np.sin(z @ wv) + 0.1 * rng.standard_normal(m)
+    if n == m:  # the reference trains on the inducing data itself (trainers.py:69-80)
+        x, y = z.copy(), yz.copy()
+    else:
+        x = rng.standard_normal((n, d))
+        y = np.sin(x @ wv) + 0.1 * rng.standard_normal(n)
+    ls, noise, const = 0.2, np.log(0.3), 0.15
+    ll = np.float64(np.log(1.0 / d)) if scalar_ll else np.log(rng.uniform(0.5, 1.5, d) / d)
+    kernel = S.ARDKernel(number_of_dimensions=d)
+    mean = S.ConstantMean()
+    gp = S.GPRegression(mean=mean, kernel=kernel, x=z, y=yz)
+    t_ls, t_ll, t_noise, t_c = dev(ls, True), dev(ll, True), dev(noise, True), dev(const, True)
+    params = {"log_observation_noise": t_noise, "mean": {"constant": t_c},
+              "kernel": {"log_scaling": t_ls, "log_lengthscales": t_ll}}
+    loss = S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, x, y)
+    loss.backward()
+    c_ls, c_ll, c_noise, c_c = cpu(ls, True), cpu(ll, True), cpu(noise, True), cpu(const, True)
+    mean_t, var_t = T.exact_gp_posterior(c_ls, c_ll, c_c, cpu(z), cpu(yz), c_noise, cpu(x))
+    ref = T.gaussian_nll(cpu(y), mean_t, var_t)
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    for got, want in ((t_ls, c_ls), (t_noise, c_noise), (t_c, c_c)):
+        assert abs(float(got.grad) - float(want.grad)) <= GTOL * max(abs(float(want.grad)), 1e-6), (got.grad, want.grad)
+    assert rel_norm(host(t_ll.grad).reshape(-1), c_ll.grad.numpy().reshape(-1)) <= GTOL
