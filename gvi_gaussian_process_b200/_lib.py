@@ -65,6 +65,8 @@ SIGNATURES = {
                                          c_void_p]),
     "gvi_multinomial_risk_grad_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p,
                                               c_void_p]),
+    "gvi_weighted_gram_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
     "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_cond_var_select_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double,

@@ -481,6 +481,34 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
   return gvi_finish_kzz_term(Fq, f, M, D, w, out, st);
 }
 
+// ---- weighted Gram C = sum_i g_i k_i k_i^T as an entry point ----------------------------------------------------------
+// For the SVGP family var_i = k_ii - k_i^T A^-1 k_i + k_i^T Sigma k_i with frozen kernel hyper-parameters, so
+// dLoss/dSigma = sum_i g_i k_i k_i^T: the weighted-Gram (SYRK) kernel on the tensor pipe IS the vector-Jacobian product
+// (cholesky_svgp_kernel.py:133-150, diagonal_svgp_kernel.py:117-129, log_svgp_kernel.py:108-124); each
+// parameterisation of Sigma is an M x M map the host framework differentiates.  C_out is [M,M] row-major.
+namespace {
+__global__ void copy_block_kernel(const double* __restrict__ src, int64_t lds, double* __restrict__ dst, int M) {
+  const int64_t total = (int64_t)M * M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    dst[idx] = src[(idx / M) * lds + idx % M];
+}
+}  // namespace
+extern "C" int gvi_weighted_gram_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g,
+                                     double* C_out, void* workspace, void* stream) {
+  GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 1, "sizes");
+  GVI_CHECK_ARG(D <= 32, "the weighted Gram supports D <= 32 in this build");
+  GVI_CHECK_ARG(factor && X && g && C_out && workspace, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const FactorLayout f = factor_layout(M, D);
+  GradWs w = carve_grad(workspace, N, M, D, nullptr);
+  int rc = gvi_weighted_gram((const double*)factor, X, g, N, M, D, w, st);
+  if (rc) return rc;
+  copy_block_kernel<<<GVI_NUM_SMS * 2, 256, 0, st>>>(w.C, f.Mp, C_out, M);
+  GVI_CHECK_LAUNCH("copy_block_kernel");
+  return GVI_OK;
+}
+
 // ---- SVGP family: value and gradient w.r.t. the extra matrix E (the kernel hyper-parameters are frozen) -------------
 // v_i = k_ii - ||L^-1 k_i||^2 + ||E k_i||^2  =>  dR/dE = 2 E C (lower triangle), C = sum_i g_i k_i k_i^T.
 // out[0..2] as out3; dm_out[N]; dE_out[M*M] row-major (only the lower triangle is meaningful).  E is the dense matrix

@@ -123,3 +123,19 @@ class ExactPredict(torch.autograd.Function):
             d_ll = out[4:4 + d].sum() if ctx.n_ll == 1 else out[4:4 + d]
             d_ll = d_ll.reshape(ctx.shapes[2])
         return None, None, None, h_mean, d_noise, d_ls, d_ll
+
+
+class SVGPVariance(torch.autograd.Function):
+    """var[N] = k_ii - ||L^-1 k_i||^2 + k_i^T Sigma k_i of an SVGP-family kernel (frozen hyper-parameters), computed by
+    the tile kernel with a lower-triangular E (E^T E = Sigma) attached to the factor state; differentiable w.r.t.
+    Sigma: dLoss/dSigma = sum_i g_i k_i k_i^T (gvi_weighted_gram_f64)."""
+
+    @staticmethod
+    def forward(ctx, factor, x, sigma):
+        _, var = L.gp_predict(factor, x, want_mean=False)
+        ctx.factor, ctx.x = factor, x
+        return var
+
+    @staticmethod
+    def backward(ctx, g_var):
+        return None, None, L.weighted_gram(ctx.factor, ctx.x, g_var.contiguous())

@@ -260,3 +260,14 @@ def exact_gp_predict_grad(factor: GpFactor, x, g_var, h_mean, log_noise):
                                             _lib.current_stream())
     _lib.check(rc, "gvi_exact_gp_predict_grad_f64")
     return out
+
+
+def weighted_gram(factor: GpFactor, x, g):
+    """C[M,M] = sum_i g_i k(Z,x_i) k(x_i,Z) (gvi_weighted_gram_f64) - dLoss/dSigma of the SVGP family."""
+    n, d = x.shape
+    c = empty(factor.m, factor.m)
+    ws = _workspace("grad", _L().gvi_fused_step_grad_workspace_bytes(n, factor.m, d))
+    rc = _L().gvi_weighted_gram_f64(_lib.ptr(factor.buf), factor.m, d, _lib.ptr(x), n, _lib.ptr(g), _lib.ptr(c),
+                                    _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_weighted_gram_f64")
+    return c

@@ -19,7 +19,7 @@ from .gps.classification_base import GPClassificationBase
 from .gps.gp_regression import GPRegression
 from .kernels.approximate.fixed_sparse_posterior_kernel import FixedSparsePosteriorKernel
 from .kernels.approximate.sparse_posterior_kernel import SparsePosteriorKernel
-from .kernels.approximate.svgp.svgp_kernels import SVGPBaseKernel
+from .kernels.approximate.svgp.svgp_kernels import LogSVGPKernel, SVGPBaseKernel
 from .regularisations.base import RegularisationBase
 from .regularisations.schemas import RegularisationMode
 from .utils.device import as_2d, as_device
@@ -187,10 +187,14 @@ class GeneralisedVariationalInference:
 
     def _calculate_loss(self, parameters, x, y):
         if self._fusable():
-            if torch.is_grad_enabled() and self._wants_grad(parameters):
+            wants = torch.is_grad_enabled() and self._wants_grad(parameters)
+            if not wants:
+                out3 = self.loss_sums(parameters, x, y)
+                return (out3[0] + out3[1]) / out3[2]
+            if not isinstance(self._empirical_risk.gp.kernel, LogSVGPKernel):
                 return _FusedLoss.apply(self, parameters, x, y, *self._grad_leaves(parameters))
-            out3 = self.loss_sums(parameters, x, y)
-            return (out3[0] + out3[1]) / out3[2]
+            # LogSVGPKernel (dense El): trained through the general path below (dLoss/dSigma from the weighted-Gram
+            # kernel, the M x M parameterisation differentiated by the host framework)
         gp = self._empirical_risk.gp
         parameters = gp._to_parameters(parameters)
         x = as_device(x)  # one device copy, so both terms see the same tensor

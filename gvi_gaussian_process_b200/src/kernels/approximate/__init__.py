@@ -3,4 +3,4 @@ from .fixed_sparse_posterior_kernel import (  # noqa: F401
     FixedSparsePosteriorKernel,
     FixedSparsePosteriorKernelParameters,
 )
-from .svgp import CholeskySVGPKernel, DiagonalSVGPKernel, KernelisedSVGPKernel  # noqa: F401
+from .svgp import CholeskySVGPKernel, DiagonalSVGPKernel, KernelisedSVGPKernel, LogSVGPKernel  # noqa: F401

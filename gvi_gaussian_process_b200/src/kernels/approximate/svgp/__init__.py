@@ -5,5 +5,7 @@ from .svgp_kernels import (  # noqa: F401
     DiagonalSVGPKernelParameters,
     KernelisedSVGPKernel,
     KernelisedSVGPKernelParameters,
+    LogSVGPKernel,
+    LogSVGPKernelParameters,
     SVGPBaseKernel,
 )

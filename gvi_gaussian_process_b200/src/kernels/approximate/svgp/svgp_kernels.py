@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 
 from .... import _lib_proxy as L
+from ...._autograd import SVGPVariance, wants_grad
 from ....utils.device import as_2d, as_device, scalar
 from ...base import KernelBase, KernelBaseParameters
 from ...standard.ard_kernel import ARDKernel
@@ -64,9 +65,19 @@ class SVGPBaseKernel(KernelBase):
         f.set_extra(self._el_matrix(parameters).contiguous())
         return f
 
+    def _sigma_matrix(self, parameters) -> torch.Tensor:
+        """Sigma = E^T E as a (host-framework differentiable) function of the trainable parameters."""
+        e = self._el_matrix(parameters)
+        return e.T @ e
+
     def _calculate_gram_diagonal(self, parameters, x):
         f = self.factorise(parameters)
-        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        x = x.reshape(x.shape[0], -1)
+        if wants_grad(*self.grad_leaves(parameters)):
+            # general (non-fused) objectives, e.g. classification: dLoss/dSigma from the weighted-Gram kernel, the
+            # M x M map parameters -> Sigma differentiated by the host framework
+            return SVGPVariance.apply(f, x, self._sigma_matrix(parameters))
+        _, var = L.gp_predict(f, x, want_mean=False)
         return var
 
     def _calculate_gram(self, parameters, x1, x2):
@@ -77,8 +88,7 @@ class SVGPBaseKernel(KernelBase):
         k1z = k.calculate_gram(kp, x1, self.inducing_points)
         k2z = k.calculate_gram(kp, x2, self.inducing_points)
         k12 = k.calculate_gram(kp, x1, x2)
-        e = self._el_matrix(parameters)
-        return k12 - (k1z @ linv.T) @ (k2z @ linv.T).T + (k1z @ e.T) @ (k2z @ e.T).T
+        return k12 - (k1z @ linv.T) @ (k2z @ linv.T).T + k1z @ self._sigma_matrix(parameters) @ k2z.T
 
 
 class CholeskySVGPKernelParameters(KernelBaseParameters):
@@ -145,6 +155,47 @@ class DiagonalSVGPKernel(SVGPBaseKernel):
         return [torch.diagonal(d_e) * 0.5 * torch.exp(0.5 * d)]
 
 
+class LogSVGPKernelParameters(KernelBaseParameters):
+    """log_el_matrix [M,M]."""
+
+
+class LogSVGPKernel(SVGPBaseKernel):
+    """reference: src/kernels/approximate/svgp/log_svgp_kernel.py:20-124 - El = exp(P) exp(P)^T (elementwise exp, dense
+    and symmetric), Sigma = El^T El.  The tile kernel wants a LOWER-triangular E with E^T E = Sigma: the triangular
+    factor of a QL factorisation of El, one M^3 library factorisation per step."""
+
+    Parameters = LogSVGPKernelParameters
+
+    def initialise_el_matrix_parameters(self):
+        """reference lines 60-79: log(clip(inv(chol(K_ZZ + K_ZX K_XZ / noise)), diagonal_regularisation))."""
+        return torch.log(torch.clamp(self._initial_inverse_cholesky(), min=self.diagonal_regularisation))
+
+    def generate_parameters(self, parameters=None) -> LogSVGPKernelParameters:
+        if parameters is None:
+            return LogSVGPKernelParameters(log_el_matrix=self.initialise_el_matrix_parameters())
+        return LogSVGPKernelParameters(log_el_matrix=parameters["log_el_matrix"])
+
+    def _sigma_matrix(self, parameters) -> torch.Tensor:
+        ex = torch.exp(as_device(parameters.log_el_matrix))
+        el = ex @ ex.T
+        return el.T @ el
+
+    def _el_matrix(self, parameters) -> torch.Tensor:
+        # "QL" factorisation El = Q Lo (Lo lower triangular) gives Sigma = El^T El = Lo^T Lo without squaring the
+        # condition number (a Cholesky of Sigma breaks down for the reference's own initialisation, whose El spans
+        # ~10 orders of magnitude).  QL through the library QR of the flipped matrix: J El J = Q R => Lo = J R J.
+        ex = torch.exp(as_device(parameters.log_el_matrix).detach())
+        el = ex @ ex.T
+        r = torch.linalg.qr(torch.flip(el, dims=(0, 1)), mode="r").R
+        return torch.flip(r, dims=(0, 1)).contiguous()
+
+    def grad_leaves(self, parameters):
+        return [parameters.log_el_matrix]
+
+    def parameter_gradients(self, parameters, d_e):
+        raise NotImplementedError("LogSVGPKernel trains through the general objective path (loss.backward())")
+
+
 class KernelisedSVGPKernelParameters(KernelBaseParameters):
     """base_kernel: parameters of the (trainable) base kernel."""
 
@@ -178,6 +229,10 @@ class KernelisedSVGPKernel(SVGPBaseKernel):
         f.set_extra(None)
         _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
         return var + self.base_kernel.calculate_gram(parameters.base_kernel, x, x, full_covariance=False)
+
+    def grad_leaves(self, parameters):
+        base = self.base_kernel._to_parameters(parameters.base_kernel)
+        return [base.log_scaling, base.log_lengthscales]
 
     def _calculate_gram(self, parameters, x1, x2):
         f = self._frozen_factor()

@@ -4,6 +4,7 @@ from __future__ import annotations
 import torch
 
 from ... import _lib_proxy as L
+from ..._autograd import wants_grad
 from ...utils.device import as_device, empty, scalar
 from ..base import KernelBase, KernelBaseParameters
 
@@ -44,6 +45,8 @@ class ARDKernel(KernelBase):
 
     def _calculate_gram_diagonal(self, parameters, x):
         ls, _ = self.device_parameters(parameters)
+        if wants_grad(ls):
+            return (torch.exp(ls) ** 2).expand(x.shape[0])  # k(x,x) = exp(log_scaling)^2, differentiable
         out = empty(x.shape[0])
         L.ard_gram_diag(x.shape[0], ls, out)
         return out

@@ -201,6 +201,13 @@ int gvi_multinomial_risk_f64(const double* prob_q, const double* y, const double
 int gvi_multinomial_risk_grad_f64(const double* prob_q, const double* y, const double* prob_p, int K, int64_t N,
                                   int power, const double* weights4, double* dprob_out, void* stream);
 
+/* Weighted Gram C = sum_i g[i] k(Z,x_i) k(x_i,Z) ([M,M] row-major) on the tensor pipe: for the SVGP family
+ * (var_i = k_ii - k_i^T A^-1 k_i + k_i^T Sigma k_i, kernel hyper-parameters frozen) this is dLoss/dSigma given
+ * g = dLoss/dvar, whatever the parameterisation of Sigma (cholesky_svgp_kernel.py:133-150, diagonal_svgp_kernel.py:
+ * 117-129, log_svgp_kernel.py:108-124).  Workspace: gvi_fused_step_grad_workspace_bytes(N, M, D).  D <= 32.      */
+int gvi_weighted_gram_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g,
+                          double* C_out, void* workspace, void* stream);
+
 /* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
 int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
 

@@ -409,3 +409,17 @@ def cross_entropy_from_probabilities(probabilities, y) -> float:
     p = np.asarray(probabilities, dtype=np.float64)
     logp = p - np.log(np.sum(np.exp(p), axis=1, keepdims=True))
     return float(np.mean(-np.sum(np.asarray(y, dtype=np.float64) * logp, axis=1)))
+
+
+def log_svgp_initial_parameters(gram_fn, inducing_points, training_points, log_observation_noise,
+                                diagonal_regularisation=1e-5):
+    """log_svgp_kernel.py:60-79: log(clip(inv(chol(K_ZZ + K_ZX K_XZ / noise)), diagonal_regularisation))."""
+    inv_chol = svgp_initial_inverse_cholesky(gram_fn, inducing_points, training_points, log_observation_noise)
+    return np.log(np.clip(inv_chol, diagonal_regularisation, None))
+
+
+def log_svgp_sigma(log_el_matrix) -> np.ndarray:
+    """log_svgp_kernel.py:108-112: El = exp(P) exp(P)^T (elementwise exp), Sigma = El^T El."""
+    ex = np.exp(np.asarray(log_el_matrix, dtype=np.float64))
+    el = ex @ ex.T
+    return el.T @ el

@@ -425,3 +425,133 @@ def test_exact_gp_nll_step_backward_matches_autograd_twin(S, n, m, d, scalar_ll)
     for got, want in ((t_ls, c_ls), (t_noise, c_noise), (t_c, c_c)):
         assert abs(float(got.grad) - float(want.grad)) <= GTOL * max(abs(float(want.grad)), 1e-6), (got.grad, want.grad)
     assert rel_norm(host(t_ll.grad).reshape(-1), c_ll.grad.numpy().reshape(-1)) <= GTOL
+
+
+# ---- SVGP family on the general path: log-SVGP (dense El) and dLoss/dSigma from the weighted-Gram kernel ----------
+def svgp_problem(n, m, d, seed, sharp=False):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d))
+    z = x[rng.permutation(n)[:m]].copy()
+    y = np.sin(x @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    # sharp: short lengthscales -> K_ZZ close to the identity, so that the log-SVGP El = exp(P) exp(P)^T (whose
+    # initialisation exponentiates log(inv(chol(.)))) stays within a few orders of magnitude
+    ls, ll = 0.1, np.log(rng.uniform(0.5, 1.5, d) * (6.0 if sharp else 1.0 / d))
+    return x, z, y, ls, ll
+
+
+def test_log_svgp_kernel_matches_oracle(S):
+    from gvi_gaussian_process_b200.src.kernels.approximate import LogSVGPKernel
+
+    n, m, d, lam = 1500, 48, 3, 1e-5
+    x, z, y, ls, ll = svgp_problem(n, m, d, seed=2, sharp=True)
+    gram = lambda a, b: O.ard_gram(ls, ll, a, b)
+    kern = LogSVGPKernel(regulariser_kernel=S.ARDKernel(number_of_dimensions=d),
+                         regulariser_kernel_parameters={"log_scaling": ls, "log_lengthscales": ll},
+                         log_observation_noise=np.log(0.5), inducing_points=z, training_points=x[:300],
+                         diagonal_regularisation=lam)
+    params = kern.generate_parameters()
+    init = O.log_svgp_initial_parameters(gram, z, x[:300], np.log(0.5), lam)
+    assert rel_norm(host(params.log_el_matrix), init) <= 1e-9
+    rng = np.random.default_rng(0)
+    log_el = init + 0.05 * rng.standard_normal(init.shape)
+    params = kern.generate_parameters({"log_el_matrix": log_el})
+    sigma = O.log_svgp_sigma(log_el)
+    ref_full = O.svgp_gram(gram, z, sigma, x[:40], x[:25], lam)
+    assert rel_norm(host(kern.calculate_gram(params, x[:40], x[:25])), ref_full) <= TOL
+    ref_diag = np.array([O.svgp_gram(gram, z, sigma, x[i:i + 1], x[i:i + 1], lam)[0, 0] for i in range(0, n, 7)])
+    got = host(kern.calculate_gram(params, x, x, full_covariance=False))[::7]
+    assert rel_norm(got, ref_diag) <= TOL
+
+
+@pytest.mark.parametrize("variant", ["cholesky", "diagonal", "log"])
+def test_svgp_general_path_backward_matches_autograd_twin(S, variant):
+    """loss = NLL + GWI regulariser evaluated term by term (not the fused launch): the SVGP variance is differentiated
+    through SVGPVariance (dLoss/dSigma = weighted Gram on the tensor pipe)."""
+    from gvi_gaussian_process_b200.src.kernels.approximate import (CholeskySVGPKernel, DiagonalSVGPKernel,
+                                                                   LogSVGPKernel)
+
+    n, m, d, lam = 900, 40, 2, 1e-4
+    x, z, y, ls, ll = svgp_problem(n, m, d, seed=5, sharp=(variant == "log"))
+    rng = np.random.default_rng(1)
+    cls = {"cholesky": CholeskySVGPKernel, "diagonal": DiagonalSVGPKernel, "log": LogSVGPKernel}[variant]
+    kern = cls(regulariser_kernel=S.ARDKernel(number_of_dimensions=d),
+               regulariser_kernel_parameters={"log_scaling": ls, "log_lengthscales": ll},
+               log_observation_noise=np.log(0.5), inducing_points=z, training_points=x[:200],
+               diagonal_regularisation=lam)
+    init = kern.generate_parameters()
+    if variant == "cholesky":
+        raw = {"el_matrix_lower_triangle": host(init.el_matrix_lower_triangle) + 0.01 * rng.standard_normal((m, m)),
+               "el_matrix_log_diagonal": host(init.el_matrix_log_diagonal) + 0.05 * rng.standard_normal(m)}
+    elif variant == "diagonal":
+        raw = {"log_el_matrix_diagonal": host(init.log_el_matrix_diagonal) + 0.05 * rng.standard_normal(m)}
+    else:
+        raw = {"log_el_matrix": host(init.log_el_matrix) + 0.02 * rng.standard_normal((m, m))}
+    leaves = {k: dev(v, True) for k, v in raw.items()}
+    w = dev(rng.standard_normal(d) / np.sqrt(d), True)
+    mean = S.CustomMean(mean_function=lambda p, xx: torch.tanh(xx @ p))
+    gp = S.ApproximateGPRegression(mean=mean, kernel=kern)
+    params = {"mean": {"custom": w}, "kernel": leaves}
+    # standalone NLL (never fused): goes through PredictiveVariance -> PointwiseRisk
+    loss = S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, x, y)
+    loss.backward()
+    # twin
+    tl = {k: cpu(v, True) for k, v in raw.items()}
+    tw = cpu(host(w), True)
+    if variant == "cholesky":
+        e = torch.tril(tl["el_matrix_lower_triangle"], diagonal=-1) + torch.diag(torch.exp(tl["el_matrix_log_diagonal"]))
+        sigma = e.T @ e
+    elif variant == "diagonal":
+        sigma = torch.diag(torch.exp(tl["log_el_matrix_diagonal"]))
+    else:
+        ex = torch.exp(tl["log_el_matrix"])
+        el = ex @ ex.T
+        sigma = el.T @ el
+    var = T.svgp_diag(cpu(ls), cpu(ll), cpu(z), cpu(x), sigma, lam, False)
+    ref = T.gaussian_nll(cpu(y), torch.tanh(cpu(x) @ tw), var)
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    assert rel_norm(host(w.grad), tw.grad.numpy()) <= GTOL
+    for k in raw:
+        got, want = host(leaves[k].grad), tl[k].grad.numpy()
+        if k == "el_matrix_lower_triangle":
+            want = np.tril(want, -1)
+        assert rel_norm(got, want) <= GTOL, k
+
+
+def test_classification_with_kernelised_svgp_kernels(S):
+    """The reference's MNIST configuration (experiments/classification/mnist/main.py:219-246): one KernelisedSVGPKernel
+    per class over that class's inducing points, trained base kernel on top of the frozen sparse-posterior part."""
+    from gvi_gaussian_process_b200.src.kernels.approximate import KernelisedSVGPKernel
+
+    n, d, k, m, lam = 700, 4, 3, 32, 1e-5
+    pr = make_classification_problem(n, d, k, m, seed=21)
+    kernels, kparams, leaves = [], [], []
+    for i in range(k):
+        reg_params = {"log_scaling": pr["ls_p"][i], "log_lengthscales": pr["ll_p"][i]}
+        kernels.append(KernelisedSVGPKernel(base_kernel=S.ARDKernel(number_of_dimensions=d),
+                                            regulariser_kernel=S.ARDKernel(number_of_dimensions=d),
+                                            regulariser_kernel_parameters=reg_params,
+                                            log_observation_noise=pr["noise_p"][i], inducing_points=pr["zs"][i],
+                                            training_points=pr["x"][:100], diagonal_regularisation=lam))
+        a = dev(pr["ls"][i], True)
+        leaves.append(a)
+        kparams.append({"base_kernel": {"log_scaling": a, "log_lengthscales": pr["ll"][i]}})
+    w1, w2 = dev(pr["w1"], True), dev(pr["w2"], True)
+    mean = S.CustomMean(mean_function=lambda p, xx: torch.tanh(xx @ p[0]) @ p[1], number_output_dimensions=k)
+    gp = S.ApproximateGPClassification(mean=mean, kernel=S.MultiOutputKernel(kernels=kernels))
+    params = {"mean": {"custom": (w1, w2)}, "kernel": {"kernels": kparams}}
+    loss = S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, pr["x"], pr["y"])
+    loss.backward()
+    # twin: var_i = frozen sparse posterior of the regulariser kernel + exp(ls_base)^2
+    tx = cpu(pr["x"])
+    tw1, tw2 = cpu(pr["w1"], True), cpu(pr["w2"], True)
+    tls = [cpu(pr["ls"][i], True) for i in range(k)]
+    m_q = (torch.tanh(tx @ tw1) @ tw2).reshape(k, -1)
+    v_q = torch.stack([T.sparse_posterior_diag(cpu(pr["ls_p"][i]), cpu(pr["ll_p"][i]), cpu(pr["zs"][i]), tx, lam, False)
+                       + torch.exp(tls[i]) ** 2 for i in range(k)])
+    ref = T.multinomial_nll(T.classification_probabilities(m_q, v_q, HERMITE[0], HERMITE[1]), cpu(pr["y"]))
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    assert rel_norm(host(w1.grad), tw1.grad.numpy()) <= GTOL
+    for i in range(k):
+        assert abs(float(leaves[i].grad) - float(tls[i].grad)) <= GTOL * abs(float(tls[i].grad))

@@ -244,3 +244,15 @@ def test_classification_regulariser_goldens():
     q = O.classification_probabilities(m_q, v_q)
     assert np.isclose(O.multinomial_wasserstein(p, q), 0.12691447, rtol=1e-7)
     assert O.multinomial_wasserstein(q, q, power=4) == 0.0
+
+
+def test_log_svgp_goldens():
+    # tests/kernels/test_svgp_kernels.py:150-199 (initial log-El) and :266-327 (Gram), identity mock kernel
+    x_train = np.array([[1.0, 2.0, 3.0], [5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    z = np.array([[5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
+    x = np.array([[5.3, 5.0, 6.0], [2.5, 4.5, 2.5]])
+    init = O.log_svgp_initial_parameters(eye_gram, z, x_train, np.log(1.0))
+    np.testing.assert_allclose(init, np.array([[-0.34657362, -11.512925], [-11.512925, -0.34657362]]), rtol=1e-6)
+    g = O.svgp_gram(eye_gram, z, O.log_svgp_sigma(init), x, x)
+    np.testing.assert_allclose(g, np.array([[2.5000998e-01, 1.4142140e-05], [1.4142140e-05, 2.5000998e-01]]),
+                               rtol=1e-6)
