@@ -331,6 +331,19 @@ def run_gpu(args):
     except Exception as e:  # pragma: no cover - reported, never hidden
         sel = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- widened rows, reported beside the headline: never part of `value` ------------------
+    widened = {}
+    if rank == 0:
+        try:
+            widened["classification_config4"] = bench_classification(dev)
+        except Exception as e:  # pragma: no cover - reported, never hidden
+            widened["classification_config4"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            widened["exact_gp_nll_step"] = bench_exact_nll_step(dev, z, yz, theta)
+        except Exception as e:  # pragma: no cover
+            widened["exact_gp_nll_step"] = {"error": f"{type(e).__name__}: {e}"}
+    barrier()
+
     # ---- end to end through the public API with HOST buffers ---------------------------------------------------
     e2e_steps = max(2, min(args.steps, 5))
     barrier()
@@ -385,6 +398,7 @@ def run_gpu(args):
                          "peak_source": "measured FP64 DMMA issue rate on this pool's B200 (profiles/fp64_peak_r01.txt; "
                                         "cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry"},
             "selector": sel,
+            "widened": widened,
             "clocks": clocks.summary(),
         }
         if cpu is not None:
@@ -393,6 +407,121 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return result
+
+
+def bench_classification(dev):
+    """BASELINE.json configs[3] (synthetic MNIST-shaped classification): N=6e4, D=784, K=10 classes, per-class ARD
+    sparse posteriors over M=2048 inducing points each, multinomial NLL + GWI (no eigendecomposition) against the
+    exact GP classifier on a combined inducing set of 2048 points - one forward objective = 20 predictive passes
+    (tensor-pipe Gram + tile kernel) + the Gauss-Hermite class-probability kernel + the reductions."""
+    import torch
+
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPClassification, GPClassification
+    from gvi_gaussian_process_b200.src.kernels import MultiOutputKernel
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
+    from gvi_gaussian_process_b200.src.regularisations import GaussianWassersteinRegularisation
+    from gvi_gaussian_process_b200.src import _lib_proxy as L
+
+    n, d, k, m = 60_000, 784, 10, 2048
+    rng = np.random.default_rng(4)
+    t = lambda a: torch.as_tensor(a, dtype=torch.float64, device=dev)
+    x = t(rng.uniform(0.0, 1.0, (n, d)))
+    labels = rng.integers(0, k, n)
+    y = t(np.eye(k)[labels])
+    ll = t(np.full(d, np.log(1.0 / d)))
+    kern_q = MultiOutputKernel(kernels=[
+        SparsePosteriorKernel(base_kernel=ARDKernel(number_of_dimensions=d),
+                              inducing_points=x[torch.as_tensor(rng.permutation(n)[:m], device=dev)].contiguous(),
+                              diagonal_regularisation=LAMBDA) for _ in range(k)])
+    w = t(rng.standard_normal((d, k)) / np.sqrt(d))
+    mean_q = CustomMean(mean_function=lambda p, xx: xx @ p, number_output_dimensions=k)
+    approx = ApproximateGPClassification(mean=mean_q, kernel=kern_q)
+    params = {"mean": {"custom": w},
+              "kernel": {"kernels": [{"base_kernel": {"log_scaling": t(0.0), "log_lengthscales": ll}}] * k}}
+    zi = torch.as_tensor(rng.permutation(n)[:m], device=dev)
+    exact = GPClassification(mean=ConstantMean(number_output_dimensions=k),
+                             kernel=MultiOutputKernel(kernels=[ARDKernel(number_of_dimensions=d) for _ in range(k)]),
+                             x=x[zi].contiguous(), y=y[zi].contiguous())
+    eparams = {"log_observation_noise": t(np.zeros(k)), "mean": {"constant": t(np.zeros(k))},
+               "kernel": {"kernels": [{"log_scaling": t(0.0), "log_lengthscales": ll}] * k}}
+    gvi = GeneralisedVariationalInference(
+        regularisation=GaussianWassersteinRegularisation(gp=approx, regulariser=exact, regulariser_parameters=eparams,
+                                                         mode="posterior"),
+        empirical_risk=NegativeLogLikelihood(gp=approx))
+    with torch.no_grad():
+        loss = gvi.calculate_loss(params, x, y)  # warm-up
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        steps = 2
+        e0.record()
+        for _ in range(steps):
+            loss = gvi.calculate_loss(params, x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # the quadrature kernel alone, on the predictive of q
+        g = approx.calculate_prediction_gaussian(params, x, full_covariance=False)
+        mq, vq = g.mean.reshape(k, -1).contiguous(), g.covariance.reshape(k, -1).contiguous()
+        roots, weights = approx._hermite_device()
+        L.class_probabilities(mq, vq, roots, weights, approx.epsilon, approx.cdf_lower_bound)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(5):
+            L.class_probabilities(mq, vq, roots, weights, approx.epsilon, approx.cdf_lower_bound)
+        c1.record()
+        torch.cuda.synchronize()
+        cms = c0.elapsed_time(c1) / 5
+    cdf_evals = float(n) * 50 * k * (k - 1)
+    flops = 2.0 * k * n * (2.0 * m * d + m * m) + 2.0 * k * n * m  # q and p: Gram contraction + triangular product
+    return {"n": n, "d": d, "classes": k, "m": m, "ms_per_objective": ms, "points_per_s": n / (ms * 1e-3),
+            "loss": float(loss), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "class_probability_kernel": {"ms": cms, "normal_cdf_evaluations_per_s": cdf_evals / (cms * 1e-3),
+                                         "points_per_s": n / (cms * 1e-3)},
+            "note": "forward objective NLL + GWI(no eig): 10 q-passes + 10 p-passes (factorisation, tensor-pipe "
+                    "Gram for D=784, tile kernel) + Gauss-Hermite class probabilities + reductions"}
+
+
+def bench_exact_nll_step(dev, z, yz, theta):
+    """one exact-GP NLL training step on the inducing set (value and gradient w.r.t.
+    log_scaling, log_lengthscales[D], log_observation_noise and the prior-mean constant), M = N = 1024."""
+    import torch
+
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.gps import GPRegression
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean
+
+    t = lambda a: torch.as_tensor(np.atleast_1d(a), dtype=torch.float64, device=dev).requires_grad_(True)
+    gp = GPRegression(mean=ConstantMean(), kernel=ARDKernel(number_of_dimensions=D), x=z, y=yz)
+    leaves = dict(ls=t(theta["ls_p"]), ll=t(theta["ll_p"]), noise=t(theta["log_noise"]), c=t(0.0))
+    params = {"log_observation_noise": leaves["noise"], "mean": {"constant": leaves["c"]},
+              "kernel": {"log_scaling": leaves["ls"], "log_lengthscales": leaves["ll"]}}
+    nll = NegativeLogLikelihood(gp=gp)
+    xz = torch.as_tensor(z, dtype=torch.float64, device=dev)
+    yy = torch.as_tensor(yz, dtype=torch.float64, device=dev)
+
+    def one():
+        for v in leaves.values():
+            v.grad = None
+        loss = nll.calculate_empirical_risk(params, xz, yy)
+        loss.backward()
+        return loss
+
+    one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    return {"m": int(z.shape[0]), "n": int(z.shape[0]), "ms_per_step": ms, "loss": float(loss.detach()),
+            "grad_log_scaling": float(leaves["ls"].grad), "grad_log_noise": float(leaves["noise"].grad)}
 
 
 def run_reference(args):
