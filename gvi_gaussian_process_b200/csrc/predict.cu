@@ -26,6 +26,10 @@ namespace {
 //   forward, larger M and gradient: 16 warps, one CTA per SM (the gradient keeps the whole b tile in shared memory).
 constexpr int MAX_WARPS = 16;
 constexpr int MT = GVI_MT;    // 8-row m-tiles per group
+#ifndef GVI_PB
+#define GVI_PB 4
+#endif
+constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phase 1 (independent exp chains)
 
 // One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
 // acc[mt][nt] += sum_{kp in [kp0, kp0+nkp)} A(group rows 8mt.., cols 8kp..) * Ktile(cols 8kp.., points 8nt..).
@@ -175,10 +179,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
           // four points at a time: all loads first, four independent exp chains, then the stores (the compiler
           // cannot prove that the K-tile stores do not alias the x tile, so the batching is explicit)
 #pragma unroll
-          for (int i0 = 0; i0 < T; i0 += 4) {
-            double s4[4];
+          for (int i0 = 0; i0 < T; i0 += PB) {
+            double s4[PB];
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < PB; q++) {
               double sa = 0.0, sb = 0.0;
               if constexpr (DR % 2 == 0) {
                 const double2* __restrict__ x2 = reinterpret_cast<const double2*>(xr + (i0 + q) * DR);
@@ -199,9 +203,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
               s4[q] = sa + sb;
             }
 #pragma unroll
-            for (int q = 0; q < 4; q++) s4[q] = scale * gvi_exp(-0.5 * s4[q]);
+            for (int q = 0; q < PB; q++) s4[q] = scale * gvi_exp(-0.5 * s4[q]);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+            for (int q = 0; q < PB; q++) {
               const int i = i0 + q;
               kcol[(i >> 3) * 64 + (i & 7) * 8] = s4[q];
               macc[i] = fma(s4[q], aj, macc[i]);
