@@ -30,6 +30,50 @@ class ModuleParameters:
     def dict_shallow(self) -> Dict[str, Any]:
         return {k: getattr(self, k) for k in self._keys}
 
+    # -- checkpoints (reference: src/module.py:27-55 writes orbax checkpoint directories; orbax is a third-party
+    #    format that is not available here, so the same `.dict()` tree is stored as one .npz with "/"-joined keys) ----
+    def save(self, path: str) -> None:
+        import os
+
+        import numpy as np
+
+        flat = {}
+
+        def walk(prefix, node):
+            if isinstance(node, dict):
+                for k, v in node.items():
+                    walk(f"{prefix}/{k}" if prefix else str(k), v)
+            elif isinstance(node, (list, tuple)):
+                for i, v in enumerate(node):
+                    walk(f"{prefix}/#{i}", v)
+            else:
+                flat[prefix] = node.detach().cpu().numpy() if hasattr(node, "detach") else np.asarray(node)
+
+        walk("", self.dict())
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        np.savez(path if path.endswith(".npz") else path + ".npz", **flat)
+
+    def load(self, path: str) -> "ModuleParameters":
+        import numpy as np
+
+        data = np.load(path if path.endswith(".npz") else path + ".npz")
+        tree: Dict[str, Any] = {}
+        for key in data.files:
+            node = tree
+            parts = key.split("/")
+            for part in parts[:-1]:
+                node = node.setdefault(part, {})
+            node[parts[-1]] = data[key]
+
+        def lists(node):
+            if isinstance(node, dict):
+                if node and all(k.startswith("#") for k in node):
+                    return [lists(node[f"#{i}"]) for i in range(len(node))]
+                return {k: lists(v) for k, v in node.items()}
+            return node
+
+        return self.construct(**lists(tree))
+
     def __repr__(self) -> str:
         return f"{type(self).__name__}({', '.join(f'{k}={getattr(self, k)!r}' for k in self._keys)})"
 
@@ -49,5 +93,9 @@ class Module:
     def _to_parameters(self, parameters):
         if not isinstance(parameters, self.Parameters):
             parameters = self.generate_parameters(dict(parameters))
+        elif any(isinstance(v, dict) for v in parameters.dict_shallow().values()):
+            # `Parameters.construct(**tree)` with plain-dict members (what the reference's trainer builds after every
+            # optimiser step, experiments/shared/trainer.py:92-94): regenerate the nested parameter objects
+            parameters = self.generate_parameters(parameters.dict_shallow())
         Module.check_parameters(parameters, self.Parameters)
         return parameters

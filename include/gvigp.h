@@ -208,6 +208,19 @@ int gvi_multinomial_risk_grad_f64(const double* prob_q, const double* y, const d
 int gvi_weighted_gram_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g,
                           double* C_out, void* workspace, void* stream);
 
+/* ---- section 8(f)-4: device-resident optimiser step (experiments/shared/trainer.py:42-100; the optax 0.1.7
+ * transformations of experiments/shared/resolvers/optimiser.py:6-16 with optax's defaults).  One elementwise launch over
+ * the flat parameter vector: param, grad, mu, nu are device arrays [n]; count is the 1-based step index.
+ *   GVI_OPT_ADAM      b1 .9  b2 .999  eps 1e-8   eps_root 0       p -= lr mu^ / (sqrt(nu^ + eps_root) + eps)
+ *   GVI_OPT_ADABELIEF b1 .9  b2 .999  eps 1e-16  eps_root 1e-16   nu tracks (g - mu_prev)^2 (+ eps_root)
+ *   GVI_OPT_RMSPROP   b2 = decay .9   eps 1e-8                    p -= lr g / sqrt(nu + eps)   (mu unused, may be NULL) */
+#define GVI_OPT_ADAM 0
+#define GVI_OPT_ADABELIEF 1
+#define GVI_OPT_RMSPROP 2
+int gvi_optimiser_step_f64(int kind, double* param, const double* grad, double* mu, double* nu, int64_t n,
+                           int64_t count, double learning_rate, double b1, double b2, double eps, double eps_root,
+                           void* stream);
+
 /* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
 int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
 

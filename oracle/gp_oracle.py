@@ -423,3 +423,31 @@ def log_svgp_sigma(log_el_matrix) -> np.ndarray:
     ex = np.exp(np.asarray(log_el_matrix, dtype=np.float64))
     el = ex @ ex.T
     return el.T @ el
+
+
+# --------------------------------------------------------------------------------------------------------------
+# section 8(f)-4: optimiser rules of the reference's trainer (experiments/shared/resolvers/optimiser.py:6-16).
+# optax 0.1.7 (third-party, pinned in poetry.lock:1916-1917, absent from /root/reference): published update rules of
+# optax.adam / optax.adabelief / optax.rmsprop with their default hyper-parameters.  PARITY UNPINNED: the reference
+# holds no golden for an optimiser step.
+# --------------------------------------------------------------------------------------------------------------
+def optimiser_step(kind, p, g, mu, nu, count, lr):
+    """One step; returns (p, mu, nu).  count is the 1-based step index."""
+    if kind == "adam":
+        b1, b2, eps, eps_root = 0.9, 0.999, 1e-8, 0.0
+        mu = b1 * mu + (1 - b1) * g
+        nu = b2 * nu + (1 - b2) * g * g
+        upd = (mu / (1 - b1**count)) / (np.sqrt(nu / (1 - b2**count) + eps_root) + eps)
+    elif kind == "adabelief":
+        b1, b2, eps, eps_root = 0.9, 0.999, 1e-16, 1e-16
+        err = g - mu  # prediction error against the PREVIOUS first moment (optax.scale_by_belief)
+        mu = b1 * mu + (1 - b1) * g
+        nu = b2 * nu + (1 - b2) * err * err + eps_root
+        upd = (mu / (1 - b1**count)) / (np.sqrt(nu / (1 - b2**count)) + eps)
+    elif kind == "rmsprop":
+        decay, eps = 0.9, 1e-8
+        nu = decay * nu + (1 - decay) * g * g
+        upd = g / np.sqrt(nu + eps)
+    else:
+        raise ValueError(kind)
+    return p - lr * upd, mu, nu

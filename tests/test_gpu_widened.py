@@ -555,3 +555,73 @@ def test_classification_with_kernelised_svgp_kernels(S):
     assert rel_norm(host(w1.grad), tw1.grad.numpy()) <= GTOL
     for i in range(k):
         assert abs(float(leaves[i].grad) - float(tls[i].grad)) <= GTOL * abs(float(tls[i].grad))
+
+
+# ---- section 8(f)-4: device-resident optimiser step and the Trainer loop ------------------------------------------
+@pytest.mark.parametrize("kind,code", [("adam", 0), ("adabelief", 1), ("rmsprop", 2)])
+def test_optimiser_step_kernel_matches_oracle(S, kind, code):
+    from gvi_gaussian_process_b200 import _lib
+    from gvi_gaussian_process_b200.experiments.shared.trainer import _OPTIMISERS, OptimiserSchema
+
+    lib = _lib.load()
+    rng = np.random.default_rng(code)
+    n = 10007
+    p = rng.standard_normal(n)
+    mu, nu = np.zeros(n), np.zeros(n)
+    dp, dmu, dnu = dev(p), dev(mu), dev(nu)
+    k, b1, b2, eps, eps_root = _OPTIMISERS[OptimiserSchema(kind)]
+    assert k == code
+    for count in range(1, 6):
+        g = rng.standard_normal(n) * 10.0 ** rng.integers(-3, 2)
+        p, mu, nu = O.optimiser_step(kind, p, g, mu, nu, count, 1e-2)
+        rc = lib.gvi_optimiser_step_f64(code, dp.data_ptr(), dev(g).data_ptr(), dmu.data_ptr(), dnu.data_ptr(), n,
+                                        count, 1e-2, b1, b2, eps, eps_root, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+    assert rel_norm(host(dp), p) <= 1e-13
+    assert rel_norm(host(dnu), nu) <= 1e-13
+
+
+def test_trainer_exact_gp_nll_matches_cpu_twin(S):
+    """train_regulariser_gp of experiments/regression/trainers.py:19-85 in miniature: the exact GP on the inducing data,
+    NLL loss, AdaBelief, shuffled mini-batches in jax.random.permutation order - against a CPU twin of the same loop
+    (torch-f64 autograd gradients, NumPy optimiser, oracle PRNG)."""
+    from gvi_gaussian_process_b200.experiments.shared import Data, OptimiserSchema, Trainer, TrainerSettings
+    from oracle import jax_prng as OP
+
+    rng = np.random.default_rng(8)
+    m, d = 96, 2
+    z = rng.standard_normal((m, d))
+    yz = np.sin(z @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(m)
+    ls0, ll0, noise0, c0 = 0.1, np.log(np.full(d, 0.7)), np.log(0.5), 0.0
+    kernel = S.ARDKernel(number_of_dimensions=d)
+    gp = S.GPRegression(mean=S.ConstantMean(), kernel=kernel, x=z, y=yz)
+    params = gp.generate_parameters({"log_observation_noise": noise0, "mean": {"constant": c0},
+                                     "kernel": {"log_scaling": ls0, "log_lengthscales": ll0}})
+    nll = S.NegativeLogLikelihood(gp=gp)
+    settings = TrainerSettings(seed=3, optimiser_schema=OptimiserSchema.adabelief, learning_rate=5e-2,
+                               number_of_epochs=3, batch_size=40, batch_shuffle=True, batch_drop_last=False)
+    trainer = Trainer(save_checkpoint_frequency=0, checkpoint_path="",
+                      post_epoch_callback=lambda p: {"empirical-risk": float(nll.calculate_empirical_risk(p, z, yz))})
+    trained, history = trainer.train(settings, params, Data(x=z, y=yz),
+                                     lambda pd, x, y: nll.calculate_empirical_risk(pd, x, y))
+    assert len(history) == 3 and history[-1]["empirical-risk"] < history[0]["empirical-risk"] + 1e-9
+    # ---- CPU twin of the same loop: leaf order of parameters.dict() = noise, mean constant, log_scaling, lengthscales
+    p = np.concatenate([[noise0], [c0], [ls0], ll0])
+    mu, nu = np.zeros_like(p), np.zeros_like(p)
+    key = OP.prng_key(3)
+    count = 0
+    for _ in range(3):
+        key, sub = OP.split(key)
+        perm = OP.permutation(sub, m)
+        for b in range(int(np.ceil(m / 40))):
+            idx = perm[b * 40:(b + 1) * 40]
+            t = [cpu(p[0], True), cpu(p[1], True), cpu(p[2], True), cpu(p[3:], True)]
+            mean_t, var_t = T.exact_gp_posterior(t[2], t[3], t[1], cpu(z), cpu(yz), t[0], cpu(z[idx]))
+            T.gaussian_nll(cpu(yz[idx]), mean_t, var_t).backward()
+            g = np.concatenate([np.atleast_1d(a.grad.numpy()) for a in t])
+            count += 1
+            p, mu, nu = O.optimiser_step("adabelief", p, g, mu, nu, count, 5e-2)
+    got = np.concatenate([host(v).reshape(-1) for v in (trained.log_observation_noise, trained.mean["constant"],
+                                                         trained.kernel["log_scaling"],
+                                                         trained.kernel["log_lengthscales"])])
+    assert rel_norm(got, p) <= 1e-7, (got, p)

@@ -78,3 +78,44 @@ def test_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             device.device()
+
+
+def test_data_and_parameter_files_round_trip(tmp_path):
+    """experiments/shared/data.py:25-35 (`<name>.npz` with x and y) and the parameter checkpoint tree."""
+    from gvi_gaussian_process_b200.experiments.shared import Data
+    from gvi_gaussian_process_b200.src.module import ModuleParameters
+
+    rng = np.random.default_rng(0)
+    a = Data(x=rng.standard_normal((5, 2)), y=rng.standard_normal(5), name="train")
+    b = Data(x=rng.standard_normal((3, 2)), y=rng.standard_normal(3), name="-more")
+    a.save(str(tmp_path))
+    back = Data.load(str(tmp_path), "train")
+    assert np.array_equal(back.x, a.x) and np.array_equal(back.y, a.y)
+    assert set(np.load(tmp_path / "train.npz").files) == {"x", "y"}
+    assert Data.load(str(tmp_path), "missing") is None
+    both = a + b
+    assert both.name == "train-more" and both.x.shape == (8, 2) and both.y.shape == (8,)
+    p = ModuleParameters(log_observation_noise=np.float64(0.3), mean={"constant": np.zeros(2)},
+                         kernel={"kernels": [{"log_scaling": 0.1, "log_lengthscales": np.ones(3)},
+                                             {"log_scaling": 0.2, "log_lengthscales": np.zeros(3)}]})
+    path = str(tmp_path / "epoch-0.ckpt")
+    p.save(path)
+    q = ModuleParameters().load(path)
+    assert float(q.log_observation_noise) == 0.3 and np.array_equal(q.mean["constant"], np.zeros(2))
+    assert float(q.kernel["kernels"][1]["log_scaling"]) == 0.2
+    assert np.array_equal(q.kernel["kernels"][0]["log_lengthscales"], np.ones(3))
+
+
+def test_generate_batch_follows_the_reference_order():
+    """src/utils/data.py:11-62: permutation order, floor/ceil step counts, at least one step."""
+    from gvi_gaussian_process_b200.src.utils import jax_prng
+    from gvi_gaussian_process_b200.src.utils.data import generate_batch
+
+    x, y = np.arange(10.0).reshape(10, 1), np.arange(10.0)
+    key = jax_prng.PRNGKey(0)
+    perm = jax_prng.permutation(key, 10)
+    batches = list(generate_batch(key, (x, y), batch_size=4, shuffle=True, drop_last=True))
+    assert len(batches) == 2 and np.array_equal(batches[0][1], y[perm[:4]]) and np.array_equal(batches[1][0], x[perm[4:8]])
+    batches = list(generate_batch(key, (x, y), batch_size=4, shuffle=False, drop_last=False))
+    assert [len(b[1]) for b in batches] == [4, 4, 2] and np.array_equal(batches[2][1], y[8:])
+    assert len(list(generate_batch(key, x, batch_size=64, shuffle=False, drop_last=True))) == 1
