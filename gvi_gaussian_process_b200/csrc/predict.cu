@@ -38,9 +38,50 @@ constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phas
 // the caller initialises acc (zero, or a parked partial sum in the multi-panel path).
 // PREFETCH_B: also fetch the B fragments (shared memory) one k-pair ahead - pays in the 16-warp one-CTA shape
 // (M=2048: 67.1 -> 65.5 ms, M=4096: 108 -> 101 ms), costs in the 8-warp two-CTA shape (71.6 -> 72.9 ms at M=1024).
+#ifndef GVI_DEEP_A
+#define GVI_DEEP_A 1
+#endif
 template <int NT, bool PREFETCH_B>
 __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
                                           const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2]) {
+  if constexpr (!PREFETCH_B && GVI_DEEP_A) {
+    // A fragments fetched TWO k-pairs ahead through three rotating register buffers (+8 registers): with two CTAs per
+    // SM a CTA is alone on the tensor pipe while its neighbour generates a K tile, i.e. two warps per sub-partition -
+    // one k-pair of lead (12 DMMAs x 2 warps ~ 400 cycles) is shorter than the L2 latency under load, two are not.
+    double2 a0[MT], a1[MT], a2[MT];
+    auto lda = [&](double2 (&a)[MT], int k) {
+      const int kc = k < nkp ? k : nkp - 1;
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) a[mt] = __ldcg(Ag + (kc * MT + mt) * 32);
+    };
+    auto step = [&](const double2 (&a)[MT], int k) {
+      double2 b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+    };
+    lda(a0, 0);
+    lda(a1, 1);
+    int k = 0;
+    for (; k + 3 <= nkp; k += 3) {
+      lda(a2, k + 2);
+      step(a0, k);
+      lda(a0, k + 3);
+      step(a1, k + 1);
+      lda(a1, k + 4);
+      step(a2, k + 2);
+    }
+    if (k < nkp) step(a0, k);
+    if (k + 1 < nkp) step(a1, k + 1);
+    return;
+  }
   if constexpr (!PREFETCH_B) {
     double2 a_cur[MT], a_nxt[MT];
 #pragma unroll
