@@ -6,7 +6,13 @@ with everything device-resident: the trainable leaves of `parameters.dict()` are
 vector, `loss_function(parameters_dict, x, y).backward()` (the CUDA vector-Jacobian products behind the torch autograd
 front end) accumulates straight into a flat gradient vector, and the optimiser (optax adam / adabelief / rmsprop rules,
 experiments/shared/resolvers/optimiser.py:6-16) is one CUDA launch over the flat vectors (gvi_optimiser_step_f64).
-Only the loss scalar visits the host (the reference's NaN test does the same)."""
+Only the loss scalar visits the host (the reference's NaN test does the same).
+
+Multi-GPU (one process per GPU, torch.distributed initialised): every rank walks the SAME batch sequence (same seed ->
+same permutation) and evaluates its contiguous slice of each batch (distributed.shard_bounds); the flat gradient vector
+is combined with ONE all-reduce per step - weighted by the slice sizes for objectives that are means over points
+(`gradient_reduction="mean"`, the default), plainly summed for objectives that are sums over points (the multinomial
+NLL) - so N ranks take exactly the single-GPU optimisation path."""
 from __future__ import annotations
 
 import math
@@ -16,8 +22,10 @@ from typing import Any, Callable, Dict, List, Tuple
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from ... import _lib
+from ...distributed import shard_bounds
 from ...src.module import ModuleParameters
 from ...src.utils import jax_prng
 from ...src.utils.data import generate_batch
@@ -105,7 +113,11 @@ class FlatParameters:
 class Trainer:
     def __init__(self, save_checkpoint_frequency: int, checkpoint_path: str,
                  post_epoch_callback: Callable[[ModuleParameters], Dict[str, float]],
-                 break_condition_function: Callable[[ModuleParameters], bool] = None):
+                 break_condition_function: Callable[[ModuleParameters], bool] = None,
+                 gradient_reduction: str = "mean", group=None):
+        assert gradient_reduction in ("mean", "sum")
+        self.gradient_reduction = gradient_reduction
+        self.group = group
         self.save_checkpoint_frequency = save_checkpoint_frequency
         self.checkpoint_path = checkpoint_path
         self.post_epoch_callback = post_epoch_callback
@@ -125,6 +137,9 @@ class Trainer:
         current = lambda: parameters.construct(**flat.detached_tree())
         key = jax_prng.PRNGKey(trainer_settings.seed)
         count = 0
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        packed = torch.zeros(flat.flat.numel() + 2, dtype=torch.float64, device=flat.flat.device) if world > 1 else None
         for epoch in range(trainer_settings.number_of_epochs):
             if self.save_checkpoint_frequency and epoch % self.save_checkpoint_frequency == 0:
                 current().save(path=os.path.join(self.checkpoint_path, f"epoch-{epoch}.ckpt"))
@@ -134,10 +149,27 @@ class Trainer:
                                                    shuffle=trainer_settings.batch_shuffle,
                                                    drop_last=trainer_settings.batch_drop_last):
                 flat.grad.zero_()
-                loss = loss_function(flat.tree, x_batch, y_batch)
-                if bool(torch.isnan(loss.detach())):
-                    return current(), post_epoch_history
-                loss.backward()
+                if world > 1:
+                    lo, hi = shard_bounds(x_batch.shape[0], rank, world)
+                    n_local = hi - lo
+                    weight = float(n_local) if self.gradient_reduction == "mean" else 1.0
+                    packed.zero_()
+                    if n_local > 0:
+                        loss = loss_function(flat.tree, x_batch[lo:hi], y_batch[lo:hi])
+                        loss.backward()
+                        packed[:-2] = flat.grad * weight
+                        packed[-2] = weight
+                        packed[-1] = loss.detach() * weight
+                    dist.all_reduce(packed, group=self.group)  # gradient, normaliser and loss in one collective
+                    norm = packed[-2] if self.gradient_reduction == "mean" else 1.0
+                    flat.grad.copy_(packed[:-2] / norm)
+                    if bool(torch.isnan(packed[-1])):
+                        return current(), post_epoch_history
+                else:
+                    loss = loss_function(flat.tree, x_batch, y_batch)
+                    if bool(torch.isnan(loss.detach())):
+                        return current(), post_epoch_history
+                    loss.backward()
                 count += 1
                 _lib.check(lib.gvi_optimiser_step_f64(kind, flat.flat.data_ptr(), flat.grad.data_ptr(), mu.data_ptr(),
                                                       nu.data_ptr(), flat.flat.numel(), count,

@@ -14,6 +14,60 @@ from gvi_gaussian_process_b200 import distributed  # noqa: E402
 from gvi_gaussian_process_b200.src import _lib_proxy as L  # noqa: E402
 
 
+def check_trainer(rank, world, dev) -> bool:
+    """Approximate-GP classification objective (multinomial NLL, a SUM over points -> gradient_reduction="sum") trained
+    for a few AdaBelief steps on `world` ranks (each evaluating its slice of every batch) and, on rank 0, once more on a
+    sub-group of size 1: the parameters must agree."""
+    from gvi_gaussian_process_b200.experiments.shared import Data, OptimiserSchema, Trainer, TrainerSettings
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPClassification
+    from gvi_gaussian_process_b200.src.kernels import MultiOutputKernel
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import CustomMean
+
+    rng = np.random.default_rng(5)
+    n, d, k, m = 1203, 3, 3, 16
+    x = rng.standard_normal((n, d))
+    y = np.eye(k)[rng.integers(0, k, n)]
+    kern = MultiOutputKernel(kernels=[
+        SparsePosteriorKernel(base_kernel=ARDKernel(number_of_dimensions=d), inducing_points=x[i * m:(i + 1) * m],
+                              diagonal_regularisation=1e-4) for i in range(k)])
+    # the mean returns [k, n]: MeanBase.predict RESHAPES its output to (k, -1) (reference means/base.py:97-100), so an
+    # (n, k) output would mix points and classes in a batch-size dependent way and the objective would not be a sum
+    # over points (true of the reference as well) - with [k, n] the reshape is the identity
+    mean = CustomMean(mean_function=lambda p, xx: (torch.tanh(xx @ p[0]) @ p[1]).T, number_output_dimensions=k)
+    gp = ApproximateGPClassification(mean=mean, kernel=kern)
+    nll = NegativeLogLikelihood(gp=gp)
+    w1, w2 = rng.standard_normal((d, 5)) / np.sqrt(d), rng.standard_normal((5, k)) / np.sqrt(5)
+
+    def fresh_parameters():
+        return gp.Parameters.construct(
+            mean={"custom": (w1.copy(), w2.copy())},
+            kernel={"kernels": [{"base_kernel": {"log_scaling": 0.1 * i, "log_lengthscales": np.full(d, -1.0)}}
+                                for i in range(k)]})
+
+    settings = TrainerSettings(seed=1, optimiser_schema=OptimiserSchema.adabelief, learning_rate=1e-2,
+                               number_of_epochs=2, batch_size=400, batch_shuffle=True, batch_drop_last=False)
+    loss_fn = lambda pd, xb, yb: nll.calculate_empirical_risk(pd, xb, yb)
+    flatten = lambda p: torch.cat([torch.as_tensor(v).reshape(-1) for v in (
+        list(p.mean["custom"]) + [kk["base_kernel"][name] for kk in p.kernel["kernels"]
+                                  for name in ("log_scaling", "log_lengthscales")])])
+    sharded, _ = Trainer(0, "", lambda p: {}, gradient_reduction="sum").train(settings, fresh_parameters(),
+                                                                               Data(x=x, y=y), loss_fn)
+    solo_group = dist.new_group([0])  # collective: every rank creates it, only rank 0 uses it
+    ok = True
+    if rank == 0:
+        single, _ = Trainer(0, "", lambda p: {}, gradient_reduction="sum", group=solo_group).train(
+            settings, fresh_parameters(), Data(x=x, y=y), loss_fn)
+        a, b = flatten(sharded), flatten(single)
+        err = float((a - b).abs().max() / b.abs().max())
+        moved = float((b - flatten(fresh_parameters()).to(b.device)).abs().max())
+        print(f"[multigpu] trainer: {world}-rank vs 1-rank parameters rel err {err:.2e} (moved {moved:.2e})")
+        ok = err < 1e-9 and moved > 1e-3
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -55,6 +109,8 @@ def main():
         # sums re-associate only (1e-12); the gradient passes through S = A^-1 C A^-1 whose rounding depends on
         # the order C was accumulated in (cond(A)^2 * eps), tolerance = the gradient parity tolerance
         ok &= err_sums < 1e-12 and err_grad < 1e-8 and dm_err < 1e-13
+    # ---- data-parallel Trainer: N ranks must take the single-GPU optimisation path -----------------------------------
+    ok &= check_trainer(rank, world, dev)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
