@@ -23,6 +23,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core (set before the BLAS libraries load)
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
