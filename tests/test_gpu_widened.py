@@ -625,3 +625,41 @@ def test_trainer_exact_gp_nll_matches_cpu_twin(S):
                                                          trained.kernel["log_scaling"],
                                                          trained.kernel["log_lengthscales"])])
     assert rel_norm(got, p) <= 1e-7, (got, p)
+
+
+def test_golden_fixture_classification(S):
+    """tests/golden/config4_mini_classification.npz (oracle outputs, script committed next to it): the product path
+    reproduces probabilities, risks and regularisers of the committed fixture."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config4_mini_classification.npz"))
+    x, y, k, d = g["x"], g["y"], g["y"].shape[1], g["x"].shape[1]
+    lam = float(g["lam"])
+    kern_q = S.MultiOutputKernel(kernels=[
+        S.SparsePosteriorKernel(base_kernel=S.ARDKernel(number_of_dimensions=d), inducing_points=g["zs"][i],
+                                diagonal_regularisation=lam) for i in range(k)])
+    mean_q = S.CustomMean(mean_function=lambda p, xx: xx @ p, number_output_dimensions=k)
+    approx = S.ApproximateGPClassification(mean=mean_q, kernel=kern_q)
+    params = {"mean": {"custom": dev(g["w"])},
+              "kernel": {"kernels": [{"base_kernel": {"log_scaling": g["ls_q"][i], "log_lengthscales": g["ll_q"][i]}}
+                                     for i in range(k)]}}
+    exact = S.GPClassification(mean=S.ConstantMean(number_output_dimensions=k),
+                               kernel=S.MultiOutputKernel(kernels=[S.ARDKernel(number_of_dimensions=d)
+                                                                   for _ in range(k)]),
+                               x=x[g["zi"]], y=y[g["zi"]])
+    eparams = {"log_observation_noise": g["noise_p"], "mean": {"constant": np.zeros(k)},
+               "kernel": {"kernels": [{"log_scaling": g["ls_p"][i], "log_lengthscales": g["ll_p"][i]}
+                                      for i in range(k)]}}
+    assert np.max(np.abs(host(approx.predict_probability(params, x).probabilities) - g["prob_q"])) <= TOL
+    assert np.max(np.abs(host(exact.predict_probability(eparams, x).probabilities) - g["prob_p"])) <= TOL
+    close = lambda a, b: abs(float(a) - float(b)) <= TOL * max(abs(float(b)), 1e-3)
+    assert close(S.NegativeLogLikelihood(gp=approx).calculate_empirical_risk(params, x, y), g["nll"])
+    assert close(S.CrossEntropy(gp=approx).calculate_empirical_risk(params, x, y), g["cross_entropy"])
+    kw = dict(gp=approx, regulariser=exact, regulariser_parameters=eparams, mode="posterior")
+    assert close(S.MultinomialWassersteinRegularisation(**kw).calculate_regularisation(params, x),
+                 g["reg_multinomial_wasserstein"])
+    assert close(S.GaussianWassersteinRegularisation(**kw).calculate_regularisation(params, x), g["reg_gwi_no_eig"])
+    for kind, cls in [("bhattacharyya", "ProjectedBhattacharyyaRegularisation"), ("kl", "ProjectedKLRegularisation"),
+                      ("gaussian_wasserstein", "ProjectedGaussianWassersteinRegularisation"),
+                      ("hellinger", "ProjectedHellingerRegularisation"), ("renyi", "ProjectedRenyiRegularisation")]:
+        assert close(getattr(S.projected, cls)(**kw).calculate_regularisation(params, x), g["reg_" + kind]), kind

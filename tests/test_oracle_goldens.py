@@ -256,3 +256,19 @@ def test_log_svgp_goldens():
     g = O.svgp_gram(eye_gram, z, O.log_svgp_sigma(init), x, x)
     np.testing.assert_allclose(g, np.array([[2.5000998e-01, 1.4142140e-05], [1.4142140e-05, 2.5000998e-01]]),
                                rtol=1e-6)
+
+
+def test_committed_classification_fixture_is_current():
+    """tests/golden/config4_mini_classification.npz must be what the oracle produces today (stale-fixture guard)."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config4_mini_classification.npz"))
+    np.testing.assert_allclose(O.classification_probabilities(g["m_q"], g["v_q"]), g["prob_q"], rtol=1e-13)
+    assert np.isclose(O.multinomial_nll(g["prob_q"], g["y"]), float(g["nll"]), rtol=1e-13)
+    assert np.isclose(O.multinomial_wasserstein(g["prob_p"], g["prob_q"]), float(g["reg_multinomial_wasserstein"]),
+                      rtol=1e-13)
+    i = 1
+    gram = lambda a, b: O.ard_gram(g["ls_q"][i], g["ll_q"][i], a, b)
+    diag = lambda a: O.ard_gram_diag(g["ls_q"][i], g["ll_q"][i], a)
+    np.testing.assert_allclose(O.sparse_posterior_diag(gram, diag, g["zs"][i], g["x"], float(g["lam"]), False),
+                               g["v_q"][i], rtol=1e-12)
