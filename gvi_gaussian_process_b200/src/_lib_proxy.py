@@ -106,12 +106,42 @@ _risk_ws = {}
 
 
 def _workspace(key, nbytes):
+    """Scratch buffer cached per (purpose, device, stream): launches on different streams never share scratch."""
     dev = device()
-    buf = _risk_ws.get((key, dev))
+    slot = (key, dev, torch.cuda.current_stream().cuda_stream)
+    buf = _risk_ws.get(slot)
     if buf is None or buf.numel() * 8 < nbytes:
         buf = empty((nbytes + 7) // 8)
-        _risk_ws[(key, dev)] = buf
+        _risk_ws[slot] = buf
     return buf
+
+
+_side_streams = {}
+
+
+def run_concurrently(jobs, n_streams: int = 4):
+    """Run independent callables round-robin on a small pool of side streams and join them into the current stream.
+    Used for the K per-class predictives of a multi-output GP: each is a latency-bound factorisation (a chain of small
+    launches that fills a fraction of the GPU) followed by wide kernels, so neighbours overlap."""
+    cur = torch.cuda.current_stream()
+    dev = device()
+    pool = _side_streams.setdefault(dev, [])
+    while len(pool) < n_streams:
+        pool.append(torch.cuda.Stream(device=dev))
+    outs = []
+    for i, job in enumerate(jobs):
+        s = pool[i % n_streams]
+        if i < n_streams:
+            s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            outs.append(job())
+    for s in pool[: min(n_streams, len(outs))]:
+        cur.wait_stream(s)
+    for o in outs:
+        for t in (o if isinstance(o, (tuple, list)) else (o,)):
+            if isinstance(t, torch.Tensor):
+                t.record_stream(cur)
+    return outs
 
 
 def risk(reg_kind, alpha, y, m_q, v_q, m_p, v_p):

@@ -39,18 +39,24 @@ class GPClassification(GPClassificationBase):
 
     def factorise(self, parameters):
         parameters = self._to_parameters(parameters)
-        k = self.number_output_dimensions
-        if self._factors is None:
-            self._factors = [L.GpFactor(self.x.shape[0], self.x.shape[1]) for _ in range(k)]
-            self._y_cols = self.y.t().contiguous()  # [K, n] (base.py:480)
-        noise = as_device(parameters.log_observation_noise).reshape(-1)
-        for i, (kp, temper) in enumerate(self._member_parameters(parameters)):
-            ls, ll = ARDKernel.device_parameters(self.kernel_member(i)._to_parameters(kp))
-            if temper is not None:
-                ls = ls + 0.5 * temper  # exp(t) k = exp(ls + t/2)^2 exp(..): tempering scales the amplitude
-            ni = noise[i:i + 1] if noise.numel() > 1 else noise[:1]
-            self._factors[i].factor(self.x, ls, ll, 0.0, True, log_noise=ni.contiguous(), y_z=self._y_cols[i])
+        self._ensure_state()
+        for i in range(self.number_output_dimensions):
+            self._factor_member(parameters, i)
         return self._factors
+
+    def _ensure_state(self):
+        if self._factors is None:
+            self._factors = [L.GpFactor(self.x.shape[0], self.x.shape[1]) for _ in range(self.number_output_dimensions)]
+            self._y_cols = self.y.t().contiguous()  # [K, n] (base.py:480)
+
+    def _factor_member(self, parameters, i):
+        noise = as_device(parameters.log_observation_noise).reshape(-1)
+        kp, temper = self._member_parameters(parameters)[i]
+        ls, ll = ARDKernel.device_parameters(self.kernel_member(i)._to_parameters(kp))
+        if temper is not None:
+            ls = ls + 0.5 * temper  # exp(t) k = exp(ls + t/2)^2 exp(..): tempering scales the amplitude
+        ni = noise[i:i + 1] if noise.numel() > 1 else noise[:1]
+        return self._factors[i].factor(self.x, ls, ll, 0.0, True, log_noise=ni.contiguous(), y_z=self._y_cols[i])
 
     def kernel_member(self, i):
         base = self.kernel.base_kernel if isinstance(self.kernel, TemperedKernel) else self.kernel
@@ -62,14 +68,13 @@ class GPClassification(GPClassificationBase):
         parameters = self._to_parameters(parameters)
         x = as_2d(x)
         x = x.reshape(x.shape[0], -1)
-        factors = self.factorise(parameters)
-        prior_mean = self.mean.predict(parameters.mean, x).reshape(self.number_output_dimensions, -1)
-        means, variances = [], []
-        for i, f in enumerate(factors):
-            m, v = L.gp_predict(f, x, prior_mean=prior_mean[i].contiguous())
-            means.append(m)
-            variances.append(v)
-        return torch.stack(means), torch.stack(variances)
+        prior_mean = self.mean.predict(parameters.mean, x).reshape(self.number_output_dimensions, -1).contiguous()
+        # K independent exact posteriors: factorisation + predictive of each output overlap on side streams
+        self._ensure_state()
+        jobs = [(lambda i=i: L.gp_predict(self._factor_member(parameters, i), x, prior_mean=prior_mean[i]))
+                for i in range(self.number_output_dimensions)]
+        outs = L.run_concurrently(jobs)
+        return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])
 
     def _calculate_prediction_gaussian(self, parameters, x, full_covariance: bool):
         return self.calculate_posterior(parameters, self.x, self.y, x, full_covariance)

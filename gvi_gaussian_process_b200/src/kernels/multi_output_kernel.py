@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import torch
 
+from .. import _lib_proxy as L
 from .base import KernelBase, KernelBaseParameters
 
 
@@ -32,5 +33,8 @@ class MultiOutputKernel(KernelBase):
                             for kernel, parameters_ in zip(self.kernels, parameters.kernels)])
 
     def _calculate_gram_diagonal(self, parameters, x):
-        return torch.stack([kernel.calculate_gram(parameters_, x, x, full_covariance=False)
-                            for kernel, parameters_ in zip(self.kernels, parameters.kernels)])
+        # the K members are independent: their factorisations and predictive launches overlap on side streams
+        jobs = [(lambda kernel=kernel, parameters_=parameters_: kernel.calculate_gram(parameters_, x, x,
+                                                                                    full_covariance=False))
+                for kernel, parameters_ in zip(self.kernels, parameters.kernels)]
+        return torch.stack(L.run_concurrently(jobs))
