@@ -673,6 +673,9 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
       return GVI_EINVAL;
     }
     if (P.acc_scratch) P.reds_scratch = P.acc_scratch + (size_t)2 * GVI_NUM_SMS * P.Mp * 24;
+    // profiling aid (env GVI_DEBUG_GRID): cap the grid, e.g. 148 in the two-CTA shape = one 8-warp CTA per SM
+    static const int debug_grid = getenv("GVI_DEBUG_GRID") ? atoi(getenv("GVI_DEBUG_GRID")) : 0;
+    if (debug_grid > 0) return launch_step_nt<3>(P, debug_grid, st);
     return launch_step_nt<3>(P, P.two_cta ? 2 * GVI_NUM_SMS : GVI_NUM_SMS, st);
   }
   // gradient mode keeps the whole b tile in shared memory
