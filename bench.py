@@ -481,10 +481,26 @@ def bench_classification(dev):
         c1.record()
         torch.cuda.synchronize()
         cms = c0.elapsed_time(c1) / 5
+    # value + gradient of the same objective w.r.t. the mean weights, K log-scalings and K x 784 log-lengthscales
+    w.requires_grad_(True)
+    leaves = [(t(0.0).requires_grad_(True), ll.clone().requires_grad_(True)) for _ in range(k)]
+    gparams = {"mean": {"custom": w},
+               "kernel": {"kernels": [{"base_kernel": {"log_scaling": a, "log_lengthscales": b}} for a, b in leaves]}}
+    gvi.calculate_loss(gparams, x, y).backward()  # warm-up
+    torch.cuda.synchronize()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    gloss = gvi.calculate_loss(gparams, x, y)
+    gloss.backward()
+    g1.record()
+    torch.cuda.synchronize()
+    grad_ms = g0.elapsed_time(g1)
+    grad_norm = float(torch.cat([b.grad for _, b in leaves]).norm())
     cdf_evals = float(n) * 50 * k * (k - 1)
     flops = 2.0 * k * n * (2.0 * m * d + m * m) + 2.0 * k * n * m  # q and p: Gram contraction + triangular product
     return {"n": n, "d": d, "classes": k, "m": m, "ms_per_objective": ms, "points_per_s": n / (ms * 1e-3),
             "loss": float(loss), "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+            "value_and_gradient_ms": grad_ms, "lengthscale_grad_norm": grad_norm,
             "class_probability_kernel": {"ms": cms, "normal_cdf_evaluations_per_s": cdf_evals / (cms * 1e-3),
                                          "points_per_s": n / (cms * 1e-3)},
             "note": "forward objective NLL + GWI(no eig): 10 q-passes + 10 p-passes (factorisation, tensor-pipe "

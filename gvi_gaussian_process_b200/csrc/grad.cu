@@ -12,6 +12,10 @@
 
 #include "predict.cuh"
 
+size_t gvi_gp_predict_grad_wide_workspace_bytes(int64_t N, int M, int D);
+int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int64_t N, const double* g, int frozen,
+                             double* out, void* workspace, cudaStream_t st);
+
 namespace {
 constexpr int CB = 128;  // C tile edge
 constexpr int PC = 32;   // points per chunk
@@ -414,6 +418,10 @@ extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
   if (N < 1 || M < 1 || D < 1) return 0;
   size_t total = 0;
   carve_grad(nullptr, N, M, D, &total);
+  if (D > 32) {
+    const size_t wide = gvi_gp_predict_grad_wide_workspace_bytes(N, M, D);
+    if (wide > total) total = wide;
+  }
   return total;
 }
 
@@ -457,10 +465,11 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
                                        void* stream) {
   GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 1, "sizes");
   GVI_CHECK_ARG(factor && X && g_var && out && workspace, "null pointer");
-  GVI_CHECK_ARG(D <= 32, "the variance VJP supports D <= 32 in this build");
   cudaStream_t st = (cudaStream_t)stream;
   const FactorLayout f = factor_layout(M, D);
   const double* Fq = (const double*)factor;
+  if (D > 32)  // wide inputs: the contraction with dK/dlog_ls runs as GEMMs over all d at once (grad_wide.cu)
+    return gvi_gp_predict_grad_wide(Fq, M, D, X, N, g_var, frozen_cholesky, out, workspace, st);
   GradWs w = carve_grad(workspace, N, M, D, nullptr);
   StepParams P{};
   P.pass[0] = PassDesc{Fq, nullptr, nullptr, nullptr, nullptr, nullptr, 0};

@@ -1,0 +1,236 @@
+// grad_wide.cu - the variance vector-Jacobian product (gvi_gp_predict_grad_f64) for WIDE inputs, D > 32 (BASELINE config
+// #4: D = 784, one log-lengthscale per pixel).  The tile kernel's gradient phase keeps a [T x D] x tile and per-lane
+// D-vectors in registers, which stops at D = 32; for wide inputs the contraction with dK/dlog_ls[d] is rewritten as
+// GEMMs so that it runs on the tensor pipe for every d at once.  With a_i = A^-1 k_i and
+//   W_ij = g_i a_ij k_ij (N x M),  r = W 1,  c = W^T 1,  Q = W^T X^,   S = sum_i g_i a_i a_i^T,  V = S o K_ZZ,
+//   T2_d    = sum_ij W_ij (x^_id - z^_jd)^2 = sum_i x^_id^2 r_i - 2 sum_j z^_jd Q_jd + sum_j z^_jd^2 c_j
+//   term3_d = -1/2 sum_jl V_jl (z^_jd - z^_ld)^2 = -sum_j z^_jd^2 (V 1)_j + sum_j z^_jd (V Z^)_jd
+//   dLoss/dlog_ls[d] = T2_d + term3_d,   dLoss/dlog_scaling = 2 sum g v - 2 jitter_abs sum g |a|^2
+// (x^ = x~ - c~, z^ = z~ - c~: scaled coordinates shifted by the first inducing point, so the expansion of the square
+// does not cancel for data far from the origin).  Per 2048-row chunk: K(x,Z) from the tensor-pipe Gram kernel
+// (gram_dmma.cu), A^-1 K^T by two library GEMMs against the dense L^-1 of the factor state, one fused elementwise pass
+// for W, diag(g) Aa and the row sums, Q (+ c as an extra column of ones) and S by library GEMMs accumulating across
+// chunks.  All reductions have a fixed order.  Reference: jax.grad through sparse_posterior_kernel.py:54-96.
+#include <cublas_v2.h>
+
+#include "common.cuh"
+
+int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st);
+int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x, int64_t nr, double* out,
+                         double* workspace, cudaStream_t st);
+int gvi_launch_wide_gram_zz(const double* F, const FactorLayout& f, double* out, double* workspace, cudaStream_t st);
+size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D);
+
+namespace {
+constexpr int WCHUNK = 2048;
+
+// out[i][d] = rows[i][d] * (sqrtw ? sqrtw[d] : 1) - shift[d]  (d < D),  out[i][D] = 1;  leading dimension Da = D + 1
+__global__ void __launch_bounds__(256) shift_aug_kernel(const double* __restrict__ rows, int64_t nr, int D,
+                                                        const double* __restrict__ sqrtw,
+                                                        const double* __restrict__ shift, double* __restrict__ out) {
+  const int Da = D + 1;
+  const int64_t total = nr * Da;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int64_t i = idx / Da;
+    const int d = (int)(idx % Da);
+    out[idx] = (d == D) ? 1.0 : rows[i * D + d] * (sqrtw ? sqrtw[d] : 1.0) - shift[d];
+  }
+}
+
+// one warp per row: W = g a k (over K), B = g a (over T), rowstats[i] = {sum_j W_ij, sum_j k_ij a_ij, sum_j a_ij^2}
+__global__ void __launch_bounds__(256) weights_kernel(double* __restrict__ K, const double* __restrict__ Aa,
+                                                      double* __restrict__ B, const double* __restrict__ g, int nr,
+                                                      int Mp, double* __restrict__ rowstats) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nr; i += gridDim.x * 8) {
+    const double gi = g[i];
+    double r = 0.0, ka = 0.0, na = 0.0;
+    for (int j = lane; j < Mp; j += 32) {
+      const int64_t idx = (int64_t)i * Mp + j;
+      const double k = K[idx], a = Aa[idx];
+      const double b = gi * a;
+      const double w = b * k;
+      K[idx] = w;
+      B[idx] = b;
+      r += w;
+      ka = fma(k, a, ka);
+      na = fma(a, a, na);
+    }
+    r = warp_sum(r);
+    ka = warp_sum(ka);
+    na = warp_sum(na);
+    if (lane == 0) {
+      rowstats[3 * i] = r;
+      rowstats[3 * i + 1] = ka;
+      rowstats[3 * i + 2] = na;
+    }
+  }
+}
+
+// t2x[d] (+)= sum_i x^_id^2 r_i   (one thread per d, rows in order)
+__global__ void __launch_bounds__(128) row_square_kernel(const double* __restrict__ Xs, int nr, int D,
+                                                         const double* __restrict__ rowstats, int first,
+                                                         double* __restrict__ t2x) {
+  const int d = blockIdx.x * 128 + threadIdx.x;
+  if (d >= D) return;
+  double acc = 0.0;
+  for (int i = 0; i < nr; i++) {
+    const double x = Xs[(int64_t)i * (D + 1) + d];
+    acc = fma(x * x, rowstats[3 * i], acc);
+  }
+  t2x[d] = first ? acc : t2x[d] + acc;
+}
+
+// scal[0] (+)= sum g v, scal[1] (+)= sum g |a|^2, scal[2] (+)= sum g;  v_i = k(x,x) - sum_j k_ij a_ij
+__global__ void __launch_bounds__(256) row_scalars_kernel(const double* __restrict__ rowstats,
+                                                          const double* __restrict__ g, int nr,
+                                                          const double* __restrict__ F, int first,
+                                                          double* __restrict__ scal) {
+  __shared__ double red[3][256];
+  const int tid = threadIdx.x;
+  const double kxx = F[1];
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int i = tid; i < nr; i += 256) {
+    a = fma(g[i], kxx - rowstats[3 * i + 1], a);
+    b = fma(g[i], rowstats[3 * i + 2], b);
+    c += g[i];
+  }
+  red[0][tid] = a;
+  red[1][tid] = b;
+  red[2][tid] = c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s)
+      for (int q = 0; q < 3; q++) red[q][tid] += red[q][tid + s];
+    __syncthreads();
+  }
+  if (tid < 3) scal[tid] = first ? red[tid][0] : scal[tid] + red[tid][0];
+}
+
+__global__ void __launch_bounds__(256) hadamard_kernel(double* __restrict__ S, const double* __restrict__ K,
+                                                       int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256)
+    S[idx] *= K[idx];
+}
+
+// out[4+d] = t2x[d] + sum_j (z^_jd^2 c_j - 2 z^_jd Q_jd) + (R3 ? sum_j (z^_jd R3_jd - z^_jd^2 (V1)_j) : 0)
+__global__ void __launch_bounds__(128) wide_finish_kernel(const double* __restrict__ Zh, const double* __restrict__ Q,
+                                                          const double* __restrict__ R3,
+                                                          const double* __restrict__ t2x, int M, int D,
+                                                          double* __restrict__ out) {
+  const int d = blockIdx.x * 128 + threadIdx.x;
+  if (d >= D) return;
+  const int Da = D + 1;
+  double acc = t2x[d];
+  for (int j = 0; j < M; j++) {
+    const double z = Zh[(int64_t)j * Da + d];
+    acc += z * (z * Q[(int64_t)j * Da + D] - 2.0 * Q[(int64_t)j * Da + d]);
+    if (R3) acc += z * (R3[(int64_t)j * Da + d] - z * R3[(int64_t)j * Da + D]);
+  }
+  out[4 + d] = acc;
+}
+
+__global__ void wide_scalars_kernel(const double* __restrict__ scal, const double* __restrict__ F, int64_t N,
+                                    double* __restrict__ out) {
+  out[0] = out[1] = 0.0;
+  out[2] = (double)N;
+  // same closed forms as finish_partials_kernel (predict.cu): A built from the trained parameters, or frozen
+  out[3] = (F[5] != 0.0) ? 4.0 * scal[0] - 2.0 * F[1] * scal[2] : 2.0 * scal[0] - 2.0 * F[4] * scal[1];
+}
+
+int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const double* A, int lda, const double* B, int ldb,
+            double beta, double* C, int ldc) {
+  const double one = 1.0;
+  cublasStatus_t s = cublasDgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, m, k, &one, B,
+                                 ldb, A, lda, &beta, C, ldc);
+  if (s != CUBLAS_STATUS_SUCCESS) {
+    gvi_set_error("cublasDgemm failed with status %d", (int)s);
+    return GVI_ECUDA;
+  }
+  return GVI_OK;
+}
+
+struct WideWs {
+  double *K, *T, *Aa, *Xs, *rowstats, *Q, *S, *Kzz, *Zh, *R3, *t2x, *scal, *gram;
+};
+size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+WideWs carve_wide(void* ws, int64_t N, int M, int D, size_t* total) {
+  const size_t Mp = (size_t)(M + 31) / 32 * 32, Da = (size_t)D + 1;
+  const size_t R = (size_t)(N < WCHUNK ? N : WCHUNK);
+  unsigned char* p = (unsigned char*)ws;
+  size_t o = 0;
+  auto take = [&](size_t doubles) { double* r = (double*)(p + o); o += align256(doubles * 8); return r; };
+  WideWs w;
+  w.K = take(R * Mp);
+  w.T = take(R * Mp);
+  w.Aa = take(R * Mp);
+  w.Xs = take(R * Da);
+  w.rowstats = take(R * 3);
+  w.Q = take(Mp * Da);
+  w.S = take(Mp * Mp);
+  w.Kzz = take(Mp * Mp);
+  w.Zh = take(Mp * Da);
+  w.R3 = take(Mp * Da);
+  w.t2x = take(D);
+  w.scal = take(4);
+  w.gram = take(gvi_gram_dmma_workspace_doubles((int64_t)(R > Mp ? R : Mp), M, D));
+  if (total) *total = o;
+  return w;
+}
+}  // namespace
+
+size_t gvi_gp_predict_grad_wide_workspace_bytes(int64_t N, int M, int D) {
+  size_t total = 0;
+  carve_wide(nullptr, N, M, D, &total);
+  return total;
+}
+
+int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int64_t N, const double* g, int frozen,
+                             double* out, void* workspace, cudaStream_t st) {
+  const FactorLayout f = factor_layout(M, D);
+  const int Mp = f.Mp, Da = D + 1;
+  const double* Linv = F + f.linv_off;
+  const double* Zs = F + f.zs_off;  // row 0 = the common shift c~
+  WideWs w = carve_wide(workspace, N, M, D, nullptr);
+  cublasHandle_t h;
+  int rc = gvi_get_cublas(&h, st);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < N; r0 += WCHUNK) {
+    const int nr = (int)(N - r0 < WCHUNK ? N - r0 : WCHUNK);
+    const int first = (r0 == 0);
+    const double beta = first ? 0.0 : 1.0;
+    // the Gram kernel writes columns < M only: the padding columns of the GEMM operands must be zero
+    if (Mp != M) GVI_CUDA(cudaMemsetAsync(w.K, 0, (size_t)nr * Mp * sizeof(double), st));
+    if ((rc = gvi_launch_wide_gram(F, f, X + r0 * D, nr, w.K, w.gram, st))) return rc;
+    shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(X + r0 * D, nr, D, F + f.sqrtw_off, Zs, w.Xs);
+    GVI_CHECK_LAUNCH("shift_aug_kernel");
+    if ((rc = gemm_rm(h, false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp))) return rc;   // K L^-T
+    if ((rc = gemm_rm(h, false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp))) return rc;  // Aa = K A^-1
+    const int wblocks = (nr + 7) / 8 < GVI_NUM_SMS * 8 ? (nr + 7) / 8 : GVI_NUM_SMS * 8;
+    weights_kernel<<<wblocks, 256, 0, st>>>(w.K, w.Aa, w.T, g + r0, nr, Mp, w.rowstats);           // K <- W, T <- B
+    GVI_CHECK_LAUNCH("weights_kernel");
+    if ((rc = gemm_rm(h, true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da))) return rc;   // Q|c += W^T [X^|1]
+    if (!frozen)
+      if ((rc = gemm_rm(h, true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp))) return rc;  // S += Aa^T B
+    row_square_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Xs, nr, D, w.rowstats, first, w.t2x);
+    GVI_CHECK_LAUNCH("row_square_kernel");
+    row_scalars_kernel<<<1, 256, 0, st>>>(w.rowstats, g + r0, nr, F, first, w.scal);
+    GVI_CHECK_LAUNCH("row_scalars_kernel");
+  }
+  shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(Zs, Mp, D, nullptr, Zs, w.Zh);
+  GVI_CHECK_LAUNCH("shift_aug_kernel");
+  const double* R3 = nullptr;
+  if (!frozen) {
+    GVI_CUDA(cudaMemsetAsync(w.Kzz, 0, (size_t)Mp * Mp * sizeof(double), st));
+    if ((rc = gvi_launch_wide_gram_zz(F, f, w.Kzz, w.gram, st))) return rc;
+    hadamard_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.S, w.Kzz, (int64_t)Mp * Mp);                // V = S o K_ZZ
+    GVI_CHECK_LAUNCH("hadamard_kernel");
+    if ((rc = gemm_rm(h, false, false, Mp, Da, Mp, w.S, Mp, w.Zh, Da, 0.0, w.R3, Da))) return rc;  // [V Z^ | V 1]
+    R3 = w.R3;
+  }
+  wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, R3, w.t2x, M, D, out);
+  GVI_CHECK_LAUNCH("wide_finish_kernel");
+  wide_scalars_kernel<<<1, 1, 0, st>>>(w.scal, F, N, out);
+  GVI_CHECK_LAUNCH("wide_scalars_kernel");
+  return GVI_OK;
+}

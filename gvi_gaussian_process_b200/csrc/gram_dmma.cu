@@ -244,3 +244,11 @@ int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x
   return launch_gram_core(x, nr, F + f.sqrtw_off, F + f.zs_off, f.M, nullptr, F + f.zs_off, f.D, nullptr, F, out, f.Mp,
                           workspace + 2 * Dp, st);
 }
+
+// K(Z, Z) from the scaled inducing points of the factor state (rows and columns < M; leading dimension Mp) - the
+// Hadamard partner of S in the wide-input gradient (grad_wide.cu)
+int gvi_launch_wide_gram_zz(const double* F, const FactorLayout& f, double* out, double* workspace, cudaStream_t st) {
+  const int Dp = (f.D + 1) / 2 * 2;
+  return launch_gram_core(F + f.zs_off, f.M, nullptr, F + f.zs_off, f.M, nullptr, F + f.zs_off, f.D, nullptr, F, out,
+                          f.Mp, workspace + 2 * Dp, st);
+}

@@ -156,7 +156,8 @@ int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p, int M, in
  * g_var[i] = dLoss/dvar_i of ANY downstream loss, out[3] = dLoss/dlog_scaling, out[4+d] = dLoss/dlog_lengthscales[d]
  * (out[0] = out[1] = 0, out[2] = N; same layout and workspace as gvi_fused_step_grad_f64).  This is what jax.grad
  * produces through SparsePosteriorKernel._calculate_gram (sparse_posterior_kernel.py:54-96) for losses that are not
- * the fused regression objective - e.g. the classification objective of section 8(f)-2.  D <= 32.            */
+ * the fused regression objective - e.g. the classification objective of section 8(f)-2.  D <= 32 runs in the tile
+ * kernel; wider inputs (config #4: D = 784) take a GEMM formulation of the same contraction on the tensor pipe.  */
 int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g_var,
                             int frozen_cholesky, double* out, void* workspace, void* stream);
 

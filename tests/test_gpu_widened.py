@@ -135,7 +135,10 @@ def test_pointwise_risk_gradient_kernel(S, kind):
 
 # ---- the variance VJP (gvi_gp_predict_grad_f64) -------------------------------------------------------------------
 @pytest.mark.parametrize("n,m,d,is_abs,scalar_ll", [(60, 12, 1, False, True), (700, 65, 3, False, False),
-                                                    (2000, 200, 8, True, False)])
+                                                    (2000, 200, 8, True, False),
+                                                    # D > 32: the GEMM formulation of grad_wide.cu (3000 > one chunk)
+                                                    (900, 70, 40, False, False), (1500, 130, 100, True, False),
+                                                    (3000, 96, 48, False, True)])
 def test_variance_vjp_matches_autograd_twin(S, n, m, d, is_abs, scalar_ll):
     rng = np.random.default_rng(n + m)
     x = rng.standard_normal((n, d))
@@ -663,3 +666,31 @@ def test_golden_fixture_classification(S):
                       ("gaussian_wasserstein", "ProjectedGaussianWassersteinRegularisation"),
                       ("hellinger", "ProjectedHellingerRegularisation"), ("renyi", "ProjectedRenyiRegularisation")]:
         assert close(getattr(S.projected, cls)(**kw).calculate_regularisation(params, x), g["reg_" + kind]), kind
+
+
+def test_classification_backward_wide_inputs(S):
+    """D > 32 (config #4's regime): the per-class variance VJP takes the GEMM formulation (grad_wide.cu)."""
+    n, d, k, m, lam = 500, 48, 3, 20, 1e-3
+    pr = make_classification_problem(n, d, k, m, seed=31)
+    approx, params, exact, eparams, leaves, (w1, w2) = build_classification_models(S, pr, lam, grad=True)
+    nll = S.NegativeLogLikelihood(gp=approx)
+    reg = S.GaussianWassersteinRegularisation(gp=approx, regulariser=exact, regulariser_parameters=eparams,
+                                              mode="posterior")
+    loss = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=nll).calculate_loss(
+        params, pr["x"], pr["y"])
+    loss.backward()
+    _, _, m_p, v_p = oracle_classification(pr, lam)
+    tx, ty = cpu(pr["x"]), cpu(pr["y"])
+    tw1, tw2 = cpu(pr["w1"], True), cpu(pr["w2"], True)
+    tls = [cpu(pr["ls"][i], True) for i in range(k)]
+    tll = [cpu(pr["ll"][i], True) for i in range(k)]
+    m_q = (torch.tanh(tx @ tw1) @ tw2).reshape(k, -1)
+    v_q = torch.stack([T.sparse_posterior_diag(tls[i], tll[i], cpu(pr["zs"][i]), tx, lam, False) for i in range(k)])
+    ref = (T.multinomial_nll(T.classification_probabilities(m_q, v_q, HERMITE[0], HERMITE[1]), ty)
+           + T.regulariser("gwi_no_eig", cpu(m_p), cpu(v_p), m_q, v_q))
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    assert rel_norm(host(w2.grad), tw2.grad.numpy()) <= GTOL
+    for i in range(k):
+        assert abs(float(leaves[i][0].grad) - float(tls[i].grad)) <= GTOL * max(abs(float(tls[i].grad)), 1e-3), i
+        assert rel_norm(host(leaves[i][1].grad), tll[i].grad.numpy()) <= GTOL, i
