@@ -8,6 +8,13 @@ import torch
 from . import _lib_proxy as L
 
 
+# The K per-class predictives of a multi-output GP run forward (and therefore backward) on side streams on purpose
+# (_lib_proxy.run_concurrently); autograd synchronises the accumulation into the leaves correctly, the warning about
+# the stream mismatch is expected.
+if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+
+
 def wants_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
 

@@ -7,6 +7,7 @@ from __future__ import annotations
 import torch
 
 from .. import _lib_proxy as L
+from .._autograd import ExactPredict, wants_grad
 from ..kernels.multi_output_kernel import MultiOutputKernel
 from ..kernels.standard.ard_kernel import ARDKernel
 from ..kernels.tempered_kernel import TemperedKernel
@@ -49,14 +50,27 @@ class GPClassification(GPClassificationBase):
             self._factors = [L.GpFactor(self.x.shape[0], self.x.shape[1]) for _ in range(self.number_output_dimensions)]
             self._y_cols = self.y.t().contiguous()  # [K, n] (base.py:480)
 
-    def _factor_member(self, parameters, i):
+    def _member_leaves(self, parameters, i):
+        """(log_scaling [1], log_lengthscales, log_noise [1]) of output i as (possibly differentiable) device tensors."""
         noise = as_device(parameters.log_observation_noise).reshape(-1)
         kp, temper = self._member_parameters(parameters)[i]
         ls, ll = ARDKernel.device_parameters(self.kernel_member(i)._to_parameters(kp))
         if temper is not None:
             ls = ls + 0.5 * temper  # exp(t) k = exp(ls + t/2)^2 exp(..): tempering scales the amplitude
         ni = noise[i:i + 1] if noise.numel() > 1 else noise[:1]
-        return self._factors[i].factor(self.x, ls, ll, 0.0, True, log_noise=ni.contiguous(), y_z=self._y_cols[i])
+        return ls, ll, ni.contiguous()
+
+    def _factor_member(self, parameters, i):
+        ls, ll, ni = self._member_leaves(parameters, i)
+        return self._factors[i].factor(self.x, ls, ll, 0.0, True, log_noise=ni, y_z=self._y_cols[i])
+
+    def _predict_member(self, parameters, i, x, prior_mean_i):
+        f = self._factor_member(parameters, i)
+        ls, ll, ni = self._member_leaves(parameters, i)
+        if wants_grad(prior_mean_i, ls, ll, ni):
+            # training the exact classifier itself (experiments/classification/trainers.py:20-100): exact-GP VJP
+            return ExactPredict.apply(f, lambda: self._factor_member(parameters, i), x, prior_mean_i, ni, ls, ll)
+        return L.gp_predict(f, x, prior_mean=prior_mean_i)
 
     def kernel_member(self, i):
         base = self.kernel.base_kernel if isinstance(self.kernel, TemperedKernel) else self.kernel
@@ -71,7 +85,7 @@ class GPClassification(GPClassificationBase):
         prior_mean = self.mean.predict(parameters.mean, x).reshape(self.number_output_dimensions, -1).contiguous()
         # K independent exact posteriors: factorisation + predictive of each output overlap on side streams
         self._ensure_state()
-        jobs = [(lambda i=i: L.gp_predict(self._factor_member(parameters, i), x, prior_mean=prior_mean[i]))
+        jobs = [(lambda i=i: self._predict_member(parameters, i, x, prior_mean[i]))
                 for i in range(self.number_output_dimensions)]
         outs = L.run_concurrently(jobs)
         return torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs])

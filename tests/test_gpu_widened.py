@@ -694,3 +694,45 @@ def test_classification_backward_wide_inputs(S):
     for i in range(k):
         assert abs(float(leaves[i][0].grad) - float(tls[i].grad)) <= GTOL * max(abs(float(tls[i].grad)), 1e-3), i
         assert rel_norm(host(leaves[i][1].grad), tll[i].grad.numpy()) <= GTOL, i
+
+
+def test_exact_gp_classifier_nll_backward_matches_autograd_twin(S):
+    """train_regulariser_gp for classification (experiments/classification/trainers.py:20-100): multinomial NLL of the
+    exact GP classifier on the inducing data, differentiated w.r.t. every output's kernel hyper-parameters, its
+    observation noise and the constant means."""
+    rng = np.random.default_rng(17)
+    m, d, k = 61, 3, 3  # m not a multiple of k: the tiled-and-reshaped constant mean differs between outputs
+    z = rng.standard_normal((m, d))
+    yz = np.eye(k)[rng.integers(0, k, m)]
+    ls = rng.uniform(-0.2, 0.2, k)
+    ll = [np.log(rng.uniform(0.5, 1.5, d) / d) for _ in range(k)]
+    noise = np.log(rng.uniform(0.3, 1.0, k))
+    const = rng.uniform(-0.1, 0.1, k)
+    gp = S.GPClassification(mean=S.ConstantMean(number_output_dimensions=k),
+                            kernel=S.MultiOutputKernel(kernels=[S.ARDKernel(number_of_dimensions=d) for _ in range(k)]),
+                            x=z, y=yz)
+    t_noise, t_c = dev(noise, True), dev(const, True)
+    leaves = [(dev(ls[i], True), dev(ll[i], True)) for i in range(k)]
+    params = {"log_observation_noise": t_noise, "mean": {"constant": t_c},
+              "kernel": {"kernels": [{"log_scaling": a, "log_lengthscales": b} for a, b in leaves]}}
+    loss = S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, z, yz)
+    loss.backward()
+    c_noise, c_c = cpu(noise, True), cpu(const, True)
+    cl = [(cpu(ls[i], True), cpu(ll[i], True)) for i in range(k)]
+    # the reference's K-output ConstantMean: jnp.tile(constant, n) RESHAPED to [K, n] (constant_mean.py:66,
+    # means/base.py:97-100) - every row cycles through all K constants; reproduced, not "fixed"
+    prior = c_c.repeat(m).reshape(k, m)
+    means, variances = [], []
+    for i in range(k):
+        mi, vi = T.exact_gp_posterior(cl[i][0], cl[i][1], prior[i], cpu(z), cpu(yz[:, i]), c_noise[i], cpu(z))
+        means.append(mi)
+        variances.append(vi)
+    q = T.classification_probabilities(torch.stack(means), torch.stack(variances), HERMITE[0], HERMITE[1])
+    ref = T.multinomial_nll(q, cpu(yz))
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= TOL * abs(float(ref.detach()))
+    assert rel_norm(host(t_noise.grad), c_noise.grad.numpy()) <= GTOL
+    assert rel_norm(host(t_c.grad), c_c.grad.numpy()) <= GTOL
+    for i in range(k):
+        assert abs(float(leaves[i][0].grad) - float(cl[i][0].grad)) <= GTOL * max(abs(float(cl[i][0].grad)), 1e-3)
+        assert rel_norm(host(leaves[i][1].grad), cl[i][1].grad.numpy()) <= GTOL
