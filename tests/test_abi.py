@@ -65,3 +65,33 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_argument_validation_of_the_widened_entry_points(lib):
+    """SURVEY.md section 8(f) entry points: bad arguments are rejected before any CUDA call; empty inputs are a no-op."""
+    # class probabilities: 2 <= K <= 64, H >= 1, N >= 0
+    assert lib.gvi_class_probabilities_f64(None, None, 1, 10, None, None, 50, 0.01, 1e-10, None, None) == -1
+    assert b"2 <= K <= 64" in lib.gvi_last_error_string()
+    assert lib.gvi_class_probabilities_f64(None, None, 65, 10, None, None, 50, 0.01, 1e-10, None, None) == -1
+    assert lib.gvi_class_probabilities_f64(None, None, 4, 10, None, None, 0, 0.01, 1e-10, None, None) == -1
+    assert lib.gvi_class_probabilities_f64(None, None, 4, 0, None, None, 50, 0.01, 1e-10, None, None) == 0
+    assert lib.gvi_class_probabilities_grad_f64(None, None, 4, 0, None, None, 50, 0.01, 1e-10, None, None, None,
+                                                None) == 0
+    assert lib.gvi_class_probabilities_f64(None, None, 4, 10, None, None, 50, 0.01, 1e-10, None, None) == -1  # nulls
+    # risks on probabilities
+    assert lib.gvi_multinomial_risk_f64(None, None, None, 1, 10, 2, None, None, None) == -1
+    assert lib.gvi_multinomial_risk_f64(None, None, None, 4, 10, 0, None, None, None) == -1  # power >= 1
+    assert lib.gvi_multinomial_risk_grad_f64(None, None, None, 4, 10, 2, None, None, None) == -1
+    assert lib.gvi_multinomial_risk_workspace_bytes(1000) > 0
+    assert lib.gvi_risk_grad_f64(99, 0.5, None, None, None, None, None, 10, None, None, None, None) == -1
+    # vector-Jacobian products
+    assert lib.gvi_gp_predict_grad_f64(None, 4, 3, None, 0, None, 0, None, None, None) == -1  # N >= 1
+    assert lib.gvi_weighted_gram_f64(None, 4, 40, None, 10, None, None, None, None) == -1  # D <= 32
+    assert b"D <= 32" in lib.gvi_last_error_string()
+    assert lib.gvi_exact_gp_predict_grad_f64(None, 4, 40, None, 10, None, None, None, None, None, None) == -1
+    assert lib.gvi_exact_gp_predict_grad_workspace_bytes(1024, 1024) >= 4 * 1024 * 1024 * 8
+    assert lib.gvi_fused_step_grad_workspace_bytes(60000, 2048, 784) >= 3 * 2048 * 2048 * 8  # wide-input route
+    # optimiser step
+    assert lib.gvi_optimiser_step_f64(7, None, None, None, None, 10, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
+    assert lib.gvi_optimiser_step_f64(0, None, None, None, None, 10, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
+    assert lib.gvi_optimiser_step_f64(0, None, None, None, None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == 0
