@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
 import torch  # noqa: F401  (loads libcudart so the .so shares torch's CUDA runtime)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgvigp.so")
+LIB_PATH = os.environ.get("GVI_LIB_PATH") or os.path.join(_HERE, "libgvigp.so")  # override: A/B builds when profiling
 
 # symbol -> (restype, argtypes); must list every symbol of include/gvigp.h (tests/test_abi.py checks this)
 SIGNATURES = {

@@ -35,6 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("GVI_NVCC_FLAGS", "").split()  # e.g. -DGVI_PHASE_CLOCKS (profiling builds)
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

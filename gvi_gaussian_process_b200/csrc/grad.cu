@@ -302,7 +302,9 @@ int launch_syrk(const SyrkParams& P, int ntri, cudaStream_t st) {
 }
 
 struct GradWs {
-  double *partials, *g, *bscratch, *Cpart, *C, *T1, *T2, *rowpart, *Kc;
+  double *partials, *tile_partials, *g, *bscratch, *Cpart, *C, *T1, *T2, *rowpart, *Kc;
+  int* tile_counter;
+  int64_t ntiles;
   int nsplit, ntri, ncb, chunk_pg;  // chunk_pg = point groups (of 32 points) per K chunk
 };
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
@@ -316,7 +318,14 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   unsigned char* p = (unsigned char*)ws;
   size_t o = 0;
   auto take = [&](size_t bytes) { double* r = (double*)(p + o); o += align256(bytes); return r; };
-  w.partials = take((size_t)GVI_NUM_SMS * STEP_PARTIAL_STRIDE * 8);
+  w.tile_counter = (int*)take(STEP_COUNTER_DOUBLES * 8);
+  w.partials = take((size_t)(GVI_NUM_SMS > STEP_REDUCE_BLOCKS ? GVI_NUM_SMS : STEP_REDUCE_BLOCKS) * STEP_PARTIAL_STRIDE * 8);
+  {  // per-tile records of the gradient launch (tile height as the launcher will choose it)
+    int tp = gvi_step_tile_points(f.Mp, D, true);
+    if (tp <= 0) tp = 8;
+    w.ntiles = (N + tp - 1) / tp;
+    w.tile_partials = take((size_t)w.ntiles * STEP_PARTIAL_STRIDE * 8);
+  }
   w.g = take((size_t)N * 8);
   w.bscratch = take((size_t)GVI_NUM_SMS * f.Mp * T * 8);
   w.Cpart = take((size_t)w.nsplit * f.Mp * f.Mp * 8);
@@ -441,12 +450,15 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   const FactorLayout f = factor_layout(M, D);
   const double* Fq = (const double*)factor_q;
   P.partials = w.partials;
+  P.tile_counter = w.tile_counter;
+  P.tile_partials = w.tile_partials;
   P.grad = 1;
   P.g_out = w.g;
   P.dm_out = dm_out;
   P.bscratch = w.bscratch;
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
+  if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
   if (frozen_cholesky) return GVI_OK;  // A does not depend on the trained parameters: no <dK_ZZ, S> term
   if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
@@ -478,12 +490,15 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
   P.X = X; P.N = N;
   P.reg_kind = GVI_REG_NONE;
   P.partials = w.partials;
+  P.tile_counter = w.tile_counter;
+  P.tile_partials = w.tile_partials;
   P.grad = 1;
   P.g_in = g_var;
   P.bscratch = w.bscratch;
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   int rc;
+  if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
   if (frozen_cholesky) return GVI_OK;
   if ((rc = gvi_weighted_gram(Fq, X, g_var, N, M, D, w, st))) return rc;
@@ -549,6 +564,8 @@ extern "C" int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p
   const FactorLayout f = factor_layout(M, D);
   const double* Fq = (const double*)factor_q;
   P.partials = w.partials;
+  P.tile_counter = w.tile_counter;
+  P.tile_partials = w.tile_partials;
   P.grad = 1;
   P.grad_pointwise_only = 1;
   P.g_out = w.g;
@@ -556,6 +573,7 @@ extern "C" int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p
   P.bscratch = w.bscratch;
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
+  if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 0, D, Fq, out3, st))) return rc;
   if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
   if (!g_cublas) {

@@ -156,11 +156,18 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ntiles = (P.N + T - 1) / T;
   const FactorLayout f = factor_layout(P.M, P.D);
-  double part_nll = 0.0, part_reg = 0.0, part_gv = 0.0, part_g = 0.0;  // threads < T
-  double part_grad = 0.0;                                  // thread d <= DR: d < DR -> T2_d, d == DR -> sum g |a|^2
   double* bscr = GRAD ? P.bscratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  long long& s_tile = *reinterpret_cast<long long*>(counter + 2);  // inside the 16 spare bytes after the group counter
+  constexpr int TILE_STRIDE = GRAD ? STEP_PARTIAL_STRIDE : 2;
+  for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
+    if (P.tile_counter) {  // dynamic tile order
+      __syncthreads();
+      if (tid == 0) s_tile = atomicAdd(P.tile_counter, 1);
+      __syncthreads();
+      tile = s_tile;
+    }
+    if (tile >= ntiles) break;
     const int64_t row0 = tile * T;
     for (int pi = 0; pi < P.npass; pi++) {
       // gradient mode runs p first so that q's tile (and b = L^-1 k of q) is the one left in shared memory
@@ -371,10 +378,14 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
       __syncthreads();
     }  // passes
     // ---- fused risk epilogue (+ pointwise derivatives in gradient mode) --------------------------------
-    if (P.partials && tid < T) {
+    // Warp 0 owns the tile's T <= 24 points; its sums go to the tile's own record (reduced in a fixed order afterwards, so
+    // the result does not depend on which CTA ran the tile) - nothing is carried across tiles in registers.
+    if (P.partials && warp == 0) {
       const int64_t r = row0 + tid;
-      double g_i = 0.0;
-      if (GRAD && P.g_in) {
+      double g_i = 0.0, part_nll = 0.0, part_reg = 0.0, part_gv = 0.0, part_g = 0.0;
+      if (tid >= T) {
+        // lanes beyond the tile contribute zeros to the shuffles below
+      } else if (GRAD && P.g_in) {
         // vector-Jacobian product of the predictive variance: the caller supplies g_i = dLoss/dvar_i
         if (r < P.N) {
           g_i = P.g_in[r];
@@ -418,7 +429,22 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
           P.g_out[r] = g_i;
         }
       }
-      if (GRAD) gs[tid] = g_i;
+      if (GRAD && tid < T) gs[tid] = g_i;
+      double* rec = P.tile_partials + (size_t)tile * TILE_STRIDE;
+      const double a = warp_sum(part_nll), b = warp_sum(part_reg);
+      if (lane == 0) {
+        rec[0] = a;
+        rec[1] = b;
+      }
+      if (GRAD) {
+        const double c = warp_sum(part_gv), d = warp_sum(part_g);
+        if (lane == 0) {
+          rec[2] = c;
+          rec[36] = d;
+          rec[37] = 0.0;
+        }
+        if (P.grad_pointwise_only) rec[3 + lane] = 0.0, rec[4 + lane] = 0.0;  // no phase 3: T2_d and sum g |a|^2 are 0
+      }
     }
     // ---- gradient phase 3: a = L^-T b for q, then sum_i g_i a_ij k_ij (x~_id - z~_jd)^2 and sum_i g_i |a_i|^2 ----
     if (GRAD && !P.grad_pointwise_only) {
@@ -483,35 +509,18 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         if (lane == 0) gpart[g * (DR + 1) + DR] = na2;
       }
       __syncthreads();
-      if (tid <= DR) {
-        double v = 0.0;
-        for (int g = 0; g < P.G; g++) v += gpart[g * (DR + 1) + tid];
-        part_grad += v;
+      {
+        double* rec = P.tile_partials + (size_t)tile * TILE_STRIDE;
+        if (tid <= DR) {  // thread d < DR -> T2_d, d == DR -> sum g |a|^2
+          double v = 0.0;
+          for (int g = 0; g < P.G; g++) v += gpart[g * (DR + 1) + tid];
+          rec[tid < DR ? 4 + tid : 3] = v;
+        }
+        for (int d = DR + tid; d < 32; d += THREADS) rec[4 + d] = 0.0;
       }
       __syncthreads();
     }
   }  // tiles
-  if (P.partials) {
-    double* out = P.partials + (size_t)blockIdx.x * STEP_PARTIAL_STRIDE;
-    if (warp == 0) {
-      // T <= 24 < 32: threads >= T hold zeros
-      double a = warp_sum(part_nll), b = warp_sum(part_reg), c = warp_sum(part_gv), d = warp_sum(part_g);
-      if (lane == 0) {
-        out[0] = a;
-        out[1] = b;
-        out[2] = c;
-        out[36] = d;
-        out[37] = 0.0;
-      }
-    }
-    if (GRAD) {
-      if (tid < DR) out[4 + tid] = part_grad;
-      if (tid == DR) out[3] = part_grad;
-      for (int d = DR + tid; d < 32; d += THREADS) out[4 + d] = 0.0;
-    } else if (tid < 33) {
-      out[3 + tid] = 0.0;
-    }
-  }
 }
 
 // fixed-order final reduction of per-CTA partial sums.
@@ -537,6 +546,29 @@ __global__ void __launch_bounds__(64) finish_partials_kernel(const double* __res
       out[3] = (Fq[5] != 0.0) ? 4.0 * tot[2] - 2.0 * Fq[1] * tot[36] : 2.0 * tot[2] - 2.0 * Fq[4] * tot[3];
   }
   if (grad && tid < D) out[4 + tid] = tot[4 + tid];
+}
+
+// stage A of the fixed-order reduction over per-tile records: block b sums the tiles [b*chunk, (b+1)*chunk) column by
+// column (thread t owns tiles t, t+256, ...; then a shared-memory tree) into one STEP_PARTIAL_STRIDE record.
+__global__ void __launch_bounds__(256) tile_reduce_kernel(const double* __restrict__ tp, int64_t ntiles, int stride,
+                                                          double* __restrict__ records) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  const int64_t chunk = (ntiles + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, ntiles);
+  for (int c = 0; c < STEP_PARTIAL_STRIDE; c++) {
+    double a = 0.0;
+    if (c < stride)
+      for (int64_t t = lo + tid; t < hi; t += 256) a += tp[(size_t)t * stride + c];
+    red[tid] = a;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (tid < s) red[tid] += red[tid + s];
+      __syncthreads();
+    }
+    if (tid == 0) records[(size_t)blockIdx.x * STEP_PARTIAL_STRIDE + c] = red[0];
+    __syncthreads();
+  }
 }
 
 // dynamic shared memory of one CTA: K panel (Pc columns) + x tile + reductions (+ per-group arrays when they fit)
@@ -568,7 +600,11 @@ int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
   }
   int64_t ntiles = (P.N + T - 1) / T;
   int grid = (int)(ntiles < grid_cap ? ntiles : grid_cap);
-  gp_step_kernel<NT, DR, GRAD, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
+  StepParams Q = P;
+  static const int static_tiles = getenv("GVI_STATIC_TILES") ? atoi(getenv("GVI_STATIC_TILES")) : 0;
+  if (ntiles <= grid || static_tiles) Q.tile_counter = nullptr;  // one tile per CTA: nothing to balance
+  if (Q.tile_counter) GVI_CUDA(cudaMemsetAsync(Q.tile_counter, 0, sizeof(int), st));
+  gp_step_kernel<NT, DR, GRAD, WARPS><<<grid, WARPS * 32, smem, st>>>(Q);
   GVI_CHECK_LAUNCH("gp_step_kernel");
   return grid;
 }
@@ -692,6 +728,12 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   }
 }
 
+int gvi_launch_tile_reduce(const double* tile_partials, int64_t ntiles, int grad, double* records, cudaStream_t st) {
+  tile_reduce_kernel<<<STEP_REDUCE_BLOCKS, 256, 0, st>>>(tile_partials, ntiles, grad ? STEP_PARTIAL_STRIDE : 2, records);
+  GVI_CHECK_LAUNCH("tile_reduce_kernel");
+  return STEP_REDUCE_BLOCKS;
+}
+
 int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
                       cudaStream_t st) {
   finish_partials_kernel<<<1, 64, 0, st>>>(partials, nblocks, N, grad, D, Fq, out);
@@ -719,7 +761,7 @@ static int64_t wide_chunk_rows(int Mp) {
 extern "C" size_t gvi_gp_predict_workspace_bytes(int M, int D) {
   if (M < 1 || D < 1) return 0;
   const int Mp = (M + 31) / 32 * 32;
-  size_t doubles = gvi_step_scratch_doubles(Mp);
+  size_t doubles = STEP_COUNTER_DOUBLES + gvi_step_scratch_doubles(Mp);
   if (D > 32) {
     const int64_t rows = wide_chunk_rows(Mp);
     doubles += (size_t)rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D);
@@ -739,7 +781,9 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   P.npass = 1;
   P.M = M; P.Mp = f.Mp; P.D = D; P.G = f.G;
   P.partials = nullptr;
-  P.acc_scratch = (double*)workspace;
+  // workspace = [tile counter][panel scratch][wide-input ring ...]
+  P.tile_counter = workspace ? (int*)workspace : nullptr;
+  P.acc_scratch = workspace ? (double*)workspace + STEP_COUNTER_DOUBLES : nullptr;
   if (D <= 32) {
     P.pass[0] = PassDesc{(const double*)factor, prior_mean, log_noise_add, mean_out, var_out, nullptr, 0};
     P.X = X; P.N = N;
@@ -749,7 +793,7 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   GVI_CHECK_ARG(workspace, "D > 32 needs a workspace of gvi_gp_predict_workspace_bytes(M, D)");
   const double* F = (const double*)factor;
   const int64_t rows = wide_chunk_rows(f.Mp);
-  double* ring = (double*)workspace + gvi_step_scratch_doubles(f.Mp);
+  double* ring = (double*)workspace + STEP_COUNTER_DOUBLES + gvi_step_scratch_doubles(f.Mp);
   double* gws = ring + (size_t)rows * f.Mp;
   // the factor buffer carries sqrt(w), the pre-scaled inducing points and amp^2: everything the Gram needs
   for (int64_t r0 = 0; r0 < N; r0 += rows) {
@@ -765,10 +809,17 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   return GVI_OK;
 }
 
+// fused-step workspace = [tile counter][reduction records][per-tile (nll, reg)][panel scratch]
+static size_t fused_records_doubles() {
+  const size_t n = (size_t)(2 * GVI_NUM_SMS > STEP_REDUCE_BLOCKS ? 2 * GVI_NUM_SMS : STEP_REDUCE_BLOCKS);
+  return n * STEP_PARTIAL_STRIDE;
+}
+static size_t fused_tile_doubles(int64_t N) { return (size_t)((N + 23) / 24) * 2 + 2; }
 extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N, int M) {
-  (void)N;
+  if (N < 1 || M < 1) return 0;
   const int Mp = (M + 31) / 32 * 32;
-  return ((size_t)2 * GVI_NUM_SMS * STEP_PARTIAL_STRIDE + gvi_step_scratch_doubles(Mp)) * sizeof(double);
+  return (STEP_COUNTER_DOUBLES + fused_records_doubles() + fused_tile_doubles(N) + gvi_step_scratch_doubles(Mp)) *
+         sizeof(double);
 }
 
 int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
@@ -805,9 +856,14 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
   int rc = gvi_fill_step_params(P, factor_q, factor_p, M, D, X, y, m_q, prior_mean_p, m_p_in, v_p_in, N, reg_kind,
                                 renyi_alpha, var_q_out, mean_p_out, var_p_out);
   if (rc) return rc;
-  P.partials = (double*)workspace;
-  P.acc_scratch = P.partials + (size_t)2 * GVI_NUM_SMS * STEP_PARTIAL_STRIDE;
+  P.tile_counter = (int*)workspace;
+  P.partials = (double*)workspace + STEP_COUNTER_DOUBLES;
+  P.tile_partials = P.partials + fused_records_doubles();
+  P.acc_scratch = P.tile_partials + fused_tile_doubles(N);
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
-  return gvi_launch_finish(P.partials, grid, N, 0, D, (const double*)factor_q, out3, st);
+  // forward launches use 24-point tiles; per-tile records -> fixed-order reduction -> out3
+  int nrec = gvi_launch_tile_reduce(P.tile_partials, (N + 23) / 24, 0, P.partials, st);
+  if (nrec < 0) return nrec;
+  return gvi_launch_finish(P.partials, nrec, N, 0, D, (const double*)factor_q, out3, st);
 }

@@ -14,6 +14,8 @@ struct PassDesc {
 
 // per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d, [36] sum g
 constexpr int STEP_PARTIAL_STRIDE = 38;
+constexpr int STEP_REDUCE_BLOCKS = 64;   // stage-A blocks of the fixed-order reduction over per-tile records
+constexpr int STEP_COUNTER_DOUBLES = 32; // workspace slot of the tile counter (256 B)
 
 struct StepParams {
   PassDesc pass[2];     // [0] = q (approximate GP), [1] = p (regulariser GP)
@@ -28,7 +30,13 @@ struct StepParams {
   const double* v_p_in; // [N]
   int reg_kind;
   double renyi_alpha;
-  double* partials;     // [gridDim.x][STEP_PARTIAL_STRIDE]
+  double* partials;     // [gridDim.x][STEP_PARTIAL_STRIDE] (static tile order) / [STEP_REDUCE_BLOCKS][..] (dynamic)
+  // dynamic tile order: CTAs draw tiles from a global counter (an SM's two co-resident CTAs do not progress at the same
+  // rate, and SMs differ slightly: with a static stride the launch ends on the slowest CTA, ~10 % after the fastest).
+  // The loss / gradient partial sums are then written PER TILE and reduced in a fixed order afterwards, so the result
+  // does not depend on which CTA ran which tile (run-to-run bit reproducible).
+  int* tile_counter;    // null = static stride; zeroed by the launcher
+  double* tile_partials;  // [ntiles][2] (forward: nll, reg) or [ntiles][STEP_PARTIAL_STRIDE] (gradient mode)
   // gradient mode
   int grad;
   double* g_out;        // [N] dR/dv_q
@@ -54,6 +62,8 @@ size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the panel pa
 int gvi_launch_step(const StepParams& P, cudaStream_t st);
 int gvi_launch_finish(const double* partials, int nblocks, int64_t N, int grad, int D, const double* Fq, double* out,
                       cudaStream_t st);
+// per-tile records -> STEP_REDUCE_BLOCKS records of STEP_PARTIAL_STRIDE (fixed order); returns the record count
+int gvi_launch_tile_reduce(const double* tile_partials, int64_t ntiles, int grad, double* records, cudaStream_t st);
 int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor_p, int M, int D, const double* X,
                          const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,
                          const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha, double* var_q_out,
