@@ -53,7 +53,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "gvi_gp_predict_grad_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_int, c_void_p,
                                         c_void_p, c_void_p]),
-    "gvi_exact_gp_predict_grad_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "gvi_exact_gp_predict_grad_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_exact_gp_predict_grad_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p]),
     "gvi_class_probabilities_f64": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_double,

@@ -18,6 +18,11 @@
 #include "common.cuh"
 
 int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st);
+// wide inputs (D > 32): GEMM formulation of the contractions with dK/dlog_ls (grad_wide.cu)
+size_t gvi_exact_gp_predict_grad_wide_workspace_bytes(int64_t N, int M, int D);
+int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int64_t N, const double* g,
+                                   const double* h_mean, const double* log_noise, double* out, void* workspace,
+                                   cudaStream_t st);
 
 namespace {
 constexpr int ECHUNK = 4096;  // rows of X per pass
@@ -181,8 +186,9 @@ ExactWs carve_exact(void* ws, int64_t N, int M, size_t* total) {
 }
 }  // namespace
 
-extern "C" size_t gvi_exact_gp_predict_grad_workspace_bytes(int64_t N, int M) {
-  if (N < 1 || M < 1) return 0;
+extern "C" size_t gvi_exact_gp_predict_grad_workspace_bytes(int64_t N, int M, int D) {
+  if (N < 1 || M < 1 || D < 1) return 0;
+  if (D > 32) return gvi_exact_gp_predict_grad_wide_workspace_bytes(N, M, D);
   size_t total = 0;
   carve_exact(nullptr, N, M, &total);
   return total;
@@ -192,9 +198,11 @@ extern "C" int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, c
                                              const double* g_var, const double* h_mean, const double* log_noise,
                                              double* out, void* workspace, void* stream) {
   GVI_CHECK_ARG(M >= 1 && D >= 1 && N >= 1, "sizes");
-  GVI_CHECK_ARG(D <= 32, "the exact-GP VJP supports D <= 32 in this build");
   GVI_CHECK_ARG(factor && X && g_var && out && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (D > 32)
+    return gvi_exact_gp_predict_grad_wide((const double*)factor, M, D, X, N, g_var, h_mean, log_noise, out, workspace,
+                                          st);
   const FactorLayout f = factor_layout(M, D);
   const double* F = (const double*)factor;
   const double* Linv = F + f.linv_off;

@@ -114,20 +114,22 @@ __global__ void __launch_bounds__(256) hadamard_kernel(double* __restrict__ S, c
 }
 
 // out[4+d] = t2x[d] + sum_j (z^_jd^2 c_j - 2 z^_jd Q_jd) + (R3 ? sum_j (z^_jd R3_jd - z^_jd^2 (V1)_j) : 0)
+// `xz_scale` multiplies the x-z part: 1 when W already carries dLoss/dk_ij * (-1/2) * (-2) (variance VJP), -1/2 when W
+// is dLoss/dk_ij o k_ij (exact-GP VJP)
 __global__ void __launch_bounds__(128) wide_finish_kernel(const double* __restrict__ Zh, const double* __restrict__ Q,
                                                           const double* __restrict__ R3,
-                                                          const double* __restrict__ t2x, int M, int D,
+                                                          const double* __restrict__ t2x, int M, int D, double xz_scale,
                                                           double* __restrict__ out) {
   const int d = blockIdx.x * 128 + threadIdx.x;
   if (d >= D) return;
   const int Da = D + 1;
-  double acc = t2x[d];
+  double acc = t2x[d], acc3 = 0.0;
   for (int j = 0; j < M; j++) {
     const double z = Zh[(int64_t)j * Da + d];
     acc += z * (z * Q[(int64_t)j * Da + D] - 2.0 * Q[(int64_t)j * Da + d]);
-    if (R3) acc += z * (R3[(int64_t)j * Da + d] - z * R3[(int64_t)j * Da + D]);
+    if (R3) acc3 += z * (R3[(int64_t)j * Da + d] - z * R3[(int64_t)j * Da + D]);
   }
-  out[4 + d] = acc;
+  out[4 + d] = fma(xz_scale, acc, acc3);
 }
 
 __global__ void wide_scalars_kernel(const double* __restrict__ scal, const double* __restrict__ F, int64_t N,
@@ -228,9 +230,186 @@ int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int
     if ((rc = gemm_rm(h, false, false, Mp, Da, Mp, w.S, Mp, w.Zh, Da, 0.0, w.R3, Da))) return rc;  // [V Z^ | V 1]
     R3 = w.R3;
   }
-  wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, R3, w.t2x, M, D, out);
+  wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, R3, w.t2x, M, D, 1.0, out);
   GVI_CHECK_LAUNCH("wide_finish_kernel");
   wide_scalars_kernel<<<1, 1, 0, st>>>(w.scal, F, N, out);
   GVI_CHECK_LAUNCH("wide_scalars_kernel");
+  return GVI_OK;
+}
+
+
+// ---- exact-GP predictive VJP (mean and variance) for wide inputs: same contraction machinery ------------------------------
+// dLoss/dK_xZ = G1 = h alpha^T - 2 diag(g) Aa,  dLoss/dA = G2 = Aa^T diag(g) Aa - w alpha^T (w = Aa^T h);  see exact.cu.
+//   dLoss/dlog_ls[d]  = -1/2 sum_ij (G1 o K)_ij (x^_id - z^_jd)^2 - 1/2 sum_jl (sym(G2) o K_ZZ)_jl (z^_jd - z^_ld)^2
+//   dLoss/dlog_scaling = 2 (sum G1 o K + sum G2 o K_ZZ + amp2 sum g),   dLoss/dlog_noise = s2 tr(G2)
+namespace {
+// one warp per row: B = g a (over T), W1 = (h_i alpha_j - 2 g_i a_ij) k_ij (over K), rowstats[i] = {sum_j W1_ij, -, -}
+__global__ void __launch_bounds__(256) exact_weights_kernel(double* __restrict__ K, const double* __restrict__ Aa,
+                                                            double* __restrict__ B, const double* __restrict__ g,
+                                                            const double* __restrict__ h,
+                                                            const double* __restrict__ alpha, int nr, int Mp,
+                                                            double* __restrict__ rowstats) {
+  const int lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < nr; i += gridDim.x * 8) {
+    const double gi = g[i], hi = h ? h[i] : 0.0;
+    double r = 0.0;
+    for (int j = lane; j < Mp; j += 32) {
+      const int64_t idx = (int64_t)i * Mp + j;
+      const double b = gi * Aa[idx];
+      const double w1 = fma(hi, alpha[j], -2.0 * b) * K[idx];
+      K[idx] = w1;
+      B[idx] = b;
+      r += w1;
+    }
+    r = warp_sum(r);
+    if (lane == 0) {
+      rowstats[3 * i] = r;
+      rowstats[3 * i + 1] = 0.0;
+      rowstats[3 * i + 2] = 0.0;
+    }
+  }
+}
+
+// scal[0] (+)= sum_i r_i, scal[2] (+)= sum_i g_i
+__global__ void __launch_bounds__(256) exact_row_scalars_kernel(const double* __restrict__ rowstats,
+                                                                const double* __restrict__ g, int nr, int first,
+                                                                double* __restrict__ scal) {
+  __shared__ double red[2][256];
+  const int tid = threadIdx.x;
+  double a = 0.0, c = 0.0;
+  for (int i = tid; i < nr; i += 256) {
+    a += rowstats[3 * i];
+    c += g[i];
+  }
+  red[0][tid] = a;
+  red[1][tid] = c;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) {
+      red[0][tid] += red[0][tid + s];
+      red[1][tid] += red[1][tid + s];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    scal[0] = first ? red[0][0] : scal[0] + red[0][0];
+    scal[2] = first ? red[1][0] : scal[2] + red[1][0];
+  }
+}
+
+// G2 <- G2 - w alpha^T in place; tr_out[0] = tr(G2) (rows < M), one block
+__global__ void __launch_bounds__(256) rank1_trace_kernel(double* __restrict__ G2, const double* __restrict__ wv,
+                                                          const double* __restrict__ alpha, int M, int Mp,
+                                                          double* __restrict__ tr_out) {
+  __shared__ double red[256];
+  const int64_t total = (int64_t)Mp * Mp;
+  for (int64_t idx = threadIdx.x; idx < total; idx += 256) G2[idx] = fma(-wv[idx / Mp], alpha[idx % Mp], G2[idx]);
+  __syncthreads();
+  double a = 0.0;
+  for (int j = threadIdx.x; j < M; j += 256) a += G2[(int64_t)j * Mp + j];
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tr_out[0] = red[0];
+}
+
+// V = 1/2 (G2 + G2^T) o K_ZZ into Vout; vsum[0] = sum V (fixed order: one block)
+__global__ void __launch_bounds__(256) sym_hadamard_kernel(const double* __restrict__ G2, const double* __restrict__ Kzz,
+                                                           int Mp, double* __restrict__ Vout,
+                                                           double* __restrict__ vsum) {
+  __shared__ double red[256];
+  const int64_t total = (int64_t)Mp * Mp;
+  double a = 0.0;
+  for (int64_t idx = threadIdx.x; idx < total; idx += 256) {
+    const int64_t r = idx / Mp, c = idx % Mp;
+    const double v = 0.5 * (G2[idx] + G2[c * Mp + r]) * Kzz[idx];
+    Vout[idx] = v;
+    a += v;
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) vsum[0] = red[0];
+}
+
+__global__ void exact_wide_scalars_kernel(const double* __restrict__ scal, const double* __restrict__ F, int64_t N,
+                                          int D, const double* __restrict__ log_noise, double* __restrict__ out) {
+  out[0] = out[1] = 0.0;
+  out[2] = (double)N;
+  // scal: [0] sum G1 o K, [1] tr(G2), [2] sum g, [3] sum sym(G2) o K_ZZ
+  out[3] = 2.0 * (scal[0] + scal[3] + F[1] * scal[2]);
+  out[4 + D] = log_noise ? exp(log_noise[0]) * scal[1] : 0.0;
+}
+}  // namespace
+
+size_t gvi_exact_gp_predict_grad_wide_workspace_bytes(int64_t N, int M, int D) {
+  // carve_wide + one extra Mp x Mp matrix (V) + w[Mp]
+  const size_t Mp = (size_t)(M + 31) / 32 * 32;
+  return gvi_gp_predict_grad_wide_workspace_bytes(N, M, D) + align256(Mp * Mp * 8) + align256(Mp * 8);
+}
+
+int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int64_t N, const double* g,
+                                   const double* h_mean, const double* log_noise, double* out, void* workspace,
+                                   cudaStream_t st) {
+  const FactorLayout f = factor_layout(M, D);
+  const int Mp = f.Mp, Da = D + 1;
+  const double* Linv = F + f.linv_off;
+  const double* alpha = F + f.alpha_off;
+  const double* Zs = F + f.zs_off;
+  size_t base = 0;
+  WideWs w = carve_wide(workspace, N, M, D, &base);
+  double* V = (double*)((unsigned char*)workspace + base);
+  double* wv = (double*)((unsigned char*)workspace + base + align256((size_t)Mp * Mp * 8));
+  cublasHandle_t hd;
+  int rc = gvi_get_cublas(&hd, st);
+  if (rc) return rc;
+  GVI_CUDA(cudaMemsetAsync(wv, 0, (size_t)Mp * sizeof(double), st));
+  for (int64_t r0 = 0; r0 < N; r0 += WCHUNK) {
+    const int nr = (int)(N - r0 < WCHUNK ? N - r0 : WCHUNK);
+    const int first = (r0 == 0);
+    const double beta = first ? 0.0 : 1.0;
+    if (Mp != M) GVI_CUDA(cudaMemsetAsync(w.K, 0, (size_t)nr * Mp * sizeof(double), st));
+    if ((rc = gvi_launch_wide_gram(F, f, X + r0 * D, nr, w.K, w.gram, st))) return rc;
+    shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(X + r0 * D, nr, D, F + f.sqrtw_off, Zs, w.Xs);
+    GVI_CHECK_LAUNCH("shift_aug_kernel");
+    if ((rc = gemm_rm(hd, false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp))) return rc;
+    if ((rc = gemm_rm(hd, false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp))) return rc;
+    const int wblocks = (nr + 7) / 8 < GVI_NUM_SMS * 8 ? (nr + 7) / 8 : GVI_NUM_SMS * 8;
+    exact_weights_kernel<<<wblocks, 256, 0, st>>>(w.K, w.Aa, w.T, g + r0, h_mean ? h_mean + r0 : nullptr, alpha, nr, Mp,
+                                                  w.rowstats);                                     // K <- W1, T <- B
+    GVI_CHECK_LAUNCH("exact_weights_kernel");
+    if ((rc = gemm_rm(hd, true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da))) return rc;   // Q|c += W1^T [X^|1]
+    if ((rc = gemm_rm(hd, true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp))) return rc;   // G2 += Aa^T B
+    if (h_mean) {
+      const double one = 1.0;
+      if (cublasDgemv(hd, CUBLAS_OP_N, Mp, nr, &one, w.Aa, Mp, h_mean + r0, 1, &one, wv, 1) != CUBLAS_STATUS_SUCCESS) {
+        gvi_set_error("cublasDgemv failed");
+        return GVI_ECUDA;
+      }
+    }
+    row_square_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Xs, nr, D, w.rowstats, first, w.t2x);
+    GVI_CHECK_LAUNCH("row_square_kernel");
+    exact_row_scalars_kernel<<<1, 256, 0, st>>>(w.rowstats, g + r0, nr, first, w.scal);
+    GVI_CHECK_LAUNCH("exact_row_scalars_kernel");
+  }
+  rank1_trace_kernel<<<1, 256, 0, st>>>(w.S, wv, alpha, M, Mp, w.scal + 1);
+  GVI_CHECK_LAUNCH("rank1_trace_kernel");
+  shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(Zs, Mp, D, nullptr, Zs, w.Zh);
+  GVI_CHECK_LAUNCH("shift_aug_kernel");
+  GVI_CUDA(cudaMemsetAsync(w.Kzz, 0, (size_t)Mp * Mp * sizeof(double), st));
+  if ((rc = gvi_launch_wide_gram_zz(F, f, w.Kzz, w.gram, st))) return rc;
+  sym_hadamard_kernel<<<1, 256, 0, st>>>(w.S, w.Kzz, Mp, V, w.scal + 3);
+  GVI_CHECK_LAUNCH("sym_hadamard_kernel");
+  if ((rc = gemm_rm(hd, false, false, Mp, Da, Mp, V, Mp, w.Zh, Da, 0.0, w.R3, Da))) return rc;     // [V Z^ | V 1]
+  wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, w.R3, w.t2x, M, D, -0.5, out);
+  GVI_CHECK_LAUNCH("wide_finish_kernel");
+  exact_wide_scalars_kernel<<<1, 1, 0, st>>>(w.scal, F, N, D, log_noise, out);
+  GVI_CHECK_LAUNCH("exact_wide_scalars_kernel");
   return GVI_OK;
 }

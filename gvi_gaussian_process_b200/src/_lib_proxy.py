@@ -284,7 +284,7 @@ def exact_gp_predict_grad(factor: GpFactor, x, g_var, h_mean, log_noise):
     exact-GP predictive (gvi_exact_gp_predict_grad_f64), given the cotangents of its variance and mean."""
     n, d = x.shape
     out = empty(5 + d)
-    ws = _workspace("exact_grad", _L().gvi_exact_gp_predict_grad_workspace_bytes(n, factor.m))
+    ws = _workspace("exact_grad", _L().gvi_exact_gp_predict_grad_workspace_bytes(n, factor.m, d))
     rc = _L().gvi_exact_gp_predict_grad_f64(_lib.ptr(factor.buf), factor.m, d, _lib.ptr(x), n, _lib.ptr(g_var),
                                             _lib.ptr(h_mean), _lib.ptr(log_noise), _lib.ptr(out), _lib.ptr(ws),
                                             _lib.current_stream())

@@ -88,8 +88,10 @@ def test_argument_validation_of_the_widened_entry_points(lib):
     assert lib.gvi_gp_predict_grad_f64(None, 4, 3, None, 0, None, 0, None, None, None) == -1  # N >= 1
     assert lib.gvi_weighted_gram_f64(None, 4, 40, None, 10, None, None, None, None) == -1  # D <= 32
     assert b"D <= 32" in lib.gvi_last_error_string()
-    assert lib.gvi_exact_gp_predict_grad_f64(None, 4, 40, None, 10, None, None, None, None, None, None) == -1
-    assert lib.gvi_exact_gp_predict_grad_workspace_bytes(1024, 1024) >= 4 * 1024 * 1024 * 8
+    assert lib.gvi_exact_gp_predict_grad_f64(None, 4, 40, None, 10, None, None, None, None, None, None) == -1  # nulls
+    assert lib.gvi_exact_gp_predict_grad_workspace_bytes(1024, 1024, 8) >= 4 * 1024 * 1024 * 8
+    assert (lib.gvi_exact_gp_predict_grad_workspace_bytes(1024, 1024, 784)
+            > lib.gvi_exact_gp_predict_grad_workspace_bytes(1024, 1024, 8))  # wide-input route
     assert lib.gvi_fused_step_grad_workspace_bytes(60000, 2048, 784) >= 3 * 2048 * 2048 * 8  # wide-input route
     # optimiser step
     assert lib.gvi_optimiser_step_f64(7, None, None, None, None, 10, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1

@@ -399,7 +399,9 @@ def test_classification_wide_inputs_mnist_shaped(S):
 
 
 # ---- section 8(f)-3: the exact-GP NLL training step on the inducing set, value and gradient -----------------------
-@pytest.mark.parametrize("n,m,d,scalar_ll", [(40, 40, 1, True), (300, 200, 3, False), (5000, 700, 8, False)])
+@pytest.mark.parametrize("n,m,d,scalar_ll", [(40, 40, 1, True), (300, 200, 3, False), (5000, 700, 8, False),
+                                             # D > 32: GEMM formulation (grad_wide.cu); 2500 rows > one chunk
+                                             (300, 200, 40, False), (2500, 130, 64, True)])
 def test_exact_gp_nll_step_backward_matches_autograd_twin(S, n, m, d, scalar_ll):
     rng = np.random.default_rng(n + d)
     z = rng.standard_normal((m, d))
