@@ -4,7 +4,8 @@ from gvi_gaussian_process_b200 import _lib
 L = _lib.load(); P = _lib.ptr; chk = _lib.check
 dev='cuda'
 def T(a): return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
-M, D = 1024, 8
+import os
+M, D = int(os.environ.get('M', 1024)), int(os.environ.get('D', 8))
 rng = np.random.default_rng(0); Z = rng.standard_normal((M, D))
 F = torch.empty(L.gvi_gp_factor_bytes(M, D)//8, dtype=torch.float64, device=dev)
 ws = torch.empty(L.gvi_gp_factor_workspace_bytes(M)//8, dtype=torch.float64, device=dev)
