@@ -70,6 +70,7 @@ SIGNATURES = {
     "gvi_optimiser_step_f64": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double,
                                        c_double, c_double, c_double, c_void_p]),
     "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "gvi_test_set_grad_chunk_waves": (c_int, [c_int]),
     "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_cond_var_select_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),

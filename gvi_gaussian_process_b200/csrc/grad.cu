@@ -2,12 +2,15 @@
 //
 // With g_i = dR/dv_q,i (from the tile kernel) and a_i = A^-1 k_i:
 //   dR/dlog_ls[d]  = sum_i g_i sum_j a_ij k_ij (x~_id - z~_jd)^2                       (tile kernel, T2_d)
-//                  + < dK_ZZ/dlog_ls[d], S >,   S = sum_i g_i a_i a_i^T = A^-1 C A^-1,  C = sum_i g_i k_i k_i^T
+//                  + < dK_ZZ/dlog_ls[d], S >,   S = sum_i g_i a_i a_i^T
 //   dR/dlog_scaling = sum_i g_i (2 v_i - 2 jitter_abs |a_i|^2)                          (tile kernel)
-// C is a weighted Gram (SYRK) over ALL points: syrk_kernel regenerates K(x,Z) column blocks on the FP64 pipe and
-// accumulates 128x128 tiles of C on the tensor pipe (DMMA), interleaved in one instruction stream; S needs four
-// M^3 products with the dense L^-1 (plain library GEMMs: cuBLAS); the contraction with dK_ZZ/dlog_ls is a small
-// reduction kernel.  Reference: jax.grad of generalised_variational_inference.py:73-94 (trainer.py:83-89).
+// S is a weighted Gram (SYRK) over ALL points.  The tile kernel leaves the a_i of a chunk of points in a ring, already in
+// DMMA operand order, and syrk_kernel accumulates 128x128 tiles of S on the tensor pipe, chunk after chunk; the
+// contraction with dK_ZZ/dlog_ls is a small reduction kernel.  (S is accumulated from the a_i, the way reverse-mode
+// differentiation of cho_solve does it: its error is ~cond(A) eps.  The algebraically equal A^-1 (sum g k k^T) A^-1
+// amplifies the rounding of the inner sum by cond(A)^2 and was dropped.)  The same SYRK kernel fed by kgen_kernel
+// gives C = sum_i g_i k_i k_i^T, the vector-Jacobian product of the SVGP family (gvi_weighted_gram_f64).
+// Reference: jax.grad of generalised_variational_inference.py:73-94 (trainer.py:83-89).
 #include <cublas_v2.h>
 
 #include "predict.cuh"
@@ -17,20 +20,17 @@ int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int
                              double* out, void* workspace, cudaStream_t st);
 
 namespace {
-constexpr int CB = 128;  // C tile edge
-constexpr int PC = 32;   // points per chunk
+constexpr int CB = SYRK_CB;  // C tile edge
+constexpr int PC = SYRK_PC;  // points per operand block
 constexpr int STHREADS = 256;
 
-// K block = the DMMA fragments of 128 columns x 32 points: [kp (4)][tile (16)][lane (32)][2] doubles, each kp
-// block padded by 4 doubles (bank spread for the generating warps), followed by the 32 weights g_i of the points.
-constexpr int KPSTRIDE = 16 * 32 * 2 + 4;
-constexpr int STAGE = 4 * KPSTRIDE;
-constexpr int BLK = STAGE + PC;               // doubles per (column block, point group)
+// operand block layout: predict.cuh (the tile kernel writes a_i blocks, kgen_kernel writes k_i blocks)
+constexpr int KPSTRIDE = SYRK_KPSTRIDE;
+constexpr int STAGE = SYRK_STAGE;
+constexpr int BLK = SYRK_BLK;                 // doubles per (column block, point group)
 constexpr uint32_t BLK_BYTES = BLK * 8;       // 33152, a multiple of 16 (cp.async.bulk granularity)
 constexpr int NSTAGE = 3;
-__device__ __forceinline__ int frag_index(int c, int i) {
-  return (i >> 3) * KPSTRIDE + (((c >> 3) * 32) + ((c & 7) * 4 + (i & 3))) * 2 + ((i >> 2) & 1);
-}
+__device__ __forceinline__ int frag_index(int c, int i) { return syrk_frag_index(c, i); }
 
 // ---- stage 1: K(x_chunk, Z) once per chunk into an L2-sized ring, already in fragment order ------------------------
 // One CTA per (32-point group, 128-column block): lane = point, warp w takes 16 columns, four at a time (independent
@@ -301,11 +301,14 @@ int launch_syrk(const SyrkParams& P, int ntri, cudaStream_t st) {
   return GVI_OK;
 }
 
+int g_chunk_waves_cap = 0;  // test hook (gvi_test_set_grad_chunk_waves)
+
 struct GradWs {
-  double *partials, *tile_partials, *g, *bscratch, *Cpart, *C, *T1, *T2, *rowpart, *Kc;
+  double *partials, *tile_partials, *g, *bscratch, *Cpart, *C, *rowpart, *Kc;
   int* tile_counter;
   int64_t ntiles;
   int nsplit, ntri, ncb, chunk_pg;  // chunk_pg = point groups (of 32 points) per K chunk
+  int64_t achunk_pts;               // points per chunk of the a_i ring (a multiple of every tile height and of 32)
 };
 size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
@@ -330,8 +333,6 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   w.bscratch = take((size_t)GVI_NUM_SMS * f.Mp * T * 8);
   w.Cpart = take((size_t)w.nsplit * f.Mp * f.Mp * 8);
   w.C = take((size_t)f.Mp * f.Mp * 8);
-  w.T1 = take((size_t)f.Mp * f.Mp * 8);
-  w.T2 = take((size_t)f.Mp * f.Mp * 8);
   w.rowpart = take((size_t)f.Mp * 32 * 8);
   // K ring: ~48 MB so that a chunk written by kgen_kernel is still L2-resident when syrk_kernel streams it
   w.ncb = Gc;
@@ -341,7 +342,19 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   const int64_t need = (N + PC - 1) / PC;
   if (pgs > need) pgs = need;
   w.chunk_pg = (int)pgs;
-  w.Kc = take((size_t)Gc * pgs * BLK * 8);
+  // the same ring takes the a_i chunks of the tile kernel (gradient step).  That accumulation is compute bound and
+  // streaming its operands from HBM costs nothing, so the chunks are long (up to 1 GB) to amortise the launch tails;
+  // a chunk is a whole number of 148 x 24-point waves (3552 = 32 x 111 points: a multiple of every tile height).
+  const int64_t wave = (int64_t)GVI_NUM_SMS * 24;
+  const int64_t wave_bytes = wave / PC * Gc * BLK * 8;
+  int64_t nw = (1LL << 30) / wave_bytes;
+  if (g_chunk_waves_cap > 0 && nw > g_chunk_waves_cap) nw = g_chunk_waves_cap;
+  const int64_t need_w = (N + wave - 1) / wave;
+  if (nw > need_w) nw = need_w;
+  if (nw < 1) nw = 1;
+  w.achunk_pts = nw * wave;
+  const size_t ring_k = (size_t)Gc * pgs * BLK * 8, ring_a = (size_t)nw * wave_bytes;
+  w.Kc = take(ring_k > ring_a ? ring_k : ring_a);
   if (total) *total = o;
   return w;
 }
@@ -353,6 +366,11 @@ __global__ void test_exp_kernel(const double* __restrict__ x, int64_t n, double*
     out[i] = gvi_exp(x[i]);
 }
 }  // namespace
+extern "C" int gvi_test_set_grad_chunk_waves(int waves) {
+  const int prev = g_chunk_waves_cap;
+  g_chunk_waves_cap = waves > 0 ? waves : 0;
+  return prev;
+}
 extern "C" int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream) {
   GVI_CHECK_ARG(x && out && n >= 1, "arguments");
   test_exp_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(x, n, out);
@@ -384,6 +402,59 @@ static int gvi_weighted_gram(const double* Fq, const double* X, const double* g,
   return GVI_OK;
 }
 
+// Gradient-mode tile launches chunk by chunk.  Each chunk leaves a_i = A^-1 k_i (and g_i) of its points in the ring in
+// operand-block order and syrk_kernel folds it into S = sum_i g_i a_i a_i^T on the tensor pipe (w.C on return).  The
+// per-tile records land at their global tile index, so the fixed-order reductions that follow see one launch.
+static int gvi_grad_launch_accumulate_S(const StepParams& P0, const GradWs& w, int* grid_out, cudaStream_t st) {
+  const FactorLayout f = factor_layout(P0.M, P0.D);
+  const int T = gvi_step_tile_points(f.Mp, P0.D, true);
+  if (T <= 0) {
+    gvi_set_error("the gradient step supports M <= 3456 in this build (got M=%d)", P0.M);
+    return GVI_EUNSUPPORTED;
+  }
+  int rc;
+  for (int64_t row0 = 0; row0 < P0.N; row0 += w.achunk_pts) {
+    const int64_t n = P0.N - row0 < w.achunk_pts ? P0.N - row0 : w.achunk_pts;
+    StepParams P = P0;
+    auto at = [&](const double* p) { return p ? p + row0 : nullptr; };
+    auto atw = [&](double* p) { return p ? p + row0 : nullptr; };
+    P.X = P0.X + row0 * P0.D;
+    P.N = n;
+    P.y = at(P0.y); P.m_q = at(P0.m_q); P.m_p_in = at(P0.m_p_in); P.v_p_in = at(P0.v_p_in); P.g_in = at(P0.g_in);
+    P.g_out = atw(P0.g_out); P.dm_out = atw(P0.dm_out);
+    for (int ps = 0; ps < P0.npass; ps++) {
+      P.pass[ps].prior_mean = at(P0.pass[ps].prior_mean);
+      P.pass[ps].mean_out = atw(P0.pass[ps].mean_out);
+      P.pass[ps].var_out = atw(P0.pass[ps].var_out);
+    }
+    P.tile_partials = P0.tile_partials + (size_t)(row0 / T) * STEP_PARTIAL_STRIDE;
+    const int64_t ntiles = (n + T - 1) / T;
+    const int npg = (int)((ntiles * T + PC - 1) / PC);
+    P.a_ring = w.Kc;
+    P.a_npg = npg;
+    if ((ntiles * T) % PC != 0 || n % T != 0)  // the last group is only partly written by the tiles: zero it first
+      GVI_CUDA(cudaMemset2DAsync(w.Kc + (size_t)(npg - 1) * BLK, (size_t)npg * BLK * 8, 0, (size_t)BLK * 8, w.ncb, st));
+    const int grid = gvi_launch_step(P, st);
+    if (grid < 0) return grid;
+    if (grid_out) *grid_out = grid;
+    SyrkParams sp{w.Kc, npg, f.Mp, w.nsplit, row0 == 0 ? 1 : 0, w.Cpart};
+    if ((rc = launch_syrk(sp, w.ntri, st))) return rc;
+  }
+  syrk_reduce_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.Cpart, w.nsplit, f.Mp, w.C);
+  GVI_CHECK_LAUNCH("syrk_reduce_kernel");
+  return GVI_OK;
+}
+
+// out[4+d] += <dK_ZZ/dlog_ls[d], S> with S in w.C
+static int gvi_contract_kzz_term(const double* Fq, const FactorLayout& f, int M, int D, const GradWs& w, double* out,
+                                 cudaStream_t st) {
+  dkzz_contract_kernel<<<M, 256, 0, st>>>(w.C, Fq, M, f.Mp, D, w.rowpart);
+  GVI_CHECK_LAUNCH("dkzz_contract_kernel");
+  grad_finish_kernel<<<1, 32, 0, st>>>(w.rowpart, M, D, out);
+  GVI_CHECK_LAUNCH("grad_finish_kernel");
+  return GVI_OK;
+}
+
 // the per-thread cuBLAS handle, bound to `st` (shared with exact.cu)
 int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st) {
   if (!g_cublas) {
@@ -395,31 +466,6 @@ int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st) {
   cublasSetStream(g_cublas, st);
   cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
   *h = g_cublas;
-  return GVI_OK;
-}
-
-// S = L^-T (L^-1 C L^-T) L^-1 (plain library GEMMs), then out[4+d] += <dK_ZZ/dlog_ls[d], S>
-static int gvi_finish_kzz_term(const double* Fq, const FactorLayout& f, int M, int D, const GradWs& w, double* out,
-                               cudaStream_t st) {
-  int rc;
-  if (!g_cublas) {
-    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
-      gvi_set_error("cublasCreate failed");
-      return GVI_ECUDA;
-    }
-  }
-  cublasSetStream(g_cublas, st);
-  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
-  const double* Linv = Fq + f.linv_off;
-  const int n = f.Mp;
-  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, Linv, n, w.C, n, w.T1, n))) return rc;   // T1 = Linv C
-  if ((rc = gemm_rm(g_cublas, false, true, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;   // T2 = T1 Linv^T
-  if ((rc = gemm_rm(g_cublas, true, false, n, n, n, Linv, n, w.T2, n, w.T1, n))) return rc;   // T1 = Linv^T T2
-  if ((rc = gemm_rm(g_cublas, false, false, n, n, n, w.T1, n, Linv, n, w.T2, n))) return rc;  // S = T1 Linv
-  dkzz_contract_kernel<<<M, 256, 0, st>>>(w.T2, Fq, M, f.Mp, D, w.rowpart);
-  GVI_CHECK_LAUNCH("dkzz_contract_kernel");
-  grad_finish_kernel<<<1, 32, 0, st>>>(w.rowpart, M, D, out);
-  GVI_CHECK_LAUNCH("grad_finish_kernel");
   return GVI_OK;
 }
 
@@ -456,13 +502,16 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   P.g_out = w.g;
   P.dm_out = dm_out;
   P.bscratch = w.bscratch;
-  int grid = gvi_launch_step(P, st);
-  if (grid < 0) return grid;
+  int grid;
+  if (frozen_cholesky) {  // A does not depend on the trained parameters: no <dK_ZZ, S> term, one launch
+    if ((grid = gvi_launch_step(P, st)) < 0) return grid;
+  } else if ((rc = gvi_grad_launch_accumulate_S(P, w, nullptr, st))) {
+    return rc;
+  }
   if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
-  if (frozen_cholesky) return GVI_OK;  // A does not depend on the trained parameters: no <dK_ZZ, S> term
-  if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
-  return gvi_finish_kzz_term(Fq, f, M, D, w, out, st);
+  if (frozen_cholesky) return GVI_OK;
+  return gvi_contract_kzz_term(Fq, f, M, D, w, out, st);
 }
 
 
@@ -495,14 +544,16 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
   P.grad = 1;
   P.g_in = g_var;
   P.bscratch = w.bscratch;
-  int grid = gvi_launch_step(P, st);
-  if (grid < 0) return grid;
-  int rc;
+  int grid, rc;
+  if (frozen_cholesky) {
+    if ((grid = gvi_launch_step(P, st)) < 0) return grid;
+  } else if ((rc = gvi_grad_launch_accumulate_S(P, w, nullptr, st))) {
+    return rc;
+  }
   if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 1, D, Fq, out, st))) return rc;
   if (frozen_cholesky) return GVI_OK;
-  if ((rc = gvi_weighted_gram(Fq, X, g_var, N, M, D, w, st))) return rc;
-  return gvi_finish_kzz_term(Fq, f, M, D, w, out, st);
+  return gvi_contract_kzz_term(Fq, f, M, D, w, out, st);
 }
 
 // ---- weighted Gram C = sum_i g_i k_i k_i^T as an entry point ----------------------------------------------------------

@@ -455,6 +455,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
       for (int idx = tid; idx < P.Mp * T / 2; idx += THREADS) Ks2w[idx] = __ldcg(scr2 + idx);  // b tile replaces K tile
       if (tid == 0) *counter = 0;
       __syncthreads();
+      if (P.a_ring && tid < T) {  // the weights g_i ride at the end of every column block of the point's group
+        const int64_t p = row0 + tid;
+        for (int cb = 0; cb * SYRK_CB < P.Mp; cb++)
+          __stcg(P.a_ring + ((size_t)cb * P.a_npg + (p >> 5)) * SYRK_BLK + SYRK_STAGE + (p & 31), gs[tid]);
+      }
       const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
       const double* __restrict__ WT = F + f.wpackT_off;
       const double* __restrict__ Zs = F + f.zs_off;
@@ -471,6 +476,23 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         const int kp0 = GVI_GROUP_ROWS * g / 8;
         group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
                       Ks2, lane, acc);
+        if (P.a_ring) {
+          // a_ij of this group -> operand blocks of the S = sum_i g_i a_i a_i^T accumulation (grad.cu): per (mt, nt)
+          // the warp covers 8 columns x 8 points = 512 contiguous bytes of the block
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) {
+            const int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
+            const int cb = j / SYRK_CB, c = j % SYRK_CB;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) {
+              const int64_t p0 = row0 + nt * 8;  // a multiple of 8: the n-tile stays inside one k-pair of one group
+              double* blk = P.a_ring + ((size_t)cb * P.a_npg + (p0 >> 5)) * SYRK_BLK;
+#pragma unroll
+              for (int e = 0; e < 2; e++)
+                __stcg(blk + syrk_frag_index(c, (int)(p0 & 31) + (lane & 3) * 2 + e), acc[mt][nt][e]);
+            }
+          }
+        }
         double t2[DR], na2 = 0.0;
 #pragma unroll
         for (int d = 0; d < DR; d++) t2[d] = 0.0;

@@ -54,7 +54,25 @@ struct StepParams {
   int reds_in_smem;     // set by the launcher
   int two_cta;          // set by the launcher: 8-warp CTAs, two per SM
   int has_extra;        // the q factor carries an extra matrix E (SVGP): single panel required
+  // gradient mode: a_i = A^-1 k_i of every tile is also written to a ring in the operand order of the weighted-Gram
+  // (SYRK) kernel of grad.cu, together with g_i, so that S = sum_i g_i a_i a_i^T is accumulated from the a_i directly
+  // (error ~ cond(A) eps; the earlier S = A^-1 (sum_i g_i k_i k_i^T) A^-1 amplified the rounding of C by cond(A)^2).
+  double* a_ring;       // [ncb][a_npg][SYRK_BLK] or null
+  int a_npg;            // 32-point groups per column block in the ring (this launch)
 };
+
+// ---- operand blocks of the weighted-Gram (SYRK) kernel (grad.cu), also written by the tile kernel -------------------
+// One block = the DMMA fragments of 128 columns x 32 points: [kp (4)][tile (16)][lane (32)][2] doubles, each kp part
+// padded by 4 doubles (bank spread for the generating warps), followed by the 32 weights g_i of the points.
+constexpr int SYRK_CB = 128;  // columns per block = C tile edge
+constexpr int SYRK_PC = 32;   // points per block
+constexpr int SYRK_KPSTRIDE = 16 * 32 * 2 + 4;
+constexpr int SYRK_STAGE = 4 * SYRK_KPSTRIDE;
+constexpr int SYRK_BLK = SYRK_STAGE + SYRK_PC;  // doubles per (column block, point group)
+// element (column c of the block, point i of the group)
+__host__ __device__ __forceinline__ int syrk_frag_index(int c, int i) {
+  return (i >> 3) * SYRK_KPSTRIDE + (((c >> 3) * 32) + ((c & 7) * 4 + (i & 3))) * 2 + ((i >> 2) & 1);
+}
 
 int gvi_step_tile_points(int Mp, int D, bool grad);
 // forward-only launches use column panels when the whole K tile does not fit: returns Pc (== Mp: single panel)

@@ -225,6 +225,10 @@ int gvi_optimiser_step_f64(int kind, double* param, const double* grad, double* 
 
 /* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
 int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
+/* test hook: cap the chunk length of the gradient step's a_i ring at `waves` x 3552 points (0 = default, up to 1 GB),
+ * so that small problems exercise the multi-chunk path; affects gvi_fused_step_grad_workspace_bytes too.  Returns the
+ * previous value. */
+int gvi_test_set_grad_chunk_waves(int waves);
 
 /* ---- a13: ConditionalVarianceInducingPointsSelector.compute_inducing_points
  * (src/inducing_points_selection.py:113-176) on ALREADY PERMUTED inputs x_perm[N,D] (the permutation is the
