@@ -353,7 +353,8 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   if (nw > need_w) nw = need_w;
   if (nw < 1) nw = 1;
   w.achunk_pts = nw * wave;
-  const size_t ring_k = (size_t)Gc * pgs * BLK * 8, ring_a = (size_t)nw * wave_bytes;
+  // (wide inputs, D > 32, take the GEMM route of grad_wide.cu and never fill the a_i ring)
+  const size_t ring_k = (size_t)Gc * pgs * BLK * 8, ring_a = D > 32 ? 0 : (size_t)nw * wave_bytes;
   w.Kc = take(ring_k > ring_a ? ring_k : ring_a);
   if (total) *total = o;
   return w;
