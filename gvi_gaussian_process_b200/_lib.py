@@ -69,6 +69,14 @@ SIGNATURES = {
                                       c_void_p]),
     "gvi_optimiser_step_f64": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double,
                                        c_double, c_double, c_double, c_void_p]),
+    "gvi_dot_gram_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_double, c_void_p,
+                                 c_int64, c_void_p]),
+    "gvi_kernel_pairs_f64": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_double,
+                                     c_void_p, c_void_p]),
+    "gvi_gp_factor_gram_f64": (c_int, [c_void_p, c_int64, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
+    "gvi_gp_predict_gram_f64": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p, c_void_p]),
     "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gvi_test_set_grad_chunk_waves": (c_int, [c_int]),
     "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),

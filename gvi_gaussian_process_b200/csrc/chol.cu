@@ -358,6 +358,26 @@ __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, con
   }
 }
 
+// header of a state built from a caller-supplied Gram: no kernel parameters (k(x,x) arrives per point)
+__global__ void factor_header_gram_kernel(double* __restrict__ F, FactorLayout f, double abs_jitter) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    F[0] = 1.0;
+    F[1] = 0.0;
+    F[4] = abs_jitter;
+    F[5] = 0.0;
+    F[6] = F[7] = 0.0;
+  }
+  if (tid < f.D) F[f.sqrtw_off + tid] = 0.0;
+  for (int64_t idx = tid; idx < (int64_t)f.Mp * f.D; idx += (int64_t)gridDim.x * blockDim.x) F[f.zs_off + idx] = 0.0;
+}
+__global__ void copy_gram_kernel(const double* __restrict__ K, int64_t ldk, int M, double* __restrict__ A, int Mp) {
+  const int64_t total = (int64_t)M * M;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    A[(idx / M) * Mp + idx % M] = K[(idx / M) * ldk + idx % M];
+}
+
 // ---- pack L^-1 in fragment order: group g (rows R g .. R g + R - 1, R = GVI_GROUP_ROWS), kp (cols 8kp..8kp+7),
 // mt (8-row tile), lane, e:  element = Linv[R g + 8 mt + lane/4][8 kp + 4 e + lane%4]; zero above the diagonal and in
 // the padding.  One CTA per group.
@@ -514,7 +534,16 @@ extern "C" size_t gvi_gp_factor_workspace_bytes(int M) {
 static int factor_impl(const double* Z, int M, int D, const double* log_scaling, const double* log_ls, int ls_len,
                        const double* chol_log_scaling, const double* chol_log_ls, int chol_ls_len, double reg,
                        int is_abs, const double* log_noise, const double* y_z, void* factor_out, void* workspace,
-                       int* info, void* stream);
+                       int* info, void* stream, const double* Kzz = nullptr, int64_t ldk = 0);
+
+// K_ZZ supplied by the caller (any base kernel): no kernel parameters, no scaled inducing points in the state
+extern "C" int gvi_gp_factor_gram_f64(const double* Kzz, int64_t ld, int M, double reg, int is_abs,
+                                      const double* log_noise, const double* y_z, void* factor_out, void* workspace,
+                                      int* info, void* stream) {
+  GVI_CHECK_ARG(Kzz && ld >= M, "Kzz");
+  return factor_impl(nullptr, M, 1, nullptr, nullptr, 1, nullptr, nullptr, 0, reg, is_abs, log_noise, y_z, factor_out,
+                     workspace, info, stream, Kzz, ld);
+}
 
 extern "C" int gvi_gp_factor_f64(const double* Z, int M, int D, const double* log_scaling, const double* log_ls,
                                  int ls_len, double reg, int is_abs, const double* log_noise, const double* y_z,
@@ -571,8 +600,8 @@ extern "C" int gvi_gp_factor_set_extra_f64(void* factor, int M, int D, const dou
 static int factor_impl(const double* Z, int M, int D, const double* log_scaling, const double* log_ls, int ls_len,
                        const double* chol_log_scaling, const double* chol_log_ls, int chol_ls_len, double reg,
                        int is_abs, const double* log_noise, const double* y_z, void* factor_out, void* workspace,
-                       int* info, void* stream) {
-  GVI_CHECK_ARG(Z && log_scaling && log_ls && factor_out && workspace, "null pointer");
+                       int* info, void* stream, const double* Kzz, int64_t ldk) {
+  GVI_CHECK_ARG((Kzz || (Z && log_scaling && log_ls)) && factor_out && workspace, "null pointer");
   GVI_CHECK_ARG(M >= 1 && D >= 1, "sizes");
   GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
   cudaStream_t st = (cudaStream_t)stream;
@@ -584,11 +613,20 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   double* tvec = X + (size_t)f.Mp * f.Mp;
   int* winfo = (int*)(tvec + 2 * f.Mp);
   int rc;
-  factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0,
-                                           chol_log_scaling != nullptr);
-  GVI_CHECK_LAUNCH("factor_header_kernel");
-  // K_ZZ of the Cholesky: the kernel's own parameters, or the frozen (regulariser) parameters
-  if (chol_log_scaling)
+  if (Kzz) {
+    factor_header_gram_kernel<<<64, 256, 0, st>>>(F, f, is_abs ? reg : 0.0);
+    GVI_CHECK_LAUNCH("factor_header_gram_kernel");
+    copy_gram_kernel<<<148 * 4, 256, 0, st>>>(Kzz, ldk, M, A, f.Mp);
+    GVI_CHECK_LAUNCH("copy_gram_kernel");
+  } else {
+    factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0,
+                                             chol_log_scaling != nullptr);
+    GVI_CHECK_LAUNCH("factor_header_kernel");
+  }
+  // K_ZZ of the Cholesky: the caller's Gram, the kernel's own parameters, or the frozen (regulariser) parameters
+  if (Kzz)
+    rc = GVI_OK;
+  else if (chol_log_scaling)
     rc = gvi_launch_ard_gram(Z, M, Z, M, D, chol_log_scaling, chol_log_ls, chol_ls_len, A, f.Mp, st);
   else
     rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st);

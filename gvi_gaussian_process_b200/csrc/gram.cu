@@ -60,7 +60,122 @@ __global__ void ard_gram_diag_kernel(int64_t n, const double* __restrict__ log_s
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = v;
 }
+
+// ---- inner-product and polynomial kernels ------------------------------------------------------------------------
+// k(x,z) = (exp(log_scaling) <x,z> + exp(log_constant))^degree   (src/kernels/non_stationary/polynomial_kernel.py:40-52;
+// inner_product_kernel.py:36-42 is the case without constant and degree 1).  jnp.power with a Python-int exponent lowers
+// to lax.integer_pow (repeated squaring), with a float exponent to pow: integral degrees take the multiplication chain.
+__device__ __forceinline__ double gvi_poly_epilogue(double dot, double scale, double constant, double degree) {
+  const double b = fma(scale, dot, constant);
+  if (degree == 1.0) return b;
+  const double r = rint(degree);
+  if (r == degree && r >= 0.0 && r <= 64.0) {
+    int n = (int)r;
+    double acc = 1.0, p = b;
+    while (n) {
+      if (n & 1) acc *= p;
+      p *= p;
+      n >>= 1;
+    }
+    return acc;
+  }
+  return pow(b, degree);
+}
+
+// same tiling as ard_gram_kernel: 32 x 256 output tile per CTA, features staged 16 at a time, coalesced stores
+__global__ void __launch_bounds__(TC) dot_gram_kernel(const double* __restrict__ x1, int64_t m1,
+                                                      const double* __restrict__ x2, int64_t m2, int D,
+                                                      const double* __restrict__ log_scaling,
+                                                      const double* __restrict__ log_constant, double degree,
+                                                      double* __restrict__ out, int64_t ld) {
+  __shared__ double xs[TR][DC];
+  __shared__ double zs[DC][TC + 1];
+  const int tid = threadIdx.x;
+  const int64_t col0 = (int64_t)blockIdx.x * TC;
+  const int64_t row0 = (int64_t)blockIdx.y * TR;
+  const double scale = exp(log_scaling[0]);
+  const double constant = log_constant ? exp(log_constant[0]) : 0.0;
+  double acc[TR];
+#pragma unroll
+  for (int r = 0; r < TR; r++) acc[r] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += DC) {
+    const int dc = min(DC, D - d0);
+    __syncthreads();
+    for (int idx = tid; idx < TR * dc; idx += TC) {
+      int r = idx / dc, d = idx % dc;
+      xs[r][d] = (row0 + r < m1) ? x1[(row0 + r) * D + d0 + d] : 0.0;
+    }
+    for (int idx = tid; idx < TC * dc; idx += TC) {
+      int c = idx / dc, d = idx % dc;
+      zs[d][c] = (col0 + c < m2) ? x2[(col0 + c) * D + d0 + d] : 0.0;
+    }
+    __syncthreads();
+    for (int d = 0; d < dc; d++) {
+      const double z = zs[d][tid];
+#pragma unroll
+      for (int r = 0; r < TR; r++) acc[r] = fma(xs[r][d], z, acc[r]);
+    }
+  }
+  if (col0 + tid < m2) {
+#pragma unroll
+    for (int r = 0; r < TR; r++) {
+      if (row0 + r < m1) out[(row0 + r) * ld + col0 + tid] = gvi_poly_epilogue(acc[r], scale, constant, degree);
+    }
+  }
+}
+
+// diagonal mode of KernelBase.calculate_gram (src/kernels/base.py:132-147): out[i] = k(x1_i, x2_i), one thread per pair
+__global__ void kernel_pairs_kernel(int kind, const double* __restrict__ x1, const double* __restrict__ x2, int64_t n,
+                                    int D, const double* __restrict__ p0, const double* __restrict__ p1, int p1_len,
+                                    double degree, double* __restrict__ out) {
+  const double e0 = exp(p0[0]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double* a = x1 + i * D;
+    const double* b = x2 + i * D;
+    double s = 0.0;
+    if (kind == GVI_KERNEL_ARD) {
+      for (int d = 0; d < D; d++) {
+        const double diff = a[d] - b[d];
+        s = fma(exp(p1[p1_len == 1 ? 0 : d]), diff * diff, s);
+      }
+      out[i] = e0 * e0 * gvi_exp(-0.5 * s);
+    } else {
+      for (int d = 0; d < D; d++) s = fma(a[d], b[d], s);
+      out[i] = gvi_poly_epilogue(s, e0, p1 ? exp(p1[0]) : 0.0, degree);
+    }
+  }
+}
 }  // namespace
+
+extern "C" int gvi_dot_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                                const double* log_scaling, const double* log_constant, double degree, double* out,
+                                int64_t ld_out, void* stream) {
+  GVI_CHECK_ARG(m1 >= 0 && m2 >= 0 && D >= 1, "sizes");
+  GVI_CHECK_ARG(ld_out >= m2, "ld_out < m2");
+  if (m1 == 0 || m2 == 0) return GVI_OK;
+  GVI_CHECK_ARG(x1 && x2 && log_scaling && out, "null pointer");
+  const int64_t gy = (m1 + TR - 1) / TR, gx = (m2 + TC - 1) / TC, max_gy = 65535;
+  for (int64_t y0 = 0; y0 < gy; y0 += max_gy) {
+    const int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
+    dot_gram_kernel<<<dim3((unsigned)gx, (unsigned)ny), TC, 0, (cudaStream_t)stream>>>(
+        x1 + y0 * TR * D, m1 - y0 * TR, x2, m2, D, log_scaling, log_constant, degree, out + y0 * TR * ld_out, ld_out);
+    GVI_CHECK_LAUNCH("dot_gram_kernel");
+  }
+  return GVI_OK;
+}
+
+extern "C" int gvi_kernel_pairs_f64(int kind, const double* x1, const double* x2, int64_t n, int D, const double* p0,
+                                    const double* p1, int p1_len, double degree, double* out, void* stream) {
+  GVI_CHECK_ARG(kind == GVI_KERNEL_ARD || kind == GVI_KERNEL_POLYNOMIAL, "kind");
+  GVI_CHECK_ARG(n >= 0 && D >= 1, "sizes");
+  if (n == 0) return GVI_OK;
+  GVI_CHECK_ARG(x1 && x2 && p0 && out, "null pointer");
+  if (kind == GVI_KERNEL_ARD) GVI_CHECK_ARG(p1 && (p1_len == 1 || p1_len == D), "log_lengthscales must have 1 or D entries");
+  const int blocks = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+  kernel_pairs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, x1, x2, n, D, p0, p1, p1_len, degree, out);
+  GVI_CHECK_LAUNCH("kernel_pairs_kernel");
+  return GVI_OK;
+}
 
 int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
                         const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,

@@ -364,9 +364,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         }
 #pragma unroll
         for (int w = 0; w < WARPS; w++) mu += redm[w * T + tid];
-        double var = have_extra ? F[1] - qfirst + q : F[1] - q;
-        if (pd.noise_add) var += exp(pd.noise_add[0]);
         const int64_t r = row0 + tid;
+        const double kxx = pd.kdiag ? (r < P.N ? pd.kdiag[r] : 0.0) : F[1];
+        double var = have_extra ? kxx - qfirst + q : kxx - q;
+        if (pd.noise_add) var += exp(pd.noise_add[0]);
         if (r < P.N) {
           if (pd.prior_mean) mu += pd.prior_mean[r];
           if (pd.mean_out) pd.mean_out[r] = mu;
@@ -829,6 +830,27 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
     if (rc < 0) return rc;
   }
   return GVI_OK;
+}
+
+// any base kernel: the K rows come from the caller (materialised by that kernel's own Gram routine, chunk by chunk on
+// the host side), k(x_i, x_i) per point; the triangular products, norms and the mean run in the same tile kernel
+extern "C" int gvi_gp_predict_gram_f64(const void* factor, int M, const double* Kxz, int64_t ld, const double* kdiag,
+                                       int64_t N, const double* prior_mean, const double* log_noise_add,
+                                       double* mean_out, double* var_out, void* workspace, void* stream) {
+  GVI_CHECK_ARG(M >= 1 && N >= 0, "sizes");
+  if (N == 0) return GVI_OK;
+  GVI_CHECK_ARG(factor && Kxz && kdiag && ld >= M, "null pointer / ld < M");
+  StepParams P{};
+  const FactorLayout f = factor_layout(M, 1);
+  P.npass = 1;
+  P.M = M; P.Mp = f.Mp; P.D = 1; P.G = f.G;
+  P.partials = nullptr;
+  P.tile_counter = workspace ? (int*)workspace : nullptr;
+  P.acc_scratch = workspace ? (double*)workspace + STEP_COUNTER_DOUBLES : nullptr;
+  P.pass[0] = PassDesc{(const double*)factor, prior_mean, log_noise_add, mean_out, var_out, Kxz, ld, kdiag};
+  P.X = nullptr; P.N = N;
+  int rc = gvi_launch_step(P, (cudaStream_t)stream);
+  return rc < 0 ? rc : GVI_OK;
 }
 
 // fused-step workspace = [tile counter][reduction records][per-tile (nll, reg)][panel scratch]

@@ -10,6 +10,8 @@ struct PassDesc {
   double* var_out;          // [N] or null
   const double* Kpre;       // optional precomputed K(x, Z) rows [N][ldk] (wide inputs, D > 32: Gram built by the
   int64_t ldk;              //   tensor-pipe Gram kernel chunk by chunk in an L2-sized ring); null = compute in phase 1
+  const double* kdiag;      // optional k(x_i, x_i) per point [N] (non-stationary kernels, gvi_gp_predict_gram_f64);
+                            //   null = the constant F[1] of a stationary kernel
 };
 
 // per-CTA partial record: [0] sum nll, [1] sum reg, [2] sum g v, [3] sum g |a|^2, [4..36) T2_d, [36] sum g

@@ -28,6 +28,25 @@ def ard_gram_diag(n, log_scaling, out):
                "gvi_ard_gram_diag_f64")
 
 
+KERNEL_ARD, KERNEL_POLYNOMIAL = 0, 1
+
+
+def dot_gram(x1, x2, log_scaling, log_constant, degree, out):
+    """out = (exp(log_scaling) x1 x2^T + exp(log_constant))^degree (log_constant None: inner-product kernel)."""
+    rc = _L().gvi_dot_gram_f64(_lib.ptr(x1), x1.shape[0], _lib.ptr(x2), x2.shape[0], x1.shape[1],
+                               _lib.ptr(log_scaling), _lib.ptr(log_constant), float(degree), _lib.ptr(out),
+                               out.stride(0), _lib.current_stream())
+    _lib.check(rc, "gvi_dot_gram_f64")
+
+
+def kernel_pairs(kind, x1, x2, p0, p1, degree, out):
+    """out[i] = k(x1_i, x2_i): the diagonal mode of KernelBase.calculate_gram for two different inputs."""
+    rc = _L().gvi_kernel_pairs_f64(int(kind), _lib.ptr(x1), _lib.ptr(x2), x1.shape[0], x1.shape[1], _lib.ptr(p0),
+                                   _lib.ptr(p1), p1.numel() if p1 is not None else 0, float(degree), _lib.ptr(out),
+                                   _lib.current_stream())
+    _lib.check(rc, "gvi_kernel_pairs_f64")
+
+
 def add_diagonal_regulariser(a, diagonal_regularisation, is_absolute):
     _lib.check(_L().gvi_add_diagonal_regulariser_f64(_lib.ptr(a), a.shape[0], a.stride(0),
                                                      float(diagonal_regularisation), int(bool(is_absolute)),
@@ -58,6 +77,17 @@ class GpFactor:
                                     _lib.ptr(log_noise), _lib.ptr(y_z), _lib.ptr(self.buf), _lib.ptr(self.ws),
                                     _lib.ptr(self.info), _lib.current_stream())
         _lib.check(rc, "gvi_gp_factor_f64")
+        self.version += 1
+        return self
+
+    def factor_from_gram(self, k_zz, diagonal_regularisation, is_absolute, log_noise=None, y_z=None):
+        """State from a caller-supplied K_ZZ (any base kernel); the buffer must have been sized with d = 1."""
+        assert self.d == 1 and k_zz.shape == (self.m, self.m)
+        rc = _L().gvi_gp_factor_gram_f64(_lib.ptr(k_zz), k_zz.stride(0), self.m, float(diagonal_regularisation),
+                                         int(bool(is_absolute)), _lib.ptr(log_noise), _lib.ptr(y_z),
+                                         _lib.ptr(self.buf), _lib.ptr(self.ws), _lib.ptr(self.info),
+                                         _lib.current_stream())
+        _lib.check(rc, "gvi_gp_factor_gram_f64")
         self.version += 1
         return self
 
@@ -99,6 +129,38 @@ def gp_predict(factor: GpFactor, x, prior_mean=None, log_noise_add=None, want_me
                                  _lib.ptr(log_noise_add), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(ws),
                                  _lib.current_stream())
     _lib.check(rc, "gvi_gp_predict_f64")
+    return mean, var
+
+
+def gp_predict_gram(factor: GpFactor, k_xz, k_diag, prior_mean=None, log_noise_add=None, mean_out=None,
+                    var_out=None):
+    """Predictive from caller-supplied Gram rows K(x, Z) [n, M] and k(x_i, x_i) [n] (any base kernel)."""
+    n = k_xz.shape[0]
+    nbytes = _L().gvi_gp_predict_workspace_bytes(factor.m, 1)
+    ws = _workspace("predict", nbytes) if nbytes else None
+    rc = _L().gvi_gp_predict_gram_f64(_lib.ptr(factor.buf), factor.m, _lib.ptr(k_xz), k_xz.stride(0),
+                                      _lib.ptr(k_diag), n, _lib.ptr(prior_mean), _lib.ptr(log_noise_add),
+                                      _lib.ptr(mean_out), _lib.ptr(var_out), _lib.ptr(ws), _lib.current_stream())
+    _lib.check(rc, "gvi_gp_predict_gram_f64")
+
+
+GRAM_CHUNK_BYTES = 256 << 20  # K(x_chunk, Z) rows materialised at a time on the generic-kernel path
+
+
+def gp_predict_any_kernel(factor: GpFactor, kernel, kernel_parameters, z, x, prior_mean=None, want_mean=True):
+    """Predictive mean / variance over ANY base kernel: K(x_chunk, Z) and k(x_i, x_i) from the kernel's own Gram routine,
+    <= GRAM_CHUNK_BYTES at a time, the rest in the tile kernel."""
+    n = x.shape[0]
+    mean = empty(n) if want_mean else None
+    var = empty(n)
+    rows = max(24, GRAM_CHUNK_BYTES // (8 * factor.m) // 24 * 24)
+    for r0 in range(0, n, rows):
+        r1 = min(n, r0 + rows)
+        xc = x[r0:r1]
+        k_xz = kernel.calculate_gram(kernel_parameters, xc, z).contiguous()
+        k_diag = kernel.calculate_gram(kernel_parameters, xc, xc, full_covariance=False).reshape(-1).contiguous()
+        gp_predict_gram(factor, k_xz, k_diag, prior_mean[r0:r1] if prior_mean is not None else None, None,
+                        mean[r0:r1] if want_mean else None, var[r0:r1])
     return mean, var
 
 

@@ -71,9 +71,11 @@ class GeneralisedVariationalInference:
             return False  # classification objectives take the general path (K predictives + quadrature epilogue)
         if getattr(gp.kernel, "factorise", None) is None or rg.kind == "none":
             return False  # SparsePosteriorKernel, FixedSparsePosteriorKernel and the SVGP kernels provide factorise()
+        if not getattr(gp.kernel, "_ard", True):
+            return False  # non-ARD base kernel: term by term over caller-supplied Grams
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
-            return (isinstance(reg, GPRegression) and reg.x.shape == gp.kernel.inducing_points.shape
+            return (isinstance(reg, GPRegression) and reg._ard and reg.x.shape == gp.kernel.inducing_points.shape
                     and reg.x.shape[1] <= 32)
         return gp.kernel.inducing_points.shape[1] <= 32
 

@@ -17,16 +17,24 @@ from .base import GPBase
 
 class GPRegression(GPBase):
     def __init__(self, mean, kernel, x, y):
-        if not isinstance(kernel, ARDKernel):
-            raise NotImplementedError("the B200 path implements the exact GP over ARDKernel only")
+        # ARD: K tiles evaluated inside the tile kernel (and the differentiable exact-GP step).  Any other kernel: its own
+        # Gram routine supplies K(x_train, x_train) and K(x_chunk, x_train) to the same factorisation / predictive kernels.
+        self._ard = isinstance(kernel, ARDKernel)
         self.x = as_2d(x)
-        self.x = self.x.reshape(self.x.shape[0], -1)
+        if self._ard:
+            self.x = self.x.reshape(self.x.shape[0], -1)
         self.y = as_device(y).reshape(-1)
         self._factor = None
         super().__init__(mean=mean, kernel=kernel)
 
     def factorise(self, parameters) -> "L.GpFactor":
         parameters = self._to_parameters(parameters)
+        if not self._ard:
+            if self._factor is None:
+                self._factor = L.GpFactor(self.x.shape[0], 1)
+            k_zz = self.kernel.calculate_gram(parameters.kernel, self.x, self.x).contiguous()
+            return self._factor.factor_from_gram(k_zz, 0.0, True,
+                                                 log_noise=scalar(parameters.log_observation_noise), y_z=self.y)
         if self._factor is None:
             self._factor = L.GpFactor(self.x.shape[0], self.x.shape[1])
         ls, ll = ARDKernel.device_parameters(parameters.kernel)
@@ -38,6 +46,11 @@ class GPRegression(GPBase):
             raise NotImplementedError("full-covariance exact posterior is off the hot path (SURVEY.md section 8)")
         parameters = self._to_parameters(parameters)
         x = as_2d(x)
+        if not self._ard:
+            f = self.factorise(parameters)
+            prior_mean = self.mean.predict(parameters.mean, x).reshape(-1).contiguous()
+            mean, var = L.gp_predict_any_kernel(f, self.kernel, parameters.kernel, self.x, x, prior_mean=prior_mean)
+            return mean.reshape(1, -1), var
         x = x.reshape(x.shape[0], -1)
         f = self.factorise(parameters)
         prior_mean = self.mean.predict(parameters.mean, x).contiguous()

@@ -23,12 +23,14 @@ class SparsePosteriorKernel(KernelBase):
 
     def __init__(self, base_kernel: KernelBase, inducing_points, diagonal_regularisation: float = 1e-5,
                  is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
-        if not isinstance(base_kernel, ARDKernel):
-            raise NotImplementedError(
-                "the B200 path implements SparsePosteriorKernel over ARDKernel only (SURVEY.md section 8)")
+        # ARD: the fused path (K tiles evaluated inside the tile kernel, gradients).  Any other base kernel: its own
+        # Gram routine supplies K_ZZ and K(x_chunk, Z); factorisation and predictive still run in the CUDA kernels.
+        assert isinstance(base_kernel, KernelBase), f"base_kernel must be a kernel, got {type(base_kernel)=}"
+        self._ard = isinstance(base_kernel, ARDKernel)
         self.base_kernel = base_kernel
         self.inducing_points = as_2d(inducing_points)
-        self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
+        if self._ard:
+            self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
         self.diagonal_regularisation = diagonal_regularisation
         self.is_diagonal_regularisation_absolute_scale = is_diagonal_regularisation_absolute_scale
         self._factor = None
@@ -42,6 +44,12 @@ class SparsePosteriorKernel(KernelBase):
         """cho_factor(add_diagonal_regulariser(K_ZZ)) of lines 63-74, plus L^-1 packed for the tensor pipe."""
         parameters = self._to_parameters(parameters)
         z = self.inducing_points
+        if not self._ard:
+            if self._factor is None:
+                self._factor = L.GpFactor(z.shape[0], 1)
+            k_zz = self.base_kernel.calculate_gram(parameters.base_kernel, z, z).contiguous()
+            return self._factor.factor_from_gram(k_zz, self.diagonal_regularisation,
+                                                 self.is_diagonal_regularisation_absolute_scale)
         if self._factor is None:
             self._factor = L.GpFactor(z.shape[0], z.shape[1])
         ls, ll = ARDKernel.device_parameters(self.base_kernel._to_parameters(parameters.base_kernel))
@@ -50,6 +58,10 @@ class SparsePosteriorKernel(KernelBase):
 
     def _calculate_gram_diagonal(self, parameters, x):
         f = self.factorise(parameters)
+        if not self._ard:
+            _, var = L.gp_predict_any_kernel(f, self.base_kernel, parameters.base_kernel, self.inducing_points, x,
+                                             want_mean=False)
+            return var
         x = x.reshape(x.shape[0], -1)
         base = self.base_kernel._to_parameters(parameters.base_kernel)
         if wants_grad(base.log_scaling, base.log_lengthscales):

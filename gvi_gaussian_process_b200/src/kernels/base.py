@@ -19,8 +19,10 @@ class KernelBase(Module):
 
     def preprocess_inputs(self, x, y=None):
         # reference: src/kernels/base.py:45-63
-        y = x if y is None else y
-        return as_2d(self.preprocess_function(x)), as_2d(self.preprocess_function(y))
+        x1 = as_2d(self.preprocess_function(x))
+        if y is None or y is x:
+            return x1, x1  # one device copy: the diagonal mode recognises k(x_i, x_i)
+        return x1, as_2d(self.preprocess_function(y))
 
     @staticmethod
     def check_inputs(x, y) -> None:
@@ -35,6 +37,12 @@ class KernelBase(Module):
     def _calculate_gram_diagonal(self, parameters, x):
         raise NotImplementedError
 
+    def _calculate_gram_pairs(self, parameters, x1, x2):
+        """k(x1_i, x2_i) for two DIFFERENT inputs of equal length (the reference's diagonal mode vmaps over the pairs,
+        src/kernels/base.py:136-147)."""
+        raise NotImplementedError(
+            f"{type(self).__name__}: diagonal mode with two different inputs is off the hot path of this build")
+
     def calculate_gram(self, parameters, x1, x2=None, full_covariance: bool = True):
         """reference: src/kernels/base.py:104-147 (same argument order and assertion behaviour)."""
         x1, x2 = self.preprocess_inputs(x1, x2)
@@ -44,4 +52,6 @@ class KernelBase(Module):
             return self._calculate_gram(parameters, x1, x2)
         assert x1.shape[0] == x2.shape[0], (
             f"{x1.shape[0]=} must be equal to {x2.shape[0]=} for diagonal only calculation")
-        return self._calculate_gram_diagonal(parameters, x1)
+        if x1 is x2 or (x1.data_ptr() == x2.data_ptr() and x1.shape == x2.shape):
+            return self._calculate_gram_diagonal(parameters, x1)
+        return self._calculate_gram_pairs(parameters, x1, x2)

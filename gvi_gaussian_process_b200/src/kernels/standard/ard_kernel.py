@@ -50,3 +50,10 @@ class ARDKernel(KernelBase):
         out = empty(x.shape[0])
         L.ard_gram_diag(x.shape[0], ls, out)
         return out
+
+    def _calculate_gram_pairs(self, parameters, x1, x2):
+        x1, x2 = self._flat(x1), self._flat(x2)
+        ls, ll = self.device_parameters(parameters)
+        out = empty(x1.shape[0])
+        L.kernel_pairs(L.KERNEL_ARD, x1, x2, ls, ll, 1.0, out)
+        return out

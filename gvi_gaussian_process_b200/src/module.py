@@ -91,6 +91,8 @@ class Module:
             f"Parameters is type: {type(parameters)=}, needs to be {parameter_type=}")
 
     def _to_parameters(self, parameters):
+        if isinstance(parameters, ModuleParameters) and not isinstance(parameters, self.Parameters):
+            Module.check_parameters(parameters, self.Parameters)  # another module's parameters: AssertionError
         if not isinstance(parameters, self.Parameters):
             parameters = self.generate_parameters(dict(parameters))
         elif any(isinstance(v, dict) for v in parameters.dict_shallow().values()):

@@ -53,6 +53,21 @@ int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2,
 /* full_covariance=False path of KernelBase.calculate_gram (src/kernels/base.py:132-147): out[i] = k(x_i,x_i). */
 int gvi_ard_gram_diag_f64(int64_t n, const double* log_scaling, double* out, void* stream);
 
+/* ---- other kernels.calculate_gram: InnerProductKernel / PolynomialKernel through StandardKernelBase._calculate_gram
+ * (src/kernels/non_stationary/inner_product_kernel.py:36-42, polynomial_kernel.py:40-52, standard/base.py:73-103):
+ * out[i*ld_out + j] = (exp(log_scaling) * <x1_i, x2_j> + exp(log_constant))^degree.  log_constant == NULL drops the
+ * constant (inner-product kernel: degree 1).  Integral degrees are evaluated by repeated multiplication (what
+ * jnp.power does for a Python-int exponent), other degrees by pow. */
+int gvi_dot_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D, const double* log_scaling,
+                     const double* log_constant, double degree, double* out, int64_t ld_out, void* stream);
+/* full_covariance=False path of KernelBase.calculate_gram for two DIFFERENT inputs (src/kernels/base.py:132-147):
+ * out[i] = k(x1_i, x2_i).  kind GVI_KERNEL_ARD: p0 = log_scaling, p1 = log_lengthscales[p1_len] (degree ignored);
+ * GVI_KERNEL_POLYNOMIAL: p0 = log_scaling, p1 = log_constant or NULL (p1_len ignored). */
+#define GVI_KERNEL_ARD 0
+#define GVI_KERNEL_POLYNOMIAL 1
+int gvi_kernel_pairs_f64(int kind, const double* x1, const double* x2, int64_t n, int D, const double* p0,
+                         const double* p1, int p1_len, double degree, double* out, void* stream);
+
 /* ---- a4: add_diagonal_regulariser (src/utils/matrix_operations.py:7-28), in place on A[M,M] (ld doubles) -- */
 int gvi_add_diagonal_regulariser_f64(double* A, int M, int64_t ld, double diagonal_regularisation,
                                      int is_absolute, void* stream);
@@ -100,6 +115,24 @@ int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_
                        const double* prior_mean, const double* log_noise_add,
                        double* mean_out, double* var_out, void* workspace, void* stream);
 
+/* ---- a5-a7 over ANY base kernel: the caller supplies the Grams -------------------------------------------------------
+ * SparsePosteriorKernel / the exact GP posterior are written against KernelBase.calculate_gram
+ * (sparse_posterior_kernel.py:63-96, src/gps/base/base.py:495-526), so they work over every kernel of the reference
+ * (polynomial, inner product, CustomKernel = the NNGP wrapper, CustomMappingKernel).  For kernels other than ARD the host
+ * side materialises K_ZZ once and K(x_chunk, Z) chunk by chunk with that kernel's own Gram routine and hands them over:
+ *   gvi_gp_factor_gram_f64 : same factor state as gvi_gp_factor_f64 from Kzz[M,M] (ld doubles; only read), D = 1 layout
+ *                            (gvi_gp_factor_bytes(M, 1)); jitter / noise / y_z as in gvi_gp_factor_f64.
+ *   gvi_gp_predict_gram_f64: var[i] = kdiag[i] - ||L^-1 Kxz[i,:]||^2 (+ exp(log_noise_add)), mean[i] = Kxz[i,:] alpha +
+ *                            prior_mean[i] on the tensor pipe (the tile kernel reads its K tile from Kxz[N,M], ld
+ *                            doubles, instead of evaluating the kernel).  kdiag[N] = k(x_i, x_i).
+ *                            Workspace: gvi_gp_predict_workspace_bytes(M, 1). */
+int gvi_gp_factor_gram_f64(const double* Kzz, int64_t ld, int M, double diagonal_regularisation, int is_absolute,
+                           const double* log_noise, const double* y_z, void* factor_out, void* workspace, int* info,
+                           void* stream);
+int gvi_gp_predict_gram_f64(const void* factor, int M, const double* Kxz, int64_t ld, const double* kdiag, int64_t N,
+                            const double* prior_mean, const double* log_noise_add, double* mean_out, double* var_out,
+                            void* workspace, void* stream);
+
 /* ---- a9-a11: risk and regulariser sums ----------------------------------------------------------------------
  * out[0] = sum_i NLL_i  (negative_log_likelihood.py:41-55), out[1] = sum_i D0_i (regulariser `kind`),
  * out[2] = N as double.  Sums, not means, so shards can be all-reduced; deterministic two-stage tree.
@@ -133,8 +166,8 @@ int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D,
  * Same inputs as gvi_fused_step_f64.  out[0..2] as out3; out[3] = d(sum_i loss_i)/dlog_scaling of q;
  * out[4+d] = d(sum_i loss_i)/dlog_lengthscales[d] of q (d < D); dm_out[i] = d(sum loss)/dm_q[i].  All in SUM form
  * (divide by the global N after the all-reduce); the regulariser GP p is constant.  The point-sized work
- * (a_i = L^-T L^-1 k_i per tile, weighted Gram C = sum_i g_i k_i k_i^T) runs on the FP64 tensor pipe; the M^3
- * products S = A^-1 C A^-1 are plain cuBLAS DGEMMs.  out has 4 + D doubles.                                    */
+ * (a_i = L^-T L^-1 k_i per tile, S = sum_i g_i a_i a_i^T accumulated from the a_i tiles chunk by chunk) runs on the
+ * FP64 tensor pipe.  out has 4 + D doubles.                                                                     */
 size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D);
 int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                             const double* y, const double* m_q, const double* prior_mean_p, const double* m_p_in,

@@ -60,6 +60,30 @@ def ard_gram_diag(log_scaling, log_lengthscales, x) -> np.ndarray:
 # --------------------------------------------------------------------------------------------------------------
 # a4: src/utils/matrix_operations.py:7-28
 # --------------------------------------------------------------------------------------------------------------
+def inner_product_gram(log_scaling, x1, x2=None) -> np.ndarray:
+    """InnerProductKernel through StandardKernelBase._calculate_gram: exp(log_scaling) * <x1_i, x2_j>
+    (src/kernels/non_stationary/inner_product_kernel.py:36-42, src/kernels/standard/base.py:95-103)."""
+    x1 = np.atleast_2d(np.asarray(x1, dtype=np.float64))
+    x2 = x1 if x2 is None else np.atleast_2d(np.asarray(x2, dtype=np.float64))
+    return np.exp(log_scaling) * (x1.reshape(x1.shape[0], -1) @ x2.reshape(x2.shape[0], -1).T)
+
+
+def polynomial_gram(log_constant, log_scaling, degree, x1, x2=None) -> np.ndarray:
+    """PolynomialKernel: (exp(log_scaling) * <x1_i, x2_j> + exp(log_constant)) ** degree
+    (src/kernels/non_stationary/polynomial_kernel.py:40-52).  jnp.power with a Python-int degree is
+    lax.integer_pow (repeated multiplication), which is what numpy's ** does for an int exponent."""
+    x1 = np.atleast_2d(np.asarray(x1, dtype=np.float64))
+    x2 = x1 if x2 is None else np.atleast_2d(np.asarray(x2, dtype=np.float64))
+    base = np.exp(log_scaling) * (x1.reshape(x1.shape[0], -1) @ x2.reshape(x2.shape[0], -1).T) + np.exp(log_constant)
+    return np.power(base, degree)
+
+
+def gram_pairs(gram_fn, x1, x2) -> np.ndarray:
+    """Diagonal mode of KernelBase.calculate_gram: k(x1_i, x2_i) by a vmap over the pairs (src/kernels/base.py:136-147)."""
+    x1, x2 = np.atleast_2d(x1), np.atleast_2d(x2)
+    return np.array([gram_fn(x1[i:i + 1], x2[i:i + 1])[0, 0] for i in range(x1.shape[0])])
+
+
 def add_diagonal_regulariser(matrix, diagonal_regularisation: float, is_absolute: bool) -> np.ndarray:
     matrix = np.asarray(matrix, dtype=np.float64)
     m = matrix.shape[0]

@@ -1,0 +1,238 @@
+"""GPU parity tests of "the other kernels.calculate_gram" (BASELINE.json north_star): InnerProductKernel, PolynomialKernel,
+CustomKernel and CustomMappingKernel through the src-compatible shim, and the predictive / regulariser path over them
+(K_ZZ and K(x, Z) from the kernel's own Gram routine, factorisation and triangular products in the CUDA kernels).
+Values against the NumPy oracle (<= 1e-10 relative), the reference's own kernel goldens through the product path."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def S():
+    import types
+
+    from gvi_gaussian_process_b200 import _lib
+    from gvi_gaussian_process_b200.src import _lib_proxy
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.kernels import CustomKernel, CustomMappingKernel
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.non_stationary import InnerProductKernel, PolynomialKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
+    from gvi_gaussian_process_b200.src.regularisations import projected
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    _lib.load()
+    return types.SimpleNamespace(**locals())
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_elem(a, ref):
+    return float(np.max(np.abs(a - ref) / np.maximum(np.abs(ref), 1e-300)))
+
+
+def rel_norm(a, ref):
+    return float(np.max(np.abs(a - ref)) / max(np.max(np.abs(ref)), 1e-300))
+
+
+# ---- the reference's own goldens through the product path (tests/kernels/test_kernels.py:16-94) --------------------
+@pytest.mark.parametrize("log_scaling,x1,x2,k", [(np.log(2.4), [1.0, 2.0, 3.0], [1.5, 2.5, 3.5], 40.8),
+                                                 (np.log(2.2), 6.0, 6.0, 79.2), (np.log(2.0), 6.0, 6.0, 72.0)])
+def test_inner_product_kernel_goldens(S, log_scaling, x1, x2, k):
+    kernel = S.InnerProductKernel()
+    parameters = kernel.Parameters.construct(log_scaling=log_scaling)
+    out = host(kernel.calculate_gram(parameters, x1=np.array(x1), x2=np.array(x2)))
+    assert out.shape == (1, 1) and np.isclose(out[0, 0], k, rtol=1e-12)
+
+
+@pytest.mark.parametrize("degree,x1,x2,k,rtol", [(3, [1.0, 2.0, 3.0], [1.5, 2.5, 3.5], 73403079.4946829, 1e-12),
+                                                 (1, 6.0, 6.0, 884.81980837, 1e-9),
+                                                 (1.5, 6.0, 6.0, 26319.78000332, 1e-9)])
+def test_polynomial_kernel_goldens(S, degree, x1, x2, k, rtol):
+    kernel = S.PolynomialKernel(polynomial_degree=degree)
+    parameters = kernel.generate_parameters({"log_constant": 0.5, "log_scaling": 3.2})
+    out = host(kernel.calculate_gram(parameters, x1=np.array(x1), x2=np.array(x2)))
+    assert out.shape == (1, 1) and np.isclose(out[0, 0], k, rtol=rtol)
+
+
+def test_inner_product_kernel_rejects_other_parameters(S):
+    # tests/kernels/test_kernels.py:214-237: parameters of another kernel raise an AssertionError
+    ard = S.ARDKernel(number_of_dimensions=3)
+    wrong = ard.Parameters.construct(log_scaling=0.5, log_lengthscales=np.zeros(3))
+    with pytest.raises(AssertionError):
+        S.InnerProductKernel().calculate_gram(wrong, x1=np.ones((1, 3)), x2=np.ones((2, 3)))
+
+
+def test_custom_kernel_goldens(S):
+    # tests/kernels/test_kernels.py:240-290: an all-ones kernel function, with and without a preprocess function
+    ones = lambda parameters, x, y: torch.ones((x.shape[0], y.shape[0]), dtype=torch.float64, device=x.device)
+    k1 = S.CustomKernel(kernel_function=ones)
+    out = k1.calculate_gram(k1.Parameters.construct(custom=None), x1=np.array([[1.0, 2.0, 3.0]]),
+                            x2=np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5]]))
+    assert np.array_equal(host(out), np.ones((1, 2)))
+    k2 = S.CustomKernel(kernel_function=ones, preprocess_function=lambda x: x.reshape(x.shape[0], -1))
+    out = k2.calculate_gram(k2.Parameters.construct(custom=None), x1=np.array([[[1.0], [2.0], [3.0]]]),
+                            x2=np.array([[[1.0], [2.0], [3.0]], [[1.5], [2.5], [3.5]]]))
+    assert np.array_equal(host(out), np.ones((1, 2)))
+
+
+# ---- Grams against the oracle, ragged shapes -------------------------------------------------------------------------
+@pytest.mark.parametrize("m1,m2,d,degree", [(1, 1, 1, 1), (33, 257, 3, 2), (300, 70, 8, 3), (65, 513, 40, 1.5),
+                                            (1000, 1024, 8, 4), (17, 5, 784, 2)])
+def test_polynomial_and_inner_product_gram_parity(S, m1, m2, d, degree):
+    rng = np.random.default_rng(m1 * 7 + m2)
+    x1, x2 = rng.standard_normal((m1, d)) / np.sqrt(d), rng.standard_normal((m2, d)) / np.sqrt(d)
+    log_constant, log_scaling = 0.3, -0.2  # base = 0.82 <x,y> + 1.35 stays positive for the fractional degree
+    if degree == 1.5:
+        x1, x2 = np.abs(x1), np.abs(x2)
+    poly = S.PolynomialKernel(polynomial_degree=degree)
+    pp = poly.Parameters.construct(log_constant=log_constant, log_scaling=log_scaling)
+    ref = O.polynomial_gram(log_constant, log_scaling, degree, x1, x2)
+    # normwise: an inner product cancels, so single entries near a zero crossing carry eps * sum |x_d z_d|
+    assert rel_norm(host(poly.calculate_gram(pp, x1, x2)), ref) <= TOL
+    inner = S.InnerProductKernel()
+    ip = inner.Parameters.construct(log_scaling=log_scaling)
+    ref_ip = O.inner_product_gram(log_scaling, x1, x2)
+    assert rel_norm(host(inner.calculate_gram(ip, x1, x2)), ref_ip) <= TOL
+    # x2 = None: the Gram of x1 with itself; diagonal mode on equal inputs and on two different inputs (pairs)
+    assert rel_norm(host(poly.calculate_gram(pp, x1)), O.polynomial_gram(log_constant, log_scaling, degree, x1)) <= TOL
+    diag = host(poly.calculate_gram(pp, x1, full_covariance=False))
+    assert diag.shape == (m1,)
+    assert rel_elem(diag, np.diag(O.polynomial_gram(log_constant, log_scaling, degree, x1))) <= TOL
+    n = min(m1, m2)
+    pairs = host(poly.calculate_gram(pp, x1[:n], x2[:n], full_covariance=False))
+    assert np.max(np.abs(pairs - np.diag(ref[:n, :n]))) <= TOL * np.max(np.abs(ref))
+
+
+def test_ard_diagonal_mode_on_two_different_inputs(S):
+    # src/kernels/base.py:132-147: full_covariance=False evaluates k(x1_i, x2_i)
+    rng = np.random.default_rng(5)
+    x1, x2 = rng.standard_normal((700, 5)), rng.standard_normal((700, 5))
+    ll = 0.3 * rng.standard_normal(5)
+    ard = S.ARDKernel(number_of_dimensions=5)
+    p = ard.Parameters.construct(log_scaling=0.4, log_lengthscales=ll)
+    out = host(ard.calculate_gram(p, x1, x2, full_covariance=False))
+    assert rel_elem(out, np.diag(O.ard_gram(0.4, ll, x1, x2))) <= TOL
+    with pytest.raises(AssertionError):
+        ard.calculate_gram(p, x1, x2[:10], full_covariance=False)
+
+
+def test_custom_mapping_kernel_matches_oracle(S):
+    # feature map (a small tanh network of the host framework) followed by a polynomial kernel on the features
+    rng = np.random.default_rng(9)
+    x1, x2 = rng.standard_normal((120, 6)), rng.standard_normal((47, 6))
+    w, b = rng.standard_normal((6, 11)) / 3.0, 0.1 * rng.standard_normal(11)
+    phi = lambda params, x: torch.tanh(x @ params["w"] + params["b"])
+    phi_np = lambda x: np.tanh(x @ w + b)
+    base = S.PolynomialKernel(polynomial_degree=2)
+    kernel = S.CustomMappingKernel(base_kernel=base, feature_mapping=phi)
+    parameters = kernel.generate_parameters({"base_kernel": {"log_constant": -0.5, "log_scaling": 0.2},
+                                             "feature_mapping": {"w": dev(w), "b": dev(b)}})
+    ref = O.polynomial_gram(-0.5, 0.2, 2, phi_np(x1), phi_np(x2))
+    assert rel_norm(host(kernel.calculate_gram(parameters, x1, x2)), ref) <= TOL
+    diag = host(kernel.calculate_gram(parameters, x1, full_covariance=False))
+    assert rel_elem(diag, np.diag(O.polynomial_gram(-0.5, 0.2, 2, phi_np(x1)))) <= TOL
+
+
+# ---- predictives over a non-ARD base kernel: Grams from the kernel, the rest in the CUDA factor / tile kernels -------
+def _poly_problem(n, m, d, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d)) / np.sqrt(d)
+    z = rng.standard_normal((m, d)) / np.sqrt(d)
+    w = rng.standard_normal(d)
+    y = np.sin(x @ w) + 0.1 * rng.standard_normal(n)
+    yz = np.sin(z @ w) + 0.1 * rng.standard_normal(m)
+    return x, z, y, yz
+
+
+@pytest.mark.parametrize("n,m,d,degree", [(50, 7, 2, 2), (3000, 40, 3, 3), (5000, 300, 8, 2), (700, 1200, 8, 2)])
+def test_sparse_posterior_and_exact_gp_over_polynomial_kernel(S, n, m, d, degree):
+    x, z, y, yz = _poly_problem(n, m, d, seed=n + m)
+    lc, ls, lam, log_noise = 0.2, -0.1, 0.1, -1.0
+    gram = lambda a, b: O.polynomial_gram(lc, ls, degree, a, b)
+    diag = lambda a: np.power(np.exp(ls) * np.einsum("ij,ij->i", a, a) + np.exp(lc), degree)
+    kernel = S.PolynomialKernel(polynomial_degree=degree)
+    kp = kernel.Parameters.construct(log_constant=lc, log_scaling=ls)
+    # approximate GP: sparse posterior kernel in diagonal mode, absolute jitter (a polynomial Gram has rank << M)
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=lam,
+                                     is_diagonal_regularisation_absolute_scale=True)
+    sp = sparse.Parameters.construct(base_kernel=kp)
+    v_q = host(sparse.calculate_gram(sp, x, full_covariance=False))
+    v_q_ref = O.sparse_posterior_diag(gram, diag, z, x, lam, True)
+    assert v_q.shape == (n,)
+    # a polynomial Gram has low rank, so v = k(x,x) - k^T A^-1 k cancels down to the jitter level: the tolerance is taken
+    # relative to the quantities that are subtracted, max k(x,x) (numerics)
+    kxx = float(np.max(diag(x)))
+    assert np.max(np.abs(v_q - v_q_ref)) <= TOL * kxx
+    # exact GP posterior over the same kernel (regulariser GP): noise keeps A well conditioned
+    const = S.ConstantMean()
+    exact = S.GPRegression(mean=const, kernel=kernel, x=z, y=yz)
+    ep = exact.Parameters.construct(log_observation_noise=log_noise, mean=const.Parameters.construct(constant=0.25),
+                                    kernel=kp)
+    p = exact.predict_probability(ep, x)
+    m_ref, v_ref = O.exact_gp_posterior(gram, diag, np.full(n, 0.25), z, yz, log_noise, x)
+    assert host(p.mean).shape == (1, n)
+    assert rel_norm(host(p.mean).reshape(-1), m_ref) <= TOL
+    assert np.max(np.abs(host(p.covariance) - v_ref)) <= TOL * kxx
+
+
+def test_gvi_objective_over_polynomial_kernels(S):
+    """NLL + projected KL with q = approximate GP over a sparse posterior polynomial kernel and p = exact GP over a
+    polynomial kernel: the general (term-by-term) objective path over caller-supplied Grams."""
+    n, m, d = 4000, 64, 4
+    x, z, y, yz = _poly_problem(n, m, d, seed=21)
+    lc, ls, lam, log_noise = 0.1, 0.0, 1e-2, -0.5
+    gram = lambda a, b: O.polynomial_gram(lc, ls, 2, a, b)
+    diag = lambda a: np.power(np.exp(ls) * np.einsum("ij,ij->i", a, a) + np.exp(lc), 2)
+    rng = np.random.default_rng(3)
+    m_q = 0.3 * np.tanh(x @ rng.standard_normal(d))
+    kernel = S.PolynomialKernel(polynomial_degree=2)
+    kp = kernel.Parameters.construct(log_constant=lc, log_scaling=ls)
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=lam,
+                                     is_diagonal_regularisation_absolute_scale=True)
+    amean = S.CustomMean(mean_function=lambda params, xx: params[: xx.shape[0]])
+    approx = S.ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(mean=amean.Parameters.construct(custom=dev(m_q)),
+                                     kernel=sparse.Parameters.construct(base_kernel=kp))
+    const = S.ConstantMean()
+    exact = S.GPRegression(mean=const, kernel=kernel, x=z, y=yz)
+    ep = exact.Parameters.construct(log_observation_noise=log_noise, mean=const.Parameters.construct(constant=0.0),
+                                    kernel=kp)
+    reg = S.projected.ProjectedKLRegularisation(gp=approx, regulariser=exact, regulariser_parameters=ep,
+                                                mode="posterior")
+    gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=S.NegativeLogLikelihood(gp=approx))
+    loss = float(gvi.calculate_loss(ap, x, y))
+    v_q = O.sparse_posterior_diag(gram, diag, z, x, lam, True)
+    m_p, v_p = O.exact_gp_posterior(gram, diag, np.zeros(n), z, yz, log_noise, x)
+    ref = O.gaussian_nll(y, m_q, v_q) + O.projected_regularisation("kl", m_p, v_p, m_q, v_q)
+    assert abs(loss - ref) <= 1e-8 * abs(ref)
+
+
+def test_generic_gram_entry_points_equal_the_ard_path(S):
+    """gvi_gp_factor_gram_f64 + gvi_gp_predict_gram_f64 fed with ARD Grams must reproduce the fused ARD path (same
+    factorisation and tile kernel, the K tile read from memory instead of evaluated): M below and above one panel."""
+    L = S._lib_proxy
+    for n, m, d in [(2000, 96, 5), (900, 1300, 8)]:
+        rng = np.random.default_rng(n)
+        x, z = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+        ard = S.ARDKernel(number_of_dimensions=d)
+        kp = ard.Parameters.construct(log_scaling=0.2, log_lengthscales=np.full(d, np.log(1.0 / d)))
+        sparse = S.SparsePosteriorKernel(base_kernel=ard, inducing_points=z)
+        v_fused = host(sparse.calculate_gram(sparse.Parameters.construct(base_kernel=kp), x, full_covariance=False))
+        f = L.GpFactor(m, 1).factor_from_gram(ard.calculate_gram(kp, z, z).contiguous(), 1e-5, False)
+        _, v_gram = L.gp_predict_any_kernel(f, ard, kp, dev(z), dev(x), want_mean=False)
+        assert rel_norm(host(v_gram), v_fused) <= 1e-12

@@ -28,6 +28,23 @@ def test_ard_scalar_exact():
         1.8095777100611745, rel=1e-15)
 
 
+def test_inner_product_and_polynomial_kernel_goldens():
+    # tests/kernels/test_kernels.py:16-47 (inner product) and 50-94 (polynomial), jnp.isclose in the reference
+    assert np.isclose(O.inner_product_gram(np.log(2.4), [[1.0, 2.0, 3.0]], [[1.5, 2.5, 3.5]])[0, 0], 40.8, rtol=1e-12)
+    assert np.isclose(O.inner_product_gram(np.log(2.2), [[6.0]], [[6.0]])[0, 0], 79.2, rtol=1e-12)
+    assert np.isclose(O.inner_product_gram(np.log(2.0), [[6.0]], [[6.0]])[0, 0], 72.0, rtol=1e-12)
+    assert np.isclose(O.polynomial_gram(0.5, 3.2, 3, [[1.0, 2.0, 3.0]], [[1.5, 2.5, 3.5]])[0, 0], 73403079.4946829,
+                      rtol=1e-12)
+    assert np.isclose(O.polynomial_gram(0.5, 3.2, 1, [[6.0]], [[6.0]])[0, 0], 884.81980837, rtol=1e-9)
+    assert np.isclose(O.polynomial_gram(0.5, 3.2, 1.5, [[6.0]], [[6.0]])[0, 0], 26319.78000332, rtol=1e-9)
+    # diagonal mode = pairs
+    x = np.array([[1.0, 2.0], [0.5, -1.0], [3.0, 0.25]])
+    z = np.array([[0.1, 0.2], [1.5, 1.0], [-2.0, 4.0]])
+    g = O.polynomial_gram(0.1, -0.3, 2, x, z)
+    np.testing.assert_allclose(O.gram_pairs(lambda a, b: O.polynomial_gram(0.1, -0.3, 2, a, b), x, z), np.diag(g),
+                               rtol=1e-15)
+
+
 def test_gram_shapes():
     # tests/kernels/test_kernels.py:145-211
     assert O.ard_gram(0.0, [0.0, 0.0, 0.0], [[1.0, 2.0, 3.0]], X).shape == (1, 2)
