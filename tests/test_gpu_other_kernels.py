@@ -236,3 +236,91 @@ def test_generic_gram_entry_points_equal_the_ard_path(S):
         f = L.GpFactor(m, 1).factor_from_gram(ard.calculate_gram(kp, z, z).contiguous(), 1e-5, False)
         _, v_gram = L.gp_predict_any_kernel(f, ard, kp, dev(z), dev(x), want_mean=False)
         assert rel_norm(host(v_gram), v_fused) <= 1e-12
+
+
+def test_svgp_mean_golden(S):
+    # tests/test_means.py:96-128: mock mean = ones, mock kernel = all-ones Gram (ARD with exp(log_ls) = 0), weights [1, 2]
+    from gvi_gaussian_process_b200.src.means import SVGPMean
+
+    class OnesMean(S.CustomMean):
+        pass
+
+    ones_mean = OnesMean(mean_function=lambda params, x: torch.ones(x.shape[0], dtype=torch.float64, device=x.device))
+    ard = S.ARDKernel(number_of_dimensions=3)
+    ones_kernel_parameters = ard.Parameters.construct(log_scaling=0.0, log_lengthscales=np.full(3, -np.inf))
+    svgp_mean = SVGPMean(regulariser_mean_parameters=ones_mean.Parameters.construct(custom=None),
+                         regulariser_mean=ones_mean, regulariser_kernel_parameters=ones_kernel_parameters,
+                         regulariser_kernel=ard, inducing_points=np.ones((2, 3)))
+    out = svgp_mean.predict(parameters=svgp_mean.generate_parameters({"weights": np.array([1.0, 2.0])}),
+                            x=np.array([[1.0, 2.0, 3.0], [1.5, 2.5, 3.5]]))
+    assert np.array_equal(host(out), 4.0 * np.ones(2))
+
+
+def test_regression_pipeline_callers(S, tmp_path):
+    """The reference's regression pipeline end to end on a toy curve (experiments/regression/trainers.py:19-85,
+    experiments/shared/trainers.py:15-114, experiments/regression/metrics.py:14-28): greedy selection + exact-GP NLL
+    training, approximate GP trained on the GVI objective, tempering, metrics - every stage through the CUDA path."""
+    from gvi_gaussian_process_b200.experiments.regression.metrics import calculate_metrics
+    from gvi_gaussian_process_b200.experiments.regression.trainers import train_regulariser_gp
+    from gvi_gaussian_process_b200.experiments.shared import (Data, TrainerSettings, inducing_points_selector_resolver,
+                                                              train_approximate_gp, train_tempered_gp)
+    from gvi_gaussian_process_b200.src.kernels import TemperedKernel
+
+    rng = np.random.default_rng(0)
+    n, m = 600, 24
+    x = np.sort(rng.uniform(-3.0, 3.0, (n, 1)), axis=0)
+    y = np.sin(2.0 * x[:, 0]) + 0.15 * rng.standard_normal(n)
+    data = Data(x=dev(x), y=dev(y), name="train")
+    kernel = S.ARDKernel(number_of_dimensions=1)
+    kp = kernel.Parameters.construct(log_scaling=0.0, log_lengthscales=np.array([0.0]))
+    settings = TrainerSettings(seed=0, optimiser_schema="adam", learning_rate=0.05, number_of_epochs=15, batch_size=m,
+                               batch_shuffle=True, batch_drop_last=False)
+    exact, exact_params, history = train_regulariser_gp(
+        data=data, empirical_risk_schema="negative_log_likelihood", trainer_settings=settings, kernel=kernel,
+        kernel_parameters=kp, inducing_points_selector=inducing_points_selector_resolver("conditional_variance"),
+        number_of_inducing_points=m, empirical_risk_break_condition=-1e9, save_checkpoint_frequency=0,
+        checkpoint_path=str(tmp_path / "regulariser"))
+    risks = [float(h["empirical-risk"]) for h in history]
+    assert len(risks) == 15 and risks[-1] < risks[0] and np.all(np.isfinite(risks))
+    assert exact.x.shape == (m, 1)
+    # approximate GP: sparse posterior kernel over the learned kernel, tanh-network mean of the host framework
+    torch.manual_seed(0)
+    w1 = (0.5 * torch.randn(1, 16, dtype=torch.float64, device="cuda"))
+    w2 = (0.1 * torch.randn(16, dtype=torch.float64, device="cuda"))
+    amean = S.CustomMean(mean_function=lambda p, xx: torch.tanh(xx @ p["w1"]) @ p["w2"])
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=exact.x)
+    approx = S.ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(
+        mean=amean.Parameters.construct(custom={"w1": w1, "w2": w2}),
+        kernel=sparse.Parameters.construct(base_kernel=kernel.Parameters.construct(**exact_params.kernel.dict())))
+    settings_q = TrainerSettings(seed=1, optimiser_schema="adabelief", learning_rate=0.02, number_of_epochs=12,
+                                 batch_size=200, batch_shuffle=True, batch_drop_last=False)
+    ap, history_q = train_approximate_gp(
+        data=data, empirical_risk_schema="negative_log_likelihood",
+        regularisation_config={"regularisation_schema": "projected_renyi",
+                               "regularisation_kwargs": {"mode": "posterior", "alpha": 0.5}},
+        trainer_settings=settings_q, approximate_gp=approx, approximate_gp_parameters=ap, regulariser=exact,
+        regulariser_parameters=exact_params, save_checkpoint_frequency=0, checkpoint_path=str(tmp_path / "approximate"))
+    objective = [float(h["gvi-objective"]) for h in history_q]
+    assert len(objective) == 12 and objective[-1] < objective[0] and np.all(np.isfinite(objective))
+    assert abs(float(history_q[-1]["empirical-risk"]) + float(history_q[-1]["regularisation"]) - objective[-1]) <= (
+        1e-10 * abs(objective[-1]))
+    # tempering: only the scalar factor of the tempered kernel is trained
+    tempered_kernel = TemperedKernel(base_kernel=sparse, base_kernel_parameters=ap.kernel)
+    tempered = S.ApproximateGPRegression(mean=amean, kernel=tempered_kernel)
+    # start clearly miscalibrated (variance x e^2), so that every optimiser step towards the optimum lowers the NLL
+    tp = tempered.generate_parameters({"mean": ap.mean, "kernel": {"log_tempering_factor": 2.0}})
+    before = calculate_metrics({"train": data}, tempered, tp)["train"]["negative-log-likelihood"]
+    settings_t = TrainerSettings(seed=2, optimiser_schema="adam", learning_rate=0.1, number_of_epochs=10,
+                                 batch_size=300, batch_shuffle=True, batch_drop_last=False)
+    tp, history_t = train_tempered_gp(data=data, empirical_risk_schema="negative_log_likelihood",
+                                      trainer_settings=settings_t, tempered_gp=tempered, tempered_gp_parameters=tp,
+                                      save_checkpoint_frequency=0, checkpoint_path=str(tmp_path / "tempered"))
+    after = calculate_metrics({"train": data, "validation": None}, tempered, tp, y_std=1.0)
+    assert set(after) == {"train"}
+    assert after["train"]["negative-log-likelihood"] < before
+    assert float(tp.kernel.log_tempering_factor) != 2.0  # (it grows: q drops the observation noise, so it is overconfident)
+    # the metric is the NLL the objective's risk term reports (+ log y_std = 0)
+    assert abs(after["train"]["negative-log-likelihood"] - float(history_t[-1]["empirical-risk"])) <= 1e-10
+    # mean parameters untouched by the tempering stage
+    assert torch.equal(tp.mean.custom["w1"], ap.mean.custom["w1"])
