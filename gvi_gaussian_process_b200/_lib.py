@@ -85,6 +85,10 @@ SIGNATURES = {
     "gvi_select_record_len": (c_int64, [c_int, c_int]),
     "gvi_select_init_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_double, c_void_p,
                                     c_void_p, c_void_p]),
+    "gvi_select_init_gram_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_double, c_void_p,
+                                         c_void_p, c_void_p]),
+    "gvi_select_update_gram_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gvi_select_resolve_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gvi_select_update_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),

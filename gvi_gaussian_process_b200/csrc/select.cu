@@ -62,16 +62,18 @@ __device__ __forceinline__ void block_argmax(double& v, double& idx, bool prefer
 }
 
 __global__ void __launch_bounds__(STHREADS) select_init_kernel(int64_t N, int64_t offset,
-                                                               const double* __restrict__ log_scaling, double jitter,
+                                                               const double* __restrict__ log_scaling,
+                                                               const double* __restrict__ kdiag, double jitter,
                                                                double* __restrict__ d, unsigned char* __restrict__ chosen,
                                                                double* __restrict__ blockcand,
                                                                double* __restrict__ blocktrace) {
   __shared__ double sv[STHREADS / 32], si[STHREADS / 32];
   const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
-  const double amp = exp(log_scaling[0]);
+  const double amp = kdiag ? 0.0 : exp(log_scaling[0]);
   double v = -1.0, idx = -1.0;
   if (i < N) {
-    v = amp * amp + jitter;  // k(x,x) + jitter, inducing_points_selection.py:124-132
+    // k(x,x) + jitter, inducing_points_selection.py:124-132 (kdiag: any kernel, supplied by the caller)
+    v = (kdiag ? kdiag[i] : amp * amp) + jitter;
     d[i] = v;
     chosen[i] = 0;
     idx = (double)(offset + i);
@@ -88,9 +90,9 @@ __global__ void __launch_bounds__(STHREADS) select_init_kernel(int64_t N, int64_
 // d = max(d - e^2, 0); per-block candidate for the next pivot and per-block partial of tr(K - Q).
 __global__ void __launch_bounds__(STHREADS) select_update_kernel(
     const double* __restrict__ X, int64_t N, int64_t offset, int D, int m, const double* __restrict__ winner,
-    const double* __restrict__ log_scaling, const double* __restrict__ log_ls, int ls_len, double jitter,
-    double* __restrict__ d, double* C, unsigned char* __restrict__ chosen,
-    double* __restrict__ blockcand, double* __restrict__ blocktrace) {
+    const double* __restrict__ log_scaling, const double* __restrict__ log_ls, int ls_len,
+    const double* __restrict__ kcol, double jitter, double* __restrict__ d, double* C,
+    unsigned char* __restrict__ chosen, double* __restrict__ blockcand, double* __restrict__ blocktrace) {
   extern __shared__ double sm[];
   double* cj = sm;          // [m]
   double* xj = sm + m;      // [D]
@@ -98,24 +100,30 @@ __global__ void __launch_bounds__(STHREADS) select_update_kernel(
   __shared__ double sv[STHREADS / 32], si[STHREADS / 32], st[STHREADS / 32];
   const int tid = threadIdx.x;
   for (int k = tid; k < m; k += STHREADS) cj[k] = winner[2 + D + k];
-  for (int k = tid; k < D; k += STHREADS) {
-    xj[k] = winner[2 + k];
-    w[k] = exp(log_ls[ls_len == 1 ? 0 : k]);
-  }
+  if (!kcol)
+    for (int k = tid; k < D; k += STHREADS) {
+      xj[k] = winner[2 + k];
+      w[k] = exp(log_ls[ls_len == 1 ? 0 : k]);
+    }
   __syncthreads();
   const double dj = sqrt(winner[0]);
   const double jglob = winner[1];
-  const double amp = exp(log_scaling[0]);
+  const double amp = kcol ? 0.0 : exp(log_scaling[0]);
   const double amp2 = amp * amp;
   const int64_t i = (int64_t)blockIdx.x * STHREADS + tid;
   double v = -1.0, idx = -1.0, tr = 0.0;
   if (i < N) {
-    double s = 0.0;
-    for (int k = 0; k < D; k++) {
-      double diff = X[i * D + k] - xj[k];
-      s = fma(w[k], diff * diff, s);
+    double g;
+    if (kcol) {
+      g = kcol[i];  // k(x_i, x_j) from the caller's kernel
+    } else {
+      double s = 0.0;
+      for (int k = 0; k < D; k++) {
+        double diff = X[i * D + k] - xj[k];
+        s = fma(w[k], diff * diff, s);
+      }
+      g = amp2 * exp(-0.5 * s);
     }
-    double g = amp2 * exp(-0.5 * s);
     g = __ddiv_rn(rint(__dmul_rn(g, 1e20)), 1e20);  // np.round(g, 20)
     const bool is_pivot = ((double)(offset + i) == jglob);
     if (is_pivot) g += jitter;
@@ -224,21 +232,36 @@ extern "C" size_t gvi_select_workspace_bytes(int64_t N, int M_sel, int D) {
          align16((size_t)nblk * 16) + align16((size_t)nblk * 8) + 2 * align16((size_t)rl * 8) + 64;
 }
 
-extern "C" int gvi_select_init_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
-                                   const double* log_scaling, double jitter, double* record_out, void* workspace,
-                                   void* stream) {
+static int select_init_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                            const double* log_scaling, const double* kdiag, double jitter, double* record_out,
+                            void* workspace, void* stream) {
   GVI_CHECK_ARG(N_local >= 1 && D >= 1, "sizes");
   GVI_CHECK_ARG(M_sel > 1, "Must have at least 2 inducing points");
-  GVI_CHECK_ARG(x_local && log_scaling && record_out && workspace, "null pointer");
+  GVI_CHECK_ARG(x_local && (log_scaling || kdiag) && record_out && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   SelectWs s = carve(workspace, N_local, M_sel, D);
-  select_init_kernel<<<(unsigned)s.nblk, STHREADS, 0, st>>>(N_local, offset, log_scaling, jitter, s.d, s.chosen,
+  select_init_kernel<<<(unsigned)s.nblk, STHREADS, 0, st>>>(N_local, offset, log_scaling, kdiag, jitter, s.d, s.chosen,
                                                             s.blockcand, s.blocktrace);
   GVI_CHECK_LAUNCH("select_init_kernel");
   select_finalize_kernel<<<1, 1024, 0, st>>>(x_local, N_local, offset, D, M_sel, 0, /*prefer_high=*/0, s.blockcand,
                                              s.blocktrace, s.nblk, s.C, record_out, nullptr, nullptr);
   GVI_CHECK_LAUNCH("select_finalize_kernel");
   return GVI_OK;
+}
+
+extern "C" int gvi_select_init_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                                   const double* log_scaling, double jitter, double* record_out, void* workspace,
+                                   void* stream) {
+  GVI_CHECK_ARG(log_scaling, "null pointer");
+  return select_init_impl(x_local, N_local, offset, D, M_sel, log_scaling, nullptr, jitter, record_out, workspace,
+                          stream);
+}
+// any kernel: k(x_i, x_i) supplied by the caller
+extern "C" int gvi_select_init_gram_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                                        const double* kdiag, double jitter, double* record_out, void* workspace,
+                                        void* stream) {
+  GVI_CHECK_ARG(kdiag, "null pointer");
+  return select_init_impl(x_local, N_local, offset, D, M_sel, nullptr, kdiag, jitter, record_out, workspace, stream);
 }
 
 extern "C" int gvi_select_resolve_f64(const double* records, int R, int D, int M_sel, int first, double* winner_out,
@@ -250,13 +273,36 @@ extern "C" int gvi_select_resolve_f64(const double* records, int R, int D, int M
   return GVI_OK;
 }
 
+static int select_update_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
+                              const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
+                              const double* kcol, double jitter, double* record_out, double* trace_partial_out,
+                              void* workspace, void* stream);
+
 extern "C" int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
                                      const double* winner, const double* log_scaling, const double* log_ls,
                                      int ls_len, double jitter, double* record_out, double* trace_partial_out,
                                      void* workspace, void* stream) {
-  GVI_CHECK_ARG(N_local >= 1 && D >= 1 && M_sel > 1 && m >= 0 && m < M_sel - 1, "sizes");
-  GVI_CHECK_ARG(x_local && winner && log_scaling && log_ls && record_out && workspace, "null pointer");
+  GVI_CHECK_ARG(log_scaling && log_ls, "null pointer");
   GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
+  return select_update_impl(x_local, N_local, offset, D, M_sel, m, winner, log_scaling, log_ls, ls_len, nullptr, jitter,
+                            record_out, trace_partial_out, workspace, stream);
+}
+// any kernel: kcol[i] = k(x_i, x_j) for the winning pivot j, supplied by the caller
+extern "C" int gvi_select_update_gram_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                                          int m, const double* winner, const double* kcol, double jitter,
+                                          double* record_out, double* trace_partial_out, void* workspace,
+                                          void* stream) {
+  GVI_CHECK_ARG(kcol, "null pointer");
+  return select_update_impl(x_local, N_local, offset, D, M_sel, m, winner, nullptr, nullptr, 1, kcol, jitter,
+                            record_out, trace_partial_out, workspace, stream);
+}
+
+static int select_update_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
+                              const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
+                              const double* kcol, double jitter, double* record_out, double* trace_partial_out,
+                              void* workspace, void* stream) {
+  GVI_CHECK_ARG(N_local >= 1 && D >= 1 && M_sel > 1 && m >= 0 && m < M_sel - 1, "sizes");
+  GVI_CHECK_ARG(x_local && winner && record_out && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   SelectWs s = carve(workspace, N_local, M_sel, D);
   size_t smem = (size_t)(m + 2 * D) * sizeof(double);
@@ -268,7 +314,7 @@ extern "C" int gvi_select_update_f64(const double* x_local, int64_t N_local, int
     }
   }
   select_update_kernel<<<(unsigned)s.nblk, STHREADS, smem, st>>>(x_local, N_local, offset, D, m, winner, log_scaling,
-                                                                 log_ls, ls_len, jitter, s.d, s.C, s.chosen,
+                                                                 log_ls, ls_len, kcol, jitter, s.d, s.C, s.chosen,
                                                                  s.blockcand, s.blocktrace);
   GVI_CHECK_LAUNCH("select_update_kernel");
   select_finalize_kernel<<<1, 1024, 0, st>>>(x_local, N_local, offset, D, M_sel, m + 1, /*prefer_high=*/1,

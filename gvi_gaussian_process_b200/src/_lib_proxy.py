@@ -276,6 +276,37 @@ def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):
     return idx, trace
 
 
+def cond_var_select_any_kernel(x_perm, m_sel, kernel, kernel_parameters, jitter):
+    """The greedy selector over ANY kernel: k(x_i, x_i) and, per pivot, the column k(X, x_j) come from the kernel's own
+    Gram routine (the pivot position stays on the device: x_j is gathered with a device index, no host sync); the
+    pivoted-Cholesky update, rounding, clipping and the tie rules run in the same CUDA kernels as the ARD selector."""
+    n = x_perm.shape[0]
+    x_flat = x_perm.reshape(n, -1).contiguous()
+    d = x_flat.shape[1]
+    lib = _L()
+    idx = torch.empty(m_sel, dtype=torch.int64, device=x_perm.device)
+    trace = empty(m_sel - 1)
+    ws = torch.empty(lib.gvi_select_workspace_bytes(n, m_sel, d), dtype=torch.uint8, device=x_perm.device)
+    rl = lib.gvi_select_record_len(d, m_sel)
+    record, winner = empty(rl), empty(rl)
+    st = _lib.current_stream
+    k_diag = kernel.calculate_gram(kernel_parameters, x_perm, x_perm, full_covariance=False).reshape(-1).contiguous()
+    _lib.check(lib.gvi_select_init_gram_f64(_lib.ptr(x_flat), n, 0, d, m_sel, _lib.ptr(k_diag), float(jitter),
+                                            _lib.ptr(record), _lib.ptr(ws), st()), "gvi_select_init_gram_f64")
+    for m in range(m_sel - 1):
+        _lib.check(lib.gvi_select_resolve_f64(_lib.ptr(record), 1, d, m_sel, int(m == 0), _lib.ptr(winner),
+                                              idx[m:].data_ptr(), st()), "gvi_select_resolve_f64")
+        x_j = x_perm.index_select(0, idx[m:m + 1])
+        k_col = kernel.calculate_gram(kernel_parameters, x_j, x_perm).reshape(-1).contiguous()  # k is symmetric
+        _lib.check(lib.gvi_select_update_gram_f64(_lib.ptr(x_flat), n, 0, d, m_sel, m, _lib.ptr(winner),
+                                                  _lib.ptr(k_col), float(jitter), _lib.ptr(record),
+                                                  trace[m:].data_ptr(), _lib.ptr(ws), st()),
+                   "gvi_select_update_gram_f64")
+    _lib.check(lib.gvi_select_resolve_f64(_lib.ptr(record), 1, d, m_sel, 0, _lib.ptr(winner),
+                                          idx[m_sel - 1:].data_ptr(), st()), "gvi_select_resolve_f64")
+    return idx, trace
+
+
 # ---- vector-Jacobian products and the classification epilogue (SURVEY.md section 8(f)-2) ---------------------------
 def gp_predict_grad(factor: GpFactor, x, g_var, frozen_cholesky: bool = False):
     """out[4+D] with out[3] = dLoss/dlog_scaling and out[4:] = dLoss/dlog_lengthscales, given g_var = dLoss/dvar."""

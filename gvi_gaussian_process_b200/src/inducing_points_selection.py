@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from . import _lib_proxy as L
+from .kernels.base import KernelBase
 from .kernels.standard.ard_kernel import ARDKernel
 from .utils import jax_prng
 from .utils.device import as_device
@@ -43,16 +44,19 @@ class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
     def compute_inducing_points(self, key, training_inputs, number_of_inducing_points, kernel=None,
                                 kernel_parameters=None, jitter: float = 1e-12):
         assert number_of_inducing_points > 1, "Must have at least 2 inducing points"
-        if not isinstance(kernel, ARDKernel):
-            raise NotImplementedError("the B200 selector implements ARDKernel only (SURVEY.md section 8, a13)")
+        assert isinstance(kernel, KernelBase), f"kernel must be a kernel of this package, got {type(kernel)=}"
         x = as_device(training_inputs)
         n = x.shape[0]
         _, subkey = jax_prng.split(np.asarray(key))
         perm = torch.as_tensor(jax_prng.permutation(subkey, n), device=x.device)
         x_perm = x[perm].contiguous()
         kernel_parameters = kernel._to_parameters(kernel_parameters)
-        ls, ll = ARDKernel.device_parameters(kernel_parameters)
-        idx, trace = L.cond_var_select(x_perm.reshape(n, -1), number_of_inducing_points, ls, ll, jitter)
+        if isinstance(kernel, ARDKernel):
+            ls, ll = ARDKernel.device_parameters(kernel_parameters)
+            idx, trace = L.cond_var_select(x_perm.reshape(n, -1), number_of_inducing_points, ls, ll, jitter)
+        else:  # any other kernel: Gram columns from the kernel itself, the pivoted Cholesky in the same CUDA kernels
+            idx, trace = L.cond_var_select_any_kernel(x_perm, number_of_inducing_points, kernel, kernel_parameters,
+                                                      jitter)
         if self.threshold > 0.0:
             # reference lines 167-172: the first step m whose tr(K - Q) < threshold truncates to indices[:m]
             below = torch.nonzero(trace < self.threshold)

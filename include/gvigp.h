@@ -284,6 +284,15 @@ int64_t gvi_select_record_len(int D, int M_sel);
 int gvi_select_init_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
                         const double* log_scaling, double jitter, double* record_out, void* workspace,
                         void* stream);
+/* The same steps for ANY kernel (the reference's selector only calls kernel.calculate_gram,
+ * src/inducing_points_selection.py:121-166): the caller supplies kdiag[i] = k(x_i, x_i) at init and, per step,
+ * kcol[i] = k(x_i, x_j) for the winning pivot j (its position is idx_out_m of resolve, a device value: the column can
+ * be produced without a host sync).  np.round(., 20), the jitter at j, the clip and the tie rules are applied here. */
+int gvi_select_init_gram_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                             const double* kdiag, double jitter, double* record_out, void* workspace, void* stream);
+int gvi_select_update_gram_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
+                               const double* winner, const double* kcol, double jitter, double* record_out,
+                               double* trace_partial_out, void* workspace, void* stream);
 int gvi_select_resolve_f64(const double* records, int R, int D, int M_sel, int first, double* winner_out,
                            int64_t* idx_out_m, void* stream);
 int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
