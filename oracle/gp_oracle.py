@@ -475,3 +475,20 @@ def optimiser_step(kind, p, g, mu, nu, count, lr):
     else:
         raise ValueError(kind)
     return p - lr * upd, mu, nu
+
+
+def conformal_gp_coverage(mean_calibration, variance_calibration, y_calibration, mean, variance, coverage):
+    """ConformalGPRegression.predict_coverage for one coverage percentage, from the predictives at the calibration and
+    the query points (src/conformal_calibration/regression/conformal_gp_regression.py:27-71 for the Gaussian intervals,
+    regression/base.py:76-137 for the calibration).  Parity unpinned: the reference has no test for this module."""
+    from scipy.special import ndtri
+
+    scale = ndtri((coverage + 1.0) / 2.0)
+    lo_c = mean_calibration - scale * np.sqrt(variance_calibration)
+    up_c = mean_calibration + scale * np.sqrt(variance_calibration)
+    scores = np.maximum(lo_c - y_calibration, y_calibration - up_c)
+    n = len(y_calibration)
+    calibration = np.quantile(scores, np.clip((n + 1) * coverage / n, 0.0, 1.0))
+    lower = mean - scale * np.sqrt(variance) - calibration
+    upper = mean + scale * np.sqrt(variance) + calibration
+    return np.minimum(lower, mean), np.maximum(upper, mean)

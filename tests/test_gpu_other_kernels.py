@@ -354,3 +354,40 @@ def test_selector_over_polynomial_and_custom_kernels_matches_oracle(S):
     _, idx_c = ConditionalVarianceInducingPointsSelector().compute_inducing_points(
         jax_prng.PRNGKey(5), x, m, custom, custom.Parameters.construct(custom=None))
     assert np.array_equal(host(idx_c), perm[piv])
+
+
+def test_conformal_gp_regression_matches_oracle(S):
+    """src/conformal_calibration/regression: Gaussian intervals of the exact GP's predictive (CUDA path), conformally
+    calibrated on a held-out split; against the NumPy restatement (no reference test exists: parity unpinned)."""
+    from gvi_gaussian_process_b200.src.conformal_calibration.regression import ConformalGPRegression
+
+    rng = np.random.default_rng(4)
+    n, m, d = 900, 40, 2
+    x = rng.standard_normal((n, d))
+    y = np.sin(x @ np.array([1.0, -0.5])) + 0.2 * rng.standard_normal(n)
+    z, yz = x[:m], y[:m]
+    x_cal, y_cal, x_test = x[m:500], y[m:500], x[500:]
+    ls, ll, log_noise = 0.1, np.array([0.2, -0.1]), -2.0
+    kernel = S.ARDKernel(number_of_dimensions=d)
+    const = S.ConstantMean()
+    gp = S.GPRegression(mean=const, kernel=kernel, x=z, y=yz)
+    gp_parameters = gp.Parameters.construct(
+        log_observation_noise=log_noise, mean=const.Parameters.construct(constant=0.1),
+        kernel=kernel.Parameters.construct(log_scaling=ls, log_lengthscales=ll))
+    conformal = ConformalGPRegression(x_calibration=x_cal, y_calibration=y_cal, gp=gp, gp_parameters=gp_parameters)
+    gram = lambda a, b: O.ard_gram(ls, ll, a, b)
+    diag = lambda a: O.ard_gram_diag(ls, ll, a)
+    m_c, v_c = O.exact_gp_posterior(gram, diag, np.full(len(x_cal), 0.1), z, yz, log_noise, x_cal)
+    m_t, v_t = O.exact_gp_posterior(gram, diag, np.full(len(x_test), 0.1), z, yz, log_noise, x_test)
+    coverages = [0.5, 0.9, 0.999]
+    lower, upper = conformal.predict_coverage(x=x_test, coverage=np.array(coverages))
+    assert lower.shape == (3, len(x_test)) and upper.shape == (3, len(x_test))
+    for i, c in enumerate(coverages):
+        lo_ref, up_ref = O.conformal_gp_coverage(m_c, v_c, y_cal, m_t, v_t, c)
+        assert rel_norm(host(lower[i]), lo_ref) <= 1e-9 and rel_norm(host(upper[i]), up_ref) <= 1e-9
+    widths = host(conformal.calculate_average_interval_width(x=x_test, coverage=np.array(coverages)))
+    assert widths.shape == (3,) and widths[0] < widths[1] < widths[2]
+    # empirical coverage on the calibration split itself is at least the nominal one (split-conformal guarantee there)
+    lo_c, up_c = conformal.predict_coverage(x=x_cal, coverage=0.9)
+    inside = (host(lo_c[0]) <= y_cal) & (y_cal <= host(up_c[0]))
+    assert inside.mean() >= 0.9
