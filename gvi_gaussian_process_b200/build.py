@@ -59,5 +59,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+FFI_SOURCE = os.path.join(CSRC, "ffi", "gvigp_xla_ffi.cc")
+FFI_LIB_PATH = os.path.join(HERE, "libgvigp_ffi.so")
+
+
+def xla_ffi_include_dir():
+    """jaxlib ships the XLA FFI headers (xla/ffi/api/ffi.h) under jaxlib/include; None when jaxlib is absent."""
+    try:
+        import jaxlib
+    except ImportError:
+        return None
+    inc = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+    return inc if os.path.exists(os.path.join(inc, "xla", "ffi", "api", "ffi.h")) else None
+
+
+def build_ffi() -> str:
+    """libgvigp_ffi.so: the XLA-FFI handlers over the C ABI (csrc/ffi/gvigp_xla_ffi.cc).  Needs a jaxlib that ships the
+    FFI headers; this repository's image has none, so the adapter has never been compiled here (build() does not call
+    this)."""
+    inc = xla_ffi_include_dir()
+    if inc is None:
+        raise RuntimeError("no jaxlib with xla/ffi/api/ffi.h importable: the XLA-FFI adapter cannot be built in this "
+                           "environment (the C ABI in libgvigp.so is the tested surface)")
+    build()
+    cmd = [_nvcc(), "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC", "-I", inc, FFI_SOURCE, "-o", FFI_LIB_PATH,
+           "-L", HERE, "-l:libgvigp.so", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-cudart", "shared"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"building the XLA-FFI adapter failed:\n{r.stdout}")
+    return FFI_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

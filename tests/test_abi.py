@@ -97,3 +97,39 @@ def test_argument_validation_of_the_widened_entry_points(lib):
     assert lib.gvi_optimiser_step_f64(7, None, None, None, None, 10, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
     assert lib.gvi_optimiser_step_f64(0, None, None, None, None, 10, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == -1
     assert lib.gvi_optimiser_step_f64(0, None, None, None, None, 0, 1, 1e-3, 0.9, 0.999, 1e-8, 0.0, None) == 0
+
+
+def test_argument_validation_of_the_other_kernel_entry_points(lib):
+    """Non-ARD kernels (caller-supplied Grams): bad arguments are rejected before any CUDA call; empty inputs are a no-op."""
+    assert lib.gvi_dot_gram_f64(None, 0, None, 4, 3, None, None, 2.0, None, 4, None) == 0
+    assert lib.gvi_dot_gram_f64(None, 2, None, 4, 3, None, None, 2.0, None, 3, None) == -1  # ld_out < m2
+    assert lib.gvi_dot_gram_f64(None, 2, None, 4, 3, None, None, 2.0, None, 4, None) == -1  # nulls
+    assert lib.gvi_kernel_pairs_f64(5, None, None, 10, 3, None, None, 3, 1.0, None, None) == -1  # unknown kind
+    assert lib.gvi_kernel_pairs_f64(0, None, None, 0, 3, None, None, 3, 1.0, None, None) == 0
+    assert lib.gvi_gp_factor_gram_f64(None, 4, 4, 1e-5, 0, None, None, None, None, None, None) == -1
+    assert lib.gvi_gp_predict_gram_f64(None, 4, None, 4, None, 0, None, None, None, None, None, None) == 0
+    assert lib.gvi_gp_predict_gram_f64(None, 4, None, 4, None, 10, None, None, None, None, None, None) == -1
+    assert lib.gvi_select_init_gram_f64(None, 10, 0, 3, 4, None, 1e-12, None, None, None) == -1
+    assert lib.gvi_select_update_gram_f64(None, 10, 0, 3, 4, 0, None, None, 1e-12, None, None, None, None) == -1
+    assert lib.gvi_test_set_grad_chunk_waves(3) == 0 and lib.gvi_test_set_grad_chunk_waves(0) == 3
+
+
+def test_xla_ffi_adapter_is_consistent_and_gated():
+    """The XLA-FFI adapter cannot be compiled here (no jaxlib): check that its handler symbols and the registration
+    table agree, that every C-ABI function it forwards to is declared in the header, and that the JAX entry points fail
+    with a clear message instead of falling back to anything."""
+    from gvi_gaussian_process_b200 import build, jax_ffi
+
+    src = open(build.FFI_SOURCE).read()
+    defined = set(re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((gvi_[a-z0-9_]+),", src))
+    assert defined == set(jax_ffi.FFI_TARGETS.values())
+    forwarded = set(re.findall(r"\b(gvi_[a-z0-9_]+_f64)\(", src))
+    assert forwarded and forwarded <= set(header_symbols())
+    try:
+        import jax  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError, match="needs jax/jaxlib"):
+            jax_ffi.register()
+        assert build.xla_ffi_include_dir() is None
+        with pytest.raises(RuntimeError, match="cannot be built"):
+            build.build_ffi()
