@@ -488,15 +488,24 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
             for (int nt = 0; nt < NT; nt++) {
               const int64_t p0 = row0 + nt * 8;  // a multiple of 8: the n-tile stays inside one k-pair of one group
               double* blk = P.a_ring + ((size_t)cb * P.a_npg + (p0 >> 5)) * SYRK_BLK;
-#pragma unroll
-              for (int e = 0; e < 2; e++)
-                __stcg(blk + syrk_frag_index(c, (int)(p0 & 31) + (lane & 3) * 2 + e), acc[mt][nt][e]);
+              // the operand order pairs point i with point i + 4: lanes q and q ^ 2 (q = lane % 4) swap one value so
+              // that every lane owns two ADJACENT doubles -> one 16-byte store per lane, full 32-byte sectors
+              const int q = lane & 3;
+              const double send = (q & 2) ? acc[mt][nt][0] : acc[mt][nt][1];
+              const double recv = __shfl_xor_sync(0xffffffffu, send, 2);
+              double2 v;
+              v.x = (q & 2) ? recv : acc[mt][nt][0];
+              v.y = (q & 2) ? acc[mt][nt][1] : recv;
+              // q = 0: points (0, 4); q = 2: points (1, 5); q = 1: points (2, 6); q = 3: points (3, 7)
+              const int i_lo = (q & 1) * 2 + (q >> 1);
+              __stcg(reinterpret_cast<double2*>(blk + syrk_frag_index(c, (int)(p0 & 31) + i_lo)), v);
             }
           }
         }
-        double t2[DR], na2 = 0.0;
-#pragma unroll
-        for (int d = 0; d < DR; d++) t2[d] = 0.0;
+        // T2_d = sum_ij g_i a_ij k_ij (x~_id - z~_jd)^2 in two passes, so that neither D running sums nor D squared
+        // differences are live across the exp (at the 128-register cap that version spilled ~115 values per group):
+        // pass 1 turns every a_ij into coef_ij = g_i a_ij k_ij in place, pass 2 takes one dimension at a time
+        double na2 = 0.0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
           const int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
@@ -508,24 +517,33 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const int i = nt * 8 + (lane & 3) * 2 + e;
-              const double a = acc[mt][nt][e];
-              const double gi = gs[i];
-              double diff2[DR], s = 0.0;
+              const double ga = gs[i] * acc[mt][nt][e];
+              double s = 0.0;
 #pragma unroll
               for (int d = 0; d < DR; d++) {
-                double diff = xs[i * DR + d] - z[d];
-                diff2[d] = diff * diff;
-                s += diff2[d];
+                const double diff = xs[i * DR + d] - z[d];
+                s = fma(diff, diff, s);
               }
-              const double coef = gi * a * amp2 * gvi_exp(-0.5 * s);
-#pragma unroll
-              for (int d = 0; d < DR; d++) t2[d] = fma(coef, diff2[d], t2[d]);
-              na2 = fma(gi * a, a, na2);
+              na2 = fma(ga, acc[mt][nt][e], na2);
+              acc[mt][nt][e] = ga * amp2 * gvi_exp(-0.5 * s);
             }
         }
 #pragma unroll
         for (int d = 0; d < DR; d++) {
-          double v = warp_sum(t2[d]);
+          double v = 0.0;
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++) {
+            const int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
+            const double zd = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const double diff = xs[(nt * 8 + (lane & 3) * 2 + e) * DR + d] - zd;
+                v = fma(acc[mt][nt][e] * diff, diff, v);
+              }
+          }
+          v = warp_sum(v);
           if (lane == 0) gpart[g * (DR + 1) + d] = v;
         }
         na2 = warp_sum(na2);
