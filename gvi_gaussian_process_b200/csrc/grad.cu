@@ -330,7 +330,7 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
     w.tile_partials = take((size_t)w.ntiles * STEP_PARTIAL_STRIDE * 8);
   }
   w.g = take((size_t)N * 8);
-  w.bscratch = take((size_t)GVI_NUM_SMS * f.Mp * T * 8);
+  w.bscratch = take((size_t)2 * GVI_NUM_SMS * f.Mp * T * 8);  // per CTA: the b tile and q's parked K tile
   w.Cpart = take((size_t)w.nsplit * f.Mp * f.Mp * 8);
   w.C = take((size_t)f.Mp * f.Mp * 8);
   w.rowpart = take((size_t)f.Mp * 32 * 8);

@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
   const int64_t ntiles = (P.N + T - 1) / T;
   const FactorLayout f = factor_layout(P.M, P.D);
   double* bscr = GRAD ? P.bscratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
+  // q's K tile is parked next to it (L2 resident): the T2 epilogue of phase 3 reads k_ij back instead of re-evaluating
+  // the kernel (37 of its 64 FP64 instructions per entry; the FP64 pipe shares its datapath with the DMMAs)
+  double* kscr = GRAD ? P.bscratch + ((size_t)GVI_NUM_SMS + blockIdx.x) * P.Mp * T : nullptr;
 
   long long& s_tile = *reinterpret_cast<long long*>(counter + 2);  // inside the 16 spare bytes after the group counter
   constexpr int TILE_STRIDE = GRAD ? STEP_PARTIAL_STRIDE : 2;
@@ -267,6 +270,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         }
       }
       __syncthreads();
+      if (keep_b) {  // park q's K tile for phase 3 (the warps go on to phase 2 as soon as their share is on its way)
+        const double2* Ks2r = reinterpret_cast<const double2*>(Ksm);
+        double2* kscr2 = reinterpret_cast<double2*>(kscr);
+        for (int idx = tid; idx < P.Mp * T / 2; idx += THREADS) __stcg(kscr2 + idx, Ks2r[idx]);
+      }
       // ---- phase 2: b = L^-1 k on the tensor pipe, accumulate ||b||^2 ----------------------------------
       auto run_groups = [&](const double* __restrict__ W, const bool store_b) {
         const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
@@ -509,23 +517,20 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
           const int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
-          double z[DR];
+          // k_ij of the parked K tile (B-fragment order of phase 1)
+          const double* kcol = kscr + (size_t)(j >> 3) * (NT * 64) + ((j >> 2) & 1) + 2 * (j & 3);
+          double kij[NT][2];
 #pragma unroll
-          for (int d = 0; d < DR; d++) z[d] = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
+          for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) kij[nt][e] = __ldcg(kcol + nt * 64 + ((lane & 3) * 2 + e) * 8);
 #pragma unroll
           for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-              const int i = nt * 8 + (lane & 3) * 2 + e;
-              const double ga = gs[i] * acc[mt][nt][e];
-              double s = 0.0;
-#pragma unroll
-              for (int d = 0; d < DR; d++) {
-                const double diff = xs[i * DR + d] - z[d];
-                s = fma(diff, diff, s);
-              }
+              const double ga = gs[nt * 8 + (lane & 3) * 2 + e] * acc[mt][nt][e];
               na2 = fma(ga, acc[mt][nt][e], na2);
-              acc[mt][nt][e] = ga * amp2 * gvi_exp(-0.5 * s);
+              acc[mt][nt][e] = ga * kij[nt][e];
             }
         }
 #pragma unroll
