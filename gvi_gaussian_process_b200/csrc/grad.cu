@@ -305,6 +305,7 @@ int g_chunk_waves_cap = 0;  // test hook (gvi_test_set_grad_chunk_waves)
 
 struct GradWs {
   double *partials, *tile_partials, *g, *bscratch, *Cpart, *C, *rowpart, *Kc;
+  double *mp, *vp, *pscratch;  // regulariser predictive of one chunk (forward launch) and that launch's panel scratch
   int* tile_counter;
   int64_t ntiles;
   int nsplit, ntri, ncb, chunk_pg;  // chunk_pg = point groups (of 32 points) per K chunk
@@ -356,6 +357,9 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   // (wide inputs, D > 32, take the GEMM route of grad_wide.cu and never fill the a_i ring)
   const size_t ring_k = (size_t)Gc * pgs * BLK * 8, ring_a = D > 32 ? 0 : (size_t)nw * wave_bytes;
   w.Kc = take(ring_k > ring_a ? ring_k : ring_a);
+  w.mp = take((size_t)w.achunk_pts * 8);
+  w.vp = take((size_t)w.achunk_pts * 8);
+  w.pscratch = take(gvi_step_scratch_doubles(f.Mp) * 8);
   if (total) *total = o;
   return w;
 }
@@ -429,6 +433,25 @@ static int gvi_grad_launch_accumulate_S(const StepParams& P0, const GradWs& w, i
       P.pass[ps].var_out = atw(P0.pass[ps].var_out);
     }
     P.tile_partials = P0.tile_partials + (size_t)(row0 / T) * STEP_PARTIAL_STRIDE;
+    if (P0.npass == 2) {
+      // the regulariser GP p is constant: its predictive needs no gradient machinery, so it runs through the FORWARD
+      // launch shape (two CTAs per SM: its kernel evaluations hide under the neighbour's DMMAs) into chunk-sized arrays
+      // and the gradient launch takes (m_p, v_p) as inputs, like a prior-mode regulariser
+      StepParams Pp{};
+      Pp.npass = 1;
+      Pp.pass[0] = P.pass[1];
+      if (!Pp.pass[0].mean_out) Pp.pass[0].mean_out = w.mp;
+      if (!Pp.pass[0].var_out) Pp.pass[0].var_out = w.vp;
+      Pp.M = P0.M; Pp.Mp = P0.Mp; Pp.D = P0.D; Pp.G = P0.G;
+      Pp.X = P.X; Pp.N = n;
+      Pp.tile_counter = P0.tile_counter;
+      Pp.acc_scratch = w.pscratch;
+      const int gp = gvi_launch_step(Pp, st);
+      if (gp < 0) return gp;
+      P.npass = 1;
+      P.m_p_in = Pp.pass[0].mean_out;
+      P.v_p_in = Pp.pass[0].var_out;
+    }
     const int64_t ntiles = (n + T - 1) / T;
     const int npg = (int)((ntiles * T + PC - 1) / PC);
     P.a_ring = w.Kc;
