@@ -146,3 +146,100 @@ class SVGPVariance(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_var):
         return None, None, L.weighted_gram(ctx.factor, ctx.x, g_var.contiguous())
+
+
+# ---- kernels other than ARD: the predictive over caller-supplied Grams, differentiable w.r.t. the Grams ------------------
+def tensor_leaves(obj):
+    """The torch tensors inside a parameter container / dict / list (used to decide whether a backward is wanted)."""
+    from .module import ModuleParameters
+
+    if isinstance(obj, torch.Tensor):
+        yield obj
+    elif isinstance(obj, ModuleParameters):
+        yield from tensor_leaves(obj.dict_shallow())
+    elif isinstance(obj, dict):
+        for v in obj.values():
+            yield from tensor_leaves(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from tensor_leaves(v)
+
+
+class DotGram(torch.autograd.Function):
+    """(exp(log_scaling) x1 x2^T + exp(log_constant))^degree: forward = the CUDA Gram kernel (gvi_dot_gram_f64); backward
+    w.r.t. the two scalars AND the inputs (the features of a CustomMappingKernel) as library GEMMs + elementwise ops."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, log_scaling, log_constant, degree):
+        x1, x2 = x1.contiguous(), x2.contiguous()
+        out = torch.empty(x1.shape[0], x2.shape[0], dtype=torch.float64, device=x1.device)
+        L.dot_gram(x1, x2, log_scaling.detach().reshape(-1)[:1].contiguous(),
+                   None if log_constant is None else log_constant.detach().reshape(-1)[:1].contiguous(), degree, out)
+        ctx.save_for_backward(x1, x2, log_scaling, log_constant if log_constant is not None else log_scaling)
+        ctx.has_constant, ctx.degree = log_constant is not None, float(degree)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x1, x2, log_scaling, log_constant = ctx.saved_tensors
+        scale = torch.exp(log_scaling.detach()).reshape(())
+        const = torch.exp(log_constant.detach()).reshape(()) if ctx.has_constant else None
+        dot = x1 @ x2.T
+        if ctx.degree != 1.0:
+            base = scale * dot + (const if const is not None else 0.0)
+            g = g * (ctx.degree * base ** (ctx.degree - 1.0))
+        d_ls = ((g * dot).sum() * scale).reshape(log_scaling.shape) if ctx.needs_input_grad[2] else None
+        d_lc = (g.sum() * const).reshape(log_constant.shape) if ctx.has_constant and ctx.needs_input_grad[3] else None
+        d_x1 = scale * (g @ x2) if ctx.needs_input_grad[0] else None
+        d_x2 = scale * (g.T @ x1) if ctx.needs_input_grad[1] else None
+        return d_x1, d_x2, d_ls, d_lc, None
+
+
+class PredictGram(torch.autograd.Function):
+    """(mean[n], var[n]) = (K_xz alpha + prior_mean, k_diag - ||L^-1 K_xz^T||^2) through gvi_gp_predict_gram_f64 on a state
+    built by gvi_gp_factor_gram_f64, differentiable w.r.t. K_zz, K_xz, k_diag, the prior mean and log_observation_noise.
+    The backward is the dense vector-Jacobian product (what reverse-mode differentiation of cho_solve gives) as library
+    GEMMs against the L^-1 of the CUDA factorisation; the kernel's own Gram routine is differentiated by whoever built
+    K (DotGram above, or the host framework for CustomKernel / feature maps).
+      A = K_zz + jitter I (+ exp(log_noise) I),  B = K_xz A^-1,  alpha = A^-1 y_z
+      dK_xz = -2 diag(g) B + h alpha^T,  dk_diag = g,  dA = B^T diag(g) B - (A^-1 K_xz^T h) alpha^T
+      dK_zz = dA (+ reg / M tr(dA) I for a trace-relative jitter),  dlog_noise = exp(log_noise) tr(dA)."""
+
+    @staticmethod
+    def forward(ctx, factor, linv, alpha, reg, is_abs, k_zz, k_xz, k_diag, prior_mean, log_noise):
+        n = k_xz.shape[0]
+        mean = torch.empty(n, dtype=torch.float64, device=k_xz.device)
+        var = torch.empty(n, dtype=torch.float64, device=k_xz.device)
+        k_xz_c = k_xz.contiguous()
+        L.gp_predict_gram(factor, k_xz_c, k_diag.contiguous(), None if prior_mean is None else prior_mean.contiguous(),
+                          None, mean, var)
+        ctx.save_for_backward(linv, k_xz_c)
+        ctx.alpha, ctx.reg, ctx.is_abs = alpha, float(reg), bool(is_abs)
+        ctx.log_noise = None if log_noise is None else log_noise.detach()
+        ctx.noise_shape = None if log_noise is None else log_noise.shape
+        ctx.has_prior = prior_mean is not None
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, h, g):
+        linv, k_xz = ctx.saved_tensors
+        m = linv.shape[0]
+        d_kxz = torch.zeros_like(k_xz)
+        d_a = torch.zeros(m, m, dtype=torch.float64, device=k_xz.device)
+        if g is not None:
+            b = (k_xz @ linv.T) @ linv
+            gb = g.reshape(-1, 1) * b
+            d_kxz -= 2.0 * gb
+            d_a += b.T @ gb
+        if h is not None and ctx.alpha is not None:
+            d_kxz += h.reshape(-1, 1) * ctx.alpha.reshape(1, -1)
+            w = linv.T @ (linv @ (k_xz.T @ h))
+            d_a -= torch.outer(w, ctx.alpha)
+        d_kzz = d_a if ctx.is_abs else d_a + (ctx.reg / m) * torch.trace(d_a) * torch.eye(
+            m, dtype=torch.float64, device=k_xz.device)
+        d_noise = None
+        if ctx.log_noise is not None and ctx.needs_input_grad[9]:
+            d_noise = (torch.exp(ctx.log_noise).reshape(()) * torch.trace(d_a)).reshape(ctx.noise_shape)
+        return (None, None, None, None, None, d_kzz if ctx.needs_input_grad[5] else None,
+                d_kxz if ctx.needs_input_grad[6] else None, g if ctx.needs_input_grad[7] else None,
+                h if ctx.has_prior and ctx.needs_input_grad[8] else None, d_noise)

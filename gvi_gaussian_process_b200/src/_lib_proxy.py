@@ -164,6 +164,33 @@ def gp_predict_any_kernel(factor: GpFactor, kernel, kernel_parameters, z, x, pri
     return mean, var
 
 
+def gp_predict_any_kernel_grad(factor: GpFactor, kernel, kernel_parameters, z, x, diagonal_regularisation, is_absolute,
+                               prior_mean=None, log_noise=None, y_z=None, want_mean=True):
+    """The differentiable variant of gp_predict_any_kernel (hyper-parameters of a non-ARD kernel, feature-map weights,
+    observation noise, prior mean): K_zz is built with the autograd graph attached, factorised once by the CUDA
+    factorisation, and every chunk goes through _autograd.PredictGram."""
+    from ._autograd import PredictGram
+
+    k_zz = kernel.calculate_gram(kernel_parameters, z, z)
+    noise = None if log_noise is None else log_noise.detach().reshape(-1)[:1].contiguous()
+    factor.factor_from_gram(k_zz.detach().contiguous(), diagonal_regularisation, is_absolute, log_noise=noise, y_z=y_z)
+    linv = factor.inverse_cholesky().clone()
+    alpha = None if y_z is None else linv.T @ (linv @ y_z)
+    n = x.shape[0]
+    rows = max(24, GRAM_CHUNK_BYTES // (8 * factor.m) // 24 * 24)
+    means, variances = [], []
+    for r0 in range(0, n, rows):
+        xc = x[r0:min(n, r0 + rows)]
+        k_xz = kernel.calculate_gram(kernel_parameters, xc, z)
+        k_diag = kernel.calculate_gram(kernel_parameters, xc, xc, full_covariance=False).reshape(-1)
+        pm = prior_mean[r0:r0 + xc.shape[0]] if prior_mean is not None else None
+        mean, var = PredictGram.apply(factor, linv, alpha, diagonal_regularisation, is_absolute, k_zz, k_xz, k_diag, pm,
+                                      log_noise)
+        means.append(mean)
+        variances.append(var)
+    return (torch.cat(means) if want_mean else None), torch.cat(variances)
+
+
 _risk_ws = {}
 
 

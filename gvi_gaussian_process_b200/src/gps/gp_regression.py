@@ -9,7 +9,7 @@ The K=1 predictive mean has shape [1,N] as in the reference (only the covariance
 from __future__ import annotations
 
 from .. import _lib_proxy as L
-from .._autograd import ExactPredict, wants_grad
+from .._autograd import ExactPredict, tensor_leaves, wants_grad
 from ..kernels.standard.ard_kernel import ARDKernel
 from ..utils.device import as_2d, as_device, scalar
 from .base import GPBase
@@ -47,8 +47,16 @@ class GPRegression(GPBase):
         parameters = self._to_parameters(parameters)
         x = as_2d(x)
         if not self._ard:
-            f = self.factorise(parameters)
             prior_mean = self.mean.predict(parameters.mean, x).reshape(-1).contiguous()
+            if wants_grad(prior_mean, parameters.log_observation_noise, *tensor_leaves(parameters.kernel)):
+                # training the exact GP over a non-ARD kernel (e.g. a feature-map kernel, train_regulariser_gp)
+                if self._factor is None:
+                    self._factor = L.GpFactor(self.x.shape[0], 1)
+                mean, var = L.gp_predict_any_kernel_grad(
+                    self._factor, self.kernel, parameters.kernel, self.x, x, 0.0, True, prior_mean=prior_mean,
+                    log_noise=as_device(parameters.log_observation_noise), y_z=self.y)
+                return mean.reshape(1, -1), var
+            f = self.factorise(parameters)
             mean, var = L.gp_predict_any_kernel(f, self.kernel, parameters.kernel, self.x, x, prior_mean=prior_mean)
             return mean.reshape(1, -1), var
         x = x.reshape(x.shape[0], -1)

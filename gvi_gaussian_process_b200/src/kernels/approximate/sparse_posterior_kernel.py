@@ -8,7 +8,7 @@ library DGEMM (cuBLAS through torch.matmul) against the L^-1 produced by the CUD
 from __future__ import annotations
 
 from ... import _lib_proxy as L
-from ..._autograd import PredictVariance, wants_grad
+from ..._autograd import PredictVariance, tensor_leaves, wants_grad
 from ...utils.device import as_2d
 from ..base import KernelBase, KernelBaseParameters
 from ..standard.ard_kernel import ARDKernel
@@ -57,6 +57,13 @@ class SparsePosteriorKernel(KernelBase):
                                    self.is_diagonal_regularisation_absolute_scale)
 
     def _calculate_gram_diagonal(self, parameters, x):
+        if not self._ard and wants_grad(*tensor_leaves(parameters.base_kernel)):
+            if self._factor is None:
+                self._factor = L.GpFactor(self.inducing_points.shape[0], 1)
+            _, var = L.gp_predict_any_kernel_grad(
+                self._factor, self.base_kernel, parameters.base_kernel, self.inducing_points, x,
+                self.diagonal_regularisation, self.is_diagonal_regularisation_absolute_scale, want_mean=False)
+            return var
         f = self.factorise(parameters)
         if not self._ard:
             _, var = L.gp_predict_any_kernel(f, self.base_kernel, parameters.base_kernel, self.inducing_points, x,

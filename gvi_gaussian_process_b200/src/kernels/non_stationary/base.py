@@ -4,7 +4,10 @@ fused (scale, constant, power) epilogue serves them; k(x, x) varies per point, s
 the caller-supplied-Gram entry points (gvi_gp_factor_gram_f64 / gvi_gp_predict_gram_f64)."""
 from __future__ import annotations
 
+import torch
+
 from ... import _lib_proxy as L
+from ..._autograd import DotGram, wants_grad
 from ...utils.device import empty, scalar
 from ..base import KernelBase, KernelBaseParameters
 
@@ -27,6 +30,9 @@ class NonStationaryKernelBase(KernelBase):
     def _calculate_gram(self, parameters, x1, x2):
         x1, x2 = self._flat(x1), self._flat(x2)
         log_scaling, log_constant, degree = self._dot_parameters(parameters)
+        if wants_grad(log_scaling, log_constant, x1, x2):
+            # forward = the same CUDA Gram kernel; backward w.r.t. the scalars and the inputs (feature maps)
+            return DotGram.apply(x1, x2, log_scaling, log_constant, degree)
         out = empty(x1.shape[0], x2.shape[0])
         L.dot_gram(x1, x2, log_scaling, log_constant, degree, out)
         return out
@@ -34,6 +40,12 @@ class NonStationaryKernelBase(KernelBase):
     def _calculate_gram_pairs(self, parameters, x1, x2):
         x1, x2 = self._flat(x1), self._flat(x2)
         log_scaling, log_constant, degree = self._dot_parameters(parameters)
+        if wants_grad(log_scaling, log_constant, x1, x2):
+            # O(n d) pairwise values: host-framework expression, differentiated by torch
+            base = torch.exp(log_scaling) * (x1 * x2).sum(-1)
+            if log_constant is not None:
+                base = base + torch.exp(log_constant)
+            return base if degree == 1.0 else base ** degree
         out = empty(x1.shape[0])
         L.kernel_pairs(L.KERNEL_POLYNOMIAL, x1, x2, log_scaling, log_constant, degree, out)
         return out

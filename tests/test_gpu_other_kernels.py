@@ -391,3 +391,115 @@ def test_conformal_gp_regression_matches_oracle(S):
     lo_c, up_c = conformal.predict_coverage(x=x_cal, coverage=0.9)
     inside = (host(lo_c[0]) <= y_cal) & (y_cal <= host(up_c[0]))
     assert inside.mean() >= 0.9
+
+
+# ---- gradients for non-ARD kernels: dense VJP of the caller-supplied-Gram predictive (PredictGram) + DotGram ------------
+def _feature_problem(n, m, d, f, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n, d))
+    z = rng.standard_normal((m, d))
+    wt = rng.standard_normal(d)
+    y = np.sin(x @ wt) + 0.1 * rng.standard_normal(n)
+    yz = np.sin(z @ wt) + 0.1 * rng.standard_normal(m)
+    w = rng.standard_normal((d, f)) / np.sqrt(d)
+    b = 0.1 * rng.standard_normal(f)
+    m_q = 0.3 * np.tanh(x @ rng.standard_normal(d))
+    return x, z, y, yz, w, b, m_q
+
+
+def test_gvi_gradients_through_feature_map_kernel_match_autograd_twin(S):
+    """The reference's "1-layer-fcnn-tanh-mapping-linear" kernel (CustomMappingKernel: dense + tanh features, polynomial
+    kernel of degree 1 on them) as the base kernel of q's sparse posterior; NLL + projected KL against a fixed
+    regulariser.  Gradients w.r.t. the network weights, log_scaling, log_constant and the mean values against a torch
+    CPU autograd twin of the same objective (<= 1e-8)."""
+    from oracle import torch_twin as T
+
+    n, m, d, f = 1500, 30, 3, 10
+    x, z, y, yz, w, b, m_q = _feature_problem(n, m, d, f, seed=8)
+    ls, lc, reg = 0.2, -0.4, 1e-3
+    rng = np.random.default_rng(1)
+    m_p, v_p = 0.2 * rng.standard_normal(n), np.exp(0.3 * rng.standard_normal(n))  # fixed regulariser predictive
+
+    leaves = {k: dev(v).requires_grad_(True) for k, v in dict(w=w, b=b, ls=np.array(ls), lc=np.array(lc), mq=m_q).items()}
+    base = S.PolynomialKernel(polynomial_degree=1)
+    kernel = S.CustomMappingKernel(base_kernel=base,
+                                   feature_mapping=lambda p, xx: torch.tanh(xx @ p["w"] + p["b"]))
+    sparse = S.SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=reg)
+    amean = S.CustomMean(mean_function=lambda p, xx: p[: xx.shape[0]])
+    approx = S.ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(
+        mean=amean.Parameters.construct(custom=leaves["mq"]),
+        kernel=sparse.Parameters.construct(base_kernel=kernel.Parameters.construct(
+            base_kernel=base.Parameters.construct(log_constant=leaves["lc"], log_scaling=leaves["ls"]),
+            feature_mapping={"w": leaves["w"], "b": leaves["b"]})))
+    # regulariser: any GP whose predictive is fixed - a prior-mode exact GP over ARD gives (m_p, v_p) through CustomMean
+    pmean = S.CustomMean(mean_function=lambda p, xx: p[: xx.shape[0]])
+
+    class FixedPredictive:  # the smallest GPBase stand-in: calculate_prior returns the fixed (m_p, v_p)
+        def calculate_prior(self, parameters, x, full_covariance):
+            return dev(m_p), dev(v_p)
+
+        def _to_parameters(self, parameters):
+            return parameters
+
+    reg_term = S.projected.ProjectedKLRegularisation(gp=approx, regulariser=FixedPredictive(),
+                                                     regulariser_parameters=None, mode="prior")
+    gvi = S.GeneralisedVariationalInference(regularisation=reg_term,
+                                            empirical_risk=S.NegativeLogLikelihood(gp=approx))
+    loss = gvi.calculate_loss(ap, dev(x), dev(y))
+    loss.backward()
+
+    t = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True)
+         for k, v in dict(w=w, b=b, ls=ls, lc=lc, mq=m_q).items()}
+    xt, zt, yt = torch.tensor(x), torch.tensor(z), torch.tensor(y)
+    phi = lambda a: torch.tanh(a @ t["w"] + t["b"])
+    kern = lambda a, c: torch.exp(t["ls"]) * (phi(a) @ phi(c).T) + torch.exp(t["lc"])
+    k_zz = kern(zt, zt)
+    a_mat = k_zz + reg * torch.trace(k_zz) / m * torch.eye(m, dtype=torch.float64)
+    k_xz = kern(xt, zt)
+    k_diag = torch.exp(t["ls"]) * (phi(xt) ** 2).sum(-1) + torch.exp(t["lc"])
+    v_q = k_diag - (k_xz * torch.cholesky_solve(k_xz.T, torch.linalg.cholesky(a_mat)).T).sum(-1)
+    ref = T.gaussian_nll(yt, t["mq"], v_q) + T.regulariser("kl", torch.tensor(m_p), torch.tensor(v_p), t["mq"],
+                                                           v_q).mean()
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-9 * abs(float(ref.detach()))
+    for k in ("w", "b", "ls", "lc", "mq"):
+        got, want = host(leaves[k].grad).reshape(-1), t[k].grad.numpy().reshape(-1)
+        assert np.max(np.abs(got - want)) <= 1e-8 * max(np.max(np.abs(want)), 1e-3), k
+
+
+def test_exact_gp_nll_gradients_over_feature_map_kernel_match_autograd_twin(S):
+    """train_regulariser_gp's objective (exact-GP NLL on the inducing data) over the feature-map kernel: gradients w.r.t.
+    the network weights, the polynomial kernel's scalars, log_observation_noise and the constant mean."""
+    from oracle import torch_twin as T
+
+    m, d, f = 120, 4, 10
+    _, z, _, yz, w, b, _ = _feature_problem(10, m, d, f, seed=3)
+    vals = dict(w=w, b=b, ls=np.array(-0.3), lc=np.array(0.1), noise=np.array(-1.2), const=np.array(0.2))
+    leaves = {k: dev(v).requires_grad_(True) for k, v in vals.items()}
+    base = S.PolynomialKernel(polynomial_degree=2)
+    kernel = S.CustomMappingKernel(base_kernel=base,
+                                   feature_mapping=lambda p, xx: torch.tanh(xx @ p["w"] + p["b"]))
+    const = S.ConstantMean()
+    gp = S.GPRegression(mean=const, kernel=kernel, x=z, y=yz)
+    params = gp.Parameters.construct(
+        log_observation_noise=leaves["noise"], mean=const.Parameters.construct(constant=leaves["const"]),
+        kernel=kernel.Parameters.construct(
+            base_kernel=base.Parameters.construct(log_constant=leaves["lc"], log_scaling=leaves["ls"]),
+            feature_mapping={"w": leaves["w"], "b": leaves["b"]}))
+    loss = S.NegativeLogLikelihood(gp=gp).calculate_empirical_risk(params, dev(z), dev(yz))
+    loss.backward()
+
+    t = {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in vals.items()}
+    zt, yzt = torch.tensor(z), torch.tensor(yz)
+    phi = torch.tanh(zt @ t["w"] + t["b"])
+    k_zz = (torch.exp(t["ls"]) * (phi @ phi.T) + torch.exp(t["lc"])) ** 2
+    chol = torch.linalg.cholesky(k_zz + torch.exp(t["noise"]) * torch.eye(m, dtype=torch.float64))
+    mean = k_zz @ torch.cholesky_solve(yzt.reshape(-1, 1), chol).reshape(-1) + t["const"]
+    var = torch.diagonal(k_zz) - (k_zz * torch.cholesky_solve(k_zz, chol)).sum(0)
+    ref = T.gaussian_nll(yzt, mean, var)
+    ref.backward()
+    assert abs(float(loss.detach()) - float(ref.detach())) <= 1e-9 * abs(float(ref.detach()))
+    for k in vals:
+        got, want = host(leaves[k].grad).reshape(-1), t[k].grad.numpy().reshape(-1)
+        assert np.max(np.abs(got - want)) <= 1e-8 * max(np.max(np.abs(want)), 1e-3), k
