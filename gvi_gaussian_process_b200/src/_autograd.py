@@ -243,3 +243,21 @@ class PredictGram(torch.autograd.Function):
         return (None, None, None, None, None, d_kzz if ctx.needs_input_grad[5] else None,
                 d_kxz if ctx.needs_input_grad[6] else None, g if ctx.needs_input_grad[7] else None,
                 h if ctx.has_prior and ctx.needs_input_grad[8] else None, d_noise)
+
+
+class SVGPVarianceGram(torch.autograd.Function):
+    """SVGPVariance for a regulariser kernel other than ARD: the variance comes from the tile kernel over a supplied
+    K_xz chunk (state with E attached), dLoss/dSigma = K_xz^T diag(g) K_xz is one library GEMM on the same chunk."""
+
+    @staticmethod
+    def forward(ctx, factor, k_xz, k_diag, sigma):
+        n = k_xz.shape[0]
+        var = torch.empty(n, dtype=torch.float64, device=k_xz.device)
+        L.gp_predict_gram(factor, k_xz, k_diag, None, None, None, var)
+        ctx.save_for_backward(k_xz)
+        return var
+
+    @staticmethod
+    def backward(ctx, g_var):
+        (k_xz,) = ctx.saved_tensors
+        return None, None, None, k_xz.T @ (g_var.reshape(-1, 1) * k_xz)

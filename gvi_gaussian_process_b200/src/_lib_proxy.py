@@ -165,15 +165,21 @@ def gp_predict_any_kernel(factor: GpFactor, kernel, kernel_parameters, z, x, pri
 
 
 def gp_predict_any_kernel_grad(factor: GpFactor, kernel, kernel_parameters, z, x, diagonal_regularisation, is_absolute,
-                               prior_mean=None, log_noise=None, y_z=None, want_mean=True):
+                               prior_mean=None, log_noise=None, y_z=None, want_mean=True, prefactored=False):
     """The differentiable variant of gp_predict_any_kernel (hyper-parameters of a non-ARD kernel, feature-map weights,
     observation noise, prior mean): K_zz is built with the autograd graph attached, factorised once by the CUDA
     factorisation, and every chunk goes through _autograd.PredictGram."""
     from ._autograd import PredictGram
 
-    k_zz = kernel.calculate_gram(kernel_parameters, z, z)
-    noise = None if log_noise is None else log_noise.detach().reshape(-1)[:1].contiguous()
-    factor.factor_from_gram(k_zz.detach().contiguous(), diagonal_regularisation, is_absolute, log_noise=noise, y_z=y_z)
+    if prefactored:
+        # the factor state was built from OTHER, frozen kernel parameters (FixedSparsePosteriorKernel): K_zz gets no
+        # gradient, only the cross-Grams of the trainable kernel do
+        k_zz = torch.zeros(factor.m, factor.m, dtype=torch.float64, device=x.device)
+    else:
+        k_zz = kernel.calculate_gram(kernel_parameters, z, z)
+        noise = None if log_noise is None else log_noise.detach().reshape(-1)[:1].contiguous()
+        factor.factor_from_gram(k_zz.detach().contiguous(), diagonal_regularisation, is_absolute, log_noise=noise,
+                                y_z=y_z)
     linv = factor.inverse_cholesky().clone()
     alpha = None if y_z is None else linv.T @ (linv @ y_z)
     n = x.shape[0]

@@ -4,7 +4,7 @@ the regulariser kernel with FIXED parameters (computed once), the cross-Grams fr
 from __future__ import annotations
 
 from ... import _lib_proxy as L
-from ..._autograd import PredictVariance, wants_grad
+from ..._autograd import PredictVariance, tensor_leaves, wants_grad
 from ...utils.device import as_2d
 from ..base import KernelBase, KernelBaseParameters
 from ..standard.ard_kernel import ARDKernel
@@ -20,13 +20,16 @@ class FixedSparsePosteriorKernel(KernelBase):
     def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, base_kernel: KernelBase,
                  inducing_points, diagonal_regularisation: float = 1e-5,
                  is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
-        if not isinstance(base_kernel, ARDKernel) or not isinstance(regulariser_kernel, ARDKernel):
-            raise NotImplementedError("the B200 path implements FixedSparsePosteriorKernel over ARDKernel only")
+        assert isinstance(base_kernel, KernelBase) and isinstance(regulariser_kernel, KernelBase)
+        # both ARD: the fused path (K tiles evaluated in the tile kernel, tensor-pipe gradients).  Otherwise the Grams
+        # come from the kernels' own routines: frozen Cholesky from the regulariser kernel once, cross-Grams per chunk.
+        self._ard = isinstance(base_kernel, ARDKernel) and isinstance(regulariser_kernel, ARDKernel)
         self.regulariser_kernel = regulariser_kernel
         self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
         self.base_kernel = base_kernel
         self.inducing_points = as_2d(inducing_points)
-        self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
+        if self._ard:
+            self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
         self.diagonal_regularisation = diagonal_regularisation
         self.is_diagonal_regularisation_absolute_scale = is_diagonal_regularisation_absolute_scale
         self._factor = None
@@ -39,6 +42,13 @@ class FixedSparsePosteriorKernel(KernelBase):
     def factorise(self, parameters) -> "L.GpFactor":
         parameters = self._to_parameters(parameters)
         z = self.inducing_points
+        if not self._ard:
+            if self._factor is None:  # the regulariser kernel is frozen: one factorisation for the kernel's lifetime
+                k_zz = self.regulariser_kernel.calculate_gram(self.regulariser_kernel_parameters, z, z)
+                self._factor = L.GpFactor(z.shape[0], 1).factor_from_gram(
+                    k_zz.detach().contiguous(), self.diagonal_regularisation,
+                    self.is_diagonal_regularisation_absolute_scale)
+            return self._factor
         if self._factor is None:
             self._factor = L.GpFactor(z.shape[0], z.shape[1])
         ls, ll = ARDKernel.device_parameters(self.base_kernel._to_parameters(parameters.base_kernel))
@@ -48,6 +58,15 @@ class FixedSparsePosteriorKernel(KernelBase):
 
     def _calculate_gram_diagonal(self, parameters, x):
         f = self.factorise(parameters)
+        if not self._ard:
+            if wants_grad(*tensor_leaves(parameters.base_kernel)):
+                _, var = L.gp_predict_any_kernel_grad(
+                    f, self.base_kernel, parameters.base_kernel, self.inducing_points, x, self.diagonal_regularisation,
+                    self.is_diagonal_regularisation_absolute_scale, want_mean=False, prefactored=True)
+                return var
+            _, var = L.gp_predict_any_kernel(f, self.base_kernel, parameters.base_kernel, self.inducing_points, x,
+                                             want_mean=False)
+            return var
         x = x.reshape(x.shape[0], -1)
         base = self.base_kernel._to_parameters(parameters.base_kernel)
         if wants_grad(base.log_scaling, base.log_lengthscales):

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch
 
 from .... import _lib_proxy as L
-from ...._autograd import SVGPVariance, wants_grad
+from ...._autograd import SVGPVariance, SVGPVarianceGram, wants_grad
 from ....utils.device import as_2d, as_device, scalar
 from ...base import KernelBase, KernelBaseParameters
 from ...standard.ard_kernel import ARDKernel
@@ -22,15 +22,18 @@ class SVGPBaseKernel(KernelBase):
     def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, log_observation_noise,
                  inducing_points, training_points, diagonal_regularisation: float = 1e-5,
                  is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
-        if not isinstance(regulariser_kernel, ARDKernel):
-            raise NotImplementedError("the B200 path implements the SVGP kernels over ARDKernel only")
+        assert isinstance(regulariser_kernel, KernelBase)
+        # ARD: K tiles evaluated inside the tile kernel.  Any other regulariser kernel: its own Gram routine supplies
+        # K_ZZ (once) and K(x_chunk, Z); factorisation, both triangular products and the norms stay in the CUDA kernels.
+        self._ard = isinstance(regulariser_kernel, ARDKernel)
         self.regulariser_kernel = regulariser_kernel
         self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
         self.log_observation_noise = log_observation_noise
         self.inducing_points = as_2d(inducing_points)
-        self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
         self.training_points = as_2d(training_points)
-        self.training_points = self.training_points.reshape(self.training_points.shape[0], -1)
+        if self._ard:
+            self.inducing_points = self.inducing_points.reshape(self.inducing_points.shape[0], -1)
+            self.training_points = self.training_points.reshape(self.training_points.shape[0], -1)
         self.number_of_dimensions = self.inducing_points.shape[1]
         self.diagonal_regularisation = diagonal_regularisation
         self.is_diagonal_regularisation_absolute_scale = is_diagonal_regularisation_absolute_scale
@@ -41,10 +44,34 @@ class SVGPBaseKernel(KernelBase):
     def _frozen_factor(self) -> "L.GpFactor":
         if self._factor is None:
             z = self.inducing_points
+            if not self._ard:
+                k_zz = self.regulariser_kernel.calculate_gram(self.regulariser_kernel_parameters, z, z)
+                self._factor = L.GpFactor(z.shape[0], 1).factor_from_gram(
+                    k_zz.detach().contiguous(), self.diagonal_regularisation,
+                    self.is_diagonal_regularisation_absolute_scale)
+                return self._factor
             ls, ll = ARDKernel.device_parameters(self.regulariser_kernel_parameters)
             self._factor = L.GpFactor(z.shape[0], z.shape[1]).factor(
                 z, ls, ll, self.diagonal_regularisation, self.is_diagonal_regularisation_absolute_scale)
         return self._factor
+
+    def _variance_over_supplied_grams(self, f, x, sigma=None):
+        """Non-ARD regulariser kernel: K(x_chunk, Z) and k(x, x) from the kernel, the tile kernel does the rest; with
+        `sigma` (requires grad) every chunk goes through SVGPVarianceGram."""
+        k, kp, z = self.regulariser_kernel, self.regulariser_kernel_parameters, self.inducing_points
+        rows = max(24, L.GRAM_CHUNK_BYTES // (8 * f.m) // 24 * 24)
+        out = []
+        for r0 in range(0, x.shape[0], rows):
+            xc = x[r0:r0 + rows]
+            k_xz = k.calculate_gram(kp, xc, z).detach().contiguous()
+            k_diag = k.calculate_gram(kp, xc, xc, full_covariance=False).detach().reshape(-1).contiguous()
+            if sigma is not None:
+                out.append(SVGPVarianceGram.apply(f, k_xz, k_diag, sigma))
+            else:
+                var = torch.empty(xc.shape[0], dtype=torch.float64, device=x.device)
+                L.gp_predict_gram(f, k_xz, k_diag, None, None, None, var)
+                out.append(var)
+        return torch.cat(out)
 
     def _initial_inverse_cholesky(self) -> torch.Tensor:
         """inv(chol(K_ZZ + exp(-log_noise) K_ZX K_XZ)) - initialisation only, M^3 once (library linear algebra)."""
@@ -72,6 +99,9 @@ class SVGPBaseKernel(KernelBase):
 
     def _calculate_gram_diagonal(self, parameters, x):
         f = self.factorise(parameters)
+        if not self._ard:
+            sigma = self._sigma_matrix(parameters) if wants_grad(*self.grad_leaves(parameters)) else None
+            return self._variance_over_supplied_grams(f, x, sigma)
         x = x.reshape(x.shape[0], -1)
         if wants_grad(*self.grad_leaves(parameters)):
             # general (non-fused) objectives, e.g. classification: dLoss/dSigma from the weighted-Gram kernel, the
@@ -227,12 +257,16 @@ class KernelisedSVGPKernel(SVGPBaseKernel):
     def _calculate_gram_diagonal(self, parameters, x):
         f = self._frozen_factor()
         f.set_extra(None)
-        _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
+        if not self._ard:
+            var = self._variance_over_supplied_grams(f, x)
+        else:
+            _, var = L.gp_predict(f, x.reshape(x.shape[0], -1), want_mean=False)
         return var + self.base_kernel.calculate_gram(parameters.base_kernel, x, x, full_covariance=False)
 
     def grad_leaves(self, parameters):
-        base = self.base_kernel._to_parameters(parameters.base_kernel)
-        return [base.log_scaling, base.log_lengthscales]
+        from ...._autograd import tensor_leaves
+
+        return list(tensor_leaves(self.base_kernel._to_parameters(parameters.base_kernel)))
 
     def _calculate_gram(self, parameters, x1, x2):
         f = self._frozen_factor()

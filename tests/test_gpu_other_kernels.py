@@ -503,3 +503,72 @@ def test_exact_gp_nll_gradients_over_feature_map_kernel_match_autograd_twin(S):
     for k in vals:
         got, want = host(leaves[k].grad).reshape(-1), t[k].grad.numpy().reshape(-1)
         assert np.max(np.abs(got - want)) <= 1e-8 * max(np.max(np.abs(want)), 1e-3), k
+
+
+def test_fixed_sparse_and_svgp_kernels_over_polynomial_kernels(S):
+    """FixedSparsePosteriorKernel and the SVGP family over a NON-ARD regulariser kernel (the reference pairs every
+    approximate kernel with every regulariser kernel, experiments/regression/base_configs): values against the oracle,
+    gradients (base-kernel scalars; el-matrix parameters) against torch CPU autograd twins."""
+    from gvi_gaussian_process_b200.src.kernels.approximate import CholeskySVGPKernel, FixedSparsePosteriorKernel
+
+    rng = np.random.default_rng(12)
+    n, m, d, reg = 900, 20, 3, 0.05
+    x, z = rng.standard_normal((n, d)) / np.sqrt(d), rng.standard_normal((m, d)) / np.sqrt(d)
+    x_train = rng.standard_normal((60, d)) / np.sqrt(d)
+    lc_r, ls_r, lc_b, ls_b = 0.1, -0.2, -0.3, 0.25
+    reg_gram = lambda a, b: O.polynomial_gram(lc_r, ls_r, 2, a, b)
+    base_gram = lambda a, b: O.polynomial_gram(lc_b, ls_b, 2, a, b)
+    poly = S.PolynomialKernel(polynomial_degree=2)
+    reg_params = poly.Parameters.construct(log_constant=lc_r, log_scaling=ls_r)
+    g_w = rng.standard_normal(n)  # a fixed linear functional of the variances: loss = <g_w, var>
+
+    # ---- FixedSparsePosteriorKernel: frozen Cholesky from the regulariser kernel, cross-Grams from the base kernel
+    leaves = {k: dev(np.array(v)).requires_grad_(True) for k, v in dict(lc=lc_b, ls=ls_b).items()}
+    fixed = FixedSparsePosteriorKernel(regulariser_kernel=poly, regulariser_kernel_parameters=reg_params,
+                                       base_kernel=poly, inducing_points=z, diagonal_regularisation=reg,
+                                       is_diagonal_regularisation_absolute_scale=True)
+    fp = fixed.Parameters.construct(base_kernel=poly.Parameters.construct(log_constant=leaves["lc"],
+                                                                          log_scaling=leaves["ls"]))
+    var = fixed.calculate_gram(fp, x, full_covariance=False)
+    ref = np.diag(O.fixed_sparse_posterior_gram(base_gram, reg_gram, z, x, None, reg, True))
+    assert np.max(np.abs(host(var) - ref)) <= TOL * np.max(np.abs(np.diag(base_gram(x, x))))
+    (dev(g_w) * var).sum().backward()
+    t = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in dict(lc=lc_b, ls=ls_b).items()}
+    xt, zt = torch.tensor(x), torch.tensor(z)
+    kb = lambda a, b: (torch.exp(t["ls"]) * (a @ b.T) + torch.exp(t["lc"])) ** 2
+    a_inv = torch.tensor(np.linalg.inv(reg_gram(z, z) + reg * np.eye(m)))
+    k_xz = kb(xt, zt)
+    var_t = torch.diagonal(kb(xt, xt)) - ((k_xz @ a_inv) * k_xz).sum(-1)
+    (torch.tensor(g_w) * var_t).sum().backward()
+    for k in ("lc", "ls"):
+        assert abs(float(leaves[k].grad) - float(t[k].grad)) <= 1e-8 * max(abs(float(t[k].grad)), 1e-3), k
+
+    # ---- CholeskySVGPKernel over the polynomial regulariser kernel: second triangular product on the supplied K tile
+    svgp = CholeskySVGPKernel(regulariser_kernel=poly, regulariser_kernel_parameters=reg_params,
+                              log_observation_noise=np.log(0.5), inducing_points=z, training_points=x_train,
+                              diagonal_regularisation=reg, is_diagonal_regularisation_absolute_scale=True)
+    lower = np.tril(0.1 * rng.standard_normal((m, m)), k=-1)
+    log_diag = -1.0 + 0.1 * rng.standard_normal(m)
+    el = {"lower": dev(lower).requires_grad_(True), "log_diag": dev(log_diag).requires_grad_(True)}
+    sp = svgp.Parameters.construct(el_matrix_lower_triangle=el["lower"], el_matrix_log_diagonal=el["log_diag"])
+    var = svgp.calculate_gram(sp, x, full_covariance=False)
+    sigma = O.cholesky_sigma(lower, log_diag)
+    ref = np.diag(O.svgp_gram(reg_gram, z, sigma, x, None, reg, True))
+    assert np.max(np.abs(host(var) - ref)) <= TOL * np.max(np.abs(ref))
+    (dev(g_w) * var).sum().backward()
+    lt = torch.tensor(lower, requires_grad=True)
+    dt = torch.tensor(log_diag, requires_grad=True)
+    e_t = torch.tril(lt, diagonal=-1) + torch.diag(torch.exp(dt))
+    k_xz_r = torch.tensor(reg_gram(x, z))
+    var_s = ((k_xz_r @ (e_t.T @ e_t)) * k_xz_r).sum(-1)  # the only part that depends on the el-matrix parameters
+    (torch.tensor(g_w) * var_s).sum().backward()
+    assert np.max(np.abs(host(el["lower"].grad) - lt.grad.numpy())) <= 1e-8 * np.max(np.abs(lt.grad.numpy()))
+    assert np.max(np.abs(host(el["log_diag"].grad) - dt.grad.numpy())) <= 1e-8 * np.max(np.abs(dt.grad.numpy()))
+    # generate_parameters() without arguments: the reference's initialisation (svgp/base.py:57-73) over this kernel.  It has
+    # no jitter, so the inducing set must not exceed the kernel's rank (10 monomials of degree <= 2 in 3-D): 6 points
+    small = CholeskySVGPKernel(regulariser_kernel=poly, regulariser_kernel_parameters=reg_params,
+                               log_observation_noise=np.log(0.5), inducing_points=z[:6], training_points=x_train,
+                               diagonal_regularisation=reg, is_diagonal_regularisation_absolute_scale=True)
+    init = small.generate_parameters()
+    inv_chol = O.svgp_initial_inverse_cholesky(reg_gram, z[:6], x_train, np.log(0.5))
+    assert rel_norm(host(init.el_matrix_lower_triangle), np.tril(inv_chol, k=-1)) <= 1e-8
