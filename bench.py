@@ -391,6 +391,8 @@ def run_gpu(args):
                                       "ms_per_step": grad_ms, "steps": grad_steps, "grad_norm": grad_norm,
                                       "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D)
                                       + 2.0 * M * M + 2.0 * M * D,
+                                      "roofline_frac": (algorithmic_flops_per_point(M, D) + 2.0 * M * M + 2.0 * M * D)
+                                      * N_PER_GPU / (grad_ms * 1e-3) / (FP64_PEAK_TFLOPS * 1e12),
                                       "note": "value and gradient w.r.t. log_scaling, log_lengthscales[D] and the "
                                               "tanh-FCN mean parameters (autograd through the mean on the host "
                                               "framework), factorisations included"},
