@@ -10,6 +10,18 @@
 
 namespace {
 constexpr int STHREADS = 256;
+constexpr int64_t FUSED_FINALIZE_MAX_POINTS = 500000;  // single-shard selector: one launch per pivot up to this N
+
+// optional tail of select_update_kernel: the LAST CTA to finish reduces the per-block candidates, gathers the record of the
+// next pivot and (single shard) makes it the next winner - one launch per pivot instead of three
+struct FusedFinalize {
+  unsigned int* ticket;  // null = not fused (select_finalize_kernel / select_resolve_kernel follow)
+  int M_sel;
+  double* record;
+  double* trace_out;     // tr(K - Q) after this step, or null
+  double* winner_next;   // where the next step reads its winner (single shard), or null
+  int64_t* idx_out_next; // pivot position of the next step, or null
+};
 
 struct SelectWs {
   double* d;
@@ -19,6 +31,7 @@ struct SelectWs {
   double* blocktrace;  // [nblk]
   double* record;
   double* winner;
+  unsigned int* ticket;  // "last CTA done" counter of the fused update (zero between launches)
   int64_t nblk;
 };
 
@@ -37,6 +50,7 @@ __host__ SelectWs carve(void* ws, int64_t N, int M_sel, int D) {
   s.blocktrace = (double*)p;   p += align16((size_t)s.nblk * 8);
   s.record = (double*)p;       p += align16((size_t)rl * 8);
   s.winner = (double*)p;       p += align16((size_t)rl * 8);
+  s.ticket = (unsigned int*)p; p += 16;
   return s;
 }
 
@@ -66,7 +80,8 @@ __global__ void __launch_bounds__(STHREADS) select_init_kernel(int64_t N, int64_
                                                                const double* __restrict__ kdiag, double jitter,
                                                                double* __restrict__ d, unsigned char* __restrict__ chosen,
                                                                double* __restrict__ blockcand,
-                                                               double* __restrict__ blocktrace) {
+                                                               double* __restrict__ blocktrace,
+                                                               unsigned int* __restrict__ ticket) {
   __shared__ double sv[STHREADS / 32], si[STHREADS / 32];
   const int64_t i = (int64_t)blockIdx.x * STHREADS + threadIdx.x;
   const double amp = kdiag ? 0.0 : exp(log_scaling[0]);
@@ -83,6 +98,7 @@ __global__ void __launch_bounds__(STHREADS) select_init_kernel(int64_t N, int64_
     blockcand[2 * blockIdx.x] = v;
     blockcand[2 * blockIdx.x + 1] = idx;
     blocktrace[blockIdx.x] = 0.0;
+    if (blockIdx.x == 0 && ticket) *ticket = 0u;
   }
 }
 
@@ -92,7 +108,8 @@ __global__ void __launch_bounds__(STHREADS) select_update_kernel(
     const double* __restrict__ X, int64_t N, int64_t offset, int D, int m, const double* __restrict__ winner,
     const double* __restrict__ log_scaling, const double* __restrict__ log_ls, int ls_len,
     const double* __restrict__ kcol, double jitter, double* __restrict__ d, double* C,
-    unsigned char* __restrict__ chosen, double* __restrict__ blockcand, double* __restrict__ blocktrace) {
+    unsigned char* __restrict__ chosen, double* __restrict__ blockcand, double* __restrict__ blocktrace,
+    const FusedFinalize fin) {
   extern __shared__ double sm[];
   double* cj = sm;          // [m]
   double* xj = sm + m;      // [D]
@@ -160,6 +177,67 @@ __global__ void __launch_bounds__(STHREADS) select_update_kernel(
     blocktrace[blockIdx.x] = t;
     blockcand[2 * blockIdx.x] = v;
     blockcand[2 * blockIdx.x + 1] = idx;
+  }
+  if (!fin.ticket) return;
+  // ---- fused finalize: every thread publishes its C / d writes, the CTA takes a ticket, the last one carries on --------
+  __shared__ bool is_last;
+  __shared__ double win_v, win_i;
+  __syncthreads();  // the CTA's C / d / candidate writes happen-before thread 0's fence (cumulative at device scope)
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(fin.ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+    if (is_last) *fin.ticket = 0u;  // ready for the next launch
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int64_t nblk = gridDim.x;
+  v = -1.0;
+  idx = -1.0;
+  tr = 0.0;
+  for (int64_t b = tid; b < nblk; b += STHREADS) {
+    const double bv = __ldcg(blockcand + 2 * b), bi = __ldcg(blockcand + 2 * b + 1);
+    if (better(bv, bi, v, idx, true)) { v = bv; idx = bi; }
+    tr += __ldcg(blocktrace + b);
+  }
+  tr = warp_sum(tr);
+  if ((tid & 31) == 0) st[tid >> 5] = tr;
+  block_argmax(v, idx, /*prefer_high=*/true, sv, si);  // contains a __syncthreads
+  if (tid == 0) {
+    win_v = v;
+    win_i = idx;
+    double t = 0.0;
+    for (int q = 0; q < STHREADS / 32; q++) t += st[q];
+    if (fin.trace_out) *fin.trace_out = t;
+    if (fin.idx_out_next) *fin.idx_out_next = (int64_t)idx;
+  }
+  __syncthreads();
+  const double wv = win_v, wi = win_i;
+  const int rl = 2 + D + (fin.M_sel - 1);
+  double* dst2 = fin.winner_next;
+  if (tid == 0) {
+    fin.record[0] = wv;
+    fin.record[1] = wi;
+    if (dst2) { dst2[0] = wv; dst2[1] = wi; }
+  }
+  if (wi < 0.0) {  // no eligible local point
+    for (int k = 2 + tid; k < rl; k += STHREADS) {
+      fin.record[k] = 0.0;
+      if (dst2) dst2[k] = 0.0;
+    }
+    return;
+  }
+  const int64_t il = (int64_t)wi - offset;
+  for (int k = tid; k < D; k += STHREADS) {
+    const double xv = X[il * D + k];
+    fin.record[2 + k] = xv;
+    if (dst2) dst2[2 + k] = xv;
+  }
+  for (int k = tid; k < fin.M_sel - 1; k += STHREADS) {
+    const double cv = (k <= m) ? __ldcg(C + (int64_t)k * N + il) : 0.0;
+    fin.record[2 + D + k] = cv;
+    if (dst2) dst2[2 + D + k] = cv;
   }
 }
 
@@ -229,7 +307,7 @@ extern "C" size_t gvi_select_workspace_bytes(int64_t N, int M_sel, int D) {
   int64_t nblk = (N + STHREADS - 1) / STHREADS;
   int64_t rl = 2 + D + (M_sel - 1);
   return align16((size_t)N * 8) + align16((size_t)N * (size_t)(M_sel - 1) * 8) + align16((size_t)N) +
-         align16((size_t)nblk * 16) + align16((size_t)nblk * 8) + 2 * align16((size_t)rl * 8) + 64;
+         align16((size_t)nblk * 16) + align16((size_t)nblk * 8) + 2 * align16((size_t)rl * 8) + 16 + 64;
 }
 
 static int select_init_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
@@ -241,7 +319,7 @@ static int select_init_impl(const double* x_local, int64_t N_local, int64_t offs
   cudaStream_t st = (cudaStream_t)stream;
   SelectWs s = carve(workspace, N_local, M_sel, D);
   select_init_kernel<<<(unsigned)s.nblk, STHREADS, 0, st>>>(N_local, offset, log_scaling, kdiag, jitter, s.d, s.chosen,
-                                                            s.blockcand, s.blocktrace);
+                                                            s.blockcand, s.blocktrace, s.ticket);
   GVI_CHECK_LAUNCH("select_init_kernel");
   select_finalize_kernel<<<1, 1024, 0, st>>>(x_local, N_local, offset, D, M_sel, 0, /*prefer_high=*/0, s.blockcand,
                                              s.blocktrace, s.nblk, s.C, record_out, nullptr, nullptr);
@@ -276,7 +354,8 @@ extern "C" int gvi_select_resolve_f64(const double* records, int R, int D, int M
 static int select_update_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
                               const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
                               const double* kcol, double jitter, double* record_out, double* trace_partial_out,
-                              void* workspace, void* stream);
+                              void* workspace, void* stream, int64_t* fused_idx_out_next = nullptr,
+                              double* fused_winner_next = nullptr, bool fused = false);
 
 extern "C" int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
                                      const double* winner, const double* log_scaling, const double* log_ls,
@@ -300,7 +379,8 @@ extern "C" int gvi_select_update_gram_f64(const double* x_local, int64_t N_local
 static int select_update_impl(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel, int m,
                               const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
                               const double* kcol, double jitter, double* record_out, double* trace_partial_out,
-                              void* workspace, void* stream) {
+                              void* workspace, void* stream, int64_t* fused_idx_out_next, double* fused_winner_next,
+                              bool fused) {
   GVI_CHECK_ARG(N_local >= 1 && D >= 1 && M_sel > 1 && m >= 0 && m < M_sel - 1, "sizes");
   GVI_CHECK_ARG(x_local && winner && record_out && workspace, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -313,10 +393,13 @@ static int select_update_impl(const double* x_local, int64_t N_local, int64_t of
       configured = true;
     }
   }
+  FusedFinalize fin{};
+  if (fused) fin = FusedFinalize{s.ticket, M_sel, record_out, trace_partial_out, fused_winner_next, fused_idx_out_next};
   select_update_kernel<<<(unsigned)s.nblk, STHREADS, smem, st>>>(x_local, N_local, offset, D, m, winner, log_scaling,
                                                                  log_ls, ls_len, kcol, jitter, s.d, s.C, s.chosen,
-                                                                 s.blockcand, s.blocktrace);
+                                                                 s.blockcand, s.blocktrace, fin);
   GVI_CHECK_LAUNCH("select_update_kernel");
+  if (fused) return GVI_OK;  // the last CTA of the launch did the reduction, the record and (single shard) the winner
   select_finalize_kernel<<<1, 1024, 0, st>>>(x_local, N_local, offset, D, M_sel, m + 1, /*prefer_high=*/1,
                                              s.blockcand, s.blocktrace, s.nblk, s.C, record_out, trace_partial_out,
                                              nullptr);
@@ -330,16 +413,31 @@ extern "C" int gvi_cond_var_select_f64(const double* x_perm, int64_t N, int D, i
   GVI_CHECK_ARG(M_sel > 1, "Must have at least 2 inducing points");
   GVI_CHECK_ARG(N >= 1 && D >= 1, "sizes");
   GVI_CHECK_ARG(x_perm && log_scaling && log_ls && idx_out && workspace, "null pointer");
-  cudaStream_t st = (cudaStream_t)stream;
+  GVI_CHECK_ARG(ls_len == 1 || ls_len == D, "log_lengthscales must have 1 or D entries");
   SelectWs s = carve(workspace, N, M_sel, D);
   int rc = gvi_select_init_f64(x_perm, N, 0, D, M_sel, log_scaling, jitter, s.record, workspace, stream);
   if (rc) return rc;
+  // single shard: the local record is the winner.
+  if (N > FUSED_FINALIZE_MAX_POINTS) {
+    // large N: three launches per pivot (update, finalize, resolve).  The fused tail below costs every CTA a fence and a
+    // ticket round trip (~2 us of its lifetime, ~2 % of the step at N = 1e6: 175.7 vs 172.5 ms for M = 512), more than the
+    // two small launches it saves once a step runs for several waves of CTAs.
+    for (int m = 0; m < M_sel - 1; m++) {
+      if ((rc = gvi_select_resolve_f64(s.record, 1, D, M_sel, m == 0, s.winner, idx_out + m, stream))) return rc;
+      if ((rc = gvi_select_update_f64(x_perm, N, 0, D, M_sel, m, s.winner, log_scaling, log_ls, ls_len, jitter,
+                                      s.record, trace_out ? trace_out + m : nullptr, workspace, stream)))
+        return rc;
+    }
+    return gvi_select_resolve_f64(s.record, 1, D, M_sel, 0, s.winner, idx_out + (M_sel - 1), stream);
+  }
+  // small N (the step is latency bound: N = 1e5, M = 512 went 25.2 -> 22.5 ms): ONE launch per pivot - the last CTA of
+  // update m reduces the per-block candidates, gathers the record of pivot m+1, copies it to `winner`, writes idx_out[m+1].
+  if ((rc = gvi_select_resolve_f64(s.record, 1, D, M_sel, 1, s.winner, idx_out, stream))) return rc;
   for (int m = 0; m < M_sel - 1; m++) {
-    // single shard: the local record is the winner
-    if ((rc = gvi_select_resolve_f64(s.record, 1, D, M_sel, m == 0, s.winner, idx_out + m, stream))) return rc;
-    if ((rc = gvi_select_update_f64(x_perm, N, 0, D, M_sel, m, s.winner, log_scaling, log_ls, ls_len, jitter,
-                                    s.record, trace_out ? trace_out + m : nullptr, workspace, stream)))
+    if ((rc = select_update_impl(x_perm, N, 0, D, M_sel, m, s.winner, log_scaling, log_ls, ls_len, nullptr, jitter,
+                                 s.record, trace_out ? trace_out + m : nullptr, workspace, stream, idx_out + m + 1,
+                                 s.winner, true)))
       return rc;
   }
-  return gvi_select_resolve_f64(s.record, 1, D, M_sel, 0, s.winner, idx_out + (M_sel - 1), st);
+  return GVI_OK;
 }
