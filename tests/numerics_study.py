@@ -1,3 +1,4 @@
+"""Numerics study of the inverse-factor formulation (CPU only, test infrastructure: uses the oracle). Not collected by pytest; run: python tests/numerics_study.py"""
 import numpy as np, sys, scipy.linalg as sl
 sys.path.insert(0,'.')
 from oracle import gp_oracle as O
