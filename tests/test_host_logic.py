@@ -22,6 +22,16 @@ def test_prng_matches_reference_pins():
     assert list(jax_prng.choice(key, 3, 2)) == [0, 2]
 
 
+def test_prng_threefry_known_answers():
+    # Random123 / jax tests/random_test.py::testThreefry2x32 vectors and the documented split(PRNGKey(0))
+    f = jax_prng._threefry2x32
+    u = lambda *v: np.array(v, dtype=np.uint32)
+    assert [int(v) for v in f(u(0, 0), u(0, 0))] == [0x6B200159, 0x99BA4EFE]
+    assert [int(v) for v in f(u(0xFFFFFFFF, 0xFFFFFFFF), u(0xFFFFFFFF, 0xFFFFFFFF))] == [0x1CB996FC, 0xBB002BE7]
+    assert [int(v) for v in f(u(0x13198A2E, 0x03707344), u(0x243F6A88, 0x85A308D3))] == [0xC4923A9C, 0x483DF7A0]
+    assert jax_prng.split(jax_prng.PRNGKey(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+
+
 @pytest.mark.parametrize("seed,n", [(0, 1), (1, 2), (7, 1625), (7, 1626), (123456789012, 5000)])
 def test_prng_product_and_oracle_agree(seed, n):
     k1, k2 = jax_prng.PRNGKey(seed), oracle_prng.prng_key(seed)

@@ -138,6 +138,19 @@ def test_prng_pins():
     assert list(P.choice_with_replacement(key, 3, 2)) == [0, 2]
 
 
+def test_threefry_known_answers():
+    """Third-party pins of the hash itself (jax 0.4.13 is not under /root/reference): the three known-answer vectors of
+    the Threefry-2x32 (20 rounds) reference implementation (Random123 test_threefry.cpp), which jax's own
+    tests/random_test.py::testThreefry2x32 asserts, and the documented output of split(PRNGKey(0))."""
+    kat = [((0x0, 0x0), (0x0, 0x0), (0x6B200159, 0x99BA4EFE)),
+           ((0xFFFFFFFF, 0xFFFFFFFF), (0xFFFFFFFF, 0xFFFFFFFF), (0x1CB996FC, 0xBB002BE7)),
+           ((0x13198A2E, 0x03707344), (0x243F6A88, 0x85A308D3), (0xC4923A9C, 0x483DF7A0))]
+    for key, count, want in kat:
+        got = P.threefry_2x32(np.array(key, dtype=np.uint32), np.array(count, dtype=np.uint32))
+        assert tuple(int(v) for v in got) == want
+    assert P.split(P.prng_key(0)).tolist() == [[4146024105, 967050713], [2718843009, 1272950319]]
+
+
 @pytest.mark.parametrize("use_argsort", [True, False])
 def test_selector_goldens(use_argsort):
     # tests/test_inducing_points_selection.py:116-182: PRNGKey(0), all-ones Gram, M=2 -> indices [2, 1]
