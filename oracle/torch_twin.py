@@ -1,8 +1,9 @@
 """torch-float64 autograd twin of gp_oracle (TEST INFRASTRUCTURE): the same reference arithmetic written with
 differentiable torch CPU ops, so that d(loss)/d{log_scaling, log_lengthscales, m_q} - which the reference obtains
 with jax.grad of GeneralisedVariationalInference.calculate_loss (experiments/shared/trainer.py:83-89) - can be
-checked.  Pinned indirectly: its forward value must equal gp_oracle's (tests/test_oracle_goldens.py checks this),
-and gp_oracle is pinned to the reference's goldens.  Gradients themselves are unpinned in the reference (no test).
+checked.  Pinned indirectly: its forward values equal gp_oracle's and its gradients equal central finite differences
+of gp_oracle's loss (tests/test_twin_consistency.py, CPU), and gp_oracle is pinned to the reference's goldens.
+Gradients themselves are unpinned in the reference (no test).
 """
 from __future__ import annotations
 
