@@ -177,6 +177,26 @@ def test_selector_argsort_and_maxrule_agree_on_real_kernel():
     assert np.array_equal(a, b) and len(set(a.tolist())) == 12
 
 
+def test_selector_equals_the_dense_definition_of_greedy_conditional_variance():
+    """Independent statement of what the pivoted-Cholesky recursion computes (no reference test pins the selector on a
+    non-degenerate kernel): pivot m+1 maximises k(x,x) - k(x,S) K_SS^-1 k(S,x) over the points not in S = pivots[:m+1]."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((200, 2))
+    g = lambda a, b: O.ard_gram(0.0, [0.5, 0.1], a, b)
+    d = lambda a: O.ard_gram_diag(0.0, [0.5, 0.1], a)
+    piv = O.conditional_variance_select(x, 10, g, d)
+    k = g(x, x)
+    s = [int(np.argmax(np.diag(k)))]
+    for _ in range(9):
+        ks = k[:, s]
+        cond = np.diag(k) - np.einsum("ij,ji->i", ks, np.linalg.solve(k[np.ix_(s, s)], ks.T))
+        cond[s] = -np.inf
+        order = np.argsort(cond)
+        assert cond[order[-1]] - cond[order[-2]] > 1e-9  # the choice is decided far above rounding
+        s.append(int(order[-1]))
+    assert piv.tolist() == s
+
+
 def test_svgp_goldens():
     # tests/kernels/test_svgp_kernels.py:20-160 (initial parameters) and :202-300 (Grams), identity mock kernel
     x_train = np.array([[1.0, 2.0, 3.0], [5.0, 1.0, 9.0], [1.5, 2.5, 3.5]])
