@@ -3,7 +3,8 @@
 // registered as JAX FFI custom calls".
 //
 // STATUS: written against the public xla/ffi/api/ffi.h of jaxlib >= 0.4.31; NOT compiled or run in this repository's
-// image (no jax / jaxlib, hence no XLA headers here).  gvi_gaussian_process_b200/build.py:build_ffi() compiles it into
+// image (no jax / jaxlib, hence no XLA headers here).  tests/test_abi.py type-checks it against tests/xla_ffi_stub (a stand-in for
+// the part of that header used here): forwarded calls vs include/gvigp.h, handler signatures vs their bindings.  gvi_gaussian_process_b200/build.py:build_ffi() compiles it into
 // libgvigp_ffi.so when a jaxlib with the header tree is importable, and gvi_gaussian_process_b200/jax_ffi.py registers
 // the handlers and wraps them in the reference's method signatures.  Every handler is a plain forwarding call: buffers
 // arrive as device pointers on XLA's stream, which is exactly what the C ABI takes; workspaces and the factor state are

@@ -2,8 +2,9 @@
 functions a maintainer of the reference drops into its `src/` methods.
 
 STATUS: jax / jaxlib are not installable in this repository's image, so this module has never been executed against JAX;
-what IS tested here (tests/test_abi.py) is that the target table below matches the handler symbols the adapter defines and
-that `register()` fails with a clear message when JAX is absent.  The tested product surface is the C ABI under the
+what IS tested here (tests/test_abi.py) is that the target table below matches the handler symbols the adapter defines,
+that `register()` fails with a clear message when JAX is absent, and - with a recording stand-in for jax - that every wrapper
+passes the operands, results, attribute names / types and buffer sizes the adapter's bindings and the C ABI declare.  The tested product surface is the C ABI under the
 torch / NumPy host code of `gvi_gaussian_process_b200.src`.
 
 Override points in the reference (file:line) and the wrapper that replaces each:

@@ -133,3 +133,134 @@ def test_xla_ffi_adapter_is_consistent_and_gated():
         assert build.xla_ffi_include_dir() is None
         with pytest.raises(RuntimeError, match="cannot be built"):
             build.build_ffi()
+
+
+def test_xla_ffi_adapter_type_checks_against_the_c_abi_and_its_bindings(tmp_path):
+    """jaxlib's headers are absent, so the adapter is compiled (syntax / type check only) against tests/xla_ffi_stub - a
+    stub of the public xla/ffi/api/ffi.h surface the adapter uses, whose binding builder accumulates the handler's
+    parameter list.  This verifies every forwarded call against include/gvigp.h and every handler signature against its
+    binding; a deliberately broken copy must be rejected (so the check has teeth)."""
+    import shutil
+    import subprocess
+
+    from gvi_gaussian_process_b200 import build
+
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the image"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stub = os.path.join(root, "tests", "xla_ffi_stub")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = [gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", stub, "-I", cuda_inc]
+    ok = subprocess.run(cmd + [build.FFI_SOURCE], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr
+    src = open(build.FFI_SOURCE).read().replace("../../../include/gvigp.h", os.path.join(root, "include", "gvigp.h"))
+    swapped = src.replace('.Attr<int64_t>("m_sel").Attr<double>("jitter")', '.Attr<double>("jitter").Attr<int64_t>("m_sel")')
+    assert swapped != src
+    bad = tmp_path / "swapped_attrs.cc"
+    bad.write_text(swapped)
+    res = subprocess.run(cmd + [str(bad)], capture_output=True, text=True)
+    assert res.returncode != 0 and "does not match its binding" in res.stderr
+    dropped = src.replace("(int)m_sel,", "", 1)  # one argument fewer than gvi_cond_var_select_f64 takes
+    assert dropped != src
+    bad = tmp_path / "dropped_argument.cc"
+    bad.write_text(dropped)
+    res = subprocess.run(cmd + [str(bad)], capture_output=True, text=True)
+    assert res.returncode != 0 and "gvi_cond_var_select_f64" in res.stderr
+
+
+def _ffi_bindings():
+    """target symbol -> (n_args, n_rets, [(attr type, attr name), ...]) parsed from the adapter's binding chains."""
+    from gvi_gaussian_process_b200 import build
+
+    src = open(build.FFI_SOURCE).read()
+    out = {}
+    for sym, chain in re.findall(r"XLA_FFI_DEFINE_HANDLER_SYMBOL\((gvi_[a-z0-9_]+),\s*\w+,\s*(.*?)\);", src, flags=re.S):
+        out[sym] = (len(re.findall(r"\.Arg<", chain)), len(re.findall(r"\.Ret<", chain)),
+                    re.findall(r'\.Attr<(\w+)>\("(\w+)"\)', chain))
+    return out
+
+
+def test_jax_wrappers_match_the_adapter_bindings(monkeypatch):
+    """jax is absent, so the wrappers of jax_ffi.py run against a recording stand-in for jax / jax.numpy / jax.ffi:
+    every ffi_call must pass as many operands and results as the C++ binding declares, with the binding's attribute
+    names, and attribute values of the Python types XLA decodes as the declared C++ types (float -> double,
+    int -> int64_t, bool -> bool).  Result buffers must have the sizes the C ABI's *_bytes queries ask for."""
+    import sys
+    import types
+
+    import numpy as np
+
+    from gvi_gaussian_process_b200 import _lib, jax_ffi
+
+    calls = []
+
+    class Spec:
+        def __init__(self, shape, dtype):
+            self.shape, self.dtype = tuple(shape), dtype
+
+    def ffi_call(target, result_specs):
+        def run(*operands, **attrs):
+            specs = result_specs if isinstance(result_specs, (tuple, list)) else (result_specs,)
+            calls.append((target, operands, specs, attrs))
+            outs = tuple(np.ones(s.shape, dtype=s.dtype) for s in specs)
+            return outs if isinstance(result_specs, (tuple, list)) else outs[0]
+        return run
+
+    class CustomVjp:
+        def __init__(self, fn):
+            self.fn = fn
+        def defvjp(self, fwd, bwd):
+            self.fwd, self.bwd = fwd, bwd
+        def __call__(self, *a):
+            return self.fn(*a)
+
+    jax = types.ModuleType("jax")
+    jnp = types.ModuleType("jax.numpy")
+    for name in ("atleast_1d", "zeros", "float64", "int64", "uint8", "ndim", "size", "sum", "shape"):
+        setattr(jnp, name, getattr(np, name))
+    jax.numpy = jnp
+    jax.ShapeDtypeStruct = Spec
+    jax.custom_vjp = CustomVjp
+    jax.ffi = types.SimpleNamespace(ffi_call=ffi_call)
+    monkeypatch.setitem(sys.modules, "jax", jax)
+    monkeypatch.setitem(sys.modules, "jax.numpy", jnp)
+
+    lib = _lib.load()
+    n, m, d = 40, 6, 3
+    x, z, y = np.zeros((n, d)), np.zeros((m, d)), np.zeros(n)
+    jax_ffi.ard_gram(0.1, np.zeros(d), x, z)
+    jax_ffi.dot_gram(0.1, None, 1, x, z)
+    jax_ffi.dot_gram(0.1, 0.2, 3, x, z)
+    factor = jax_ffi.gp_factor(z, 0.1, np.zeros(d))
+    jax_ffi.gp_factor(z, 0.1, np.zeros(d), 1e-5, True, log_noise=0.0, y_z=np.zeros(m))
+    mean, var = jax_ffi.gp_predict(factor, m, x)
+    jax_ffi.risk(2, 0.5, y, mean, var)
+    loss = jax_ffi.fused_loss(m, 5)
+    args = (0.1, np.zeros(d), np.zeros(n), z, factor, np.zeros(n), x, y)
+    loss(*args)
+    grads = loss.bwd(args, 1.0)
+    assert len(grads) == len(args) and np.shape(grads[1]) == (d,) and np.shape(grads[2]) == (n,)
+    idx, trace = jax_ffi.cond_var_select(x, m, 0.1, np.zeros(d))
+    assert idx.shape == (m,) and idx.dtype == np.int64 and trace.shape == (m - 1,)
+
+    bindings = _ffi_bindings()
+    py_type = {"double": float, "int64_t": int, "bool": bool}
+    seen = set()
+    for target, operands, specs, attrs in calls:
+        n_args, n_rets, attr_decl = bindings[jax_ffi.FFI_TARGETS[target]]
+        seen.add(target)
+        assert len(operands) == n_args, target
+        assert len(specs) == n_rets, target
+        assert list(attrs) == [name for _, name in attr_decl], target  # same names, same order
+        for ctype, name in attr_decl:
+            assert type(attrs[name]) is py_type[ctype], (target, name)
+        for op in operands:
+            assert np.asarray(op).dtype == np.float64, target  # every operand is an F64 buffer in the adapter
+    assert seen == set(jax_ffi.FFI_TARGETS)
+    # result buffers sized by the C ABI's own queries (f64 words; the selector workspace is bytes)
+    sizes = {t: [int(np.prod(s.shape)) for s in specs] for t, _, specs, _ in calls}
+    assert sizes["gvi_gp_factor"] == [lib.gvi_gp_factor_bytes(m, d) // 8, lib.gvi_gp_factor_workspace_bytes(m) // 8]
+    assert sizes["gvi_gp_predict"] == [n, n, lib.gvi_gp_predict_workspace_bytes(m, d) // 8]
+    assert sizes["gvi_fused_step"] == [3, lib.gvi_fused_step_workspace_bytes(n, m) // 8]
+    assert sizes["gvi_fused_step_grad"] == [4 + d, n, lib.gvi_fused_step_grad_workspace_bytes(n, m, d) // 8]
+    assert sizes["gvi_cond_var_select"] == [m, m - 1, lib.gvi_select_workspace_bytes(n, m, d)]
