@@ -322,3 +322,22 @@ def test_committed_classification_fixture_is_current():
     diag = lambda a: O.ard_gram_diag(g["ls_q"][i], g["ll_q"][i], a)
     np.testing.assert_allclose(O.sparse_posterior_diag(gram, diag, g["zs"][i], g["x"], float(g["lam"]), False),
                                g["v_q"][i], rtol=1e-12)
+
+
+def test_adam_rule_equals_an_independent_implementation():
+    """The reference holds no golden for an optimiser step (optax is third-party); the oracle's Adam rule is checked against
+    torch.optim.Adam, an independent implementation of the same published update (bias-corrected moments, eps outside the
+    square root).  AdaBelief / RMSprop have no second implementation in this image: they stay 'parity unpinned'."""
+    import torch
+
+    rng = np.random.default_rng(2)
+    p0 = rng.standard_normal(17)
+    grads = [rng.standard_normal(17) * (10.0 ** rng.integers(-3, 2)) for _ in range(6)]
+    w = torch.tensor(p0.copy(), dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([w], lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    p, mu, nu = p0.copy(), np.zeros(17), np.zeros(17)
+    for count, g in enumerate(grads, start=1):
+        w.grad = torch.tensor(g, dtype=torch.float64)
+        opt.step()
+        p, mu, nu = O.optimiser_step("adam", p, g, mu, nu, count, 1e-2)
+        np.testing.assert_allclose(p, w.detach().numpy(), rtol=1e-13, atol=1e-15)
