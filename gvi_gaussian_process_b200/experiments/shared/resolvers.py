@@ -5,7 +5,7 @@ part of the hot path; callers construct kernels and means directly."""
 from __future__ import annotations
 
 from ...src.empirical_risks import CrossEntropy, NegativeLogLikelihood
-from ...src.gps.classification_base import GPClassificationBase
+from ...src.gps.base.classification_base import GPClassificationBase
 from ...src.inducing_points_selection import (ConditionalVarianceInducingPointsSelector,
                                                RandomInducingPointsSelector)
 from ...src.regularisations import (GaussianSquaredDifferenceRegularisation, GaussianWassersteinRegularisation,

@@ -15,7 +15,7 @@ from . import _lib_proxy as L
 from .empirical_risks.base import EmpiricalRiskBase
 from .empirical_risks.negative_log_likelihood import NegativeLogLikelihood
 from .gps.approximate_gp_regression import ApproximateGPRegression
-from .gps.classification_base import GPClassificationBase
+from .gps.base.classification_base import GPClassificationBase
 from .gps.gp_regression import GPRegression
 from .kernels.approximate.fixed_sparse_posterior_kernel import FixedSparsePosteriorKernel
 from .kernels.approximate.sparse_posterior_kernel import SparsePosteriorKernel

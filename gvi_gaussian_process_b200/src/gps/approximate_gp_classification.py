@@ -5,7 +5,10 @@ tempered golden 0.1690632.. of tests/gps/test_classification.py, which passes a 
 from __future__ import annotations
 
 from .approximate_gp_regression import ApproximateGPRegression
-from .classification_base import GPClassificationBase
+from .base import GPBaseParameters, GPClassificationBase
+
+
+ApproximateGPClassificationParameters = GPBaseParameters  # the reference's name for this GP's parameter container
 
 
 class ApproximateGPClassification(GPClassificationBase, ApproximateGPRegression):

@@ -3,10 +3,13 @@ src/gps/base/approximate_base.py:16,31-39).  The predictive is the "prior" of th
 observation noise defaults to log(0) and is dropped by generate_parameters, so it contributes exp(-inf) = 0."""
 from __future__ import annotations
 
-from .base import GPBase, LOG_ZERO
+from .base import ApproximateGPBase, GPBaseParameters, GPRegressionBase, LOG_ZERO
 
 
-class ApproximateGPRegression(GPBase):
+ApproximateGPRegressionParameters = GPBaseParameters  # the reference's name for this GP's parameter container
+
+
+class ApproximateGPRegression(ApproximateGPBase, GPRegressionBase):
     def generate_parameters(self, parameters):
         return self.Parameters(
             log_observation_noise=LOG_ZERO,

@@ -3,11 +3,11 @@ from __future__ import annotations
 
 import math
 
-from ..distributions import Gaussian
-from ..kernels.base import KernelBase
-from ..means.base import MeanBase
-from ..module import Module, ModuleParameters
-from ..utils.device import as_2d, as_device, scalar
+from ...distributions import Gaussian
+from ...kernels.base import KernelBase
+from ...means.base import MeanBase
+from ...module import Module, ModuleParameters
+from ...utils.device import as_2d, as_device, scalar
 
 
 class GPBaseParameters(ModuleParameters):

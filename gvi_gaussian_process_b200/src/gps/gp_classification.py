@@ -12,10 +12,13 @@ from ..kernels.multi_output_kernel import MultiOutputKernel
 from ..kernels.standard.ard_kernel import ARDKernel
 from ..kernels.tempered_kernel import TemperedKernel
 from ..utils.device import as_2d, as_device
-from .classification_base import GPClassificationBase
+from .base import ExactGPBase, GPBaseParameters, GPClassificationBase
 
 
-class GPClassification(GPClassificationBase):
+GPClassificationParameters = GPBaseParameters  # the reference's name for this GP's parameter container
+
+
+class GPClassification(ExactGPBase, GPClassificationBase):
     def __init__(self, mean, kernel, x, y, epsilon: float = 0.01, hermite_polynomial_order: int = 50,
                  cdf_lower_bound: float = 1e-10):
         base = kernel.base_kernel if isinstance(kernel, TemperedKernel) else kernel

@@ -12,10 +12,13 @@ from .. import _lib_proxy as L
 from .._autograd import ExactPredict, tensor_leaves, wants_grad
 from ..kernels.standard.ard_kernel import ARDKernel
 from ..utils.device import as_2d, as_device, scalar
-from .base import GPBase
+from .base import ExactGPBase, GPBaseParameters, GPRegressionBase
 
 
-class GPRegression(GPBase):
+GPRegressionParameters = GPBaseParameters  # the reference's name for this GP's parameter container
+
+
+class GPRegression(ExactGPBase, GPRegressionBase):
     def __init__(self, mean, kernel, x, y):
         # ARD: K tiles evaluated inside the tile kernel (and the differentiable exact-GP step).  Any other kernel: its own
         # Gram routine supplies K(x_train, x_train) and K(x_chunk, x_train) to the same factorisation / predictive kernels.

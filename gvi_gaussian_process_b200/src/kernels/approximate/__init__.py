@@ -3,4 +3,13 @@ from .fixed_sparse_posterior_kernel import (  # noqa: F401
     FixedSparsePosteriorKernel,
     FixedSparsePosteriorKernelParameters,
 )
-from .svgp import CholeskySVGPKernel, DiagonalSVGPKernel, KernelisedSVGPKernel, LogSVGPKernel  # noqa: F401
+from .svgp import (  # noqa: F401
+    CholeskySVGPKernel,
+    CholeskySVGPKernelParameters,
+    DiagonalSVGPKernel,
+    DiagonalSVGPKernelParameters,
+    KernelisedSVGPKernel,
+    KernelisedSVGPKernelParameters,
+    LogSVGPKernel,
+    LogSVGPKernelParameters,
+)

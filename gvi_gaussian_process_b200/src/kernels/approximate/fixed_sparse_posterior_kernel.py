@@ -6,15 +6,16 @@ from __future__ import annotations
 from ... import _lib_proxy as L
 from ..._autograd import PredictVariance, tensor_leaves, wants_grad
 from ...utils.device import as_2d
-from ..base import KernelBase, KernelBaseParameters
+from ..base import KernelBase
+from .base import ApproximateBaseKernel, ApproximateBaseKernelParameters
 from ..standard.ard_kernel import ARDKernel
 
 
-class FixedSparsePosteriorKernelParameters(KernelBaseParameters):
+class FixedSparsePosteriorKernelParameters(ApproximateBaseKernelParameters):
     """base_kernel: parameters of the base kernel."""
 
 
-class FixedSparsePosteriorKernel(KernelBase):
+class FixedSparsePosteriorKernel(ApproximateBaseKernel):
     Parameters = FixedSparsePosteriorKernelParameters
 
     def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, base_kernel: KernelBase,

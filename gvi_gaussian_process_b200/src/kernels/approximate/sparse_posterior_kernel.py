@@ -10,15 +10,16 @@ from __future__ import annotations
 from ... import _lib_proxy as L
 from ..._autograd import PredictVariance, tensor_leaves, wants_grad
 from ...utils.device import as_2d
-from ..base import KernelBase, KernelBaseParameters
+from ..base import KernelBase
+from .base import ApproximateBaseKernel, ApproximateBaseKernelParameters
 from ..standard.ard_kernel import ARDKernel
 
 
-class SparsePosteriorKernelParameters(KernelBaseParameters):
+class SparsePosteriorKernelParameters(ApproximateBaseKernelParameters):
     """base_kernel: parameters of the base kernel."""
 
 
-class SparsePosteriorKernel(KernelBase):
+class SparsePosteriorKernel(ApproximateBaseKernel):
     Parameters = SparsePosteriorKernelParameters
 
     def __init__(self, base_kernel: KernelBase, inducing_points, diagonal_regularisation: float = 1e-5,

@@ -8,4 +8,5 @@ from .svgp_kernels import (  # noqa: F401
     LogSVGPKernel,
     LogSVGPKernelParameters,
     SVGPBaseKernel,
+    SVGPBaseKernelParameters,
 )

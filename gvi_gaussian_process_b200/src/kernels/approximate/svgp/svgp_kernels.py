@@ -14,11 +14,16 @@ import torch
 from .... import _lib_proxy as L
 from ...._autograd import SVGPVariance, SVGPVarianceGram, wants_grad
 from ....utils.device import as_2d, as_device, scalar
-from ...base import KernelBase, KernelBaseParameters
+from ...base import KernelBase
+from ..base import ApproximateBaseKernel, ApproximateBaseKernelParameters
 from ...standard.ard_kernel import ARDKernel
 
 
-class SVGPBaseKernel(KernelBase):
+class SVGPBaseKernelParameters(ApproximateBaseKernelParameters):
+    pass
+
+
+class SVGPBaseKernel(ApproximateBaseKernel):
     def __init__(self, regulariser_kernel: KernelBase, regulariser_kernel_parameters, log_observation_noise,
                  inducing_points, training_points, diagonal_regularisation: float = 1e-5,
                  is_diagonal_regularisation_absolute_scale: bool = False, preprocess_function=None):
@@ -121,7 +126,7 @@ class SVGPBaseKernel(KernelBase):
         return k12 - (k1z @ linv.T) @ (k2z @ linv.T).T + k1z @ self._sigma_matrix(parameters) @ k2z.T
 
 
-class CholeskySVGPKernelParameters(KernelBaseParameters):
+class CholeskySVGPKernelParameters(SVGPBaseKernelParameters):
     """el_matrix_lower_triangle [M,M], el_matrix_log_diagonal [M]."""
 
 
@@ -155,7 +160,7 @@ class CholeskySVGPKernel(SVGPBaseKernel):
         return [torch.tril(d_e, diagonal=-1), torch.diagonal(d_e) * torch.exp(d)]
 
 
-class DiagonalSVGPKernelParameters(KernelBaseParameters):
+class DiagonalSVGPKernelParameters(SVGPBaseKernelParameters):
     """log_el_matrix_diagonal [M]."""
 
 
@@ -185,7 +190,7 @@ class DiagonalSVGPKernel(SVGPBaseKernel):
         return [torch.diagonal(d_e) * 0.5 * torch.exp(0.5 * d)]
 
 
-class LogSVGPKernelParameters(KernelBaseParameters):
+class LogSVGPKernelParameters(SVGPBaseKernelParameters):
     """log_el_matrix [M,M]."""
 
 
@@ -226,7 +231,7 @@ class LogSVGPKernel(SVGPBaseKernel):
         raise NotImplementedError("LogSVGPKernel trains through the general objective path (loss.backward())")
 
 
-class KernelisedSVGPKernelParameters(KernelBaseParameters):
+class KernelisedSVGPKernelParameters(SVGPBaseKernelParameters):
     """base_kernel: parameters of the (trainable) base kernel."""
 
 

@@ -6,14 +6,14 @@ import torch
 from ... import _lib_proxy as L
 from ..._autograd import wants_grad
 from ...utils.device import as_device, empty, scalar
-from ..base import KernelBase, KernelBaseParameters
+from .base import StandardKernelBase, StandardKernelBaseParameters
 
 
-class ARDKernelParameters(KernelBaseParameters):
+class ARDKernelParameters(StandardKernelBaseParameters):
     """log_scaling: scalar; log_lengthscales: [D] (or a scalar when D == 1, README.md:92-94)."""
 
 
-class ARDKernel(KernelBase):
+class ARDKernel(StandardKernelBase):
     Parameters = ARDKernelParameters
 
     def __init__(self, number_of_dimensions: int, preprocess_function=None):
