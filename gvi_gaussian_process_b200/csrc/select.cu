@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(STHREADS) select_init_kernel(int64_t N, int64_
 
 // step m for the local slice: e = (round20(k(X,x_j)) [+jitter at j] - c_j . C[:m]) / sqrt(d_j); C[m] = e;
 // d = max(d - e^2, 0); per-block candidate for the next pivot and per-block partial of tr(K - Q).
+// `winner` carries no __restrict__: in the fused form the last CTA's tail writes the NEXT winner into the same buffer
+// (fin.winner_next), after every CTA has consumed the current one and taken its ticket.
 __global__ void __launch_bounds__(STHREADS) select_update_kernel(
-    const double* __restrict__ X, int64_t N, int64_t offset, int D, int m, const double* __restrict__ winner,
+    const double* __restrict__ X, int64_t N, int64_t offset, int D, int m, const double* winner,
     const double* __restrict__ log_scaling, const double* __restrict__ log_ls, int ls_len,
     const double* __restrict__ kcol, double jitter, double* __restrict__ d, double* C,
     unsigned char* __restrict__ chosen, double* __restrict__ blockcand, double* __restrict__ blocktrace,
