@@ -264,3 +264,35 @@ def test_jax_wrappers_match_the_adapter_bindings(monkeypatch):
     assert sizes["gvi_fused_step"] == [3, lib.gvi_fused_step_workspace_bytes(n, m) // 8]
     assert sizes["gvi_fused_step_grad"] == [4 + d, n, lib.gvi_fused_step_grad_workspace_bytes(n, m, d) // 8]
     assert sizes["gvi_cond_var_select"] == [m, m - 1, lib.gvi_select_workspace_bytes(n, m, d)]
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(lib, tmp_path):
+    """The boundary is a C ABI: include/gvigp.h compiles as C99 (-pedantic-errors: no C++ isms, no torch types), and a
+    C program with no Python in the process links against libgvigp.so, reads the ABI version, runs a size query and
+    gets the documented error code + message from an argument check that needs no device."""
+    import shutil
+
+    from gvi_gaussian_process_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    src = tmp_path / "abi_probe.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "gvigp.h"\n'
+        "int main(void) {\n"
+        "  if (gvi_abi_version() != 1) return 1;\n"
+        "  if (gvi_select_record_len(8, 1024) != 2 + 8 + 1023) return 2;\n"
+        "  if (gvi_ard_gram_f64(NULL, -1, NULL, 4, 3, NULL, NULL, 3, NULL, 4, NULL, NULL) != GVI_EINVAL) return 3;\n"
+        '  if (!strstr(gvi_last_error_string(), "invalid argument")) return 4;\n'
+        "  if (gvi_ard_gram_f64(NULL, 0, NULL, 4, 3, NULL, NULL, 3, NULL, 4, NULL, NULL) != GVI_OK) return 5;\n"
+        '  printf("abi %d ok\\n", gvi_abi_version());\n  return 0;\n}\n')
+    exe = tmp_path / "abi_probe"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    libname = os.path.basename(_lib.LIB_PATH)
+    build = subprocess.run([gcc, "-std=c99", "-pedantic-errors", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                            str(src), "-o", str(exe), "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.strip() == "abi 1 ok"
