@@ -296,3 +296,29 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(lib, tmp_pa
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     assert run.stdout.strip() == "abi 1 ok"
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and C type of every prototype in include/gvigp.h against the ctypes table the host code calls
+    through (a drifted table would pass garbage without any error: ctypes cannot see the real prototype)."""
+    from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+
+    from gvi_gaussian_process_b200 import _lib
+
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    text = re.sub(r"^\s*#.*$", "", text, flags=re.M)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(gvi_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert sorted(p[1] for p in protos) == header_symbols()
+
+    def ctype(t):
+        t = t.strip()
+        if "*" in t:
+            return c_char_p if t.replace(" ", "") == "constchar*" else c_void_p
+        return {"int": c_int, "int64_t": c_int64, "double": c_double, "size_t": c_size_t}[t.replace("const", "").strip()]
+
+    for ret, name, args in protos:
+        args = [] if args.strip() == "void" else [a.strip() for a in args.split(",")]
+        expected = [ctype(re.match(r"(.*?)[A-Za-z_][A-Za-z0-9_]*$", a).group(1)) for a in args]
+        res, sig = _lib.SIGNATURES[name]
+        assert res == ctype(ret), name
+        assert sig == expected, (name, len(sig), len(expected))
