@@ -117,7 +117,8 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // the slow-path branches, so independent evaluations interleave on the FP64 pipe and between DMMA issue slots.
 __device__ __forceinline__ double gvi_exp(double x) {
   const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the low word of (y + SHIFT) is rint(y)
-  const double xc = fmax(x, -708.0);
+  const bool tiny = x < -708.0;
+  const double xc = tiny ? -708.0 : x;  // not fmax(): a NaN argument has to come out as NaN, as jnp.exp gives it
   const double t = fma(xc, 1.4426950408889634074, SHIFT);
   const int n = __double2loint(t);
   const double nf = t - SHIFT;
@@ -138,7 +139,7 @@ __device__ __forceinline__ double gvi_exp(double x) {
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-  return x < -708.0 ? 0.0 : res;
+  return tiny ? 0.0 : res;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(GTHREADS, 1) gram_dmma_kernel(const GramParams
     for (int nt = 0; nt < 8; nt++) {
       const int cl = (8 * wl + nt) * 8 + (lane & 3) * 2;
       double2 v;
-      v.x = amp2 * gvi_exp(-0.5 * fmax(nr + n2s[cl] - 2.0 * acc[mt][nt][0], 0.0));
-      v.y = amp2 * gvi_exp(-0.5 * fmax(nr + n2s[cl + 1] - 2.0 * acc[mt][nt][1], 0.0));
+      // clamp rounding-negative squared distances at 0 with a compare (fmax would turn a NaN input into k = amp^2)
+      const double s0 = nr + n2s[cl] - 2.0 * acc[mt][nt][0], s1 = nr + n2s[cl + 1] - 2.0 * acc[mt][nt][1];
+      v.x = amp2 * gvi_exp(-0.5 * (s0 < 0.0 ? 0.0 : s0));
+      v.y = amp2 * gvi_exp(-0.5 * (s1 < 0.0 ? 0.0 : s1));
       *reinterpret_cast<double2*>(otile + rl * OSTRIDE + cl) = v;
     }
   }

@@ -757,6 +757,18 @@ def test_branch_free_exp_is_within_one_ulp(S):
     assert np.all(got[~keep] == 0.0) and got[np.flatnonzero(x == 0.0)[0]] == 1.0
 
 
+@pytest.mark.xfail(strict=False, reason="added in a CPU-only session (no GPU minutes left): first device run pending; "
+                   "the host evaluation of the same source propagates NaN (tests/test_host_logic.py)")
+def test_nan_arguments_come_out_as_nan(S):
+    """A NaN in the inputs or hyper-parameters must surface as NaN (the reference's trainer stops on a NaN loss,
+    experiments/shared/trainer.py:75-82): the exp clamp is a compare-select, not fmax."""
+    x = np.array([np.nan, -1.0, -np.nan])
+    xd, out = dev(x), torch.empty(x.size, dtype=torch.float64, device="cuda")
+    S._lib.check(S._lib.load().gvi_test_exp_f64(xd.data_ptr(), x.size, out.data_ptr(), S._lib.current_stream()), "exp")
+    got = host(out)
+    assert np.isnan(got[0]) and np.isnan(got[2]) and got[1] == np.exp(-1.0)
+
+
 def test_multi_gpu_sharding_when_two_gpus_are_visible(S):
     """Runs tests/run_multigpu.py under torchrun on 2 GPUs (skipped on a 1-GPU box; the N>1 host logic is also
     covered on CPU by tests/test_distributed_gloo.py)."""

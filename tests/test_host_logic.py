@@ -1,5 +1,7 @@
 """CPU-only tests of the host-side mirror of the reference API: PRNG restatement, parameter containers,
 assertion behaviour that fires before any launch, sharding helpers."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -180,3 +182,33 @@ def test_gp_and_kernel_families_share_the_reference_base_classes():
     for kernel in (SparsePosteriorKernel, FixedSparsePosteriorKernel, SVGPBaseKernel, CholeskySVGPKernel):
         assert issubclass(kernel, ApproximateBaseKernel)
     assert issubclass(ARDKernel, StandardKernelBase) and not issubclass(ARDKernel, ApproximateBaseKernel)
+
+
+def test_device_exp_source_evaluated_on_the_host(tmp_path):
+    """gvi_exp (csrc/common.cuh) is the exp of every kernel evaluation on the hot path.  Its body is plain IEEE-754
+    double arithmetic (fma, add, compare, an integer add into the exponent field), so the DEVICE SOURCE itself is
+    compiled for the host here (tests/csrc/gvi_exp_host.c supplies the three bit-cast intrinsics) and swept over 8e6
+    arguments of the range the kernels use: <= 1 ulp against expl(), exact 1 at 0, exact 0 below -708 (and at -inf),
+    and a NaN argument comes out as NaN (diverged hyper-parameters must surface as a NaN loss, as in the reference:
+    experiments/shared/trainer.py:75-82)."""
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "gvi_gaussian_process_b200", "csrc", "common.cuh")).read()
+    body = re.search(r"__device__ __forceinline__ double gvi_exp\(double x\) \{.*?\n\}\n", src, flags=re.S)
+    assert body, "gvi_exp not found in common.cuh"
+    (tmp_path / "gvi_exp_body.inc").write_text(body.group(0))
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    exe = tmp_path / "gvi_exp_host"
+    build = subprocess.run([gcc, "-O2", "-ffp-contract=off", "-I", str(tmp_path),
+                            os.path.join(root, "tests", "csrc", "gvi_exp_host.c"), "-o", str(exe), "-lm"],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120).stdout
+    fields = dict(line.split(None, 1) for line in out.strip().splitlines())
+    assert float(fields["max_ulp"].split()[0]) <= 1.0, out
+    for flag in ("exp0", "below", "edge", "nan"):
+        assert fields[flag].strip() == "1", out
