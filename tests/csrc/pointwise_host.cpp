@@ -1,0 +1,29 @@
+// TEST INFRASTRUCTURE.  Compiles the DEVICE source of the pointwise loss terms (gvi_nll_term, gvi_nll_grad,
+// gvi_reg_term, gvi_reg_grad: the text of csrc/common.cuh pasted in by tests/test_host_logic.py as
+// pointwise_body.inc) for the host, so the formulas the kernels execute can be held against the reference's golden
+// values and their hand-derived derivatives against central differences without a GPU.
+// stdin: one "kind alpha y mp cp mq cq" per line; stdout: "nll dnll_dm dnll_dv d0 dd0_dmq dd0_dcq" per line.
+#include <cmath>
+#include <cstdio>
+
+#include "gvigp.h"
+#define __device__
+#define __forceinline__ inline
+using std::exp;
+using std::log;
+using std::sqrt;
+
+#include "pointwise_body.inc"
+
+int main() {
+  int kind;
+  double alpha, y, mp, cp, mq, cq;
+  while (std::scanf("%d %lf %lf %lf %lf %lf %lf", &kind, &alpha, &y, &mp, &cp, &mq, &cq) == 7) {
+    double dm, dv, dmq, dcq;
+    gvi_nll_grad(y, mq, cq, dm, dv);
+    gvi_reg_grad(kind, alpha, mp, cp, mq, cq, dmq, dcq);
+    std::printf("%.17g %.17g %.17g %.17g %.17g %.17g\n", gvi_nll_term(y, mq, cq), dm, dv,
+                gvi_reg_term(kind, alpha, mp, cp, mq, cq), dmq, dcq);
+  }
+  return 0;
+}

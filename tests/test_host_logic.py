@@ -212,3 +212,91 @@ def test_device_exp_source_evaluated_on_the_host(tmp_path):
     assert float(fields["max_ulp"].split()[0]) <= 1.0, out
     for flag in ("exp0", "below", "edge", "nan"):
         assert fields[flag].strip() == "1", out
+
+
+def _pointwise_host(tmp_path):
+    """Compile the device source of the pointwise loss terms (csrc/common.cuh) for the host; returns a callable
+    rows[kind, alpha, y, mp, cp, mq, cq] -> array [n, 6] = (nll, dnll/dm, dnll/dv, D0, dD0/dmq, dD0/dcq)."""
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "gvi_gaussian_process_b200", "csrc", "common.cuh")).read()
+    body = re.search(r"__device__ __forceinline__ double gvi_nll_term\(.*?__device__ __forceinline__ double gvi_reg_term\(.*?\n\}\n",
+                     src, flags=re.S)
+    assert body, "pointwise loss terms not found in common.cuh"
+    for name in ("gvi_nll_term", "gvi_nll_grad", "gvi_reg_grad", "gvi_reg_term"):
+        assert name in body.group(0)
+    (tmp_path / "pointwise_body.inc").write_text(body.group(0))
+    gxx = shutil.which("g++")
+    assert gxx, "g++ is part of the image"
+    exe = tmp_path / "pointwise_host"
+    build = subprocess.run([gxx, "-O2", "-ffp-contract=off", "-I", str(tmp_path), "-I", os.path.join(root, "include"),
+                            os.path.join(root, "tests", "csrc", "pointwise_host.cpp"), "-o", str(exe)],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+
+    def run(rows):
+        text = "".join("%d %.17g %.17g %.17g %.17g %.17g %.17g\n" % tuple(r) for r in rows)
+        out = subprocess.run([str(exe)], input=text, capture_output=True, text=True, timeout=120).stdout
+        return np.array([[float(v) for v in line.split()] for line in out.strip().splitlines()])
+
+    return run
+
+
+def test_device_source_of_the_pointwise_loss_terms_against_reference_goldens_and_the_oracle(tmp_path):
+    """The formulas the risk / fused kernels execute per point, compiled for the host from the device source:
+    the reference's golden values (tests/regularisations/projected/test_projected_*.py:120-176 regression case
+    p = (1.8333.., 1/3), q = (1, 1); tests/test_empirical_risks.py), the NumPy oracle on random arguments, and the
+    hand-derived derivatives (the gradient kernels' epilogues) against central differences of the terms."""
+    from gvi_gaussian_process_b200._lib import REG_KINDS
+    from oracle import gp_oracle as O
+
+    run = _pointwise_host(tmp_path)
+    mp, cp, mq, cq = 1.8333333333333335, 0.33333333333333326, 1.0, 1.0
+    goldens = {"bhattacharyya": 0.13702468, "gaussian_wasserstein": 0.87307724, "hellinger": 0.18301035,
+               "kl": 0.56319503, "renyi": 0.4042577, "squared_difference": 1.13888889}
+    got = run([(REG_KINDS[k], 0.5, 0.0, mp, cp, mq, cq) for k in goldens])
+    for (k, g), row in zip(goldens.items(), got):
+        assert abs(row[3] - g) <= 1e-8, (k, row[3], g)
+    # p == q  =>  every D0 is 0 (the reference's "same Gaussian" cases)
+    same = run([(REG_KINDS[k], 0.5, 0.0, 0.7, 1.3, 0.7, 1.3) for k in goldens])
+    assert np.all(np.abs(same[:, 3]) <= 1e-15)
+    # Gaussian NLL golden of the approximate GP (mean 1, variance 1, y = [1.2, 4.2]): 3.48893853
+    nll = run([(0, 0.5, y, 0.0, 1.0, 1.0, 1.0) for y in (1.2, 4.2)])[:, 0]
+    assert abs(nll.mean() - 3.48893853) <= 1e-8
+    # random arguments against the oracle
+    rng = np.random.default_rng(3)
+    n = 400
+    y, m_p, m_q = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+    c_p, c_q = np.exp(rng.uniform(-3, 2, n)), np.exp(rng.uniform(-3, 2, n))
+    for name, kind in REG_KINDS.items():
+        if name == "none":
+            continue
+        for alpha in ((0.5, 0.2, 0.9) if name == "renyi" else (0.5,)):
+            rows = run([(kind, alpha, y[i], m_p[i], c_p[i], m_q[i], c_q[i]) for i in range(n)])
+            if name == "gwi_no_eig":
+                ref = (m_p - m_q) ** 2 + c_p + c_q
+            elif name == "squared_difference":
+                ref = (m_p - m_q) ** 2 + (c_p - c_q) ** 2
+            elif name == "renyi":
+                ref = O.d0_renyi(m_p, c_p, m_q, c_q, alpha)
+            else:
+                ref = O.D0[name](m_p, c_p, m_q, c_q)
+            assert np.max(np.abs(rows[:, 3] - ref) / (1.0 + np.abs(ref))) <= 1e-13, name
+            ref_nll = np.array([O.gaussian_nll([y[i]], [m_q[i]], [c_q[i]]) for i in range(n)])
+            assert np.max(np.abs(rows[:, 0] - ref_nll) / (1.0 + np.abs(ref_nll))) <= 1e-13
+            # derivatives: central differences of the terms themselves (relative steps)
+            hm, hc = 1e-6, 1e-6 * c_q
+            up = run([(kind, alpha, y[i], m_p[i], c_p[i], m_q[i] + hm, c_q[i]) for i in range(n)])
+            dn = run([(kind, alpha, y[i], m_p[i], c_p[i], m_q[i] - hm, c_q[i]) for i in range(n)])
+            uc = run([(kind, alpha, y[i], m_p[i], c_p[i], m_q[i], c_q[i] + hc[i]) for i in range(n)])
+            dc = run([(kind, alpha, y[i], m_p[i], c_p[i], m_q[i], c_q[i] - hc[i]) for i in range(n)])
+            for col_term, col_dm, col_dc in ((0, 1, 2), (3, 4, 5)):
+                fd_m = (up[:, col_term] - dn[:, col_term]) / (2 * hm)
+                fd_c = (uc[:, col_term] - dc[:, col_term]) / (2 * hc)
+                scale_m = 1.0 + np.abs(fd_m)
+                scale_c = 1.0 + np.abs(fd_c)
+                assert np.max(np.abs(rows[:, col_dm] - fd_m) / scale_m) <= 1e-6, (name, "d/dm", col_term)
+                assert np.max(np.abs(rows[:, col_dc] - fd_c) / scale_c) <= 1e-6, (name, "d/dc", col_term)
