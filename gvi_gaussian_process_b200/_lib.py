@@ -92,6 +92,22 @@ SIGNATURES = {
     "gvi_select_resolve_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gvi_select_update_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_threefry_random_bits": (c_int, [ctypes.c_uint32, ctypes.c_uint32, c_int64, c_void_p, c_void_p]),
+    "gvi_comm_unique_id_h": (c_int, [c_void_p]),
+    "gvi_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
+    "gvi_comm_destroy": (c_int, [c_void_p]),
+    "gvi_comm_rank": (c_int, [c_void_p]),
+    "gvi_comm_size": (c_int, [c_void_p]),
+    "gvi_comm_has_peer_window": (c_int, [c_void_p]),
+    "gvi_comm_allreduce_sum_f64": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "gvi_comm_allgather_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "gvi_select_sharded_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
+    "gvi_cond_var_select_sharded_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
+                                                c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_select_virtual_shards_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int]),
+    "gvi_cond_var_select_virtual_shards_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
+                                                       c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                       c_void_p]),
 }
 
 REG_KINDS = {

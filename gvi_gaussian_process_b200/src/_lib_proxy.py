@@ -309,6 +309,36 @@ def cond_var_select(x_perm, m_sel, log_scaling, log_ls, jitter):
     return idx, trace
 
 
+def cond_var_select_virtual_shards(x_perm, m_sel, log_scaling, log_ls, jitter, bounds):
+    """The sharded selector's kernels and exchange protocol over len(bounds)-1 VIRTUAL shards of one device's points
+    (gvi_cond_var_select_virtual_shards_f64).  Returns idx [R, m_sel] (every shard's view of the pivots) and
+    trace [R, m_sel - 1]."""
+    import numpy as np
+
+    n, d = x_perm.shape
+    r = len(bounds) - 1
+    b = np.ascontiguousarray(bounds, dtype=np.int64)
+    idx = torch.empty((r, m_sel), dtype=torch.int64, device=x_perm.device)
+    trace = torch.empty((r, m_sel - 1), dtype=torch.float64, device=x_perm.device)
+    nbytes = _L().gvi_select_virtual_shards_workspace_bytes(n, m_sel, d, r)
+    assert nbytes > 0, "unsupported sizes"
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x_perm.device)
+    rc = _L().gvi_cond_var_select_virtual_shards_f64(_lib.ptr(x_perm), n, d, m_sel, _lib.ptr(log_scaling),
+                                                     _lib.ptr(log_ls), log_ls.numel(), float(jitter), r,
+                                                     b.ctypes.data, _lib.ptr(idx), _lib.ptr(trace), _lib.ptr(ws),
+                                                     _lib.current_stream())
+    _lib.check(rc, "gvi_cond_var_select_virtual_shards_f64")
+    return idx, trace
+
+
+def threefry_random_bits(key, n, device):
+    """jax.random.bits(key, (n,), uint32) as an int64 device tensor (gvi_threefry_random_bits)."""
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    rc = _L().gvi_threefry_random_bits(int(key[0]), int(key[1]), n, _lib.ptr(out), _lib.current_stream())
+    _lib.check(rc, "gvi_threefry_random_bits")
+    return out
+
+
 def cond_var_select_any_kernel(x_perm, m_sel, kernel, kernel_parameters, jitter):
     """The greedy selector over ANY kernel: k(x_i, x_i) and, per pivot, the column k(X, x_j) come from the kernel's own
     Gram routine (the pivot position stays on the device: x_j is gathered with a device index, no host sync); the

@@ -35,11 +35,18 @@ class RandomInducingPointsSelector(InducingPointsSelectorBase):
 class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
     """Greedy conditional-variance selection (reference lines 49-176) as a GPU pivoted Cholesky.
 
-    The PRNG permutation is reproduced on the host (utils/jax_prng.py), the permuted inputs are gathered on the
-    device and the whole M-step loop runs in CUDA (gvi_cond_var_select_f64) with the C matrix resident in HBM."""
+    jax.random's permutation is reproduced on the device (utils/jax_prng.permutation_device: threefry hash kernel +
+    stable key sort), the permuted inputs are gathered there and the whole M-step loop runs in CUDA
+    (gvi_cond_var_select_f64) with the C matrix resident in HBM.
 
-    def __init__(self, threshold: float = 0.0):
+    Multi-GPU (`comm`: a gvi_gaussian_process_b200.distributed.Comm): every rank passes the SAME full training_inputs
+    (8 N D bytes - small; it is C, 8 N M bytes, that has to be sharded), works on its contiguous slice of the permuted
+    points (gvi_cond_var_select_sharded_f64: one exchange per pivot inside the kernels) and receives the same
+    (points, indices) as the single-GPU call."""
+
+    def __init__(self, threshold: float = 0.0, comm=None):
         self.threshold = threshold
+        self.comm = comm
 
     def compute_inducing_points(self, key, training_inputs, number_of_inducing_points, kernel=None,
                                 kernel_parameters=None, jitter: float = 1e-12):
@@ -48,10 +55,20 @@ class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
         x = as_device(training_inputs)
         n = x.shape[0]
         _, subkey = jax_prng.split(np.asarray(key))
-        perm = torch.as_tensor(jax_prng.permutation(subkey, n), device=x.device)
+        perm = jax_prng.permutation_device(subkey, n, x.device)
         x_perm = x[perm].contiguous()
         kernel_parameters = kernel._to_parameters(kernel_parameters)
-        if isinstance(kernel, ARDKernel):
+        if self.comm is not None and self.comm.world > 1:
+            assert isinstance(kernel, ARDKernel), "the sharded selector evaluates the ARD kernel inside its CUDA kernels"
+            from ..distributed import ShardedSelector, shard_bounds
+
+            ls, ll = ARDKernel.device_parameters(kernel_parameters)
+            lo, hi = shard_bounds(n, self.comm.rank, self.comm.world)
+            x_flat = x_perm.reshape(n, -1)
+            idx, trace = ShardedSelector(self.comm).select(x_flat[lo:hi].contiguous(), lo, number_of_inducing_points,
+                                                           ls, ll, jitter)
+            assert int(idx.min()) >= 0, "sharded selection: the per-pivot exchange timed out (a rank never answered)"
+        elif isinstance(kernel, ARDKernel):
             ls, ll = ARDKernel.device_parameters(kernel_parameters)
             idx, trace = L.cond_var_select(x_perm.reshape(n, -1), number_of_inducing_points, ls, ll, jitter)
         else:  # any other kernel: Gram columns from the kernel itself, the pivoted Cholesky in the same CUDA kernels

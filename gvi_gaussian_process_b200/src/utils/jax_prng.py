@@ -81,3 +81,24 @@ def choice(key: np.ndarray, n_items: int, k: int) -> np.ndarray:
     finally:
         np.seterr(**old)
     return out.astype(np.int64)
+
+
+def permutation_device(key: np.ndarray, n: int, device):
+    """`permutation(key, n)` computed on `device` (a CUDA torch device): the threefry hash is one CUDA launch per shuffle
+    round (gvi_threefry_random_bits) and the stable key sort is the host framework's device sort; key splitting (a few
+    hashes) stays on the host.  Bit-identical to `permutation` (tests/test_gpu_parity.py); at N = 1e7 the host version
+    costs seconds of NumPy sorting, this one milliseconds."""
+    import torch
+
+    from .. import _lib_proxy as L
+
+    order = torch.arange(n, dtype=torch.int64, device=device)
+    if n <= 1:
+        return order
+    rounds = int(np.ceil(3.0 * np.log(n) / np.log(float(np.iinfo(np.uint32).max))))
+    key = np.asarray(key, dtype=_U32)
+    for _ in range(rounds):
+        key, sub = split(key)
+        bits = L.threefry_random_bits(sub, n, device)
+        order = order[torch.sort(bits, stable=True).indices]
+    return order

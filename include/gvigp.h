@@ -25,6 +25,7 @@ extern "C" {
 #define GVI_EINVAL (-1)   /* bad argument (shape/size/null) - the Python shim raises AssertionError first */
 #define GVI_ECUDA (-2)    /* CUDA runtime error, see gvi_last_error_string() */
 #define GVI_EUNSUPPORTED (-3) /* size outside what this build supports */
+#define GVI_ECOMM (-4)    /* communicator / NCCL error, see gvi_last_error_string() */
 
 /* regulariser kinds for gvi_risk_f64 / gvi_fused_step_f64 (src/regularisations/...) */
 #define GVI_REG_NONE 0
@@ -299,6 +300,64 @@ int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset
                           const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
                           double jitter, double* record_out, double* trace_partial_out, void* workspace,
                           void* stream);
+
+/* ---- the permutation of a13 on the device (src/inducing_points_selection.py:115-119: jax.random.permutation) --------
+ * out[i] = jax.random.bits(key, (n,), uint32)[i] widened to int64: threefry2x32 of jax 0.4.13 (third-party, pinned in the
+ * reference's poetry.lock; jax_threefry_partitionable=False) over the counters arange(n).  key0/key1 are the two
+ * uint32 words of the (sub)key - key splitting is a handful of hashes and stays on the host.  One shuffle round of
+ * jax.random.permutation = a stable sort of the current order by these keys.                                       */
+int gvi_threefry_random_bits(uint32_t key0, uint32_t key1, int64_t n, int64_t* out, void* stream);
+
+/* ---- multi-GPU: the communicator (SURVEY.md section 8(b) "gvi_comm_init/destroy (wraps ncclComm_t)", 8(e)) -----------
+ * The reference is single-process JAX and has no counterpart; the split these calls serve is: the N points sharded
+ * contiguously by rank, Z / theta replicated, only the risk / gradient SUMS and the selector's per-pivot candidate cross
+ * NVLink.  One rank per process and device (the device current at gvi_comm_init).  A communicator wraps an ncclComm_t
+ * (libnccl.so.2 is bound with dlopen at the first multi-rank init: a single-GPU host does not need NCCL) and owns a
+ * small PEER WINDOW that every other rank maps with CUDA IPC; the sharded selector writes its per-pivot records
+ * straight into the peers' windows from its kernels.  Where the mapping is not possible (or GVI_COMM_NO_PEER_WINDOW is
+ * passed by every rank) the same kernels exchange through ncclAllGather enqueued from C on the caller's stream.
+ *   bootstrap: rank 0 fills id128_h (HOST buffer, GVI_COMM_UNIQUE_ID_BYTES) with gvi_comm_unique_id_h, the host
+ *   distributes the bytes by its own means (torch.distributed / MPI / a file), every rank calls gvi_comm_init
+ *   (collective, synchronises).  world == 1 needs no id.  Calls on one communicator are collective and must be made
+ *   in the same order by every rank; a communicator is thread-compatible, not thread-safe.                          */
+typedef struct gvi_comm gvi_comm;
+#define GVI_COMM_UNIQUE_ID_BYTES 128
+#define GVI_COMM_NO_PEER_WINDOW 1
+int gvi_comm_unique_id_h(void* id128_h);
+int gvi_comm_init(gvi_comm** comm_out, int rank, int world, const void* id128_h, int flags);
+int gvi_comm_destroy(gvi_comm* comm);
+int gvi_comm_rank(const gvi_comm* comm);
+int gvi_comm_size(const gvi_comm* comm);
+int gvi_comm_has_peer_window(const gvi_comm* comm);
+/* buf[count] <- sum over ranks, in place, on the caller's stream.  Up to 8192 doubles x ranks the partials are gathered
+ * and summed in RANK ORDER, so every rank holds the same bits whatever the transport did (the [sum NLL, sum D0, N]
+ * triple of gvi_fused_step_f64, the 4 + D gradient vector); longer vectors (flat parameter gradients) go to
+ * ncclAllReduce.                                                                                                */
+int gvi_comm_allreduce_sum_f64(gvi_comm* comm, double* buf, int64_t count, void* stream);
+/* recv[world][count] <- every rank's send[count] */
+int gvi_comm_allgather_f64(gvi_comm* comm, const double* send, double* recv, int64_t count, void* stream);
+
+/* ---- a13 sharded: ONE call runs the whole greedy selection over points sharded across the communicator's ranks
+ * (reference loop: src/inducing_points_selection.py:137-172).  x_local[N_local, D] is this rank's contiguous slice of
+ * the PERMUTED inputs, starting at global position `offset` (N_local == 0 is allowed).  Every rank receives the same
+ * idx_out[M_sel] (global positions into the permuted order; -1 entries = the exchange timed out) and trace_out[M_sel-1]
+ * (tr(K - Q) over ALL points after each step, summed in rank order; NULL ok).  Per pivot one update launch and one
+ * one-CTA launch; the candidate record of a slice (d, index, x_j, c_j[0..m]) goes to every peer's window from that
+ * kernel and the next update kernel resolves the winner itself - no host code and no collective call between pivots.
+ * workspace: gvi_select_sharded_workspace_bytes(N_local, M_sel, D) (the slice's C [(M_sel-1), N_local], d, scratch). */
+size_t gvi_select_sharded_workspace_bytes(int64_t N_local, int M_sel, int D);
+int gvi_cond_var_select_sharded_f64(const double* x_local, int64_t N_local, int64_t offset, int D, int M_sel,
+                                    const double* log_scaling, const double* log_ls, int ls_len, double jitter,
+                                    int64_t* idx_out, double* trace_out, void* workspace, gvi_comm* comm, void* stream);
+/* The same kernels and exchange protocol over R VIRTUAL shards of one device's points (mailboxes local): shard r owns
+ * [bounds_h[r], bounds_h[r+1]) (HOST array of R+1 ascending positions from 0 to N; empty shards allowed).
+ * idx_out is [R][M_sel]: every shard's own view of the pivots (they agree); trace_out [R][M_sel-1] or NULL.  Lets a
+ * one-GPU host check the multi-rank protocol bit for bit.                                                        */
+size_t gvi_select_virtual_shards_workspace_bytes(int64_t N, int M_sel, int D, int R);
+int gvi_cond_var_select_virtual_shards_f64(const double* x_perm, int64_t N, int D, int M_sel,
+                                           const double* log_scaling, const double* log_ls, int ls_len, double jitter,
+                                           int R, const int64_t* bounds_h, int64_t* idx_out, double* trace_out,
+                                           void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -81,15 +81,46 @@ def main():
     mq = 0.3 * rng.standard_normal(n)
     ls, ll = t([0.0]), t(np.full(d, np.log(1.0 / d)))
     lo, hi = distributed.shard_bounds(n, rank, world)
-    # ---- selector ------------------------------------------------------------------------------------------
-    idx, trace = distributed.ShardedSelector().select(t(x[lo:hi]), lo, m, ls, ll)
+    # ---- selector: one library call per rank, the exchange inside the kernels (peer windows, then the NCCL transport) ------
+    comm = distributed.Comm()
+    comm_nccl = distributed.Comm(peer_window=False)
     ok = True
     if rank == 0:
+        print(f"[multigpu] world={world} peer window mapped: {comm.has_peer_window}; forced NCCL transport: "
+              f"{not comm_nccl.has_peer_window}")
         ref_idx, ref_trace = L.cond_var_select(t(x), m, ls, ll, 1e-12)
-        same = bool(torch.equal(idx, ref_idx))
-        tr_err = float((trace - ref_trace).abs().max() / ref_trace.abs().max())
-        print(f"[multigpu] world={world} selector pivots identical: {same}; trace rel err {tr_err:.2e}")
-        ok &= same and tr_err < 1e-12
+        ok &= not comm_nccl.has_peer_window
+    for name, c in (("peer-window", comm), ("nccl", comm_nccl), ("peer-window again", comm)):
+        idx, trace = distributed.ShardedSelector(c).select(t(x[lo:hi]), lo, m, ls, ll)
+        gathered = c.allgather(idx.to(torch.float64))
+        if rank == 0:
+            same = bool(torch.equal(idx, ref_idx)) and all(bool(torch.equal(gathered[r].long(), ref_idx)) for r in range(world))
+            tr_err = float((trace - ref_trace).abs().max() / ref_trace.abs().max())
+            print(f"[multigpu] selector ({name}) pivots identical on every rank: {same}; trace rel err {tr_err:.2e}")
+            ok &= same and tr_err < 1e-12
+    # the public API: every rank passes the full inputs, works on its slice of the permuted points
+    from gvi_gaussian_process_b200.src.inducing_points_selection import ConditionalVarianceInducingPointsSelector
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.utils import jax_prng
+
+    kern = ARDKernel(number_of_dimensions=d)
+    kp = kern.Parameters.construct(log_scaling=0.0, log_lengthscales=np.full(d, np.log(1.0 / d)))
+    xs = t(x[:50_001])
+    z_sh, i_sh = ConditionalVarianceInducingPointsSelector(comm=comm).compute_inducing_points(
+        jax_prng.PRNGKey(3), xs, 64, kern, kp)
+    if rank == 0:
+        z_1, i_1 = ConditionalVarianceInducingPointsSelector().compute_inducing_points(jax_prng.PRNGKey(3), xs, 64, kern, kp)
+        same = bool(torch.equal(i_sh, i_1) and torch.equal(z_sh, z_1))
+        print(f"[multigpu] compute_inducing_points(comm=...) equals the single-GPU call: {same}")
+        ok &= same
+    # row-sharded calculate_gram
+    blk = distributed.calculate_gram_row_sharded(kern, kp, t(x[lo:lo + 1000]), t(x[:77]), comm, gather=True)
+    if rank == 0:
+        full = torch.cat([kern.calculate_gram(kp, t(x[distributed.shard_bounds(n, r, world)[0]:][:1000]), t(x[:77]))
+                          for r in range(world)])
+        same = bool(torch.equal(blk, full))
+        print(f"[multigpu] row-sharded calculate_gram (gathered) equals the per-block Grams: {same}")
+        ok &= same
     # ---- fused step value + gradient -------------------------------------------------------------------------
     z = t(x[idx.cpu().numpy()])
     yz = t(y[idx.cpu().numpy()])
@@ -97,7 +128,7 @@ def main():
     fp = L.GpFactor(m, d).factor(z, ls, ll, 0.0, True, log_noise=t([0.0]), y_z=yz)
     pm = torch.zeros(hi - lo, dtype=torch.float64, device=dev)
     out, dm = L.fused_step_grad(fq, fp, t(x[lo:hi]), t(y[lo:hi]), t(mq[lo:hi]), pm, None, None, 5, 0.5)
-    distributed.allreduce_loss_sums(out)
+    comm.allreduce_sum(out)
     if rank == 0:
         pm_full = torch.zeros(n, dtype=torch.float64, device=dev)
         ref, dm_ref = L.fused_step_grad(fq, fp, t(x), t(y), t(mq), pm_full, None, None, 5, 0.5)
@@ -111,6 +142,8 @@ def main():
         ok &= err_sums < 1e-12 and err_grad < 1e-8 and dm_err < 1e-13
     # ---- data-parallel Trainer: N ranks must take the single-GPU optimisation path -----------------------------------
     ok &= check_trainer(rank, world, dev)
+    comm.destroy()
+    comm_nccl.destroy()
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
