@@ -301,7 +301,7 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(lib, tmp_pa
 def test_ctypes_signatures_match_the_header_prototypes():
     """Argument count and C type of every prototype in include/gvigp.h against the ctypes table the host code calls
     through (a drifted table would pass garbage without any error: ctypes cannot see the real prototype)."""
-    from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_void_p
+    from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint32, c_void_p
 
     from gvi_gaussian_process_b200 import _lib
 
@@ -314,7 +314,7 @@ def test_ctypes_signatures_match_the_header_prototypes():
         t = t.strip()
         if "*" in t:
             return c_char_p if t.replace(" ", "") == "constchar*" else c_void_p
-        return {"int": c_int, "int64_t": c_int64, "double": c_double, "size_t": c_size_t}[t.replace("const", "").strip()]
+        return {"int": c_int, "int64_t": c_int64, "double": c_double, "size_t": c_size_t, "uint32_t": c_uint32}[t.replace("const", "").strip()]
 
     for ret, name, args in protos:
         args = [] if args.strip() == "void" else [a.strip() for a in args.split(",")]
