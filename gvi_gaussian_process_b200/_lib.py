@@ -77,8 +77,6 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     "gvi_gp_predict_gram_f64": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
-    "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "gvi_test_set_grad_chunk_waves": (c_int, [c_int]),
     "gvi_select_workspace_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_cond_var_select_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_double,
                                         c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -92,6 +90,8 @@ SIGNATURES = {
     "gvi_select_resolve_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "gvi_select_update_f64": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gvi_fp64_tensor_peak_scratch_bytes": (c_size_t, []),
+    "gvi_fp64_tensor_peak_tflops": (c_int, [c_double, c_void_p, c_void_p, c_void_p]),
     "gvi_threefry_random_bits": (c_int, [ctypes.c_uint32, ctypes.c_uint32, c_int64, c_void_p, c_void_p]),
     "gvi_comm_unique_id_h": (c_int, [c_void_p]),
     "gvi_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int]),
@@ -108,6 +108,13 @@ SIGNATURES = {
     "gvi_cond_var_select_virtual_shards_f64": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
                                                        c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                        c_void_p]),
+}
+
+# include/gvigp_test.h: exported only by libgvigp_test.so (tests and tools; never the product path)
+TEST_LIB_PATH = os.path.join(_HERE, "libgvigp_test.so")
+TEST_SIGNATURES = {
+    "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "gvi_test_set_grad_chunk_waves": (c_int, [c_int]),
 }
 
 REG_KINDS = {
@@ -145,6 +152,41 @@ def load() -> ctypes.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+_test_lib = None
+
+
+def load_test() -> ctypes.CDLL:
+    """libgvigp_test.so: the library compiled with -DGVI_TEST_HOOKS (test hooks + profiling environment switches)."""
+    global _test_lib
+    if _test_lib is None:
+        if not os.path.exists(TEST_LIB_PATH):
+            raise GviError(f"{TEST_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(TEST_LIB_PATH)
+        for name, (res, args) in {**SIGNATURES, **TEST_SIGNATURES}.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _test_lib = lib
+    return _test_lib
+
+
+class test_library:
+    """`with _lib.test_library() as lib:` - every call of the shim goes to libgvigp_test.so inside the block (tests that
+    need a hook in effect while the public API runs; tools that use the profiling switches)."""
+
+    def __enter__(self):
+        global _lib
+        load()
+        self._prev = _lib
+        _lib = load_test()
+        return _lib
+
+    def __exit__(self, *exc):
+        global _lib
+        _lib = self._prev
+        return False
 
 
 def check(rc: int, what: str) -> None:

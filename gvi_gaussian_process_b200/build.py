@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gram.cu", "gram_dmma.cu", "chol.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu"]
+SOURCES = ["gram.cu", "gram_dmma.cu", "chol.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu", "diag.cu"]
 LIB_PATH = os.path.join(HERE, "libgvigp.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -22,40 +22,61 @@ def _nvcc() -> str:
     return "nvcc"
 
 
-def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
+TEST_LIB_PATH = os.path.join(HERE, "libgvigp_test.so")  # same sources + -DGVI_TEST_HOOKS (include/gvigp_test.h)
+
+
+def _deps():
+    return [os.path.join(CSRC, s) for s in SOURCES] + [
+        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "predict.cuh"), os.path.join(CSRC, "comm.cuh"),
+        os.path.join(HERE, "..", "include", "gvigp.h"), os.path.join(HERE, "..", "include", "gvigp_test.h")]
+
+
+def needs_build(lib_path: str = LIB_PATH) -> bool:
+    if not os.path.exists(lib_path):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "predict.cuh"), os.path.join(CSRC, "comm.cuh"),
-                                                        os.path.join(HERE, "..", "include", "gvigp.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    t = os.path.getmtime(lib_path)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB_PATH
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+def _compile_and_link(lib_path: str, obj_dir: str, extra_flags, verbose: bool):
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + list(extra_flags)
     flags += os.environ.get("GVI_NVCC_FLAGS", "").split()  # e.g. -DGVI_PHASE_CLOCKS (profiling builds)
-    objs = []
-    procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
+    objs, procs = [], []
     for s in SOURCES:
-        obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, s.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, s), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
-    for s, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            print(out)
-        if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {s}:\n{out}")
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-lcublas", "-ldl"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}")
+
+    def finish():
+        for s, p in procs:
+            out, _ = p.communicate()
+            if verbose and out:
+                print(out)
+            if p.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {s}:\n{out}")
+        cmd = [_nvcc(), "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
+               "-lcublas", "-ldl"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}")
+        return lib_path
+
+    return finish
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """libgvigp.so (the product) and libgvigp_test.so (tests / tools: the same sources with -DGVI_TEST_HOOKS)."""
+    jobs = []
+    if force or needs_build(LIB_PATH):
+        jobs.append(_compile_and_link(LIB_PATH, os.path.join(HERE, "build"), [], verbose))
+    if force or needs_build(TEST_LIB_PATH):
+        jobs.append(_compile_and_link(TEST_LIB_PATH, os.path.join(HERE, "build", "test"), ["-DGVI_TEST_HOOKS"], verbose))
+    for finish in jobs:  # both compilations run concurrently; wait and link
+        finish()
     return LIB_PATH
 
 

@@ -41,6 +41,28 @@ void gvi_count_launch();
 
 constexpr int GVI_NUM_SMS = 148;  // B200: 2 dies x 74 SMs
 
+// cudaFuncSetAttribute is per device: `mask` (one static per kernel instantiation) remembers which devices are done, so
+// a host that drives several GPUs from one process configures each of them.  True on the first call per device.
+#include <atomic>
+inline bool gvi_first_use_on_this_device(std::atomic<unsigned long long>& mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  return !(mask.fetch_or(bit, std::memory_order_relaxed) & bit);
+}
+
+// profiling switches (GVI_DEBUG_SKIP, GVI_DEBUG_GRID, GVI_ONE_CTA, GVI_STATIC_TILES) exist only in libgvigp_test.so, the
+// build with -DGVI_TEST_HOOKS that tests and tools load; the product library never reads the environment
+#ifdef GVI_TEST_HOOKS
+#include <cstdlib>
+inline int gvi_debug_env(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+#else
+constexpr int gvi_debug_env(const char*) { return 0; }
+#endif
+
 // ---- factor buffer layout (doubles) ---------------------------------------------------------------------------
 // [0] amp2 = exp(log_scaling)^2   [1] k(x,x)   [2] jitter actually added   [3] chol info (as double)
 // [4] absolute jitter (0 when the regulariser is trace-relative; used by d var / d log_scaling)

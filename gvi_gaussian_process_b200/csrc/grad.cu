@@ -291,17 +291,19 @@ int launch_kgen(const double* F, const double* X, const double* g, int64_t N, in
 
 int launch_syrk(const SyrkParams& P, int ntri, cudaStream_t st) {
   size_t smem = (size_t)NSTAGE * 2 * BLK * sizeof(double) + NSTAGE * sizeof(uint64_t) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (gvi_first_use_on_this_device(configured))
     GVI_CUDA(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   syrk_kernel<<<dim3(ntri, P.nsplit), STHREADS, smem, st>>>(P);
   GVI_CHECK_LAUNCH("syrk_kernel");
   return GVI_OK;
 }
 
-int g_chunk_waves_cap = 0;  // test hook (gvi_test_set_grad_chunk_waves)
+#ifdef GVI_TEST_HOOKS
+int g_chunk_waves_cap = 0;  // libgvigp_test.so only: gvi_test_set_grad_chunk_waves (include/gvigp_test.h)
+#else
+constexpr int g_chunk_waves_cap = 0;
+#endif
 
 struct GradWs {
   double *partials, *tile_partials, *g, *bscratch, *Cpart, *C, *rowpart, *Kc;
@@ -365,6 +367,7 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
 }
 }  // namespace
 
+#ifdef GVI_TEST_HOOKS  // libgvigp_test.so only (include/gvigp_test.h): never part of the product library
 namespace {
 __global__ void test_exp_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -382,6 +385,7 @@ extern "C" int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* s
   GVI_CHECK_LAUNCH("test_exp_kernel");
   return GVI_OK;
 }
+#endif  // GVI_TEST_HOOKS
 
 // C = sum_i g_i k_i k_i^T (symmetric, full matrix in w.C), chunk by chunk through the L2-sized K ring
 static int gvi_weighted_gram(const double* Fq, const double* X, const double* g, int64_t N, int M, int D,

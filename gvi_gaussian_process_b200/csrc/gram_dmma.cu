@@ -216,11 +216,9 @@ static int launch_gram_core(const double* x1, int64_t m1, const double* sqrtw1, 
   GVI_CHECK_LAUNCH("gram_prep_kernel");
   GramParams P{Ab, Bb, n1, n2, nrb1, nrb2, nchunk, D, m1, m2, ld, log_scaling, amp2_ptr, out};
   size_t smem = ((size_t)NSTAGE * 2 * BLKD + 2 * CB) * sizeof(double) + NSTAGE * sizeof(uint64_t) + 64;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};
+  if (gvi_first_use_on_this_device(configured))
     GVI_CUDA(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
   gram_dmma_kernel<<<dim3(nrb2, nrb1), GTHREADS, smem, st>>>(P);
   GVI_CHECK_LAUNCH("gram_dmma_kernel");
   return GVI_OK;

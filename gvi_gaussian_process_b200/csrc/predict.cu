@@ -636,19 +636,18 @@ template <int NT, int DR, bool GRAD, int WARPS>
 int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
   constexpr int T = 8 * NT;
   size_t smem = step_smem_bytes<NT, DR>(P.Mp, P.Pc, GRAD, WARPS, P.reds_in_smem != 0);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  static std::atomic<unsigned long long> configured{0};  // per instantiation, one bit per device
+  if (gvi_first_use_on_this_device(configured)) {
     GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(WARPS == 8 ? SMEM_LIMIT_2CTA : SMEM_LIMIT)));
     if (WARPS == 8)
       GVI_CUDA(cudaFuncSetAttribute(gp_step_kernel<NT, DR, GRAD, WARPS>,
                                     cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    configured = true;
   }
   int64_t ntiles = (P.N + T - 1) / T;
   int grid = (int)(ntiles < grid_cap ? ntiles : grid_cap);
   StepParams Q = P;
-  static const int static_tiles = getenv("GVI_STATIC_TILES") ? atoi(getenv("GVI_STATIC_TILES")) : 0;
+  static const int static_tiles = gvi_debug_env("GVI_STATIC_TILES");
   if (ntiles <= grid || static_tiles) Q.tile_counter = nullptr;  // one tile per CTA: nothing to balance
   if (Q.tile_counter) GVI_CUDA(cudaMemsetAsync(Q.tile_counter, 0, sizeof(int), st));
   gp_step_kernel<NT, DR, GRAD, WARPS><<<grid, WARPS * 32, smem, st>>>(Q);
@@ -735,8 +734,8 @@ bool gvi_factor_has_extra(const void* factor);
 int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
   StepParams P = P_in;
   P.has_extra = gvi_factor_has_extra(P.pass[0].F) ? 1 : 0;
-  static const int debug_skip = getenv("GVI_DEBUG_SKIP") ? atoi(getenv("GVI_DEBUG_SKIP")) : 0;
-  static const int one_cta = getenv("GVI_ONE_CTA") ? atoi(getenv("GVI_ONE_CTA")) : 0;
+  static const int debug_skip = gvi_debug_env("GVI_DEBUG_SKIP");
+  static const int one_cta = gvi_debug_env("GVI_ONE_CTA");
   P.debug_skip = debug_skip;
   const bool pre = P.pass[0].Kpre != nullptr;
   if (P.D > 32 && !pre) {
@@ -757,7 +756,7 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
     }
     if (P.acc_scratch) P.reds_scratch = P.acc_scratch + (size_t)2 * GVI_NUM_SMS * P.Mp * 24;
     // profiling aid (env GVI_DEBUG_GRID): cap the grid, e.g. 148 in the two-CTA shape = one 8-warp CTA per SM
-    static const int debug_grid = getenv("GVI_DEBUG_GRID") ? atoi(getenv("GVI_DEBUG_GRID")) : 0;
+    static const int debug_grid = gvi_debug_env("GVI_DEBUG_GRID");
     if (debug_grid > 0) return launch_step_nt<3>(P, debug_grid, st);
     return launch_step_nt<3>(P, P.two_cta ? 2 * GVI_NUM_SMS : GVI_NUM_SMS, st);
   }

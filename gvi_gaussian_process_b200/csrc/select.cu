@@ -399,11 +399,9 @@ static int select_update_impl(const double* x_local, int64_t N_local, int64_t of
   SelectWs s = carve(workspace, N_local, M_sel, D);
   size_t smem = (size_t)(m + 2 * D) * sizeof(double);
   if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<unsigned long long> configured{0};
+    if (gvi_first_use_on_this_device(configured))
       GVI_CUDA(cudaFuncSetAttribute(select_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
   }
   FusedFinalize fin{};
   if (fused) fin = FusedFinalize{s.ticket, M_sel, record_out, trace_partial_out, fused_winner_next, fused_idx_out_next};
@@ -713,7 +711,9 @@ int run_sharded_selection(const ShardSet& S, int R, int pos0, const TargetSet& T
   int64_t total_blocks = 0;
   for (int s = 0; s < S.n; s++) total_blocks += S.s[s].nblk;
   GVI_CHECK_ARG(total_blocks < (1ll << 31), "too many points for one launch");
-  GVI_CUDA(cudaFuncSetAttribute(select_update_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static std::atomic<unsigned long long> configured{0};
+  if (gvi_first_use_on_this_device(configured))
+    GVI_CUDA(cudaFuncSetAttribute(select_update_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   for (int s = 0; s < S.n; s++) {
     const ShardView& sh = S.s[s];
     select_prepare_kernel<<<1, 256, 0, st>>>(sh.idx_out, M_sel, sh.status);

@@ -257,13 +257,6 @@ int gvi_optimiser_step_f64(int kind, double* param, const double* grad, double* 
                            int64_t count, double learning_rate, double b1, double b2, double eps, double eps_root,
                            void* stream);
 
-/* test hook: out[i] = the branch-free exp used inside the fused kernels (<= 1 ulp; tests/test_gpu_parity.py) */
-int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
-/* test hook: cap the chunk length of the gradient step's a_i ring at `waves` x 3552 points (0 = default, up to 1 GB),
- * so that small problems exercise the multi-chunk path; affects gvi_fused_step_grad_workspace_bytes too.  Returns the
- * previous value. */
-int gvi_test_set_grad_chunk_waves(int waves);
-
 /* ---- a13: ConditionalVarianceInducingPointsSelector.compute_inducing_points
  * (src/inducing_points_selection.py:113-176) on ALREADY PERMUTED inputs x_perm[N,D] (the permutation is the
  * host's job).  Writes pivot positions into x_perm to idx_out[M_sel] (int64) and
@@ -300,6 +293,13 @@ int gvi_select_update_f64(const double* x_local, int64_t N_local, int64_t offset
                           const double* winner, const double* log_scaling, const double* log_ls, int ls_len,
                           double jitter, double* record_out, double* trace_partial_out, void* workspace,
                           void* stream);
+
+/* ---- measurement aid (no reference counterpart): the FP64 tensor-pipe (DMMA m8n8k4) issue rate of the current device.
+ * Runs a register-resident mma loop for about target_ms milliseconds on `stream`, SYNCHRONISES it and writes TFLOP/s
+ * (2 flop per multiply-add) to the HOST double *tflops_out_h: the roofline denominator of the tile kernels, measured on
+ * the box the bench line comes from.  scratch: device buffer of gvi_fp64_tensor_peak_scratch_bytes().                */
+size_t gvi_fp64_tensor_peak_scratch_bytes(void);
+int gvi_fp64_tensor_peak_tflops(double target_ms, double* tflops_out_h, void* scratch, void* stream);
 
 /* ---- the permutation of a13 on the device (src/inducing_points_selection.py:115-119: jax.random.permutation) --------
  * out[i] = jax.random.bits(key, (n,), uint32)[i] widened to int64: threefry2x32 of jax 0.4.13 (third-party, pinned in the

@@ -111,7 +111,11 @@ def test_argument_validation_of_the_other_kernel_entry_points(lib):
     assert lib.gvi_gp_predict_gram_f64(None, 4, None, 4, None, 10, None, None, None, None, None, None) == -1
     assert lib.gvi_select_init_gram_f64(None, 10, 0, 3, 4, None, 1e-12, None, None, None) == -1
     assert lib.gvi_select_update_gram_f64(None, 10, 0, 3, 4, 0, None, None, 1e-12, None, None, None, None) == -1
-    assert lib.gvi_test_set_grad_chunk_waves(3) == 0 and lib.gvi_test_set_grad_chunk_waves(0) == 3
+    from gvi_gaussian_process_b200 import _lib
+
+    assert not hasattr(lib, "gvi_test_set_grad_chunk_waves"), "test hooks must not be exported by the product library"
+    tlib = _lib.load_test()
+    assert tlib.gvi_test_set_grad_chunk_waves(3) == 0 and tlib.gvi_test_set_grad_chunk_waves(0) == 3
 
 
 def test_xla_ffi_adapter_is_consistent_and_gated():

@@ -691,13 +691,13 @@ def test_gradient_step_in_several_chunks(S):
     reg = S.projected.ProjectedKLRegularisation(gp=approx_gp, regulariser=exact_gp,
                                                 regulariser_parameters=exact_params, mode="posterior")
     gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=S.NegativeLogLikelihood(gp=approx_gp))
-    lib = S._lib.load()
     loss1, g1 = gvi.calculate_loss_and_gradients(approx_params, x_dev, dev(pr["y"]))
-    prev = lib.gvi_test_set_grad_chunk_waves(1)
-    try:
-        loss3, g3 = gvi.calculate_loss_and_gradients(approx_params, x_dev, dev(pr["y"]))
-    finally:
-        lib.gvi_test_set_grad_chunk_waves(prev)
+    with S._lib.test_library() as lib:  # the hook lives in libgvigp_test.so only; the shim calls go there in this block
+        prev = lib.gvi_test_set_grad_chunk_waves(1)
+        try:
+            loss3, g3 = gvi.calculate_loss_and_gradients(approx_params, x_dev, dev(pr["y"]))
+        finally:
+            lib.gvi_test_set_grad_chunk_waves(prev)
     assert float(loss1) == float(loss3)
     assert np.array_equal(host(g1["mean_output"]), host(g3["mean_output"]))
     a, b = host(g1["log_lengthscales"]), host(g3["log_lengthscales"])
@@ -749,7 +749,7 @@ def test_branch_free_exp_is_within_one_ulp(S):
     x = np.concatenate([-rng.uniform(0, 700, 200000), -rng.uniform(0, 2, 200000), -10.0 ** rng.uniform(-300, 2, 50000),
                         [0.0, -0.0, -1e-320, -708.0, -708.5, -745.0, -1e6, -np.inf, -0.34657359027997264]])
     xd, out = dev(x), torch.empty(x.size, dtype=torch.float64, device="cuda")
-    S._lib.check(S._lib.load().gvi_test_exp_f64(xd.data_ptr(), x.size, out.data_ptr(), S._lib.current_stream()), "exp")
+    S._lib.check(S._lib.load_test().gvi_test_exp_f64(xd.data_ptr(), x.size, out.data_ptr(), S._lib.current_stream()), "exp")
     got, ref = host(out), np.exp(x)
     keep = x >= -708.0
     ulps = np.abs(got[keep] - ref[keep]) / np.spacing(ref[keep])
@@ -762,7 +762,7 @@ def test_nan_arguments_come_out_as_nan(S):
     experiments/shared/trainer.py:75-82): the exp clamp is a compare-select, not fmax."""
     x = np.array([np.nan, -1.0, -np.nan])
     xd, out = dev(x), torch.empty(x.size, dtype=torch.float64, device="cuda")
-    S._lib.check(S._lib.load().gvi_test_exp_f64(xd.data_ptr(), x.size, out.data_ptr(), S._lib.current_stream()), "exp")
+    S._lib.check(S._lib.load_test().gvi_test_exp_f64(xd.data_ptr(), x.size, out.data_ptr(), S._lib.current_stream()), "exp")
     got = host(out)
     assert np.isnan(got[0]) and np.isnan(got[2]) and got[1] == np.exp(-1.0)
 
