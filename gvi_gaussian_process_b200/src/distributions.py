@@ -17,7 +17,12 @@ class Gaussian(Distribution):
 
     @property
     def full_covariance(self) -> bool:
-        return self.covariance.ndim > self.mean.ndim
+        # reference src/distributions.py:24-29 compares with `!=`: the exact GP's quirk (mean [1,N], diagonal [N]) reads True
+        return self.covariance.ndim != self.mean.ndim
+
+    def dict(self):
+        # reference: Gaussian is a ModuleParameters, so `Gaussian(**gp.predict_probability(...).dict())` works
+        return {"mean": self.mean, "covariance": self.covariance}
 
 
 @dataclass

@@ -24,7 +24,11 @@ class NegativeLogLikelihood(EmpiricalRiskBase):
         gaussian = self._gp.predict_probability(parameters, x)
         mean = gaussian.mean.reshape(-1).contiguous()
         variance = gaussian.covariance.reshape(-1).contiguous()
-        y = as_device(y).reshape(-1)
+        y = as_device(y)
+        k = getattr(self._gp.kernel, "number_output_dimensions", 1)
+        if k > 1 and y.ndim == 2 and y.shape[1] == k:
+            y = y.T  # reference negative_log_likelihood.py:27-40 pairs y.T [K,N] with mean / covariance [K,N]
+        y = y.reshape(-1).contiguous()
         assert y.numel() == mean.numel(), f"{y.numel()=} responses for {mean.numel()=} predictions"
         if wants_grad(mean, variance):
             out3 = PointwiseRisk.apply(L.REG_KINDS["none"], 0.0, y, None, None, mean, variance)

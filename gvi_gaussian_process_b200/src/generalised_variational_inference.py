@@ -72,7 +72,9 @@ class GeneralisedVariationalInference:
         if getattr(gp.kernel, "factorise", None) is None or rg.kind == "none":
             return False  # SparsePosteriorKernel, FixedSparsePosteriorKernel and the SVGP kernels provide factorise()
         if not getattr(gp.kernel, "_ard", True):
-            return False  # non-ARD base kernel: term by term over caller-supplied Grams
+            return False  # non-ARD base kernel (or one with a preprocess_function): term by term over supplied Grams
+        if gp.kernel.has_preprocess_function:
+            return False  # the wrapper kernel's own preprocess_function is applied by calculate_gram on the general path
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
             return (isinstance(reg, GPRegression) and reg._ard and reg.x.shape == gp.kernel.inducing_points.shape

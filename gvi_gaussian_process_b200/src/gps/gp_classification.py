@@ -22,9 +22,9 @@ class GPClassification(ExactGPBase, GPClassificationBase):
     def __init__(self, mean, kernel, x, y, epsilon: float = 0.01, hermite_polynomial_order: int = 50,
                  cdf_lower_bound: float = 1e-10):
         base = kernel.base_kernel if isinstance(kernel, TemperedKernel) else kernel
-        if not isinstance(base, MultiOutputKernel) or not all(isinstance(k, ARDKernel) for k in base.kernels):
+        if not isinstance(base, MultiOutputKernel) or not all(ARDKernel.is_fast_path(k) for k in base.kernels):
             raise NotImplementedError("the B200 path implements exact GP classification over a MultiOutputKernel of "
-                                      "ARDKernels (optionally tempered)")
+                                      "ARDKernels without preprocess_function (optionally tempered)")
         self.x = as_2d(x)
         self.x = self.x.reshape(self.x.shape[0], -1)
         self.y = as_device(y).reshape(self.x.shape[0], -1)

@@ -22,7 +22,7 @@ class GPRegression(ExactGPBase, GPRegressionBase):
     def __init__(self, mean, kernel, x, y):
         # ARD: K tiles evaluated inside the tile kernel (and the differentiable exact-GP step).  Any other kernel: its own
         # Gram routine supplies K(x_train, x_train) and K(x_chunk, x_train) to the same factorisation / predictive kernels.
-        self._ard = isinstance(kernel, ARDKernel)
+        self._ard = ARDKernel.is_fast_path(kernel)
         self.x = as_2d(x)
         if self._ard:
             self.x = self.x.reshape(self.x.shape[0], -1)

@@ -59,7 +59,8 @@ class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
         x_perm = x[perm].contiguous()
         kernel_parameters = kernel._to_parameters(kernel_parameters)
         if self.comm is not None and self.comm.world > 1:
-            assert isinstance(kernel, ARDKernel), "the sharded selector evaluates the ARD kernel inside its CUDA kernels"
+            assert ARDKernel.is_fast_path(kernel), (
+                "the sharded selector evaluates the ARD kernel (no preprocess_function) inside its CUDA kernels")
             from ..distributed import ShardedSelector, shard_bounds
 
             ls, ll = ARDKernel.device_parameters(kernel_parameters)
@@ -68,7 +69,7 @@ class ConditionalVarianceInducingPointsSelector(InducingPointsSelectorBase):
             idx, trace = ShardedSelector(self.comm).select(x_flat[lo:hi].contiguous(), lo, number_of_inducing_points,
                                                            ls, ll, jitter)
             assert int(idx.min()) >= 0, "sharded selection: the per-pivot exchange timed out (a rank never answered)"
-        elif isinstance(kernel, ARDKernel):
+        elif ARDKernel.is_fast_path(kernel):
             ls, ll = ARDKernel.device_parameters(kernel_parameters)
             idx, trace = L.cond_var_select(x_perm.reshape(n, -1), number_of_inducing_points, ls, ll, jitter)
         else:  # any other kernel: Gram columns from the kernel itself, the pivoted Cholesky in the same CUDA kernels

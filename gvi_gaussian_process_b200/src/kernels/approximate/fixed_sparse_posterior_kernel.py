@@ -24,7 +24,7 @@ class FixedSparsePosteriorKernel(ApproximateBaseKernel):
         assert isinstance(base_kernel, KernelBase) and isinstance(regulariser_kernel, KernelBase)
         # both ARD: the fused path (K tiles evaluated in the tile kernel, tensor-pipe gradients).  Otherwise the Grams
         # come from the kernels' own routines: frozen Cholesky from the regulariser kernel once, cross-Grams per chunk.
-        self._ard = isinstance(base_kernel, ARDKernel) and isinstance(regulariser_kernel, ARDKernel)
+        self._ard = ARDKernel.is_fast_path(base_kernel) and ARDKernel.is_fast_path(regulariser_kernel)
         self.regulariser_kernel = regulariser_kernel
         self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
         self.base_kernel = base_kernel

@@ -27,7 +27,7 @@ class SparsePosteriorKernel(ApproximateBaseKernel):
         # ARD: the fused path (K tiles evaluated inside the tile kernel, gradients).  Any other base kernel: its own
         # Gram routine supplies K_ZZ and K(x_chunk, Z); factorisation and predictive still run in the CUDA kernels.
         assert isinstance(base_kernel, KernelBase), f"base_kernel must be a kernel, got {type(base_kernel)=}"
-        self._ard = isinstance(base_kernel, ARDKernel)
+        self._ard = ARDKernel.is_fast_path(base_kernel)
         self.base_kernel = base_kernel
         self.inducing_points = as_2d(inducing_points)
         if self._ard:

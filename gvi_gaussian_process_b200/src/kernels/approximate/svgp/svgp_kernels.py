@@ -30,7 +30,7 @@ class SVGPBaseKernel(ApproximateBaseKernel):
         assert isinstance(regulariser_kernel, KernelBase)
         # ARD: K tiles evaluated inside the tile kernel.  Any other regulariser kernel: its own Gram routine supplies
         # K_ZZ (once) and K(x_chunk, Z); factorisation, both triangular products and the norms stay in the CUDA kernels.
-        self._ard = isinstance(regulariser_kernel, ARDKernel)
+        self._ard = ARDKernel.is_fast_path(regulariser_kernel)
         self.regulariser_kernel = regulariser_kernel
         self.regulariser_kernel_parameters = regulariser_kernel._to_parameters(regulariser_kernel_parameters)
         self.log_observation_noise = log_observation_noise

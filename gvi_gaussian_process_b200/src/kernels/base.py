@@ -15,6 +15,11 @@ class KernelBase(Module):
     number_output_dimensions = 1
 
     def __init__(self, preprocess_function=None):
+        # reference: every calculate_gram call applies the kernel's preprocess_function first (src/kernels/base.py:45-63).
+        # The ARD fast paths (K tiles evaluated inside the CUDA tile kernels from raw inputs) are only taken for kernels
+        # WITHOUT one (`has_preprocess_function` False); otherwise the general Gram-supplied path runs, which calls
+        # calculate_gram and therefore preprocesses exactly as the reference does.
+        self.has_preprocess_function = preprocess_function is not None
         self.preprocess_function = preprocess_function if preprocess_function is not None else (lambda x: x)
 
     def preprocess_inputs(self, x, y=None):

@@ -24,6 +24,12 @@ class ARDKernel(StandardKernelBase):
         return ARDKernel.Parameters(log_scaling=parameters["log_scaling"],
                                     log_lengthscales=parameters["log_lengthscales"])
 
+    @staticmethod
+    def is_fast_path(kernel) -> bool:
+        """True when `kernel` is an ARD kernel the CUDA tile kernels may evaluate from RAW inputs: no preprocess_function
+        (the reference applies it inside every calculate_gram call, src/kernels/base.py:45-63)."""
+        return isinstance(kernel, ARDKernel) and not kernel.has_preprocess_function
+
     # -- device views of the hyper-parameters (no host sync) --------------------------------------------
     @staticmethod
     def device_parameters(parameters):

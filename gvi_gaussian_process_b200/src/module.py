@@ -33,30 +33,51 @@ class ModuleParameters:
     # -- checkpoints (reference: src/module.py:27-55 writes orbax checkpoint directories; orbax is a third-party
     #    format that is not available here, so the same `.dict()` tree is stored as one .npz with "/"-joined keys) ----
     def save(self, path: str) -> None:
+        import json
         import os
 
         import numpy as np
 
-        flat = {}
+        arrays = {}
 
-        def walk(prefix, node):
+        def walk(node):
+            """JSON description of the tree; leaves are stored as arrays a0, a1, ... (empty containers, None leaves, tuples
+            and arbitrary dict keys survive the round trip)."""
             if isinstance(node, dict):
-                for k, v in node.items():
-                    walk(f"{prefix}/{k}" if prefix else str(k), v)
-            elif isinstance(node, (list, tuple)):
-                for i, v in enumerate(node):
-                    walk(f"{prefix}/#{i}", v)
-            else:
-                flat[prefix] = node.detach().cpu().numpy() if hasattr(node, "detach") else np.asarray(node)
+                return {"t": "dict", "k": [str(k) for k in node], "v": [walk(v) for v in node.values()]}
+            if isinstance(node, (list, tuple)):
+                return {"t": "tuple" if isinstance(node, tuple) else "list", "v": [walk(v) for v in node]}
+            if node is None:
+                return {"t": "none"}
+            name = f"a{len(arrays)}"
+            arrays[name] = node.detach().cpu().numpy() if hasattr(node, "detach") else np.asarray(node)
+            return {"t": "array", "a": name}
 
-        walk("", self.dict())
+        structure = json.dumps(walk(self.dict()))
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-        np.savez(path if path.endswith(".npz") else path + ".npz", **flat)
+        np.savez(path if path.endswith(".npz") else path + ".npz", __structure__=np.array(structure), **arrays)
 
     def load(self, path: str) -> "ModuleParameters":
+        import json
+
         import numpy as np
 
         data = np.load(path if path.endswith(".npz") else path + ".npz")
+        if "__structure__" in data.files:
+
+            def build(desc):
+                kind = desc["t"]
+                if kind == "dict":
+                    return {k: build(v) for k, v in zip(desc["k"], desc["v"])}
+                if kind in ("list", "tuple"):
+                    out = [build(v) for v in desc["v"]]
+                    return tuple(out) if kind == "tuple" else out
+                if kind == "none":
+                    return None
+                return data[desc["a"]]
+
+            return self.construct(**build(json.loads(str(data["__structure__"]))))
+        # files written before the structure manifest existed: "/"-joined keys, "#i" list members
         tree: Dict[str, Any] = {}
         for key in data.files:
             node = tree

@@ -202,3 +202,59 @@ def test_multi_gpu_when_two_gpus_are_visible(S):
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
                         os.path.join(root, "tests", "run_multigpu.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "[multigpu] OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_preprocess_function_is_applied_like_the_reference():
+    """the reference applies `preprocess_function` inside every calculate_gram call
+    (src/kernels/base.py:45-63, sparse_posterior_kernel.py:63-90).  A kernel that carries one must not take the raw-input
+    ARD fast paths: predictive, exact posterior and the (then unfused) GVI loss equal the oracle on the preprocessed
+    inputs - for a preprocess_function on the ARD base kernel and for one on the sparse wrapper kernel."""
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean
+    from gvi_gaussian_process_b200.src.regularisations.projected import ProjectedKLRegularisation
+
+    rng = np.random.default_rng(3)
+    n, m, d = 600, 40, 3
+    x, z = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    y, yz = rng.standard_normal(n), rng.standard_normal(m)
+    ls, ll = 0.1, rng.normal(-0.3, 0.1, d)
+    f = lambda a: 2.0 * a + 0.5
+    gram = lambda a, b: O.ard_gram(ls, ll, a, b)
+    diag = lambda a: O.ard_gram_diag(ls, ll, a)
+
+    def reference_loss(fx, fz):
+        v_q = O.sparse_posterior_diag(gram, diag, fz, fx, 1e-5, False)
+        m_p, v_p = O.exact_gp_posterior(gram, diag, np.zeros(n), fz, yz, 0.0, fx)
+        return v_q, O.gaussian_nll(y, np.zeros(n), v_q) + O.projected_regularisation("kl", m_p, v_p, np.zeros(n), v_q, 0.5)
+
+    for where in ("base", "wrapper"):
+        base = ARDKernel(number_of_dimensions=d, preprocess_function=f if where == "base" else None)
+        kp = base.Parameters.construct(log_scaling=ls, log_lengthscales=ll)
+        sparse = SparsePosteriorKernel(base_kernel=base, inducing_points=z,
+                                       preprocess_function=f if where == "wrapper" else None)
+        mean = ConstantMean()
+        approx = ApproximateGPRegression(mean=mean, kernel=sparse)
+        ap = approx.Parameters.construct(mean=mean.Parameters.construct(constant=0.0),
+                                         kernel=sparse.Parameters.construct(base_kernel=kp))
+        exact = GPRegression(mean=mean, kernel=base, x=z, y=yz)
+        ep = exact.Parameters.construct(log_observation_noise=0.0, mean=mean.Parameters.construct(constant=0.0), kernel=kp)
+        gvi = GeneralisedVariationalInference(
+            regularisation=ProjectedKLRegularisation(gp=approx, regulariser=exact, regulariser_parameters=ep,
+                                                     mode="posterior"),
+            empirical_risk=NegativeLogLikelihood(gp=approx))
+        assert not gvi._fusable()
+        if where == "base":   # the base kernel preprocesses everything it is handed: x and Z (and the exact GP's x)
+            v_ref, loss_ref = reference_loss(f(x), f(z))
+        else:                 # the wrapper preprocesses x only; Z and the exact GP see raw inputs
+            v_q = O.sparse_posterior_diag(gram, diag, z, f(x), 1e-5, False)
+            m_p, v_p = O.exact_gp_posterior(gram, diag, np.zeros(n), z, yz, 0.0, x)
+            v_ref = v_q
+            loss_ref = O.gaussian_nll(y, np.zeros(n), v_q) + O.projected_regularisation("kl", m_p, v_p, np.zeros(n), v_q, 0.5)
+        var = host(approx.predict_probability(ap, dev(x)).covariance)
+        assert np.max(np.abs(var - v_ref)) <= 1e-10 * np.max(np.abs(v_ref)), where
+        loss = float(gvi.calculate_loss(ap, dev(x), dev(y)))
+        assert abs(loss - loss_ref) <= 1e-10 * abs(loss_ref), (where, loss, loss_ref)

@@ -116,6 +116,25 @@ def test_data_and_parameter_files_round_trip(tmp_path):
     assert float(q.log_observation_noise) == 0.3 and np.array_equal(q.mean["constant"], np.zeros(2))
     assert float(q.kernel["kernels"][1]["log_scaling"]) == 0.2
     assert np.array_equal(q.kernel["kernels"][0]["log_lengthscales"], np.ones(3))
+    # empty containers, None leaves, tuples and awkward keys survive (a CustomKernel / CustomMean with no parameters)
+    odd = ModuleParameters(custom={}, nothing=None, pair=(np.ones(2), np.zeros(1)), keys={"a/b": 1.0, "#0": 2.0},
+                           empty_list=[])
+    odd.save(str(tmp_path / "odd"))
+    back = ModuleParameters().load(str(tmp_path / "odd"))
+    assert back.custom == {} and back.nothing is None and back.empty_list == []
+    assert isinstance(back.pair, tuple) and np.array_equal(back.pair[0], np.ones(2))
+    assert float(back.keys["a/b"]) == 1.0 and float(back.keys["#0"]) == 2.0
+
+
+def test_gaussian_container_follows_the_reference():
+    """src/distributions.py:14-29: `.dict()` exists (ModuleParameters in the reference) and full_covariance compares the
+    ranks with != (the exact GP's [1,N] mean with an [N] diagonal reads True there)."""
+    from gvi_gaussian_process_b200.src.distributions import Gaussian
+
+    g = Gaussian(mean=np.zeros((1, 4)), covariance=np.ones(4))
+    assert g.full_covariance and set(g.dict()) == {"mean", "covariance"}
+    assert not Gaussian(**Gaussian(mean=np.zeros(4), covariance=np.ones(4)).dict()).full_covariance
+    assert Gaussian(mean=np.zeros(4), covariance=np.eye(4)).full_covariance
 
 
 def test_generate_batch_follows_the_reference_order():
