@@ -76,11 +76,15 @@ def make_replicated(seed: int = 7):
 # CPU arm: the oracle (a port of the reference arithmetic) on the host cores
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_step(x, y, z, yz, fcn, theta):
+    """One objective evaluation of the reference (src/generalised_variational_inference.py:73-94) in NumPy/SciPy f64 on
+    all host cores: the oracle's functions with its BLAS-form Gram (a jit-compiled reference fuses the per-dimension
+    loop the faithful `ard_gram` spells out in Python; see oracle/gp_oracle.py:ard_gram_blas)."""
     from oracle import gp_oracle as O
 
-    gq = lambda a, b: O.ard_gram(theta["ls_q"], theta["ll_q"], a, b)
+    th = os.cpu_count() or 1
+    gq = lambda a, b: O.ard_gram_blas(theta["ls_q"], theta["ll_q"], a, b, threads=th)
     dq = lambda a: O.ard_gram_diag(theta["ls_q"], theta["ll_q"], a)
-    gp = lambda a, b: O.ard_gram(theta["ls_p"], theta["ll_p"], a, b)
+    gp = lambda a, b: O.ard_gram_blas(theta["ls_p"], theta["ll_p"], a, b, threads=th)
     dp = lambda a: O.ard_gram_diag(theta["ls_p"], theta["ll_p"], a)
     m_q = (np.tanh(x @ fcn["w1"] + fcn["b1"]) @ fcn["w2"] + fcn["b2"]).reshape(-1)
     v_q = O.sparse_posterior_diag(gq, dq, z, x, LAMBDA, False)
@@ -110,7 +114,7 @@ def time_cpu(steps: int, warmup: int):
     sec = float(np.mean(times))
     return dict(value=CPU_SAMPLE_ROWS / sec, unit=UNIT, cores=cores, kind="port",
                 sample=f"{CPU_SAMPLE_ROWS} rows x M={M} (the reference's batch size), mean of {steps} step(s), "
-                       f"NumPy/SciPy restatement of the reference (not JAX), loss={loss:.6f}"), sec
+                       f"NumPy/SciPy restatement of the reference (not JAX; Gram through BLAS, all cores), loss={loss:.6f}"), sec
 
 
 def cpu_model() -> str:
@@ -172,18 +176,41 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
+def hbm_peak_gbs() -> float:
+    mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(mp):
+        return float(json.load(open(mp)).get("hbm_gbs", 6558.1))
+    return 6650.0  # fallback stated in B200_PROFILING.md
+
+
+def timed_ms(torch, fn, reps=1, sync_all=None):
+    """CUDA-event time of reps calls of fn on the current stream (ms per call)."""
+    if sync_all:
+        sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from gvi_gaussian_process_b200 import _lib, distributed
+    from gvi_gaussian_process_b200.src import _lib_proxy as L
     from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
     from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
     from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.inducing_points_selection import ConditionalVarianceInducingPointsSelector
     from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
     from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
     from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
     from gvi_gaussian_process_b200.src.regularisations.projected import ProjectedRenyiRegularisation
+    from gvi_gaussian_process_b200.src.utils import jax_prng
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,6 +221,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
+    comm = distributed.Comm()  # gvi_comm: NCCL + peer windows; the data plane of every multi-rank number below
 
     z, yz, fcn, theta = make_replicated()
     # two rotating input batches: 2 x (64 + 8) MB > 126 MB of L2 together with the factor workspaces
@@ -223,23 +251,24 @@ def run_gpu(args):
     reg = ProjectedRenyiRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
                                        mode="posterior", alpha=RENYI_ALPHA)
     gvi = GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
+    dgvi = distributed.DistributedGVI(gvi, comm)
 
     def step(x, y):
-        out3 = gvi.loss_sums(approx_params, x, y)
-        distributed.allreduce_loss_sums(out3)
-        return distributed.loss_from_sums(out3)
+        """The reference's public call (GeneralisedVariationalInference.calculate_loss, src/...inference.py:96-119); with
+        several ranks its distributed wrapper: every rank passes its slice, the sums cross NVLink once."""
+        with torch.no_grad():
+            return gvi.calculate_loss(approx_params, x, y) if world == 1 else dgvi.calculate_loss(approx_params, x, y)
 
     def grad_step(x, y):
         """value and gradient (what jax.grad of calculate_loss gives the reference's trainer): loss,
         d/dlog_scaling, d/dlog_lengthscales[D] all-reduced as one packed (D+4)-vector; d/dm_q back-propagated
         through the tanh-FCN mean by the host framework (torch autograd), its parameter grads all-reduced."""
         out, dm, m_q = gvi.loss_and_grad_sums(approx_params, x, y)
-        distributed.allreduce_loss_sums(out)
+        comm.allreduce_sum(out)
         m_q.backward(dm / out[2])
-        if world > 1:
-            for p_ in fcn_d.values():
-                dist.all_reduce(p_.grad)
-        g = torch.cat([out[3:] / out[2]] + [p_.grad.reshape(-1) for p_ in fcn_d.values()])
+        flat = torch.cat([p_.grad.reshape(-1) for p_ in fcn_d.values()])
+        comm.allreduce_sum(flat)
+        g = torch.cat([out[3:] / out[2], flat])
         for p_ in fcn_d.values():
             p_.grad = None
         return (out[0] + out[1]) / out[2], g
@@ -248,6 +277,22 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- FP64 tensor-pipe peak of THIS device (the roofline denominator), ~50 ms --------------------------------
+    scratch = torch.empty(lib.gvi_fp64_tensor_peak_scratch_bytes(), dtype=torch.uint8, device=dev)
+    import ctypes
+
+    peak_here = ctypes.c_double(0.0)
+    _lib.check(lib.gvi_fp64_tensor_peak_tflops(50.0, ctypes.byref(peak_here), scratch.data_ptr(), _lib.current_stream()),
+               "gvi_fp64_tensor_peak_tflops")
+    peak_here = float(peak_here.value)
+    fp64_peak = max(peak_here, FP64_PEAK_TFLOPS)  # the harder denominator of the two
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------------------
     for i in range(args.warmup):
@@ -262,8 +307,10 @@ def run_gpu(args):
             loss = step(*dev_batches[i % 2])
         e1.record()
         barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_per_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     launches = lib.gvi_launch_count() - launches0
+    loss_value = float(loss.item())
+
     # ---- forward + gradient step (reported beside the forward number) -----------------------------------------
     for p_ in fcn_d.values():
         p_.requires_grad_(True)
@@ -277,22 +324,12 @@ def run_gpu(args):
         gl, gvec = grad_step(*dev_batches[i % 2])
     g1.record()
     barrier()
-    tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-    grad_ms = float(tg.item()) / grad_steps
+    grad_ms = max_over_ranks(g0.elapsed_time(g1)) / grad_steps
     grad_norm = float(gvec.norm().item())
     for p_ in fcn_d.values():
         p_.requires_grad_(False)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / args.steps
-    loss_value = float(loss.item())
 
     # ---- the dominant kernel alone (roofline): events around the fused launch only, factors prepared before ------
-    from gvi_gaussian_process_b200.src import _lib_proxy as L
-
     f_q = sparse.factorise(approx_params.kernel)
     f_p = exact_gp.factorise(exact_params)
     kt = []
@@ -309,37 +346,61 @@ def run_gpu(args):
     kernel_ms = float(np.mean(kt[1:]))
     flops = algorithmic_flops_per_point(M, D) * N_PER_GPU
     achieved = flops / (kernel_ms * 1e-3) / 1e12
+    hbm_peak = hbm_peak_gbs()
 
-    # ---- greedy conditional-variance selection (the other metric of BASELINE.json: selector points*M/s) ----------
+    # ---- multi-GPU parity, checked in the run the numbers come from ------------------------------------------------
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(torch, dist, comm, L, distributed, gvi, dgvi, approx_params, dev_batches[0], to_d, theta,
+                                  rank, world)
+
+    # ---- greedy conditional-variance selection: N_PER_GPU points per rank, sharded over all ranks ----------------------
     sel_m = 512
-    sel = None
     try:
-        xs_sel = dev_batches[0][0]
-        # warm-up at full size: the timed call must not include the first cudaMalloc of the 4 GB C matrix
-        L.cond_var_select(xs_sel, sel_m, to_d(theta["ls_q"]), to_d(theta["ll_q"]), 1e-12)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        sel_idx, _ = L.cond_var_select(xs_sel, sel_m, to_d(theta["ls_q"]), to_d(theta["ll_q"]), 1e-12)
-        s1.record()
-        torch.cuda.synchronize()
-        sel_ms = s0.elapsed_time(s1)
-        sel_bytes = 4.0 * N_PER_GPU * sel_m * sel_m + 32.0 * N_PER_GPU * sel_m
-        hbm_peak = 6558.1
-        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(mp):
-            hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
-        sel = {"n": N_PER_GPU, "m": sel_m, "ms": sel_ms, "points_times_m_per_s": N_PER_GPU * sel_m / (sel_ms * 1e-3),
-               "roofline": {"bound": "hbm", "achieved": sel_bytes / (sel_ms * 1e-3) / 1e9, "peak": hbm_peak,
-                            "unit": "GB/s", "frac": sel_bytes / (sel_ms * 1e-3) / 1e9 / hbm_peak,
-                            "algorithmic_bytes": sel_bytes},
-               "unique_pivots": int(torch.unique(sel_idx).numel())}
+        sel = bench_selector(torch, comm, L, distributed, dev_batches[0][0], to_d, theta, rank, world, sel_m, barrier,
+                             max_over_ranks, hbm_peak)
     except Exception as e:  # pragma: no cover - reported, never hidden
         sel = {"error": f"{type(e).__name__}: {e}"}
+    # the public call, end to end: PRNG permutation (device), gather, selection (N_PER_GPU points in total)
+    try:
+        selector = ConditionalVarianceInducingPointsSelector(comm=comm if world > 1 else None)
+        kp = kernel.Parameters.construct(log_scaling=to_d(theta["ls_q"]), log_lengthscales=to_d(theta["ll_q"]))
+        x_full = dev_batches[1][0]  # every rank passes the same full inputs in the multi-GPU form of the public call
+        if world > 1:
+            dist.broadcast(x_full, 0)
+        selector.compute_inducing_points(jax_prng.PRNGKey(0), x_full, sel_m, kernel, kp)
+        barrier()
+        t0 = time.perf_counter()
+        _, pub_idx = selector.compute_inducing_points(jax_prng.PRNGKey(0), x_full, sel_m, kernel, kp)
+        torch.cuda.synchronize()
+        sel["compute_inducing_points_public_api"] = {
+            "n": N_PER_GPU, "m": sel_m, "ms": max_over_ranks((time.perf_counter() - t0) * 1e3),
+            "note": "wall clock of ConditionalVarianceInducingPointsSelector.compute_inducing_points incl. the "
+                    "jax.random.permutation restatement on the device (threefry kernel + stable sort), the gather and "
+                    "the selection; the same N in total at every rank count (strong scaling)",
+            "unique_indices": int(torch.unique(pub_idx).numel())}
+    except Exception as e:  # pragma: no cover
+        sel["compute_inducing_points_public_api"] = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- configs[4]: scaling sweep, inducing selection + predictive variance over the global N sharded by rank ------------
+    try:
+        config5 = bench_config5(torch, comm, L, distributed, dev, to_d, theta, rank, world, barrier, max_over_ranks,
+                                hbm_peak, fp64_peak, quick=args.quick)
+    except Exception as e:  # pragma: no cover
+        config5 = {"error": f"{type(e).__name__}: {e}"}
+
+    # ---- HBM-bound rows of the path on their own: the materialised Gram and the risk reduction ---------------------------
+    hbm_rows = {}
+    if rank == 0:
+        try:
+            hbm_rows = bench_hbm_rows(torch, L, kernel, dev, to_d, theta, hbm_peak)
+        except Exception as e:  # pragma: no cover
+            hbm_rows = {"error": f"{type(e).__name__}: {e}"}
+    barrier()
 
     # ---- widened rows, reported beside the headline: never part of `value` ------------------
     widened = {}
-    if rank == 0:
+    if rank == 0 and not args.quick:
         try:
             widened["classification_config4"] = bench_classification(dev)
         except Exception as e:  # pragma: no cover - reported, never hidden
@@ -360,22 +421,21 @@ def run_gpu(args):
     for i in range(e2e_steps):
         loss_e2e = float(step(*pinned[i % 2]).item())  # H2D of x, y inside; D2H of the loss
     torch.cuda.synchronize()
-    e2e_sec = time.perf_counter() - t0
-    t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_sec = float(t.item()) / e2e_steps
+    e2e_sec = max_over_ranks(time.perf_counter() - t0) / e2e_steps
 
     result = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu, _ = time_cpu(steps=2, warmup=1)
+            cpu, _ = time_cpu(steps=4, warmup=1)
             cpu["cpu_model"] = cpu_model()
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tpath = os.path.join(ROOT, "profiles", "traffic_r02.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("gp_step_kernel_dram_bytes_per_launch")
+        grad_flops = algorithmic_flops_per_point(M, D) + 2.0 * M * M + 2.0 * M * D
         result = {
             "metric": METRIC, "value": N_PER_GPU * world / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -385,14 +445,16 @@ def run_gpu(args):
                                    f"forward step incl. both factorisations",
                        "n_per_gpu": N_PER_GPU, "d": D, "m": M, "jitter": LAMBDA,
                        "l2_policy": "2 rotating input batches (2 x 72 MB) plus factor state > 126 MB L2",
-                       "parallelism": f"points sharded over {world} rank(s), Z and theta replicated"},
+                       "parallelism": f"points sharded over {world} rank(s), Z and theta replicated; sums all-reduced by "
+                                      f"gvi_comm (NCCL), selector exchange over "
+                                      f"{'CUDA-IPC peer windows' if comm.has_peer_window else 'ncclAllGather'}",
+                       "api": "GeneralisedVariationalInference.calculate_loss" + (" via distributed.DistributedGVI"
+                                                                                 if world > 1 else "")},
             "loss": loss_value, "gpu_launches": int(launches),
             "forward_plus_gradient": {"value": N_PER_GPU * world / (grad_ms * 1e-3), "unit": UNIT,
                                       "ms_per_step": grad_ms, "steps": grad_steps, "grad_norm": grad_norm,
-                                      "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D)
-                                      + 2.0 * M * M + 2.0 * M * D,
-                                      "roofline_frac": (algorithmic_flops_per_point(M, D) + 2.0 * M * M + 2.0 * M * D)
-                                      * N_PER_GPU / (grad_ms * 1e-3) / (FP64_PEAK_TFLOPS * 1e12),
+                                      "algorithmic_flops_per_point": grad_flops,
+                                      "roofline_frac": grad_flops * N_PER_GPU / (grad_ms * 1e-3) / (fp64_peak * 1e12),
                                       "note": "value and gradient w.r.t. log_scaling, log_lengthscales[D] and the "
                                               "tanh-FCN mean parameters (autograd through the mean on the host "
                                               "framework), factorisations included"},
@@ -400,21 +462,179 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(N_PER_GPU * (D + 1) * 8), "d2h_bytes_per_step": 8,
                     "steps": e2e_steps, "loss": loss_e2e},
             "roofline": {"bound": "tensor", "kernel": "gp_step_kernel<3,8> (FP64 DMMA m8n8k4)",
-                         "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic, "kernel_ms": kernel_ms,
+                         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak, "traffic": traffic, "kernel_ms": kernel_ms,
                          "algorithmic_flops_per_point": algorithmic_flops_per_point(M, D),
-                         "peak_source": "measured FP64 DMMA issue rate on this pool's B200 (profiles/fp64_peak_r01.txt; "
-                                        "cuBLAS DGEMM 8192^3 = 35.4); MEASURED_PEAKS.json has no FP64 entry"},
+                         "peak_measured_here": peak_here, "peak_constant_r01": FP64_PEAK_TFLOPS,
+                         "peak_source": "max(FP64 DMMA m8n8k4 issue rate measured in this run by "
+                                        "gvi_fp64_tensor_peak_tflops, the r01 measurement 37.1 in "
+                                        "profiles/fp64_peak_r01.txt); cuBLAS DGEMM 8192^3 = 35.4; MEASURED_PEAKS.json has "
+                                        "no FP64 entry"},
             "selector": sel,
+            "config5": config5,
+            "hbm_rows": hbm_rows,
             "widened": widened,
             "clocks": clocks.summary(),
         }
+        if parity is not None:
+            result["multi_gpu_parity_rel"] = parity["loss_rel"]
+            result["multi_gpu_parity"] = parity
         if cpu is not None:
             result["cpu_baseline"] = cpu
+    comm.destroy()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return result
+
+
+def multi_gpu_parity(torch, dist, comm, L, distributed, gvi, dgvi, approx_params, batch, to_d, theta, rank, world):
+    """A 2e5-point subsample evaluated twice: sharded over the ranks (the path every number of this run takes) and once
+    more on rank 0 alone.  Loss to <= 1e-12 relative; selector pivots bit-identical."""
+    sub = 200_000 // world
+    xs, ys = batch[0][:sub].contiguous(), batch[1][:sub].contiguous()
+    with torch.no_grad():
+        loss_sharded = dgvi.calculate_loss(approx_params, xs, ys)
+    x_all = comm.allgather(xs).reshape(world * sub, -1)
+    y_all = comm.allgather(ys).reshape(-1)
+    sel_m = 96
+    ls, ll = to_d(theta["ls_q"]), to_d(theta["ll_q"])
+    idx_sharded, _ = distributed.ShardedSelector(comm).select(xs, rank * sub, sel_m, ls, ll)
+    out = {"points": world * sub, "selector_m": sel_m}
+    flag = torch.zeros(2, dtype=torch.float64, device=xs.device)
+    if rank == 0:
+        with torch.no_grad():
+            loss_single = gvi.calculate_loss(approx_params, x_all, y_all)
+        idx_single, _ = L.cond_var_select(x_all, sel_m, ls, ll, 1e-12)
+        flag[0] = (loss_sharded - loss_single).abs() / loss_single.abs()
+        flag[1] = 1.0 if torch.equal(idx_sharded, idx_single) else 0.0
+    dist.broadcast(flag, 0)
+    out["loss_rel"] = float(flag[0].item())
+    out["loss_ok_1e-12"] = bool(out["loss_rel"] <= 1e-12)
+    out["selector_pivots_bit_identical"] = bool(flag[1].item() == 1.0)
+    return out
+
+
+def bench_selector(torch, comm, L, distributed, x_local, to_d, theta, rank, world, sel_m, barrier, max_over_ranks,
+                   hbm_peak):
+    """BASELINE.json's second metric (selector points*M/s): every rank owns N_PER_GPU permuted points (weak scaling); with
+    several ranks the one-call sharded selector (exchange inside the kernels), at one rank the single-shard call."""
+    ls, ll = to_d(theta["ls_q"]), to_d(theta["ll_q"])
+    n_local = x_local.shape[0]
+    if world > 1:
+        sharded = distributed.ShardedSelector(comm)
+        run = lambda: sharded.select(x_local, rank * n_local, sel_m, ls, ll)
+    else:
+        run = lambda: L.cond_var_select(x_local, sel_m, ls, ll, 1e-12)
+    run()  # warm-up at full size: the timed call must not include the first cudaMalloc of the 4 GB C matrix
+    ms, (sel_idx, _) = timed_ms(torch, run, sync_all=barrier)
+    ms = max_over_ranks(ms)
+    n_total = n_local * world
+    sel_bytes = 4.0 * n_total * sel_m * sel_m + 32.0 * n_total * sel_m
+    gbs = sel_bytes / (ms * 1e-3) / 1e9 / world
+    return {"n": n_total, "n_per_gpu": n_local, "m": sel_m, "ms": ms, "points_times_m_per_s": n_total * sel_m / (ms * 1e-3),
+            "sharded_over_ranks": world,
+            "exchange": ("none (single shard)" if world == 1 else
+                         "in-kernel stores into CUDA-IPC peer windows" if comm.has_peer_window else
+                         "ncclAllGather enqueued from C"),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s per GPU",
+                         "frac": gbs / hbm_peak, "algorithmic_bytes": sel_bytes},
+            "unique_pivots": int(torch.unique(sel_idx).numel()), "timed_out": bool(int(sel_idx.min()) < 0)}
+
+
+def bench_config5(torch, comm, L, distributed, dev, to_d, theta, rank, world, barrier, max_over_ranks, hbm_peak,
+                  fp64_peak, quick=False):
+    """BASELINE.json configs[4]: N = 1e5 - 1e7 (GLOBAL, sharded contiguously over the ranks), D = 8, M = 512 - 4096:
+    greedy selection (C = 8 N M bytes sharded over the ranks: N = 1e7 with M >= 2048 only fits on several GPUs) followed by
+    the predictive variance of the sparse posterior over the selected points."""
+    ls, ll = to_d(theta["ls_q"]), to_d(theta["ll_q"])
+    total_mem = torch.cuda.get_device_properties(dev).total_memory
+    rows = []
+    sizes = [(100_000, 512), (1_000_000, 1024)] if quick else [
+        (n, m) for n in (100_000, 1_000_000, 10_000_000) for m in (512, 1024, 2048, 4096)]
+    for n, m in sizes:
+        lo, hi = distributed.shard_bounds(n, rank, world)
+        row = {"n": n, "m": m, "n_per_gpu": hi - lo}
+        c_bytes = 8.0 * (hi - lo) * (m - 1)
+        rng = np.random.default_rng(10_000 + rank)
+        x = torch.as_tensor(rng.standard_normal((hi - lo, D)), dtype=torch.float64, device=dev)
+        z = None
+        if c_bytes > 0.8 * total_mem:
+            row["selection"] = (f"skipped: C = {8.0 * n * m / 1e9:.0f} GB does not fit {world} GPU(s) "
+                                f"({c_bytes / 1e9:.0f} GB per rank > 0.8 x {total_mem / 1e9:.0f} GB)")
+        else:
+            if world > 1:
+                sharded = distributed.ShardedSelector(comm)
+                run = lambda: sharded.select(x, lo, m, ls, ll)
+            else:
+                run = lambda: L.cond_var_select(x, m, ls, ll, 1e-12)
+            if n <= 1_000_000 and m <= 1024:
+                run()  # small cases: take the allocation out of the timing; the big ones are dominated by HBM streaming
+            ms, (idx, _) = timed_ms(torch, run, sync_all=barrier)
+            ms = max_over_ranks(ms)
+            by = 4.0 * n * m * m + 32.0 * n * m
+            row["selection"] = {"ms": ms, "points_times_m_per_s": n * m / (ms * 1e-3),
+                                "hbm_gbs_per_gpu": by / (ms * 1e-3) / 1e9 / world,
+                                "hbm_frac": by / (ms * 1e-3) / 1e9 / world / hbm_peak,
+                                "unique_pivots": int(torch.unique(idx).numel())}
+            # the selected points, replicated: the owner of each pivot contributes its row, everyone else zeros
+            mine = (idx >= lo) & (idx < hi)
+            z = torch.zeros((m, D), dtype=torch.float64, device=dev)
+            z[mine] = x[idx[mine] - lo]
+            comm.allreduce_sum(z)
+            del idx
+        torch.cuda.empty_cache()
+        if z is None:  # selection did not fit: predictive variance over a random inducing set of the same size
+            z = torch.as_tensor(np.random.default_rng(77).standard_normal((m, D)), dtype=torch.float64, device=dev)
+            row["inducing_points"] = "random (selection skipped)"
+        factor = L.GpFactor(m, D)
+
+        def predictive():
+            f = factor.factor(z, ls, ll, LAMBDA, False)
+            return L.gp_predict(f, x, want_mean=False)[1]
+
+        predictive()
+        ms, var = timed_ms(torch, predictive, sync_all=barrier)
+        ms = max_over_ranks(ms)
+        fl = (float(m) * m + 4.0 * m * D) * n
+        row["predictive_variance"] = {"ms": ms, "points_per_s": n / (ms * 1e-3),
+                                      "tflops_per_gpu": fl / (ms * 1e-3) / 1e12 / world,
+                                      "fp64_tensor_frac": fl / (ms * 1e-3) / 1e12 / world / fp64_peak,
+                                      "min_variance": float(var.min().item())}
+        rows.append(row)
+        del x, z, var, factor
+        torch.cuda.empty_cache()
+    return {"workload": "configs[4]: N global, sharded over the ranks; selection then predictive variance (factorisation "
+                        "included); times are max over ranks", "n_gpus": world, "rows": rows}
+
+
+def bench_hbm_rows(torch, L, kernel, dev, to_d, theta, hbm_peak):
+    """north_star bullets 1 and 3 on their own (single GPU): the materialised ARD Gram (store-bound: 8 N M bytes written)
+    and the risk + regulariser reduction (reads 40 bytes per point), both against the measured HBM copy bandwidth."""
+    out = {}
+    rng = np.random.default_rng(5)
+    kp = kernel.Parameters.construct(log_scaling=to_d(theta["ls_q"]), log_lengthscales=to_d(theta["ll_q"]))
+    n, m = 400_000, 1024
+    x = torch.as_tensor(rng.standard_normal((n, D)), dtype=torch.float64, device=dev)
+    zz = torch.as_tensor(rng.standard_normal((m, D)), dtype=torch.float64, device=dev)
+    kernel.calculate_gram(kp, x, zz)
+    ms, g = timed_ms(torch, lambda: kernel.calculate_gram(kp, x, zz), reps=3)
+    out["materialised_gram"] = {"n": n, "m": m, "d": D, "ms": ms, "gb_written": 8.0 * n * m / 1e9,
+                                "store_gbs": 8.0 * n * m / (ms * 1e-3) / 1e9,
+                                "hbm_frac": 8.0 * n * m / (ms * 1e-3) / 1e9 / hbm_peak,
+                                "api": "ARDKernel.calculate_gram (output allocation included)"}
+    del g
+    torch.cuda.empty_cache()
+    for n in (1_000_000, 10_000_000, 100_000_000):
+        v = [torch.rand(n, dtype=torch.float64, device=dev) + 0.5 for _ in range(5)]
+        y, mq, vq, mp, vp = v
+        L.risk(L.REG_KINDS["renyi"], RENYI_ALPHA, y, mq, vq, mp, vp)
+        ms, _ = timed_ms(torch, lambda: L.risk(L.REG_KINDS["renyi"], RENYI_ALPHA, y, mq, vq, mp, vp), reps=5)
+        out[f"risk_reduction_n{n:.0e}".replace("+0", "")] = {
+            "n": n, "ms": ms, "read_gbs": 40.0 * n / (ms * 1e-3) / 1e9, "hbm_frac": 40.0 * n / (ms * 1e-3) / 1e9 / hbm_peak}
+        del v, y, mq, vq, mp, vp
+        torch.cuda.empty_cache()
+    return out
 
 
 def bench_classification(dev):
@@ -576,6 +796,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="profiling runs: skip the widened rows, shorten the config5 sweep")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     result = run_reference(args) if args.impl == "reference" else run_gpu(args)
