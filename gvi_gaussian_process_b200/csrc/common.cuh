@@ -164,6 +164,33 @@ __device__ __forceinline__ double gvi_exp(double x) {
   return tiny ? 0.0 : res;
 }
 
+// Table-driven variant for kernels that are bound by the FP64 pipe itself (the materialised Gram: one exp per 8 bytes
+// stored): x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^k (T_j + T_j (e^r - 1)) with T_j = 2^(j/32) from a 32-entry
+// table in shared memory and e^r - 1 = r (1 + r/2 + ... + r^5/720) (remainder r^7/5040 < 4e-18): 12 FP64 instructions
+// instead of 19.  T_j is held as hi + lo, so only the final add rounds: ~0.5 ulp; exactly 0 below -708, NaN -> NaN.
+// `tab` points at a copy of GVI_EXP2_TABLE (shared memory: the lookups are data dependent, one LDS.128 each).
+__device__ __forceinline__ double gvi_exp_t32(double x, const double2* tab) {
+  const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the low word of (y + SHIFT) is rint(y)
+  const bool tiny = x < -708.0;
+  const double xc = tiny ? -708.0 : x;  // compare-select, not fmax(): NaN stays NaN
+  const double t = fma(xc, 46.16624130844683, SHIFT);  // 32 / ln2
+  const int n = __double2loint(t);
+  const double nf = t - SHIFT;
+  double r = fma(nf, -0.021660849392446835, xc);  // ln2/32, leading 36 bits: nf * hi is exact
+  r = fma(nf, -5.145609244655338e-14, r);
+  double p = 1.3888888888888889e-03;             // 1/6!
+  p = fma(p, r, 8.333333333333333e-03);          // 1/5!
+  p = fma(p, r, 4.1666666666666664e-02);         // 1/4!
+  p = fma(p, r, 1.6666666666666666e-01);         // 1/3!
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  const double q = p * r;                        // e^r - 1
+  const double2 tj = tab[n & 31];
+  const double res = fma(tj.x, q, tj.y) + tj.x;
+  const double scaled = __hiloint2double(__double2hiint(res) + ((n >> 5) << 20), __double2loint(res));
+  return tiny ? 0.0 : scaled;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -54,6 +54,138 @@ __global__ void __launch_bounds__(TC) ard_gram_kernel(const double* __restrict__
   }
 }
 
+// 2^(j/32), j = 0 .. 31, as correctly rounded double + the remainder (hi, lo): gvi_exp_t32
+__device__ const double2 GVI_EXP2_TABLE[32] = {
+    {1.0, 0.0},
+    {1.0218971486541166, 5.109225028973444e-17},
+    {1.0442737824274138, 8.551889705537965e-17},
+    {1.0671404006768237, -7.899853966841582e-17},
+    {1.0905077326652577, -3.046782079812471e-17},
+    {1.1143867425958924, 1.0410278456845571e-16},
+    {1.1387886347566916, 8.912812676025408e-17},
+    {1.1637248587775775, 3.8292048369240935e-17},
+    {1.189207115002721, 3.982015231465646e-17},
+    {1.215247359980469, -7.712630692681488e-17},
+    {1.241857812073484, 4.658027591836937e-17},
+    {1.2690509571917332, 2.667932131342186e-18},
+    {1.2968395546510096, 2.5382502794888315e-17},
+    {1.3252366431597413, -2.8587312100388614e-17},
+    {1.3542555469368927, 7.70094837980299e-17},
+    {1.383909881963832, -6.770511658794786e-17},
+    {1.4142135623730951, -9.667293313452913e-17},
+    {1.4451808069770467, -3.0237581349939873e-17},
+    {1.4768261459394993, -3.483994556892796e-17},
+    {1.5091644275934228, -1.016455327754295e-16},
+    {1.5422108254079407, 7.949834809697621e-17},
+    {1.5759808451078865, -1.0136916471278304e-17},
+    {1.6104903319492543, 2.4707192569797888e-17},
+    {1.645755478153965, -1.0125679913674773e-16},
+    {1.681792830507429, 8.199010020581497e-17},
+    {1.718619298122478, -1.851380418263111e-17},
+    {1.7562521603732995, 2.960140695448873e-17},
+    {1.7947090750031072, 1.8227458427912087e-17},
+    {1.8340080864093424, 3.283107224245627e-17},
+    {1.8741676341103, -6.122763413004143e-17},
+    {1.9152065613971474, -1.0619946056195963e-16},
+    {1.9571441241754002, 8.960767791036668e-17}};
+
+// Materialised Gram for D <= 16 - the API call ARDKernel.calculate_gram (src/kernels/standard/base.py:95-103,
+// ard_kernel.py:58-66).  The output is written once (8 B per element: the HBM store roofline), so the kernel is shaped
+// around the FP64 instruction count per element, which is what actually bounds it:
+//   - inputs are centred on x2[0] and pre-scaled by sqrt(exp(log_ls_d) / 2) when they are staged (x rows in shared
+//     memory, the thread's own columns in registers), so a dimension costs one subtract and one fma per element and the
+//     exponent -0.5 sum_d w_d (x_d - z_d)^2 needs no further scaling; still DIRECT differences (no ||x||^2 + ||z||^2 -
+//     2 x.z cancellation), the centring keeps the pre-scaled operands as small as the data spread;
+//   - the table-driven exp (12 FP64 instructions instead of 19);
+//   - RT x CT independent accumulator / exp chains per thread, x rows read as broadcast LDS.128 (two dimensions each);
+//   - adjacent column pairs per thread -> 16-byte streaming stores, 512 contiguous bytes per warp and row.
+template <int DP, int CT>
+__global__ void __launch_bounds__(256) ard_gram_tile_kernel(const double* __restrict__ x1, int64_t m1,
+                                                            const double* __restrict__ x2, int64_t m2, int D,
+                                                            const double* __restrict__ log_scaling,
+                                                            const double* __restrict__ log_ls, int ls_len,
+                                                            double* __restrict__ out, int64_t ld) {
+  constexpr int RB = 64;  // rows of x1 per CTA
+  constexpr int RT = 4;   // rows per inner step
+  __shared__ __align__(16) double xs[RB][DP];
+  __shared__ double2 tab[32];
+  __shared__ double sc[DP], ctr[DP];
+  const int tid = threadIdx.x;
+  const int64_t col0 = (int64_t)blockIdx.x * (256 * CT) + (int64_t)tid * CT;
+  const int64_t row0 = (int64_t)blockIdx.y * RB;
+  if (tid < 32) tab[tid] = GVI_EXP2_TABLE[tid];
+  if (tid < DP) {
+    sc[tid] = tid < D ? sqrt(0.5 * exp(log_ls[ls_len == 1 ? 0 : tid])) : 0.0;
+    ctr[tid] = tid < D ? x2[tid] : 0.0;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < RB * DP; idx += 256) {
+    const int r = idx / DP, d = idx % DP;
+    xs[r][d] = (row0 + r < m1 && d < D) ? sc[d] * (x1[(row0 + r) * D + d] - ctr[d]) : 0.0;
+  }
+  double z[CT][DP];
+#pragma unroll
+  for (int c = 0; c < CT; c++)
+#pragma unroll
+    for (int d = 0; d < DP; d++) z[c][d] = (col0 + c < m2 && d < D) ? sc[d] * (x2[(col0 + c) * D + d] - ctr[d]) : 0.0;
+  const double amp = exp(log_scaling[0]);
+  const double amp2 = amp * amp;
+  __syncthreads();
+  const bool vec2 = CT == 2 && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (col0 + 1 < m2);
+  const int rows = (int)((m1 - row0) < RB ? (m1 - row0) : RB);
+  for (int r0 = 0; r0 < rows; r0 += RT) {
+    double acc[RT][CT];
+#pragma unroll
+    for (int rr = 0; rr < RT; rr++)
+#pragma unroll
+      for (int c = 0; c < CT; c++) acc[rr][c] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DP; d += 2) {
+#pragma unroll
+      for (int rr = 0; rr < RT; rr++) {
+        const double2 xv = *reinterpret_cast<const double2*>(&xs[r0 + rr][d]);
+#pragma unroll
+        for (int c = 0; c < CT; c++) {
+          const double d0 = xv.x - z[c][d];
+          acc[rr][c] = fma(d0, d0, acc[rr][c]);
+          const double d1 = xv.y - z[c][d + 1];
+          acc[rr][c] = fma(d1, d1, acc[rr][c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < RT; rr++) {
+      if (r0 + rr >= rows) break;
+      double v[CT];
+#pragma unroll
+      for (int c = 0; c < CT; c++) v[c] = amp2 * gvi_exp_t32(-acc[rr][c], tab);
+      double* dst = out + (row0 + r0 + rr) * ld + col0;
+      if (vec2) {
+        __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[CT - 1]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < CT; c++)
+          if (col0 + c < m2) __stcs(dst + c, v[c]);
+      }
+    }
+  }
+}
+
+template <int DP, int CT>
+int launch_ard_gram_tile(const double* x1, int64_t m1, const double* x2, int64_t m2, int D, const double* log_scaling,
+                         const double* log_ls, int ls_len, double* out, int64_t ld, cudaStream_t st) {
+  const int64_t gx = (m2 + 256 * CT - 1) / (256 * CT);
+  const int64_t gy = (m1 + 63) / 64;
+  const int64_t max_gy = 65535;  // grid.y limit: loop over row super-blocks
+  for (int64_t y0 = 0; y0 < gy; y0 += max_gy) {
+    const int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
+    ard_gram_tile_kernel<DP, CT><<<dim3((unsigned)gx, (unsigned)ny), 256, 0, st>>>(
+        x1 + y0 * 64 * D, m1 - y0 * 64, x2, m2, D, log_scaling, log_ls, ls_len, out + y0 * 64 * ld, ld);
+    GVI_CHECK_LAUNCH("ard_gram_tile_kernel");
+  }
+  return GVI_OK;
+}
+
 __global__ void ard_gram_diag_kernel(int64_t n, const double* __restrict__ log_scaling, double* __restrict__ out) {
   const double amp = exp(log_scaling[0]);
   const double v = amp * amp;  // * exp(-0.5 * 0)
@@ -181,6 +313,11 @@ int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t 
                         const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
                         cudaStream_t st) {
   if (m1 == 0 || m2 == 0) return GVI_OK;
+  if (D <= 2) return launch_ard_gram_tile<2, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
+  if (D <= 4) return launch_ard_gram_tile<4, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
+  if (D <= 8) return launch_ard_gram_tile<8, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
+  if (D <= 16) return launch_ard_gram_tile<16, 1>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
+  // 16 < D < 24 (or no workspace for the tensor-pipe kernel): one column per thread, features staged 16 at a time
   int64_t gy = (m1 + TR - 1) / TR;
   int64_t gx = (m2 + TC - 1) / TC;
   // grid.y is limited to 65535: loop over row super-blocks
