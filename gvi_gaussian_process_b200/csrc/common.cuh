@@ -165,18 +165,25 @@ __device__ __forceinline__ double gvi_exp(double x) {
 }
 
 // Table-driven variant for kernels that are bound by the FP64 pipe itself (the materialised Gram: one exp per 8 bytes
-// stored): x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp(x) = 2^k (T_j + T_j (e^r - 1)) with T_j = 2^(j/32) from a 32-entry
-// table in shared memory and e^r - 1 = r (1 + r/2 + ... + r^5/720) (remainder r^7/5040 < 4e-18): 12 FP64 instructions
-// instead of 19.  T_j is held as hi + lo, so only the final add rounds: ~0.5 ulp; exactly 0 below -708, NaN -> NaN.
-// `tab` points at a copy of GVI_EXP2_TABLE (shared memory: the lookups are data dependent, one LDS.128 each).
-__device__ __forceinline__ double gvi_exp_t32(double x, const double2* tab) {
+// stored).  Takes s >= 0 and returns exp(-s): -s = (32 k + j) ln2/32 + r, |r| <= ln2/64,
+// exp(-s) = 2^k (T_j + T_j (e^r - 1)) with T_j = 2^(j/32) = hi_j + lo_j from 32-entry tables and
+// e^r - 1 = r (1 + r/2 + ... + r^5/720) (remainder r^7/5040 < 4e-18): 12 FP64 instructions instead of 20; only the final
+// add rounds (0.56 ulp over the host sweep in tests/test_host_logic.py).  Exactly 0 for s > 708 (incl. +inf; the range test
+// is two integer compares on the bit pattern, not an FP64 instruction), NaN -> NaN.  tab: entry j = (hi, lo) at
+// [j * stride] (shared-memory copies of GVI_EXP2_TABLE; the lookups are data dependent, so the Gram kernel keeps 8
+// interleaved copies - one per lane of a quarter-warp, the unit a 16-byte shared load is served in - and every lookup
+// is one bank-conflict-free LDS.128).
+// CHECKED = false skips the range test: the caller has established s <= 708 (or NaN) for a whole group of arguments.
+template <bool CHECKED = true>
+__device__ __forceinline__ double gvi_exp_neg_t32(double s, const double2* tab, int stride) {
   const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52: the low word of (y + SHIFT) is rint(y)
-  const bool tiny = x < -708.0;
-  const double xc = tiny ? -708.0 : x;  // compare-select, not fmax(): NaN stays NaN
-  const double t = fma(xc, 46.16624130844683, SHIFT);  // 32 / ln2
+  const long long bs = __double_as_longlong(s);
+  const bool tiny = CHECKED && bs > 0x4086200000000000ll && bs <= 0x7ff0000000000000ll;  // s > 708 (or +inf), not NaN
+  const double sc = tiny ? 708.0 : s;
+  const double t = fma(sc, -46.16624130844683, SHIFT);  // -32 / ln2
   const int n = __double2loint(t);
   const double nf = t - SHIFT;
-  double r = fma(nf, -0.021660849392446835, xc);  // ln2/32, leading 36 bits: nf * hi is exact
+  double r = fma(nf, -0.021660849392446835, -sc);  // ln2/32, leading 36 bits: nf * hi is exact
   r = fma(nf, -5.145609244655338e-14, r);
   double p = 1.3888888888888889e-03;             // 1/6!
   p = fma(p, r, 8.333333333333333e-03);          // 1/5!
@@ -185,7 +192,7 @@ __device__ __forceinline__ double gvi_exp_t32(double x, const double2* tab) {
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   const double q = p * r;                        // e^r - 1
-  const double2 tj = tab[n & 31];
+  const double2 tj = tab[(n & 31) * stride];
   const double res = fma(tj.x, q, tj.y) + tj.x;
   const double scaled = __hiloint2double(__double2hiint(res) + ((n >> 5) << 20), __double2loint(res));
   return tiny ? 0.0 : scaled;

@@ -54,7 +54,10 @@ __global__ void __launch_bounds__(TC) ard_gram_kernel(const double* __restrict__
   }
 }
 
-// 2^(j/32), j = 0 .. 31, as correctly rounded double + the remainder (hi, lo): gvi_exp_t32
+constexpr int GRAM_RB = 64;      // rows of x1 staged per block of the tile kernel
+constexpr int GRAM_RBLOCKS = 4;  // row blocks per CTA
+
+// 2^(j/32), j = 0 .. 31, as correctly rounded double + the remainder (hi, lo): gvi_exp_neg_t32
 __device__ const double2 GVI_EXP2_TABLE[32] = {
     {1.0, 0.0},
     {1.0218971486541166, 5.109225028973444e-17},
@@ -91,81 +94,121 @@ __device__ const double2 GVI_EXP2_TABLE[32] = {
 
 // Materialised Gram for D <= 16 - the API call ARDKernel.calculate_gram (src/kernels/standard/base.py:95-103,
 // ard_kernel.py:58-66).  The output is written once (8 B per element: the HBM store roofline), so the kernel is shaped
-// around the FP64 instruction count per element, which is what actually bounds it:
+// around the FP64 instruction count per element, which is what actually bounds it (28 per element at D = 8):
 //   - inputs are centred on x2[0] and pre-scaled by sqrt(exp(log_ls_d) / 2) when they are staged (x rows in shared
 //     memory, the thread's own columns in registers), so a dimension costs one subtract and one fma per element and the
-//     exponent -0.5 sum_d w_d (x_d - z_d)^2 needs no further scaling; still DIRECT differences (no ||x||^2 + ||z||^2 -
+//     exponent 0.5 sum_d w_d (x_d - z_d)^2 needs no further scaling; still DIRECT differences (no ||x||^2 + ||z||^2 -
 //     2 x.z cancellation), the centring keeps the pre-scaled operands as small as the data spread;
-//   - the table-driven exp (12 FP64 instructions instead of 19);
+//   - the amplitude enters through the accumulator's start value -2 log_scaling (exp(-s) exp(2 ls));
+//   - the table-driven exp (12 FP64 instructions instead of 20), its tables replicated per half-warp lane;
 //   - RT x CT independent accumulator / exp chains per thread, x rows read as broadcast LDS.128 (two dimensions each);
-//   - adjacent column pairs per thread -> 16-byte streaming stores, 512 contiguous bytes per warp and row.
+//   - adjacent column pairs per thread -> 16-byte streaming stores, 512 contiguous bytes per warp and row;
+//   - a CTA keeps its columns in registers over RBLOCKS row blocks (the column loads and table fill amortise).
 template <int DP, int CT>
-__global__ void __launch_bounds__(256) ard_gram_tile_kernel(const double* __restrict__ x1, int64_t m1,
-                                                            const double* __restrict__ x2, int64_t m2, int D,
-                                                            const double* __restrict__ log_scaling,
-                                                            const double* __restrict__ log_ls, int ls_len,
-                                                            double* __restrict__ out, int64_t ld) {
-  constexpr int RB = 64;  // rows of x1 per CTA
-  constexpr int RT = 4;   // rows per inner step
+#ifndef GRAM_MIN_CTAS
+#define GRAM_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, GRAM_MIN_CTAS) ard_gram_tile_kernel(const double* __restrict__ x1, int64_t m1,
+                                                               const double* __restrict__ x2, int64_t m2, int D,
+                                                               const double* __restrict__ log_scaling,
+                                                               const double* __restrict__ log_ls, int ls_len,
+                                                               double* __restrict__ out, int64_t ld) {
+  constexpr int RB = GRAM_RB;  // rows of x1 per staged block
+  constexpr int RT = DP <= 8 ? 8 : 4;  // rows per inner step (lab: tools/lab/gram_lab.cu - 8 x 2 chains per thread at 3 CTAs/SM was best)
   __shared__ __align__(16) double xs[RB][DP];
-  __shared__ double2 tab[32];
+  __shared__ double2 tab[32][8];
   __shared__ double sc[DP], ctr[DP];
   const int tid = threadIdx.x;
   const int64_t col0 = (int64_t)blockIdx.x * (256 * CT) + (int64_t)tid * CT;
-  const int64_t row0 = (int64_t)blockIdx.y * RB;
-  if (tid < 32) tab[tid] = GVI_EXP2_TABLE[tid];
+  tab[tid >> 3][tid & 7] = GVI_EXP2_TABLE[tid >> 3];
   if (tid < DP) {
     sc[tid] = tid < D ? sqrt(0.5 * exp(log_ls[ls_len == 1 ? 0 : tid])) : 0.0;
     ctr[tid] = tid < D ? x2[tid] : 0.0;
   }
   __syncthreads();
-  for (int idx = tid; idx < RB * DP; idx += 256) {
-    const int r = idx / DP, d = idx % DP;
-    xs[r][d] = (row0 + r < m1 && d < D) ? sc[d] * (x1[(row0 + r) * D + d] - ctr[d]) : 0.0;
-  }
   double z[CT][DP];
 #pragma unroll
   for (int c = 0; c < CT; c++)
 #pragma unroll
     for (int d = 0; d < DP; d++) z[c][d] = (col0 + c < m2 && d < D) ? sc[d] * (x2[(col0 + c) * D + d] - ctr[d]) : 0.0;
-  const double amp = exp(log_scaling[0]);
-  const double amp2 = amp * amp;
-  __syncthreads();
+  const double acc0 = -2.0 * log_scaling[0];  // exp(-(acc0 + s)) = exp(log_scaling)^2 exp(-s)
+  const double2* tb = &tab[0][tid & 7];
   const bool vec2 = CT == 2 && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (col0 + 1 < m2);
-  const int rows = (int)((m1 - row0) < RB ? (m1 - row0) : RB);
-  for (int r0 = 0; r0 < rows; r0 += RT) {
-    double acc[RT][CT];
+  for (int blk = 0; blk < GRAM_RBLOCKS; blk++) {
+    const int64_t row0 = ((int64_t)blockIdx.y * GRAM_RBLOCKS + blk) * RB;
+    if (row0 >= m1) break;
+    __syncthreads();  // the previous block's readers are done with xs
+    for (int idx = tid; idx < RB * DP; idx += 256) {
+      const int r = idx / DP, d = idx % DP;
+      xs[r][d] = (row0 + r < m1 && d < D) ? sc[d] * (x1[(row0 + r) * D + d] - ctr[d]) : 0.0;
+    }
+    __syncthreads();
+    const int rows = (int)((m1 - row0) < RB ? (m1 - row0) : RB);
+    for (int r0 = 0; r0 < rows; r0 += RT) {
+      double acc[RT][CT];
 #pragma unroll
-    for (int rr = 0; rr < RT; rr++)
+      for (int rr = 0; rr < RT; rr++)
 #pragma unroll
-      for (int c = 0; c < CT; c++) acc[rr][c] = 0.0;
+        for (int c = 0; c < CT; c++) acc[rr][c] = acc0;
 #pragma unroll
-    for (int d = 0; d < DP; d += 2) {
+      for (int d = 0; d < DP; d += 2) {
 #pragma unroll
-      for (int rr = 0; rr < RT; rr++) {
-        const double2 xv = *reinterpret_cast<const double2*>(&xs[r0 + rr][d]);
+        for (int rr = 0; rr < RT; rr++) {
+          const double2 xv = *reinterpret_cast<const double2*>(&xs[r0 + rr][d]);
 #pragma unroll
-        for (int c = 0; c < CT; c++) {
-          const double d0 = xv.x - z[c][d];
-          acc[rr][c] = fma(d0, d0, acc[rr][c]);
-          const double d1 = xv.y - z[c][d + 1];
-          acc[rr][c] = fma(d1, d1, acc[rr][c]);
+          for (int c = 0; c < CT; c++) {
+            const double d0 = xv.x - z[c][d];
+            acc[rr][c] = fma(d0, d0, acc[rr][c]);
+            const double d1 = xv.y - z[c][d + 1];
+            acc[rr][c] = fma(d1, d1, acc[rr][c]);
+          }
         }
       }
-    }
+      // one range test for the thread's RT x CT exponents (high words as integers: s > 708, +inf and NaN read as large);
+      // the rare out-of-range ones are parked at 0 and patched afterwards, so that ALL RT x CT exponentials run as one
+      // straight-line block of independent chains without per-element range logic
+      int hmax = __double2hiint(acc[0][0]);
 #pragma unroll
-    for (int rr = 0; rr < RT; rr++) {
-      if (r0 + rr >= rows) break;
-      double v[CT];
+      for (int rr = 0; rr < RT; rr++)
 #pragma unroll
-      for (int c = 0; c < CT; c++) v[c] = amp2 * gvi_exp_t32(-acc[rr][c], tab);
-      double* dst = out + (row0 + r0 + rr) * ld + col0;
-      if (vec2) {
-        __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[CT - 1]));
+        for (int c = 0; c < CT; c++) hmax = max(hmax, __double2hiint(acc[rr][c]));
+      unsigned zero_mask = 0u, nan_mask = 0u;
+      if (hmax >= 0x40862000) {
+#pragma unroll
+        for (int rr = 0; rr < RT; rr++)
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            const double a = acc[rr][c];
+            if (a != a) nan_mask |= 1u << (rr * CT + c);
+            else if (a > 708.0) zero_mask |= 1u << (rr * CT + c);
+            if (!(a <= 708.0)) acc[rr][c] = 0.0;
+          }
+      }
+      double v[RT][CT];
+#pragma unroll
+      for (int rr = 0; rr < RT; rr++)
+#pragma unroll
+        for (int c = 0; c < CT; c++) v[rr][c] = gvi_exp_neg_t32<false>(acc[rr][c], tb, 8);
+      if (zero_mask | nan_mask) {
+#pragma unroll
+        for (int rr = 0; rr < RT; rr++)
+#pragma unroll
+          for (int c = 0; c < CT; c++) {
+            if (zero_mask >> (rr * CT + c) & 1u) v[rr][c] = 0.0;  // exp(-s) < 1e-307: as gvi_exp
+            if (nan_mask >> (rr * CT + c) & 1u) v[rr][c] = __longlong_as_double(0x7ff8000000000000ll);
+          }
+      }
+      double* dst = out + (row0 + r0) * ld + col0;
+      if (vec2 && r0 + RT <= rows) {
+#pragma unroll
+        for (int rr = 0; rr < RT; rr++)
+          __stcs(reinterpret_cast<double2*>(dst + rr * ld), make_double2(v[rr][0], v[rr][CT - 1]));
       } else {
 #pragma unroll
-        for (int c = 0; c < CT; c++)
-          if (col0 + c < m2) __stcs(dst + c, v[c]);
+        for (int rr = 0; rr < RT; rr++)
+#pragma unroll
+          for (int c = 0; c < CT; c++)
+            if (r0 + rr < rows && col0 + c < m2) __stcs(dst + rr * ld + c, v[rr][c]);
       }
     }
   }
@@ -175,12 +218,14 @@ template <int DP, int CT>
 int launch_ard_gram_tile(const double* x1, int64_t m1, const double* x2, int64_t m2, int D, const double* log_scaling,
                          const double* log_ls, int ls_len, double* out, int64_t ld, cudaStream_t st) {
   const int64_t gx = (m2 + 256 * CT - 1) / (256 * CT);
-  const int64_t gy = (m1 + 63) / 64;
+  constexpr int64_t rows_per_cta = (int64_t)GRAM_RB * GRAM_RBLOCKS;
+  const int64_t gy = (m1 + rows_per_cta - 1) / rows_per_cta;
   const int64_t max_gy = 65535;  // grid.y limit: loop over row super-blocks
   for (int64_t y0 = 0; y0 < gy; y0 += max_gy) {
     const int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
     ard_gram_tile_kernel<DP, CT><<<dim3((unsigned)gx, (unsigned)ny), 256, 0, st>>>(
-        x1 + y0 * 64 * D, m1 - y0 * 64, x2, m2, D, log_scaling, log_ls, ls_len, out + y0 * 64 * ld, ld);
+        x1 + y0 * rows_per_cta * D, m1 - y0 * rows_per_cta, x2, m2, D, log_scaling, log_ls, ls_len,
+        out + y0 * rows_per_cta * ld, ld);
     GVI_CHECK_LAUNCH("ard_gram_tile_kernel");
   }
   return GVI_OK;
