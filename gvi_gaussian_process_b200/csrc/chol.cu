@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(256) pack_linv_kernel(const double* __restrict
 
 // L^-T in the same fragment order: group g holds rows j in [R g, R g + R) and the k-range c in [R g, Mp):
 // element = Linv[c = 8kp + 4e + lane%4][j = R g + 8mt + lane/4] for kp >= R g / 8.  One CTA per group.
-__global__ void __launch_bounds__(256) pack_linvT_kernel(const double* __restrict__ X, int Mp, int M, int G,
-                                                         double* __restrict__ W) {
+__global__ void __launch_bounds__(256) pack_linvT_kernel(const double* __restrict__ X, int64_t ldx, int Mp, int M,
+                                                         int G, double* __restrict__ W) {
   const int g = blockIdx.x;
   double2* out = reinterpret_cast<double2*>(W + wpackT_group_off(g, G));
   const int kp0 = GVI_GROUP_ROWS * g / 8;
@@ -410,33 +410,33 @@ __global__ void __launch_bounds__(256) pack_linvT_kernel(const double* __restric
     int j = GVI_GROUP_ROWS * g + 8 * mt + (lane >> 2);
     int c0 = 8 * (kp0 + kpl) + (lane & 3), c1 = c0 + 4;
     double2 v;
-    v.x = (j < M && c0 < M && c0 >= j) ? X[(int64_t)c0 * Mp + j] : 0.0;
-    v.y = (j < M && c1 < M && c1 >= j) ? X[(int64_t)c1 * Mp + j] : 0.0;
+    v.x = (j < M && c0 < M && c0 >= j) ? X[(int64_t)c0 * ldx + j] : 0.0;
+    v.y = (j < M && c1 < M && c1 >= j) ? X[(int64_t)c1 * ldx + j] : 0.0;
     out[it] = v;
   }
 }
-__global__ void copy_linv_kernel(const double* __restrict__ X, int Mp, int M, double* __restrict__ out) {
+__global__ void copy_linv_kernel(const double* __restrict__ X, int64_t ldx, int Mp, int M, double* __restrict__ out) {
   const int64_t total = (int64_t)Mp * Mp;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int r = (int)(idx / Mp), c = (int)(idx % Mp);
-    out[idx] = (r < M && c <= r) ? X[idx] : 0.0;
+    out[idx] = (r < M && c <= r) ? X[(int64_t)r * ldx + c] : 0.0;
   }
 }
 
 // ---- alpha = L^-T (L^-1 y): two triangular matvecs with the explicit inverse, fixed summation order ------------
-__global__ void __launch_bounds__(256) linv_matvec_kernel(const double* __restrict__ X, int Mp, int M,
+__global__ void __launch_bounds__(256) linv_matvec_kernel(const double* __restrict__ X, int64_t ldx, int Mp, int M,
                                                           const double* __restrict__ y, double* __restrict__ t) {
   // warp per row c: t[c] = sum_{j<=c} X[c][j] y[j]
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= Mp) return;
   double s = 0.0;
   if (warp < M)
-    for (int j = lane; j <= warp; j += 32) s = fma(X[(int64_t)warp * Mp + j], y[j], s);
+    for (int j = lane; j <= warp; j += 32) s = fma(X[(int64_t)warp * ldx + j], y[j], s);
   s = warp_sum(s);
   if (lane == 0) t[warp] = s;
 }
-__global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ X, int Mp, int M,
+__global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ X, int64_t ldx, int Mp, int M,
                                                            const double* __restrict__ t, double* __restrict__ a) {
   // a[j] = sum_{c>=j} X[c][j] t[c]: 32 columns per CTA (coalesced across lanes), rows split over the 8 warps,
   // fixed-order combination
@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restr
   double s = 0.0;
   if (j < M)
     for (int c = blockIdx.x * 32 + warp; c < M; c += 8)
-      if (c >= j) s = fma(X[(int64_t)c * Mp + j], t[c], s);
+      if (c >= j) s = fma(X[(int64_t)c * ldx + j], t[c], s);
   part[warp][lane] = s;
   __syncthreads();
   if (warp == 0 && j < Mp) {
@@ -525,10 +525,14 @@ extern "C" size_t gvi_gp_factor_bytes(int M, int D) {
   if (M < 1 || D < 1) return 0;
   return (size_t)factor_layout(M, D).total * sizeof(double);
 }
+size_t gvi_chol_coop_scratch_doubles(int Mw);
+int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int* info, cudaStream_t st);
+static inline int factor_ws_dim(int M) { return (M + 63) / 64 * 64; }  // the factorisation works on 64 x 64 blocks
+
 extern "C" size_t gvi_gp_factor_workspace_bytes(int M) {
   if (M < 1) return 0;
-  size_t Mp = (size_t)(M + 31) / 32 * 32;
-  return (2 * Mp * Mp + 2 * Mp + 8) * sizeof(double);
+  const size_t Mw = (size_t)factor_ws_dim(M);
+  return (2 * Mw * Mw + 2 * Mw + 8 + gvi_chol_coop_scratch_doubles((int)Mw)) * sizeof(double);
 }
 
 static int factor_impl(const double* Z, int M, int D, const double* log_scaling, const double* log_ls, int ls_len,
@@ -608,15 +612,18 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   const FactorLayout f = factor_layout(M, D);
   double* F = (double*)factor_out;
   note_extra(factor_out, false);  // a fresh factorisation clears the extra-matrix flag (F[6] = 0 in the header kernel)
+  // workspace: A and X are [Mw, Mw] with Mw = M rounded up to the 64-wide blocks of the cooperative factorisation
+  const int Mw = factor_ws_dim(M);
   double* A = (double*)workspace;
-  double* X = A + (size_t)f.Mp * f.Mp;
-  double* tvec = X + (size_t)f.Mp * f.Mp;
-  int* winfo = (int*)(tvec + 2 * f.Mp);
+  double* X = A + (size_t)Mw * Mw;
+  double* tvec = X + (size_t)Mw * Mw;
+  int* winfo = (int*)(tvec + 2 * Mw);
+  double* P = tvec + 2 * Mw + 8;
   int rc;
   if (Kzz) {
     factor_header_gram_kernel<<<64, 256, 0, st>>>(F, f, is_abs ? reg : 0.0);
     GVI_CHECK_LAUNCH("factor_header_gram_kernel");
-    copy_gram_kernel<<<148 * 4, 256, 0, st>>>(Kzz, ldk, M, A, f.Mp);
+    copy_gram_kernel<<<148 * 4, 256, 0, st>>>(Kzz, ldk, M, A, Mw);
     GVI_CHECK_LAUNCH("copy_gram_kernel");
   } else {
     factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0,
@@ -627,44 +634,37 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   if (Kzz)
     rc = GVI_OK;
   else if (chol_log_scaling)
-    rc = gvi_launch_ard_gram(Z, M, Z, M, D, chol_log_scaling, chol_log_ls, chol_ls_len, A, f.Mp, st);
+    rc = gvi_launch_ard_gram(Z, M, Z, M, D, chol_log_scaling, chol_log_ls, chol_ls_len, A, Mw, st);
   else
-    rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, f.Mp, st);
+    rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, Mw, st);
   if (rc) return rc;
-  add_diag_kernel<<<1, 1024, 0, st>>>(A, M, f.Mp, reg, is_abs, log_noise, F + 2);
+  add_diag_kernel<<<1, 1024, 0, st>>>(A, M, Mw, reg, is_abs, log_noise, F + 2);
   GVI_CHECK_LAUNCH("add_diag_kernel");
-  if (f.Mp != M) {
-    pad_identity_kernel<<<148, 256, 0, st>>>(A, M, f.Mp);
+  if (Mw != M) {
+    pad_identity_kernel<<<148, 256, 0, st>>>(A, M, Mw);
     GVI_CHECK_LAUNCH("pad_identity_kernel");
   }
   info_init_kernel<<<1, 1, 0, st>>>(winfo);
   GVI_CHECK_LAUNCH("info_init_kernel");
-  if ((rc = launch_chol(A, f.Mp, f.Mp, winfo, st))) return rc;
+  // Cholesky and L^-1 in ONE cooperative launch (chol_coop.cu)
+  if ((rc = gvi_launch_chol_inverse_coop(A, X, P, Mw, winfo, st))) return rc;
   info_final_kernel<<<1, 1, 0, st>>>(winfo);
   GVI_CHECK_LAUNCH("info_final_kernel");
   info_to_header_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp);
   GVI_CHECK_LAUNCH("info_to_header_kernel");
   if (info) GVI_CUDA(cudaMemcpyAsync(info, winfo, sizeof(int), cudaMemcpyDeviceToDevice, st));
-  zero_kernel<<<148 * 4, 256, 0, st>>>(X, (int64_t)f.Mp * f.Mp);
-  GVI_CHECK_LAUNCH("zero_kernel");
-  diag_inverse_kernel<<<f.Mp / NB, 32, 0, st>>>(A, f.Mp, X, f.Mp);
-  GVI_CHECK_LAUNCH("diag_inverse_kernel");
-  if (f.Mp / NB > 1) {
-    linv_sweep_kernel<<<f.Mp / NB - 1, 256, 10 * NB * (NB + 1) * sizeof(double), st>>>(A, f.Mp, X, f.Mp, f.Mp / NB);
-    GVI_CHECK_LAUNCH("linv_sweep_kernel");
-  }
   {
-    pack_linv_kernel<<<f.G, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpack_off);
+    pack_linv_kernel<<<f.G, 256, 0, st>>>(X, Mw, M, f.G, F + f.wpack_off);
     GVI_CHECK_LAUNCH("pack_linv_kernel");
-    pack_linvT_kernel<<<f.G, 256, 0, st>>>(X, f.Mp, M, f.G, F + f.wpackT_off);
+    pack_linvT_kernel<<<f.G, 256, 0, st>>>(X, Mw, f.Mp, M, f.G, F + f.wpackT_off);
     GVI_CHECK_LAUNCH("pack_linvT_kernel");
-    copy_linv_kernel<<<148 * 4, 256, 0, st>>>(X, f.Mp, M, F + f.linv_off);
+    copy_linv_kernel<<<148 * 4, 256, 0, st>>>(X, Mw, f.Mp, M, F + f.linv_off);
     GVI_CHECK_LAUNCH("copy_linv_kernel");
   }
   if (y_z) {
-    linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, f.Mp, M, y_z, tvec);
+    linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, Mw, f.Mp, M, y_z, tvec);
     GVI_CHECK_LAUNCH("linv_matvec_kernel");
-    linvT_matvec_kernel<<<f.Mp / 32, 256, 0, st>>>(X, f.Mp, M, tvec, F + f.alpha_off);
+    linvT_matvec_kernel<<<f.Mp / 32, 256, 0, st>>>(X, Mw, f.Mp, M, tvec, F + f.alpha_off);
     GVI_CHECK_LAUNCH("linvT_matvec_kernel");
   } else {
     zero_kernel<<<4, 256, 0, st>>>(F + f.alpha_off, f.Mp);

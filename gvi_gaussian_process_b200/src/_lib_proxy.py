@@ -113,10 +113,12 @@ class GpFactor:
 
     # views into the workspace (valid until the next factor() call) -- used by the full-covariance API only
     def cholesky(self):
-        return self.ws[: self.mp * self.mp].view(self.mp, self.mp)[: self.m, : self.m]
+        mw = (self.m + 63) // 64 * 64  # the factorisation works on 64 x 64 blocks (csrc/chol_coop.cu)
+        return self.ws[: mw * mw].view(mw, mw)[: self.m, : self.m]
 
     def inverse_cholesky(self):
-        return self.ws[self.mp * self.mp: 2 * self.mp * self.mp].view(self.mp, self.mp)[: self.m, : self.m]
+        mw = (self.m + 63) // 64 * 64
+        return self.ws[mw * mw: 2 * mw * mw].view(mw, mw)[: self.m, : self.m]
 
 
 def gp_predict(factor: GpFactor, x, prior_mean=None, log_noise_add=None, want_mean=True):
