@@ -526,7 +526,8 @@ extern "C" size_t gvi_gp_factor_bytes(int M, int D) {
   return (size_t)factor_layout(M, D).total * sizeof(double);
 }
 size_t gvi_chol_coop_scratch_doubles(int Mw);
-int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int* info, cudaStream_t st);
+int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int M, int* info, cudaStream_t st,
+                                 long long* stamps = nullptr);
 static inline int factor_ws_dim(int M) { return (M + 63) / 64 * 64; }  // the factorisation works on 64 x 64 blocks
 
 extern "C" size_t gvi_gp_factor_workspace_bytes(int M) {
@@ -647,7 +648,7 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   info_init_kernel<<<1, 1, 0, st>>>(winfo);
   GVI_CHECK_LAUNCH("info_init_kernel");
   // Cholesky and L^-1 in ONE cooperative launch (chol_coop.cu)
-  if ((rc = gvi_launch_chol_inverse_coop(A, X, P, Mw, winfo, st))) return rc;
+  if ((rc = gvi_launch_chol_inverse_coop(A, X, P, Mw, M, winfo, st))) return rc;
   info_final_kernel<<<1, 1, 0, st>>>(winfo);
   GVI_CHECK_LAUNCH("info_final_kernel");
   info_to_header_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp);

@@ -72,107 +72,214 @@ __device__ __forceinline__ void acc_visit(double (&acc)[2][4][2], F f) {
     for (int nt = 0; nt < 4; nt++) f(16 * wm + 8 * mt + (lane >> 2), 32 * wn + 8 * nt + 2 * (lane & 3), acc[mt][nt]);
 }
 
+#ifdef GVI_COOP_STAMPS  // lab builds (tools/lab/chol_lab.cu): CTA 0 records %globaltimer at phase boundaries
+__device__ long long* g_lab_stamps = nullptr;
+#define STAMP(id)                                                                          \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && g_lab_stamps) {                             \
+      long long t__;                                                                       \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t__));                              \
+      g_lab_stamps[2 * g_lab_stamps[0] + 2] = (id);                                        \
+      g_lab_stamps[2 * g_lab_stamps[0] + 3] = t__;                                         \
+      g_lab_stamps[0]++;                                                                   \
+    }                                                                                      \
+  } while (0)
+#else
+#define STAMP(id)
+#endif
+
 // ---- diagonal block: L = chol(T) and its inverse --------------------------------------------------------------
-// 32 x 32 Cholesky of the sub-block at (o, o) of T, one warp, lane r owns row r - the arithmetic of chol.cu's panel kernel
-__device__ __forceinline__ void chol32(Tile& T, int o, int lane, int col0, int* __restrict__ info) {
-  double row[HB];
+// 32 x 32 Cholesky of the sub-block at (o, o) of T, one warp, lane r owns row r (column-by-column right-looking).
+// FAST = false: pivot sq = sqrt(d), column = row / sq - IEEE square root and division, the arithmetic chol.cu's panel kernel
+//   has always used (bit-identical results for matrices that fit one 32 x 32 block, e.g. the reference's 2-point goldens).
+// FAST = true : r = rsqrt(d), pivot = d r, column = row r.  A factorisation is a serial chain of M pivots; an IEEE
+//   sqrt followed by a divide is ~60 dependent FP64 instructions (~800 cycles for a lone warp), i.e. 0.4 ms at M = 1024
+//   before any other work - the reciprocal square root (MUFU seed + Newton steps) and a multiply are ~10.
+template <bool FAST>
+__device__ __forceinline__ void chol32(Tile& T, int o, Tile& Wscratch, int col0, int* __restrict__ info) {
+  // Works on a [32][33] copy (stride 33: a warp's accesses to its own rows are bank-conflict free) in panels of 8 columns:
+  // warp 0 eliminates a panel in registers (lane = row, pivots and multipliers travel by shuffle), then all 256 threads
+  // apply the panel to the trailing sub-block.  Every element still receives its fma updates in ascending column order
+  // followed by the pivot scaling, i.e. the arithmetic of the plain column-by-column elimination; but the serial chain is
+  // one shuffle + pivot + fma per column instead of a warp-wide sweep over shared memory (a fully unrolled 32-column
+  // version was instruction-fetch bound, a compact shared-memory loop latency bound: 17-18 us per call either way).
+  double(*D)[HB + 1] = reinterpret_cast<double(*)[HB + 1]>(&Wscratch[0][0]);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int idx = tid; idx < HB * HB; idx += 256) D[idx >> 5][idx & 31] = T[o + (idx >> 5)][o + (idx & 31)];
+  __syncthreads();
+#pragma unroll 1
+  for (int jb = 0; jb < HB; jb += 8) {
+    if (warp == 0) {
+      double p[8];
 #pragma unroll
-  for (int c = 0; c < HB; c++) row[c] = T[o + lane][o + c];
+      for (int jj = 0; jj < 8; jj++) p[jj] = D[lane][jb + jj];
 #pragma unroll
-  for (int j = 0; j < HB; j++) {
-    const double djj = __shfl_sync(0xffffffffu, row[j], j);
-    if (lane == j && !(djj > 0.0) && info) atomicMin(info, col0 + j + 1);
-    const double sq = sqrt(djj);
-    row[j] = (lane == j) ? sq : row[j] / sq;
-    T[o + lane][o + j] = row[j];  // column j of L (valid for lanes >= j)
-    __syncwarp();
+      for (int jj = 0; jj < 8; jj++) {
+        const int j = jb + jj;
+        const double djj = __shfl_sync(0xffffffffu, p[jj], j);
+        if (lane == j && !(djj > 0.0) && info) atomicMin(info, col0 + j + 1);
+        if (FAST) {
+          const double r = rsqrt(djj);
+          p[jj] = (lane == j) ? djj * r : p[jj] * r;
+        } else {
+          const double sq = sqrt(djj);
+          p[jj] = (lane == j) ? sq : p[jj] / sq;
+        }
 #pragma unroll
-    for (int k = j + 1; k < HB; k++) {
-      const double lkj = T[o + k][o + j];  // broadcast
-      if (lane >= k) row[k] = fma(-row[j], lkj, row[k]);
+        for (int kk = jj + 1; kk < 8; kk++) {
+          const double lkj = __shfl_sync(0xffffffffu, p[jj], jb + kk);  // L[jb + kk][j]
+          if (lane >= jb + kk) p[kk] = fma(-p[jj], lkj, p[kk]);
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; jj++)
+        if (lane >= jb + jj) D[lane][jb + jj] = p[jj];
+    }
+    __syncthreads();
+    // trailing sub-block: D[r][c] -= sum_{j in panel} L[r][j] L[c][j], r >= c >= jb + 8, j ascending
+    const int n = HB - jb - 8;
+    for (int idx = tid; idx < n * n; idx += 256) {
+      const int r = jb + 8 + idx / n, c = jb + 8 + idx % n;
+      if (c <= r) {
+        double v = D[r][c];
+#pragma unroll
+        for (int jj = 0; jj < 8; jj++) v = fma(-D[r][jb + jj], D[c][jb + jj], v);
+        D[r][c] = v;
+      }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < HB * HB; idx += 256) {
+    const int r = idx >> 5, c = idx & 31;
+    T[o + r][o + c] = (c <= r) ? D[r][c] : 0.0;
+  }
+  __syncthreads();
+}
+// Inverse of the lower-triangular 32 x 32 sub-block at (o, o) of T into Dv (same position), all 256 threads, W scratch.
+// Leaves: the four 8 x 8 diagonal blocks by the column recurrence x[i] = (delta_ij - sum_{k=j}^{i-1} L[i][k] x[k]) / L[i][i]
+// (lane = column; the arithmetic chol.cu's diag_inverse_kernel used for whole 32 x 32 blocks, so results that depend
+// on the first 8 columns only - the reference's 2-point goldens - keep their bits).  Then two doubling levels:
+// inv([[a, 0], [b, c]]) = [[a^-1, 0], [-c^-1 b a^-1, c^-1]] with the two small products spread over the CTA.  The serial
+// chain is 8 divisions long instead of 32 and the dependent fma chains are 8 / 8 / 16 long instead of 496 in total.
+__device__ __forceinline__ void inv32_blocked(const Tile& T, Tile& Dv, Tile& W, int o) {
+  const int tid = threadIdx.x;
+  if (tid < HB) {
+    const int lb = tid >> 3, j = tid & 7, oo = o + 8 * lb;  // leaf lb, column j
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      double v = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; k++) v = fma(-T[oo + i][oo + k], (k >= j) ? x[k] : 0.0, v);
+      x[i] = (i >= j) ? v / T[oo + i][oo + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) Dv[oo + i][oo + j] = x[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int h = 8; h < HB; h *= 2) {  // pairs of h x h inverses -> 2h x 2h inverses
+    const int npair = HB / (2 * h), outs = npair * h * h;
+    // W = b a^-1   (b = T[lower-left h x h of the pair], a^-1 = Dv[upper-left])
+    for (int idx = tid; idx < outs; idx += 256) {
+      const int pr = idx / (h * h), r = (idx / h) % h, c = idx % h, oo = o + pr * 2 * h;
+      double v = 0.0;
+      for (int k = c; k < h; k++) v = fma(T[oo + h + r][oo + k], Dv[oo + k][oo + c], v);
+      W[oo + h + r][oo + c] = v;
+    }
+    __syncthreads();
+    // Dv[lower-left] = -c^-1 W, upper-right = 0
+    for (int idx = tid; idx < outs; idx += 256) {
+      const int pr = idx / (h * h), r = (idx / h) % h, c = idx % h, oo = o + pr * 2 * h;
+      double v = 0.0;
+      for (int k = 0; k <= r; k++) v = fma(Dv[oo + h + r][oo + h + k], W[oo + h + k][oo + c], v);
+      Dv[oo + h + r][oo + c] = -v;
+      Dv[oo + r][oo + h + c] = 0.0;
+    }
+    __syncthreads();
+  }
+}
+
+// 32 x 32 x 32 product of sub-blocks on the tensor pipe: 8 warps, warp w owns the 8 x 8 output tiles 2w and 2w + 1 of the
+// 4 x 4 tile grid.  A block at (ar, ac) of tile A; TB: B^T with B block at (br, bc) read as B[n][k], else B[k][n].
+// acc[t][e] = C[8 (tile / 4) + lane / 4][8 (tile % 4) + 2 (lane % 4) + e], tile = 2 warp + t.
+template <bool TB>
+__device__ __forceinline__ void mma32(const Tile& A, int ar, int ac, const Tile& B, int br, int bc, double (&acc)[2][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
+#pragma unroll
+  for (int k0 = 0; k0 < HB; k0 += 4) {
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+      const int tile = 2 * warp + t, mt = tile >> 2, nt = tile & 3;
+      const double av = A[ar + 8 * mt + fr][ac + k0 + fk];
+      const double bv = TB ? B[br + 8 * nt + fr][bc + k0 + fk] : B[br + k0 + fk][bc + 8 * nt + fr];
+      dmma884(acc[t][0], acc[t][1], av, bv);
     }
   }
-#pragma unroll
-  for (int c = 0; c < HB; c++) T[o + lane][o + c] = (c <= lane) ? row[c] : 0.0;
-  __syncwarp();
 }
-// inverse of the lower-triangular 32 x 32 sub-block at (o, o) of T into Dv (same position): lane j owns column j,
-// x[i] = (delta_ij - sum_{k=j}^{i-1} L[i][k] x[k]) / L[i][i] - the arithmetic of chol.cu's diag_inverse_kernel
-__device__ __forceinline__ void inv32(const Tile& T, Tile& Dv, int o, int lane) {
-  double x[HB];
+template <typename F>
+__device__ __forceinline__ void mma32_visit(double (&acc)[2][2], F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int i = 0; i < HB; i++) {
-    double v = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; k++) v = fma(-T[o + i][o + k], (k >= lane) ? x[k] : 0.0, v);
-    x[i] = (i >= lane) ? v / T[o + i][o + i] : 0.0;
+  for (int t = 0; t < 2; t++) {
+    const int tile = 2 * warp + t;
+    f(8 * (tile >> 2) + (lane >> 2), 8 * (tile & 3) + 2 * (lane & 3), acc[t]);
   }
-#pragma unroll
-  for (int i = 0; i < HB; i++) Dv[o + i][o + lane] = x[i];
 }
 
 // T (64 x 64, symmetric input, lower part used) -> L in T (upper part zeroed), L^-1 in Dv; W is scratch.  256 threads.
+template <bool FAST>
 __device__ void diag_factor(Tile& T, Tile& Dv, Tile& W, int col0, int* __restrict__ info) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  double acc[2][2];
   __syncthreads();
-  if (warp == 0) chol32(T, 0, lane, col0, info);
+  STAMP(20);
+  chol32<FAST>(T, 0, W, col0, info);
+  STAMP(21);
+  inv32_blocked(T, Dv, W, 0);  // D1 = L11^-1
+  STAMP(22);
+  // L21 = A21 D1^T (the triangular solve as a product)
+  mma32<true>(T, HB, 0, Dv, 0, 0, acc);
   __syncthreads();
-  // L21 = A21 L11^-T (warp 0, lane owns a row: forward substitution) while warp 1 inverts L11
-  if (warp == 0) {
-    double x[HB];
-#pragma unroll
-    for (int c = 0; c < HB; c++) x[c] = T[HB + lane][c];
-#pragma unroll
-    for (int c = 0; c < HB; c++) {
-      double v = x[c];
-#pragma unroll
-      for (int k = 0; k < c; k++) v = fma(-x[k], T[c][k], v);
-      x[c] = v / T[c][c];
-    }
-#pragma unroll
-    for (int c = 0; c < HB; c++) T[HB + lane][c] = x[c];
-  } else if (warp == 1) {
-    inv32(T, Dv, 0, lane);
-  }
+  mma32_visit(acc, [&](int r, int c, double (&v)[2]) {
+    T[HB + r][c] = v[0];
+    T[HB + r][c + 1] = v[1];
+  });
   __syncthreads();
-  // A22 -= L21 L21^T (lower part), 4 entries per thread, k ascending
-  for (int idx = tid; idx < HB * HB; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
-    if (c <= r) {
-      double v = T[HB + r][HB + c];
-#pragma unroll 8
-      for (int k = 0; k < HB; k++) v = fma(-T[HB + r][k], T[HB + c][k], v);
-      T[HB + r][HB + c] = v;
-    }
-  }
-  __syncthreads();
-  if (warp == 0) chol32(T, HB, lane, col0 + HB, info);
-  __syncthreads();
-  if (warp == 0) inv32(T, Dv, HB, lane);
-  // zero blocks: upper right of L and of L^-1
+  // A22 -= L21 L21^T
+  mma32<true>(T, HB, 0, T, HB, 0, acc);
+  mma32_visit(acc, [&](int r, int c, double (&v)[2]) {
+    T[HB + r][HB + c] -= v[0];
+    T[HB + r][HB + c + 1] -= v[1];
+  });
+  // upper right blocks of L and of L^-1 are zero
   for (int idx = tid; idx < HB * HB; idx += 256) {
     const int r = idx >> 5, c = idx & 31;
     T[r][HB + c] = 0.0;
     Dv[r][HB + c] = 0.0;
   }
   __syncthreads();
-  // Dv21 = -D2 (L21 D1): W = L21 D1, then Dv21 = -D2 W
-  for (int idx = tid; idx < HB * HB; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
-    double v = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < HB; k++) v = fma(T[HB + r][k], Dv[k][c], v);
-    W[r][c] = v;
-  }
+  STAMP(23);
+  chol32<FAST>(T, HB, W, col0 + HB, info);
+  STAMP(24);
+  inv32_blocked(T, Dv, W, HB);  // D2 = L22^-1
+  STAMP(25);
+  // Dv21 = -D2 (L21 D1)
+  mma32<false>(T, HB, 0, Dv, 0, 0, acc);
+  mma32_visit(acc, [&](int r, int c, double (&v)[2]) {
+    W[r][c] = v[0];
+    W[r][c + 1] = v[1];
+  });
   __syncthreads();
-  for (int idx = tid; idx < HB * HB; idx += 256) {
-    const int r = idx >> 5, c = idx & 31;
-    double v = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < HB; k++) v = fma(Dv[HB + r][HB + k], W[k][c], v);
-    Dv[HB + r][c] = -v;
-  }
+  mma32<false>(Dv, HB, HB, W, 0, 0, acc);
+  mma32_visit(acc, [&](int r, int c, double (&v)[2]) {
+    Dv[HB + r][c] = -v[0];
+    Dv[HB + r][c + 1] = -v[1];
+  });
   __syncthreads();
+  STAMP(26);
 }
 
 struct CoopArgs {
@@ -181,6 +288,8 @@ struct CoopArgs {
   double* P;    // split-K partial tiles of the inverse: (G/2)^2 x 64 x 64 doubles
   int Mw, G;
   int* info;
+  int fast_pivots;    // see chol32
+  long long* stamps;  // lab builds only
 };
 
 __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArgs a) {
@@ -201,13 +310,17 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
     if (j > i)
       for (int idx = threadIdx.x; idx < CB * CB; idx += 256) blk(X, i, j)[(int64_t)(idx >> 6) * ld + (idx & 63)] = 0.0;
   }
+  STAMP(0);
   if (b == 0) {  // step 0: the first diagonal block
     load_tile(Cs, blk(A, 0, 0), ld);
-    diag_factor(Cs, As, Bs, 0, a.info);
+    if (a.fast_pivots) diag_factor<true>(Cs, As, Bs, 0, a.info);
+    else diag_factor<false>(Cs, As, Bs, 0, a.info);
     store_tile(blk(A, 0, 0), ld, Cs);
     store_tile(blk(X, 0, 0), ld, As);
   }
+  STAMP(1);
   grid.sync();
+  STAMP(2);
   for (int k = 0; k < G - 1; k++) {
     // ---- panel: L[i,k] = A[i,k] Dinv_k^T, i > k --------------------------------------------------------------
     bool have_d = false;
@@ -227,7 +340,9 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = make_double2(v[0], v[1]);
       });
     }
+    STAMP(3);
     grid.sync();
+    STAMP(4);
     // ---- trailing update A[i,j] -= L[i,k] L[j,k]^T for k < j <= i; task 0 = (k+1, k+1) goes on to factorise it ----
     const int n = G - k - 1;             // blocks per side of the trailing matrix
     const int ntask = n * (n + 1) / 2;
@@ -256,12 +371,15 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         else *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = old;
       });
       if (diag_next) {  // look-ahead: this CTA factorises block (k+1, k+1) while the others finish the update
-        diag_factor(Cs, As, Bs, (k + 1) * CB, a.info);
+        STAMP(5);
+        diag_factor<true>(Cs, As, Bs, (k + 1) * CB, a.info);  // G > 1 implies M > 32
         store_tile(blk(A, k + 1, k + 1), ld, Cs);
         store_tile(blk(X, k + 1, k + 1), ld, As);
       }
     }
+    STAMP(6);
     grid.sync();
+    STAMP(7);
   }
   // ---- X = L^-1 by block sub-diagonals d = i - j: X[i,j] = -Dinv_i sum_{k=j}^{i-1} L[i,k] X[k,j] --------------------
   for (int d = 1; d < G; d++) {
@@ -282,7 +400,9 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         *reinterpret_cast<double2*>(dst + r * CB + c) = make_double2(v[0], v[1]);
       });
     }
+    STAMP(8);
     grid.sync();
+    STAMP(9);
     for (int j = b; j < nblk; j += nb) {
       const int i = j + d;
       __syncthreads();
@@ -308,7 +428,9 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = make_double2(-v[0], -v[1]);
       });
     }
+    STAMP(10);
     grid.sync();
+    STAMP(11);
   }
 }
 }  // namespace
@@ -319,14 +441,18 @@ size_t gvi_chol_coop_scratch_doubles(int Mw) {
   return (size_t)tasks * CB * CB;
 }
 
-// A, X: [Mw, Mw] row-major, Mw a multiple of 64 (identity-padded by the caller); *info must hold INT_MAX on entry
+// A, X: [Mw, Mw] row-major, Mw a multiple of 64 (identity-padded by the caller beyond the true size M); *info must hold INT_MAX on entry
 // (atomicMin of 1 + the first non-positive pivot column).  One cooperative launch on `st`.
-int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int* info, cudaStream_t st) {
+int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int M, int* info, cudaStream_t st,
+                                 long long* stamps = nullptr) {
   static std::atomic<unsigned long long> configured{0};
   const size_t smem = 3 * sizeof(Tile);
+#ifdef GVI_COOP_STAMPS
+  cudaMemcpyToSymbolAsync(g_lab_stamps, &stamps, sizeof(stamps), 0, cudaMemcpyHostToDevice, st);
+#endif
   if (gvi_first_use_on_this_device(configured))
     GVI_CUDA(cudaFuncSetAttribute(chol_inverse_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CoopArgs args{A, X, P, Mw, Mw / CB, info};
+  CoopArgs args{A, X, P, Mw, Mw / CB, info, M > HB ? 1 : 0, stamps};
   const int G = Mw / CB;
   int want = G * (G - 1) / 2;  // widest phase: the first trailing update
   const int quarter = ((G + 1) / 2) * (G / 2);
