@@ -1,5 +1,6 @@
-// chol.cu - per-step M x M work for one GP: A = K_ZZ + jitter I (+ noise I), blocked Cholesky, L^-1,
-// fragment-order packing of L^-1 for the DMMA predict kernel, alpha = A^-1 y.
+// chol.cu - per-step M x M work for one GP: A = K_ZZ + jitter I (+ noise I), Cholesky and L^-1 (one cooperative launch,
+// chol_coop.cu), fragment-order packing of L^-1 for the DMMA predict kernel, alpha = A^-1 y.  The per-panel launch chain
+// below (chol_panel_kernel) now only serves the public in-place gvi_chol_factor_f64.
 // Reference: src/utils/matrix_operations.py:7-28 (a4); cho_factor call sites sparse_posterior_kernel.py:68-74 and
 // src/gps/base/base.py:516-521 (a5/a7).  M <= a few thousand: O(M^3) here is <2% of the O(N M^2) predict pass.
 #include "common.cuh"
@@ -14,7 +15,8 @@ constexpr int NB = 32;
 // ---- a4: trace-relative (or absolute) diagonal regulariser, single CTA, fixed-order trace --------------------
 __global__ void __launch_bounds__(1024) add_diag_kernel(double* __restrict__ A, int M, int64_t ld, double reg,
                                                         int is_abs, const double* __restrict__ log_noise,
-                                                        double* __restrict__ jitter_out) {
+                                                        double* __restrict__ jitter_out,
+                                                        int* __restrict__ info_init = nullptr) {
   __shared__ double part[32];
   __shared__ double add_s;
   const int tid = threadIdx.x;
@@ -29,6 +31,7 @@ __global__ void __launch_bounds__(1024) add_diag_kernel(double* __restrict__ A, 
     for (int w = 0; w < 32; w++) tr += part[w];
     double jit = is_abs ? reg : reg * tr / (double)M;
     if (jitter_out) *jitter_out = jit;
+    if (info_init) *info_init = 0x7fffffff;  // the factorisation's atomicMin word
     add_s = jit + (log_noise ? exp(log_noise[0]) : 0.0);
   }
   __syncthreads();
@@ -265,79 +268,6 @@ __global__ void __launch_bounds__(256) chol_panel_guard_kernel(double* __restric
   }
 }
 
-// ---- L^-1: (1) invert the 32x32 diagonal blocks, (2) one CTA per block column sweeps downwards ----------------
-__global__ void __launch_bounds__(32) diag_inverse_kernel(const double* __restrict__ L, int64_t ld,
-                                                          double* __restrict__ X, int64_t ldx) {
-  __shared__ double Ls[NB][NB + 1];
-  const int b = blockIdx.x, lane = threadIdx.x;
-  for (int r = 0; r < NB; r++) Ls[r][lane] = L[(int64_t)(b * NB + r) * ld + b * NB + lane];
-  __syncwarp();
-  // lane j owns column j of the inverse: x[i] = (delta_ij - sum_{k=j}^{i-1} L[i][k] x[k]) / L[i][i]
-  double x[NB];
-#pragma unroll
-  for (int i = 0; i < NB; i++) {
-    double v = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-    for (int k = 0; k < i; k++) v = fma(-Ls[i][k], (k >= lane) ? x[k] : 0.0, v);
-    x[i] = (i >= lane) ? v / Ls[i][i] : 0.0;
-  }
-#pragma unroll
-  for (int i = 0; i < NB; i++) X[(int64_t)(b * NB + i) * ldx + b * NB + lane] = x[i];
-}
-
-// One CTA per block column jb sweeps downwards: X[ib,jb] = -Dinv[ib] * sum_{k=jb}^{ib-1} L[ib,k] X[k,jb].  The
-// 32 x 32 x 32(ib-jb) product runs on the tensor pipe, contraction split over the 8 warps.
-__global__ void __launch_bounds__(256) linv_sweep_kernel(const double* __restrict__ L, int64_t ld,
-                                                         double* __restrict__ X, int64_t ldx, int G) {
-  extern __shared__ __align__(16) unsigned char sweep_smem[];
-  typedef double Tile[NB][NB + 1];
-  Tile* part = reinterpret_cast<Tile*>(sweep_smem);  // [8]
-  Tile& Ts = part[8];
-  Tile& Ds = part[9];
-  const int jb = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & 15, ty = tid >> 4;
-  for (int ib = jb + 1; ib < G; ib++) {
-    double acc[4][4][2];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-      for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-    // rows of L[ib, jb..ib) and of X[jb..ib, jb]: k runs over 32 (ib - jb) columns starting at column 32 jb
-    tile32_mma<false>(L + (int64_t)ib * NB * ld + jb * NB, ld, X + (int64_t)jb * NB * ldx + jb * NB, ldx,
-                      (ib - jb) * NB / 4, warp, 8, lane, acc);
-    tile32_store(part[warp], lane, acc);
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      int r = idx >> 5, c = idx & 31;
-      Ds[r][c] = X[(int64_t)(ib * NB + r) * ldx + ib * NB + c];  // Dinv[ib]
-    }
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      int r = idx >> 5, c = idx & 31;
-      double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < 8; w++) v += part[w][r][c];
-      Ts[r][c] = v;
-    }
-    __syncthreads();
-    double o[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll 8
-    for (int k = 0; k < NB; k++) {
-      double a0 = Ds[2 * ty][k], a1 = Ds[2 * ty + 1][k];
-      double b0 = Ts[k][2 * tx], b1 = Ts[k][2 * tx + 1];
-      o[0][0] = fma(a0, b0, o[0][0]);
-      o[0][1] = fma(a0, b1, o[0][1]);
-      o[1][0] = fma(a1, b0, o[1][0]);
-      o[1][1] = fma(a1, b1, o[1][1]);
-    }
-#pragma unroll
-    for (int a = 0; a < 2; a++)
-#pragma unroll
-      for (int b = 0; b < 2; b++)
-        X[(int64_t)(ib * NB + 2 * ty + a) * ldx + jb * NB + 2 * tx + b] = -o[a][b];
-    __syncthreads();  // X[ib,jb] visible to the whole CTA before the next row block reads it
-  }
-}
-
 // ---- header, scaled inducing points -----------------------------------------------------------------------------
 __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, const double* __restrict__ Z,
                                      const double* __restrict__ log_scaling, const double* __restrict__ log_ls,
@@ -436,33 +366,59 @@ __global__ void __launch_bounds__(256) linv_matvec_kernel(const double* __restri
   s = warp_sum(s);
   if (lane == 0) t[warp] = s;
 }
+constexpr int MV_SEG = 8;  // row segments of the transposed matvec (partials combined in segment order)
 __global__ void __launch_bounds__(256) linvT_matvec_kernel(const double* __restrict__ X, int64_t ldx, int Mp, int M,
-                                                           const double* __restrict__ t, double* __restrict__ a) {
-  // a[j] = sum_{c>=j} X[c][j] t[c]: 32 columns per CTA (coalesced across lanes), rows split over the 8 warps,
-  // fixed-order combination
+                                                           const double* __restrict__ t, double* __restrict__ part_out) {
+  // part_out[seg][j] = sum over the rows c of segment seg, c >= j, of X[c][j] t[c]: 32 columns per CTA (coalesced across
+  // lanes), the segment's rows split over the 8 warps with 4 independent accumulators each, fixed-order combination
   __shared__ double part[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
-  double s = 0.0;
-  if (j < M)
-    for (int c = blockIdx.x * 32 + warp; c < M; c += 8)
-      if (c >= j) s = fma(X[(int64_t)c * ldx + j], t[c], s);
-  part[warp][lane] = s;
+  const int seg = blockIdx.y;
+  const int rows_per_seg = (M + MV_SEG - 1) / MV_SEG;
+  const int c_lo = seg * rows_per_seg, c_hi = min(M, c_lo + rows_per_seg);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (j < M) {
+    int c = max(c_lo, blockIdx.x * 32) + warp;
+    for (; c + 24 < c_hi; c += 32) {
+      const double x0 = X[(int64_t)c * ldx + j], x1 = X[(int64_t)(c + 8) * ldx + j];
+      const double x2 = X[(int64_t)(c + 16) * ldx + j], x3 = X[(int64_t)(c + 24) * ldx + j];
+      if (c >= j) s0 = fma(x0, t[c], s0);
+      if (c + 8 >= j) s1 = fma(x1, t[c + 8], s1);
+      if (c + 16 >= j) s2 = fma(x2, t[c + 16], s2);
+      if (c + 24 >= j) s3 = fma(x3, t[c + 24], s3);
+    }
+    for (; c < c_hi; c += 8)
+      if (c >= j) s0 = fma(X[(int64_t)c * ldx + j], t[c], s0);
+  }
+  part[warp][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (warp == 0 && j < Mp) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; w++) v += part[w][lane];
-    a[j] = v;
+    part_out[(int64_t)seg * Mp + j] = v;
   }
+}
+__global__ void __launch_bounds__(256) matvec_combine_kernel(const double* __restrict__ part, int Mp, double* __restrict__ a) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= Mp) return;
+  double v = 0.0;
+#pragma unroll
+  for (int s = 0; s < MV_SEG; s++) v += part[(int64_t)s * Mp + j];
+  a[j] = v;
 }
 __global__ void zero_kernel(double* p, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     p[i] = 0.0;
 }
-__global__ void info_to_header_kernel(double* F, const int* info, int Mp) {
+// after the factorisation: info word -> 0 / 1 + first non-PD column, into the factor header and the caller's info
+__global__ void info_finish_kernel(double* F, int* info, int Mp, int* caller_info) {
   int v = *info;
+  if (v == 0x7fffffff) v = 0;
+  *info = v;
   F[3] = (v > Mp) ? 0.0 : (double)v;
+  if (caller_info) *caller_info = v;
 }
 __global__ void info_init_kernel(int* info) { *info = 0x7fffffff; }
 __global__ void info_final_kernel(int* info) {
@@ -471,14 +427,10 @@ __global__ void info_final_kernel(int* info) {
 }  // namespace
 
 static int configure_factor_kernels() {
-  static bool done = false;
-  if (!done) {
+  static std::atomic<unsigned long long> configured{0};
+  if (gvi_first_use_on_this_device(configured))
     GVI_CUDA(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(6 * NB * (NB + 1) * sizeof(double))));
-    GVI_CUDA(cudaFuncSetAttribute(linv_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(10 * NB * (NB + 1) * sizeof(double))));
-    done = true;
-  }
   return GVI_OK;
 }
 
@@ -639,21 +591,16 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   else
     rc = gvi_launch_ard_gram(Z, M, Z, M, D, log_scaling, log_ls, ls_len, A, Mw, st);
   if (rc) return rc;
-  add_diag_kernel<<<1, 1024, 0, st>>>(A, M, Mw, reg, is_abs, log_noise, F + 2);
+  add_diag_kernel<<<1, 1024, 0, st>>>(A, M, Mw, reg, is_abs, log_noise, F + 2, winfo);
   GVI_CHECK_LAUNCH("add_diag_kernel");
   if (Mw != M) {
     pad_identity_kernel<<<148, 256, 0, st>>>(A, M, Mw);
     GVI_CHECK_LAUNCH("pad_identity_kernel");
   }
-  info_init_kernel<<<1, 1, 0, st>>>(winfo);
-  GVI_CHECK_LAUNCH("info_init_kernel");
   // Cholesky and L^-1 in ONE cooperative launch (chol_coop.cu)
   if ((rc = gvi_launch_chol_inverse_coop(A, X, P, Mw, M, winfo, st))) return rc;
-  info_final_kernel<<<1, 1, 0, st>>>(winfo);
-  GVI_CHECK_LAUNCH("info_final_kernel");
-  info_to_header_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp);
-  GVI_CHECK_LAUNCH("info_to_header_kernel");
-  if (info) GVI_CUDA(cudaMemcpyAsync(info, winfo, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  info_finish_kernel<<<1, 1, 0, st>>>(F, winfo, f.Mp, info);
+  GVI_CHECK_LAUNCH("info_finish_kernel");
   {
     pack_linv_kernel<<<f.G, 256, 0, st>>>(X, Mw, M, f.G, F + f.wpack_off);
     GVI_CHECK_LAUNCH("pack_linv_kernel");
@@ -665,8 +612,11 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
   if (y_z) {
     linv_matvec_kernel<<<(f.Mp * 32 + 255) / 256, 256, 0, st>>>(X, Mw, f.Mp, M, y_z, tvec);
     GVI_CHECK_LAUNCH("linv_matvec_kernel");
-    linvT_matvec_kernel<<<f.Mp / 32, 256, 0, st>>>(X, Mw, f.Mp, M, tvec, F + f.alpha_off);
+    // the partials live in the (now free) split-K scratch of the cooperative kernel
+    linvT_matvec_kernel<<<dim3(f.Mp / 32, MV_SEG), 256, 0, st>>>(X, Mw, f.Mp, M, tvec, P);
     GVI_CHECK_LAUNCH("linvT_matvec_kernel");
+    matvec_combine_kernel<<<(f.Mp + 255) / 256, 256, 0, st>>>(P, f.Mp, F + f.alpha_off);
+    GVI_CHECK_LAUNCH("matvec_combine_kernel");
   } else {
     zero_kernel<<<4, 256, 0, st>>>(F + f.alpha_off, f.Mp);
     GVI_CHECK_LAUNCH("zero_kernel");

@@ -292,6 +292,9 @@ struct CoopArgs {
   long long* stamps;  // lab builds only
 };
 
+// chunk length of the split-K partial products of the inverse (products accumulated in registers per task)
+__host__ __device__ inline int inv_chunk(int G) { return G <= 16 ? 1 : (G <= 32 ? 2 : 4); }
+
 __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArgs a) {
   extern __shared__ __align__(16) unsigned char coop_smem[];
   Tile& As = *reinterpret_cast<Tile*>(coop_smem);
@@ -299,10 +302,74 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
   Tile& Cs = *reinterpret_cast<Tile*>(coop_smem + 2 * sizeof(Tile));
   cg::grid_group grid = cg::this_grid();
   const int G = a.G, nb = gridDim.x, b = blockIdx.x;
+  const int KC = inv_chunk(G);
   const int64_t ld = a.Mw;
   double* const A = a.A;
   double* const X = a.X;
   auto blk = [&](double* base, int i, int j) { return base + ((int64_t)i * CB) * ld + (int64_t)j * CB; };
+
+  // X[i,j] = -Dinv_i sum_{q=j}^{i-1} L[i,q] X[q,j] (block row i of L^-1) rides along with the factorisation: row i needs
+  // L[i, :i] (final after the panel of step i-1), the rows of X above it and Dinv_i (the look-ahead diagonal of step i-1),
+  // so its split-K partial products are extra tasks of the PANEL phase of step i and their fixed-order sums times -Dinv_i
+  // extra tasks of the UPDATE phase: L^-1 costs no barrier of its own, and the CTAs the shrinking trailing update leaves
+  // idle do the work.
+  // partial products of row i: task (j, ch) = sum over q in chunk ch of [j, i) of L[i,q] X[q,j]  ->  P[prefix(j) + ch]
+  auto x_partials = [&](int i, int first_task, int stride_tasks, int my_first) {
+    int tix = first_task;
+    for (int j = 0; j < i; j++) {
+      const int nch = (i - j + KC - 1) / KC;
+      for (int ch = 0; ch < nch; ch++, tix++) {
+        if (tix % stride_tasks != my_first) continue;
+        double acc[2][4][2];
+        acc_zero(acc);
+        const int q0 = j + ch * KC, q1 = min(i, q0 + KC);
+        for (int q = q0; q < q1; q++) {
+          __syncthreads();
+          load_tile(As, blk(A, i, q), ld);
+          load_tile(Bs, blk(X, q, j), ld);
+          __syncthreads();
+          tile_mma<false>(As, Bs, acc);
+        }
+        double* dst = a.P + (int64_t)(tix - first_task) * CB * CB;
+        acc_visit(acc, [&](int r, int c, double (&v)[2]) {
+          *reinterpret_cast<double2*>(dst + r * CB + c) = make_double2(v[0], v[1]);
+        });
+      }
+    }
+    return tix;
+  };
+  // X[i,j] = -Dinv_i (sum of the partials of (i, j), in chunk order)
+  auto x_reduce = [&](int i, int first_task, int stride_tasks, int my_first) {
+    int tix = first_task, pfx = 0;
+    for (int j = 0; j < i; j++, tix++) {
+      const int nch = (i - j + KC - 1) / KC;
+      if (tix % stride_tasks == my_first) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < CB * CB / 2; idx += 256) {
+          const int r = idx >> 5, c = (idx & 31) * 2;
+          const double* p = a.P + (int64_t)pfx * CB * CB + r * CB + c;
+          double2 s = *reinterpret_cast<const double2*>(p);
+          for (int ch = 1; ch < nch; ch++) {
+            const double2 q = *reinterpret_cast<const double2*>(p + (int64_t)ch * CB * CB);
+            s.x += q.x;
+            s.y += q.y;
+          }
+          *reinterpret_cast<double2*>(&Bs[r][c]) = s;
+        }
+        load_tile(As, blk(X, i, i), ld);  // Dinv_i
+        __syncthreads();
+        double acc[2][4][2];
+        acc_zero(acc);
+        tile_mma<false>(As, Bs, acc);
+        double* dst = blk(X, i, j);
+        acc_visit(acc, [&](int r, int c, double (&v)[2]) {
+          *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = make_double2(-v[0], -v[1]);
+        });
+      }
+      pfx += nch;
+    }
+    return tix;
+  };
 
   // upper block triangle of X := 0 (the diagonal and lower blocks are all written below)
   for (int t = b; t < G * G; t += nb) {
@@ -321,8 +388,12 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
   STAMP(1);
   grid.sync();
   STAMP(2);
+  // CTA 0 carries the critical chain (update of the next diagonal block, then its factorisation); the other CTAs
+  // share everything else.  With a single CTA it does it all.
+  const int nw = nb > 1 ? nb - 1 : 1;        // CTAs sharing the non-critical tasks
+  const int me = nb > 1 ? b - 1 : 0;         // index among them (-1: CTA 0 of a multi-CTA grid takes none)
   for (int k = 0; k < G - 1; k++) {
-    // ---- panel: L[i,k] = A[i,k] Dinv_k^T, i > k --------------------------------------------------------------
+    // ---- panel: L[i,k] = A[i,k] Dinv_k^T, i > k; plus the partial products of row k of L^-1 -------------------------
     bool have_d = false;
     for (int i = k + 1 + b; i < G; i += nb) {
       __syncthreads();
@@ -340,13 +411,15 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = make_double2(v[0], v[1]);
       });
     }
+    // the panel took CTAs 0 .. G-k-2 (round robin): start the X tasks behind them
+    x_partials(k, (G - k - 1) % nb, nb, b);
     STAMP(3);
     grid.sync();
     STAMP(4);
-    // ---- trailing update A[i,j] -= L[i,k] L[j,k]^T for k < j <= i; task 0 = (k+1, k+1) goes on to factorise it ----
+    // ---- trailing update A[i,j] -= L[i,k] L[j,k]^T for k < j <= i; task 0 = (k+1, k+1) goes on to factorise it;
+    //      plus the finished blocks of row k of L^-1 -----------------------------------------------------------------
     const int n = G - k - 1;             // blocks per side of the trailing matrix
     const int ntask = n * (n + 1) / 2;
-    // CTA 0 takes task 0 only (and then the diagonal factorisation); the other tasks go round the remaining CTAs
     for (int t = (nb == 1 ? 0 : (b == 0 ? 0 : b)); t < ntask; t += (nb == 1 ? 1 : (b == 0 ? ntask : nb - 1))) {
       // t -> (i, j), row-major over the lower triangle: t = i'(i'+1)/2 + j'
       int ip = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -357,19 +430,41 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
       __syncthreads();
       load_tile(As, blk(A, i, k), ld);
       load_tile(Bs, blk(A, j, k), ld);
+      // the block being updated travels while the product runs
+      double* dst = blk(A, i, j);
+      double2 old[2][4];
+      {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++)
+            old[mt][nt] = *reinterpret_cast<const double2*>(dst + (int64_t)(16 * (warp & 3) + 8 * mt + (lane >> 2)) * ld +
+                                                            32 * (warp >> 2) + 8 * nt + 2 * (lane & 3));
+      }
       __syncthreads();
       double acc[2][4][2];
       acc_zero(acc);
       tile_mma<true>(As, Bs, acc);
-      double* dst = blk(A, i, j);
       const bool diag_next = (t == 0);
-      acc_visit(acc, [&](int r, int c, double (&v)[2]) {
-        double2 old = *reinterpret_cast<const double2*>(dst + (int64_t)r * ld + c);
-        old.x -= v[0];
-        old.y -= v[1];
-        if (diag_next) *reinterpret_cast<double2*>(&Cs[r][c]) = old;
-        else *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = old;
-      });
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+          old[mt][nt].x -= acc[mt][nt][0];
+          old[mt][nt].y -= acc[mt][nt][1];
+        }
+      {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+          for (int nt = 0; nt < 4; nt++) {
+            const int r = 16 * (warp & 3) + 8 * mt + (lane >> 2), c = 32 * (warp >> 2) + 8 * nt + 2 * (lane & 3);
+            if (diag_next) *reinterpret_cast<double2*>(&Cs[r][c]) = old[mt][nt];
+            else *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = old[mt][nt];
+          }
+      }
       if (diag_next) {  // look-ahead: this CTA factorises block (k+1, k+1) while the others finish the update
         STAMP(5);
         diag_factor<true>(Cs, As, Bs, (k + 1) * CB, a.info);  // G > 1 implies M > 32
@@ -377,67 +472,24 @@ __global__ void __launch_bounds__(256, 1) chol_inverse_coop_kernel(const CoopArg
         store_tile(blk(X, k + 1, k + 1), ld, As);
       }
     }
+    if (me >= 0) x_reduce(k, (ntask - 1) % nw, nw, me);
     STAMP(6);
     grid.sync();
     STAMP(7);
   }
-  // ---- X = L^-1 by block sub-diagonals d = i - j: X[i,j] = -Dinv_i sum_{k=j}^{i-1} L[i,k] X[k,j] --------------------
-  for (int d = 1; d < G; d++) {
-    const int nblk = G - d;        // blocks on this sub-diagonal
-    const int ntask = nblk * d;    // one product per task: (j, kk), k = j + kk
-    for (int t = b; t < ntask; t += nb) {
-      const int j = t / d, kk = t % d;
-      const int i = j + d, kq = j + kk;
-      __syncthreads();
-      load_tile(As, blk(A, i, kq), ld);
-      load_tile(Bs, blk(X, kq, j), ld);
-      __syncthreads();
-      double acc[2][4][2];
-      acc_zero(acc);
-      tile_mma<false>(As, Bs, acc);
-      double* dst = a.P + (int64_t)t * CB * CB;
-      acc_visit(acc, [&](int r, int c, double (&v)[2]) {
-        *reinterpret_cast<double2*>(dst + r * CB + c) = make_double2(v[0], v[1]);
-      });
-    }
-    STAMP(8);
+  // ---- the last block row of L^-1 ----------------------------------------------------------------------------------
+  if (G > 1) {
+    x_partials(G - 1, 0, nb, b);
     grid.sync();
-    STAMP(9);
-    for (int j = b; j < nblk; j += nb) {
-      const int i = j + d;
-      __syncthreads();
-      // Bs = sum of the d partial tiles in task order (fixed: the result does not depend on which CTA produced which)
-      for (int idx = threadIdx.x; idx < CB * CB / 2; idx += 256) {
-        const int r = idx >> 5, c = (idx & 31) * 2;
-        const double* p = a.P + (int64_t)(j * d) * CB * CB + r * CB + c;
-        double2 s = *reinterpret_cast<const double2*>(p);
-        for (int kk = 1; kk < d; kk++) {
-          const double2 q = *reinterpret_cast<const double2*>(p + (int64_t)kk * CB * CB);
-          s.x += q.x;
-          s.y += q.y;
-        }
-        *reinterpret_cast<double2*>(&Bs[r][c]) = s;
-      }
-      load_tile(As, blk(X, i, i), ld);  // Dinv_i
-      __syncthreads();
-      double acc[2][4][2];
-      acc_zero(acc);
-      tile_mma<false>(As, Bs, acc);
-      double* dst = blk(X, i, j);
-      acc_visit(acc, [&](int r, int c, double (&v)[2]) {
-        *reinterpret_cast<double2*>(dst + (int64_t)r * ld + c) = make_double2(-v[0], -v[1]);
-      });
-    }
-    STAMP(10);
-    grid.sync();
-    STAMP(11);
+    x_reduce(G - 1, 0, nb, b);
   }
 }
 }  // namespace
 
 size_t gvi_chol_coop_scratch_doubles(int Mw) {
-  const int64_t G = Mw / CB;
-  const int64_t tasks = ((G + 1) / 2) * (G / 2) + 1;  // max over d of (G - d) d
+  const int G = Mw / CB, KC = inv_chunk(G);
+  int64_t tasks = 1;  // partial tiles of the last (longest) block row of the inverse
+  for (int j = 0; j < G - 1; j++) tasks += (G - 1 - j + KC - 1) / KC;
   return (size_t)tasks * CB * CB;
 }
 
@@ -454,9 +506,7 @@ int gvi_launch_chol_inverse_coop(double* A, double* X, double* P, int Mw, int M,
     GVI_CUDA(cudaFuncSetAttribute(chol_inverse_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CoopArgs args{A, X, P, Mw, Mw / CB, info, M > HB ? 1 : 0, stamps};
   const int G = Mw / CB;
-  int want = G * (G - 1) / 2;  // widest phase: the first trailing update
-  const int quarter = ((G + 1) / 2) * (G / 2);
-  if (quarter > want) want = quarter;
+  int want = G * (G - 1) / 2 + 1;  // widest phase: the first trailing update / the last row of the inverse
   int grid = want < 1 ? 1 : (want < GVI_NUM_SMS ? want : GVI_NUM_SMS);
   int dev = 0, sms = 0, coop = 0;
   GVI_CUDA(cudaGetDevice(&dev));
