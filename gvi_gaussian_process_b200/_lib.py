@@ -115,6 +115,9 @@ TEST_LIB_PATH = os.path.join(_HERE, "libgvigp_test.so")
 TEST_SIGNATURES = {
     "gvi_test_exp_f64": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gvi_test_set_grad_chunk_waves": (c_int, [c_int]),
+    "gvi_test_dgemm_f64": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_int64, c_double,
+                                   c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "gvi_test_dgemv_f64": (c_int, [c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_double, c_void_p, c_void_p]),
 }
 
 REG_KINDS = {

@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gram.cu", "gram_dmma.cu", "chol.cu", "chol_coop.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu", "diag.cu"]
+SOURCES = ["gram.cu", "gram_dmma.cu", "chol.cu", "chol_coop.cu", "dgemm.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu", "diag.cu"]
 LIB_PATH = os.path.join(HERE, "libgvigp.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -27,7 +27,7 @@ TEST_LIB_PATH = os.path.join(HERE, "libgvigp_test.so")  # same sources + -DGVI_T
 
 def _deps():
     return [os.path.join(CSRC, s) for s in SOURCES] + [
-        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "predict.cuh"), os.path.join(CSRC, "comm.cuh"),
+        os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "predict.cuh"), os.path.join(CSRC, "comm.cuh"), os.path.join(CSRC, "dgemm.cuh"),
         os.path.join(HERE, "..", "include", "gvigp.h"), os.path.join(HERE, "..", "include", "gvigp_test.h")]
 
 
@@ -58,8 +58,7 @@ def _compile_and_link(lib_path: str, obj_dir: str, extra_flags, verbose: bool):
                 print(out)
             if p.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {s}:\n{out}")
-        cmd = [_nvcc(), "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared",
-               "-lcublas", "-ldl"]
+        cmd = [_nvcc(), "-shared", "-o", lib_path, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared", "-ldl"]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}")

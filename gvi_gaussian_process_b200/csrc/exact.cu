@@ -13,11 +13,10 @@
 // materialised chunk by chunk, the M^3-shaped products are plain library GEMMs (cuBLAS) against the dense L^-1 kept
 // in the factor state, and hand-written kernels do the Gram chunk, the elementwise cotangents and the contractions
 // with dK/dtheta (recomputing k_ij on the fly, fixed-order reductions).
-#include <cublas_v2.h>
+#include "dgemm.cuh"
 
 #include "common.cuh"
 
-int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st);
 // wide inputs (D > 32): GEMM formulation of the contractions with dK/dlog_ls (grad_wide.cu)
 size_t gvi_exact_gp_predict_grad_wide_workspace_bytes(int64_t N, int M, int D);
 int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int64_t N, const double* g,
@@ -150,18 +149,6 @@ __global__ void exact_finish_kernel(const double* __restrict__ acc1, const doubl
   }
 }
 
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const double* A, int lda, const double* B, int ldb,
-            double beta, double* C, int ldc) {
-  const double one = 1.0;
-  cublasStatus_t s = cublasDgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, m, k, &one, B,
-                                 ldb, A, lda, &beta, C, ldc);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    gvi_set_error("cublasDgemm failed with status %d", (int)s);
-    return GVI_ECUDA;
-  }
-  return GVI_OK;
-}
-
 struct ExactWs {
   double *K, *T, *Aa, *G2, *w, *rowpart, *acc1, *acc2;
 };
@@ -209,9 +196,7 @@ extern "C" int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, c
   const double* alpha = F + f.alpha_off;
   const int Mp = f.Mp;
   ExactWs w = carve_exact(workspace, N, M, nullptr);
-  cublasHandle_t h;
-  int rc = gvi_get_cublas(&h, st);
-  if (rc) return rc;
+  int rc = GVI_OK;
   GVI_CUDA(cudaMemsetAsync(w.w, 0, (size_t)Mp * 8, st));
   for (int64_t r0 = 0; r0 < N; r0 += ECHUNK) {
     const int nr = (int)(N - r0 < ECHUNK ? N - r0 : ECHUNK);
@@ -221,21 +206,20 @@ extern "C" int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, c
     kxz_kernel<<<blocks, 256, 0, st>>>(F, f, X + r0 * D, nr, w.K);
     GVI_CHECK_LAUNCH("kxz_kernel");
     // Aa = K A^-1 = (K L^-T) L^-1
-    if ((rc = gemm_rm(h, false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp))) return rc;
-    if ((rc = gemm_rm(h, false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp))) return rc;
+    // (in-tree tensor-pipe GEMM, dgemm.cu: L^-1 is lower triangular, so both products run over half the k range)
+    if ((rc = gvi_dgemm_rm(false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp, GVI_GEMM_K_UPTO_N, false, st)))
+      return rc;
+    if ((rc = gvi_dgemm_rm(false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp, GVI_GEMM_K_FROM_N, false, st)))
+      return rc;
     // B = diag(g) Aa -> T,  G1 = h alpha^T - 2 B -> K
     cotangent_kernel<<<blocks, 256, 0, st>>>(w.Aa, g_var + r0, h_mean ? h_mean + r0 : nullptr, alpha, nr, Mp, w.T, w.K);
     GVI_CHECK_LAUNCH("cotangent_kernel");
     // G2 (+)= Aa^T B ;  w += Aa^T h
-    if ((rc = gemm_rm(h, true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, first ? 0.0 : 1.0, w.G2, Mp))) return rc;
-    if (h_mean) {
-      const double one = 1.0;
-      // row-major Aa [nr x Mp] is column-major [Mp x nr]: w += that matrix times h
-      if (cublasDgemv(h, CUBLAS_OP_N, Mp, nr, &one, w.Aa, Mp, h_mean + r0, 1, &one, w.w, 1) != CUBLAS_STATUS_SUCCESS) {
-        gvi_set_error("cublasDgemv failed");
-        return GVI_ECUDA;
-      }
-    }
+    // (symmetric: B = diag(g) Aa - only the tiles on or below the diagonal are multiplied)
+    if ((rc = gvi_dgemm_rm(true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, first ? 0.0 : 1.0, w.G2, Mp, GVI_GEMM_K_FULL, true,
+                           st)))
+      return rc;
+    if (h_mean && (rc = gvi_dgemv_rm(true, Mp, nr, w.Aa, Mp, h_mean + r0, 1.0, w.w, st))) return rc;
     ard_contract_kernel<<<nr, 256, 0, st>>>(w.K, Mp, M, X + r0 * D, 1, F, f, g_var + r0, w.rowpart);
     GVI_CHECK_LAUNCH("ard_contract_kernel");
     contract_finish_kernel<<<1, 64, 0, st>>>(w.rowpart, nr, D, first, w.acc1);

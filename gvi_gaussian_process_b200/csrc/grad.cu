@@ -11,7 +11,7 @@
 // amplifies the rounding of the inner sum by cond(A)^2 and was dropped.)  The same SYRK kernel fed by kgen_kernel
 // gives C = sum_i g_i k_i k_i^T, the vector-Jacobian product of the SVGP family (gvi_weighted_gram_f64).
 // Reference: jax.grad of generalised_variational_inference.py:73-94 (trainer.py:83-89).
-#include <cublas_v2.h>
+#include "dgemm.cuh"
 
 #include "predict.cuh"
 
@@ -266,21 +266,6 @@ __global__ void grad_finish_kernel(const double* __restrict__ rowpart, int M, in
   out[4 + d] += a;
 }
 
-thread_local cublasHandle_t g_cublas = nullptr;
-
-// row-major C[m x n] = op(A) op(B) through column-major cuBLAS (swap operands)
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const double* A, int lda, const double* B,
-            int ldb, double* C, int ldc) {
-  const double one = 1.0, zero = 0.0;
-  cublasStatus_t s = cublasDgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, m, k, &one, B,
-                                 ldb, A, lda, &zero, C, ldc);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    gvi_set_error("cublasDgemm failed with status %d", (int)s);
-    return GVI_ECUDA;
-  }
-  return GVI_OK;
-}
-
 template <int DR>
 int launch_kgen(const double* F, const double* X, const double* g, int64_t N, int64_t row0, int npg, int M, int Mp,
                 int D, double* Kc, cudaStream_t st) {
@@ -483,20 +468,6 @@ static int gvi_contract_kzz_term(const double* Fq, const FactorLayout& f, int M,
   return GVI_OK;
 }
 
-// the per-thread cuBLAS handle, bound to `st` (shared with exact.cu)
-int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st) {
-  if (!g_cublas) {
-    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
-      gvi_set_error("cublasCreate failed");
-      return GVI_ECUDA;
-    }
-  }
-  cublasSetStream(g_cublas, st);
-  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
-  *h = g_cublas;
-  return GVI_OK;
-}
-
 extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
   if (N < 1 || M < 1 || D < 1) return 0;
   size_t total = 0;
@@ -655,16 +626,8 @@ extern "C" int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p
   if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;
   if ((rc = gvi_launch_finish(P.partials, grid, N, 0, D, Fq, out3, st))) return rc;
   if ((rc = gvi_weighted_gram(Fq, X, w.g, N, M, D, w, st))) return rc;
-  if (!g_cublas) {
-    if (cublasCreate(&g_cublas) != CUBLAS_STATUS_SUCCESS) {
-      gvi_set_error("cublasCreate failed");
-      return GVI_ECUDA;
-    }
-  }
-  cublasSetStream(g_cublas, st);
-  cublasSetPointerMode(g_cublas, CUBLAS_POINTER_MODE_HOST);
-  // dE = 2 tril(E C): one plain library GEMM on the M x M blocks
-  if ((rc = gemm_rm(g_cublas, false, false, M, M, M, E, (int)lde, w.C, f.Mp, dE_out, M))) return rc;
+  // dE = 2 tril(E C): the in-tree tensor-pipe GEMM (dgemm.cu) on the M x M blocks
+  if ((rc = gvi_dgemm_rm(false, false, M, M, M, E, lde, w.C, f.Mp, 0.0, dE_out, M, GVI_GEMM_K_FULL, false, st))) return rc;
   tril_scale_kernel<<<GVI_NUM_SMS * 2, 256, 0, st>>>(dE_out, M, M, 2.0);
   GVI_CHECK_LAUNCH("tril_scale_kernel");
   return GVI_OK;

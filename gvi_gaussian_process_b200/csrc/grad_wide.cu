@@ -11,11 +11,10 @@
 // (gram_dmma.cu), A^-1 K^T by two library GEMMs against the dense L^-1 of the factor state, one fused elementwise pass
 // for W, diag(g) Aa and the row sums, Q (+ c as an extra column of ones) and S by library GEMMs accumulating across
 // chunks.  All reductions have a fixed order.  Reference: jax.grad through sparse_posterior_kernel.py:54-96.
-#include <cublas_v2.h>
+#include "dgemm.cuh"
 
 #include "common.cuh"
 
-int gvi_get_cublas(cublasHandle_t* h, cudaStream_t st);
 int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x, int64_t nr, double* out,
                          double* workspace, cudaStream_t st);
 int gvi_launch_wide_gram_zz(const double* F, const FactorLayout& f, double* out, double* workspace, cudaStream_t st);
@@ -140,18 +139,6 @@ __global__ void wide_scalars_kernel(const double* __restrict__ scal, const doubl
   out[3] = (F[5] != 0.0) ? 4.0 * scal[0] - 2.0 * F[1] * scal[2] : 2.0 * scal[0] - 2.0 * F[4] * scal[1];
 }
 
-int gemm_rm(cublasHandle_t h, bool ta, bool tb, int m, int n, int k, const double* A, int lda, const double* B, int ldb,
-            double beta, double* C, int ldc) {
-  const double one = 1.0;
-  cublasStatus_t s = cublasDgemm(h, tb ? CUBLAS_OP_T : CUBLAS_OP_N, ta ? CUBLAS_OP_T : CUBLAS_OP_N, n, m, k, &one, B,
-                                 ldb, A, lda, &beta, C, ldc);
-  if (s != CUBLAS_STATUS_SUCCESS) {
-    gvi_set_error("cublasDgemm failed with status %d", (int)s);
-    return GVI_ECUDA;
-  }
-  return GVI_OK;
-}
-
 struct WideWs {
   double *K, *T, *Aa, *Xs, *rowstats, *Q, *S, *Kzz, *Zh, *R3, *t2x, *scal, *gram;
 };
@@ -194,9 +181,7 @@ int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int
   const double* Linv = F + f.linv_off;
   const double* Zs = F + f.zs_off;  // row 0 = the common shift c~
   WideWs w = carve_wide(workspace, N, M, D, nullptr);
-  cublasHandle_t h;
-  int rc = gvi_get_cublas(&h, st);
-  if (rc) return rc;
+  int rc = GVI_OK;
   for (int64_t r0 = 0; r0 < N; r0 += WCHUNK) {
     const int nr = (int)(N - r0 < WCHUNK ? N - r0 : WCHUNK);
     const int first = (r0 == 0);
@@ -206,14 +191,19 @@ int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int
     if ((rc = gvi_launch_wide_gram(F, f, X + r0 * D, nr, w.K, w.gram, st))) return rc;
     shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(X + r0 * D, nr, D, F + f.sqrtw_off, Zs, w.Xs);
     GVI_CHECK_LAUNCH("shift_aug_kernel");
-    if ((rc = gemm_rm(h, false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp))) return rc;   // K L^-T
-    if ((rc = gemm_rm(h, false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp))) return rc;  // Aa = K A^-1
+    // in-tree tensor-pipe GEMM (dgemm.cu): triangular L^-1 -> half the k range; symmetric S -> half the tiles
+    if ((rc = gvi_dgemm_rm(false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp, GVI_GEMM_K_UPTO_N, false, st)))
+      return rc;  // K L^-T
+    if ((rc = gvi_dgemm_rm(false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp, GVI_GEMM_K_FROM_N, false, st)))
+      return rc;  // Aa = K A^-1
     const int wblocks = (nr + 7) / 8 < GVI_NUM_SMS * 8 ? (nr + 7) / 8 : GVI_NUM_SMS * 8;
     weights_kernel<<<wblocks, 256, 0, st>>>(w.K, w.Aa, w.T, g + r0, nr, Mp, w.rowstats);           // K <- W, T <- B
     GVI_CHECK_LAUNCH("weights_kernel");
-    if ((rc = gemm_rm(h, true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da))) return rc;   // Q|c += W^T [X^|1]
+    if ((rc = gvi_dgemm_rm(true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da, GVI_GEMM_K_FULL, false, st)))
+      return rc;  // Q|c += W^T [X^|1]
     if (!frozen)
-      if ((rc = gemm_rm(h, true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp))) return rc;  // S += Aa^T B
+      if ((rc = gvi_dgemm_rm(true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp, GVI_GEMM_K_FULL, true, st)))
+        return rc;  // S += Aa^T B (B = diag(g) Aa: symmetric)
     row_square_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Xs, nr, D, w.rowstats, first, w.t2x);
     GVI_CHECK_LAUNCH("row_square_kernel");
     row_scalars_kernel<<<1, 256, 0, st>>>(w.rowstats, g + r0, nr, F, first, w.scal);
@@ -227,7 +217,8 @@ int gvi_gp_predict_grad_wide(const double* F, int M, int D, const double* X, int
     if ((rc = gvi_launch_wide_gram_zz(F, f, w.Kzz, w.gram, st))) return rc;
     hadamard_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.S, w.Kzz, (int64_t)Mp * Mp);                // V = S o K_ZZ
     GVI_CHECK_LAUNCH("hadamard_kernel");
-    if ((rc = gemm_rm(h, false, false, Mp, Da, Mp, w.S, Mp, w.Zh, Da, 0.0, w.R3, Da))) return rc;  // [V Z^ | V 1]
+    if ((rc = gvi_dgemm_rm(false, false, Mp, Da, Mp, w.S, Mp, w.Zh, Da, 0.0, w.R3, Da, GVI_GEMM_K_FULL, false, st)))
+      return rc;  // [V Z^ | V 1]
     R3 = w.R3;
   }
   wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, R3, w.t2x, M, D, 1.0, out);
@@ -366,9 +357,7 @@ int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* 
   WideWs w = carve_wide(workspace, N, M, D, &base);
   double* V = (double*)((unsigned char*)workspace + base);
   double* wv = (double*)((unsigned char*)workspace + base + align256((size_t)Mp * Mp * 8));
-  cublasHandle_t hd;
-  int rc = gvi_get_cublas(&hd, st);
-  if (rc) return rc;
+  int rc = GVI_OK;
   GVI_CUDA(cudaMemsetAsync(wv, 0, (size_t)Mp * sizeof(double), st));
   for (int64_t r0 = 0; r0 < N; r0 += WCHUNK) {
     const int nr = (int)(N - r0 < WCHUNK ? N - r0 : WCHUNK);
@@ -378,21 +367,19 @@ int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* 
     if ((rc = gvi_launch_wide_gram(F, f, X + r0 * D, nr, w.K, w.gram, st))) return rc;
     shift_aug_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(X + r0 * D, nr, D, F + f.sqrtw_off, Zs, w.Xs);
     GVI_CHECK_LAUNCH("shift_aug_kernel");
-    if ((rc = gemm_rm(hd, false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp))) return rc;
-    if ((rc = gemm_rm(hd, false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp))) return rc;
+    if ((rc = gvi_dgemm_rm(false, true, nr, Mp, Mp, w.K, Mp, Linv, Mp, 0.0, w.T, Mp, GVI_GEMM_K_UPTO_N, false, st)))
+      return rc;
+    if ((rc = gvi_dgemm_rm(false, false, nr, Mp, Mp, w.T, Mp, Linv, Mp, 0.0, w.Aa, Mp, GVI_GEMM_K_FROM_N, false, st)))
+      return rc;
     const int wblocks = (nr + 7) / 8 < GVI_NUM_SMS * 8 ? (nr + 7) / 8 : GVI_NUM_SMS * 8;
     exact_weights_kernel<<<wblocks, 256, 0, st>>>(w.K, w.Aa, w.T, g + r0, h_mean ? h_mean + r0 : nullptr, alpha, nr, Mp,
                                                   w.rowstats);                                     // K <- W1, T <- B
     GVI_CHECK_LAUNCH("exact_weights_kernel");
-    if ((rc = gemm_rm(hd, true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da))) return rc;   // Q|c += W1^T [X^|1]
-    if ((rc = gemm_rm(hd, true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp))) return rc;   // G2 += Aa^T B
-    if (h_mean) {
-      const double one = 1.0;
-      if (cublasDgemv(hd, CUBLAS_OP_N, Mp, nr, &one, w.Aa, Mp, h_mean + r0, 1, &one, wv, 1) != CUBLAS_STATUS_SUCCESS) {
-        gvi_set_error("cublasDgemv failed");
-        return GVI_ECUDA;
-      }
-    }
+    if ((rc = gvi_dgemm_rm(true, false, Mp, Da, nr, w.K, Mp, w.Xs, Da, beta, w.Q, Da, GVI_GEMM_K_FULL, false, st)))
+      return rc;  // Q|c += W1^T [X^|1]
+    if ((rc = gvi_dgemm_rm(true, false, Mp, Mp, nr, w.Aa, Mp, w.T, Mp, beta, w.S, Mp, GVI_GEMM_K_FULL, true, st)))
+      return rc;  // G2 += Aa^T B
+    if (h_mean && (rc = gvi_dgemv_rm(true, Mp, nr, w.Aa, Mp, h_mean + r0, 1.0, wv, st))) return rc;
     row_square_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Xs, nr, D, w.rowstats, first, w.t2x);
     GVI_CHECK_LAUNCH("row_square_kernel");
     exact_row_scalars_kernel<<<1, 256, 0, st>>>(w.rowstats, g + r0, nr, first, w.scal);
@@ -406,7 +393,8 @@ int gvi_exact_gp_predict_grad_wide(const double* F, int M, int D, const double* 
   if ((rc = gvi_launch_wide_gram_zz(F, f, w.Kzz, w.gram, st))) return rc;
   sym_hadamard_kernel<<<1, 256, 0, st>>>(w.S, w.Kzz, Mp, V, w.scal + 3);
   GVI_CHECK_LAUNCH("sym_hadamard_kernel");
-  if ((rc = gemm_rm(hd, false, false, Mp, Da, Mp, V, Mp, w.Zh, Da, 0.0, w.R3, Da))) return rc;     // [V Z^ | V 1]
+  if ((rc = gvi_dgemm_rm(false, false, Mp, Da, Mp, V, Mp, w.Zh, Da, 0.0, w.R3, Da, GVI_GEMM_K_FULL, false, st)))
+    return rc;  // [V Z^ | V 1]
   wide_finish_kernel<<<(D + 127) / 128, 128, 0, st>>>(w.Zh, w.Q, w.R3, w.t2x, M, D, -0.5, out);
   GVI_CHECK_LAUNCH("wide_finish_kernel");
   exact_wide_scalars_kernel<<<1, 1, 0, st>>>(w.scal, F, N, D, log_noise, out);

@@ -18,6 +18,14 @@ int gvi_test_exp_f64(const double* x, int64_t n, double* out, void* stream);
  * previous value. */
 int gvi_test_set_grad_chunk_waves(int waves);
 
+/* test hooks: the in-tree FP64 tensor-pipe GEMM / GEMV (csrc/dgemm.cu) on their own.  Row-major C[m,n] = op(A) op(B) +
+ * beta C; kmode 0 = full k range, 1 = op(B)[k][n] is zero for k > n, 2 = zero for k < n; symmetric: only the tiles on or
+ * below the diagonal are multiplied, the others mirrored.  y[m] = op(A) x + beta y. */
+int gvi_test_dgemm_f64(int ta, int tb, int m, int n, int k, const double* A, int64_t lda, const double* B, int64_t ldb,
+                       double beta, double* C, int64_t ldc, int kmode, int symmetric, void* stream);
+int gvi_test_dgemv_f64(int ta, int m, int k, const double* A, int64_t lda, const double* x, double beta, double* y,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,3 +258,60 @@ def test_preprocess_function_is_applied_like_the_reference():
         assert np.max(np.abs(var - v_ref)) <= 1e-10 * np.max(np.abs(v_ref)), where
         loss = float(gvi.calculate_loss(ap, dev(x), dev(y)))
         assert abs(loss - loss_ref) <= 1e-10 * abs(loss_ref), (where, loss, loss_ref)
+
+
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (37, 129, 70), (256, 128, 64), (300, 300, 513), (1000, 257, 19)])
+def test_in_tree_dgemm_matches_a_float64_matmul(S, ta, tb, m, n, k):
+    """csrc/dgemm.cu (the tensor-pipe GEMM that replaced the library GEMMs of the exact-GP / wide-input / SVGP gradient
+    routes) against torch.matmul in float64: all four operand orientations, ragged sizes, beta accumulation."""
+    lib = S._lib.load_test()
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a = dev(rng.standard_normal((k, m) if ta else (m, k)))
+    b = dev(rng.standard_normal((n, k) if tb else (k, n)))
+    c0 = dev(rng.standard_normal((m, n)))
+    ref = (a.T if ta else a) @ (b.T if tb else b)
+    for beta in (0.0, 1.0, -0.5):
+        c = c0.clone()
+        S._lib.check(lib.gvi_test_dgemm_f64(ta, tb, m, n, k, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), beta,
+                                            c.data_ptr(), c.stride(0), 0, 0, S._lib.current_stream()), "dgemm")
+        want = ref + beta * c0
+        assert float((c - want).abs().max()) <= 1e-12 * max(1.0, float(want.abs().max())), (beta, ta, tb)
+
+
+def test_in_tree_dgemm_triangular_and_symmetric_modes(S):
+    """The two structure short-cuts: a lower-triangular operand (k range cut at the tile's columns) and a symmetric result
+    (only tiles on or below the diagonal multiplied, the rest mirrored) give the full-GEMM answer."""
+    lib = S._lib.load_test()
+    rng = np.random.default_rng(0)
+    nr, mp = 500, 392
+    kmat = dev(rng.standard_normal((nr, mp)))
+    linv = torch.tril(dev(rng.standard_normal((mp, mp))))
+    t = torch.empty(nr, mp, dtype=torch.float64, device="cuda")
+    S._lib.check(lib.gvi_test_dgemm_f64(0, 1, nr, mp, mp, kmat.data_ptr(), mp, linv.data_ptr(), mp, 0.0, t.data_ptr(), mp,
+                                        1, 0, S._lib.current_stream()), "K L^-T")
+    assert float((t - kmat @ linv.T).abs().max()) <= 1e-12 * float((kmat @ linv.T).abs().max())
+    aa = torch.empty_like(t)
+    S._lib.check(lib.gvi_test_dgemm_f64(0, 0, nr, mp, mp, t.data_ptr(), mp, linv.data_ptr(), mp, 0.0, aa.data_ptr(), mp,
+                                        2, 0, S._lib.current_stream()), "T L^-1")
+    assert float((aa - t @ linv).abs().max()) <= 1e-12 * float((t @ linv).abs().max())
+    g = dev(rng.standard_normal(nr))
+    bmat = (aa * g[:, None]).contiguous()
+    s0 = dev(rng.standard_normal((mp, mp)))
+    s0 = (s0 + s0.T).contiguous()
+    sm = s0.clone()
+    S._lib.check(lib.gvi_test_dgemm_f64(1, 0, mp, mp, nr, aa.data_ptr(), mp, bmat.data_ptr(), mp, 1.0, sm.data_ptr(), mp,
+                                        0, 1, S._lib.current_stream()), "Aa^T B")
+    want = s0 + aa.T @ bmat
+    assert float((sm - want).abs().max()) <= 1e-12 * float(want.abs().max())
+    assert torch.equal(sm, sm.T)  # mirrored, so exactly symmetric
+    x = dev(rng.standard_normal(nr))
+    y0 = dev(rng.standard_normal(mp))
+    y = y0.clone()
+    S._lib.check(lib.gvi_test_dgemv_f64(1, mp, nr, aa.data_ptr(), mp, x.data_ptr(), 1.0, y.data_ptr(),
+                                        S._lib.current_stream()), "gemv T")
+    assert float((y - (y0 + aa.T @ x)).abs().max()) <= 1e-12 * float((aa.T @ x).abs().max())
+    y2 = torch.empty(nr, dtype=torch.float64, device="cuda")
+    S._lib.check(lib.gvi_test_dgemv_f64(0, nr, mp, aa.data_ptr(), mp, y0.data_ptr(), 0.0, y2.data_ptr(),
+                                        S._lib.current_stream()), "gemv N")
+    assert float((y2 - aa @ y0).abs().max()) <= 1e-12 * float((aa @ y0).abs().max())
