@@ -617,8 +617,9 @@ def bench_hbm_rows(torch, L, kernel, dev, to_d, theta, hbm_peak):
     n, m = 400_000, 1024
     x = torch.as_tensor(rng.standard_normal((n, D)), dtype=torch.float64, device=dev)
     zz = torch.as_tensor(rng.standard_normal((m, D)), dtype=torch.float64, device=dev)
-    kernel.calculate_gram(kp, x, zz)
-    ms, g = timed_ms(torch, lambda: kernel.calculate_gram(kp, x, zz), reps=3)
+    warm = [kernel.calculate_gram(kp, x, zz) for _ in range(2)]  # two result buffers in the caching allocator: the timed
+    del warm                                                      # calls then allocate without a cudaMalloc
+    ms, g = timed_ms(torch, lambda: kernel.calculate_gram(kp, x, zz), reps=4)
     out["materialised_gram"] = {"n": n, "m": m, "d": D, "ms": ms, "gb_written": 8.0 * n * m / 1e9,
                                 "store_gbs": 8.0 * n * m / (ms * 1e-3) / 1e9,
                                 "hbm_frac": 8.0 * n * m / (ms * 1e-3) / 1e9 / hbm_peak,
