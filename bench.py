@@ -527,8 +527,11 @@ def bench_selector(torch, comm, L, distributed, x_local, to_d, theta, rank, worl
     else:
         run = lambda: L.cond_var_select(x_local, sel_m, ls, ll, 1e-12)
     run()  # warm-up at full size: the timed call must not include the first cudaMalloc of the 4 GB C matrix
-    ms, (sel_idx, _) = timed_ms(torch, run, sync_all=barrier)
-    ms = max_over_ranks(ms)
+    ms = None
+    for _ in range(2):  # best of two (a pivot chain of 511 dependent steps picks up every hiccup of every rank)
+        t_ms, (sel_idx, _) = timed_ms(torch, run, sync_all=barrier)
+        t_ms = max_over_ranks(t_ms)
+        ms = t_ms if ms is None else min(ms, t_ms)
     n_total = n_local * world
     sel_bytes = 4.0 * n_total * sel_m * sel_m + 32.0 * n_total * sel_m
     gbs = sel_bytes / (ms * 1e-3) / 1e9 / world
