@@ -164,6 +164,41 @@ __device__ __forceinline__ double gvi_exp(double x) {
   return tiny ? 0.0 : res;
 }
 
+// 2^(j/32), j = 0 .. 31, as correctly rounded double + the remainder (hi, lo): gvi_exp_neg_t32
+static __device__ const double2 GVI_EXP2_TABLE[32] = {
+    {1.0, 0.0},
+    {1.0218971486541166, 5.109225028973444e-17},
+    {1.0442737824274138, 8.551889705537965e-17},
+    {1.0671404006768237, -7.899853966841582e-17},
+    {1.0905077326652577, -3.046782079812471e-17},
+    {1.1143867425958924, 1.0410278456845571e-16},
+    {1.1387886347566916, 8.912812676025408e-17},
+    {1.1637248587775775, 3.8292048369240935e-17},
+    {1.189207115002721, 3.982015231465646e-17},
+    {1.215247359980469, -7.712630692681488e-17},
+    {1.241857812073484, 4.658027591836937e-17},
+    {1.2690509571917332, 2.667932131342186e-18},
+    {1.2968395546510096, 2.5382502794888315e-17},
+    {1.3252366431597413, -2.8587312100388614e-17},
+    {1.3542555469368927, 7.70094837980299e-17},
+    {1.383909881963832, -6.770511658794786e-17},
+    {1.4142135623730951, -9.667293313452913e-17},
+    {1.4451808069770467, -3.0237581349939873e-17},
+    {1.4768261459394993, -3.483994556892796e-17},
+    {1.5091644275934228, -1.016455327754295e-16},
+    {1.5422108254079407, 7.949834809697621e-17},
+    {1.5759808451078865, -1.0136916471278304e-17},
+    {1.6104903319492543, 2.4707192569797888e-17},
+    {1.645755478153965, -1.0125679913674773e-16},
+    {1.681792830507429, 8.199010020581497e-17},
+    {1.718619298122478, -1.851380418263111e-17},
+    {1.7562521603732995, 2.960140695448873e-17},
+    {1.7947090750031072, 1.8227458427912087e-17},
+    {1.8340080864093424, 3.283107224245627e-17},
+    {1.8741676341103, -6.122763413004143e-17},
+    {1.9152065613971474, -1.0619946056195963e-16},
+    {1.9571441241754002, 8.960767791036668e-17}};
+
 // Table-driven variant for kernels that are bound by the FP64 pipe itself (the materialised Gram: one exp per 8 bytes
 // stored).  Takes s >= 0 and returns exp(-s): -s = (32 k + j) ln2/32 + r, |r| <= ln2/64,
 // exp(-s) = 2^k (T_j + T_j (e^r - 1)) with T_j = 2^(j/32) = hi_j + lo_j from 32-entry tables and

@@ -206,7 +206,7 @@ def test_gp_and_kernel_families_share_the_reference_base_classes():
 @pytest.mark.parametrize("variant", ["polynomial", "table32"])
 def test_device_exp_source_evaluated_on_the_host(tmp_path, variant):
     """gvi_exp (csrc/common.cuh) is the exp of every kernel evaluation on the hot path; gvi_exp_neg_t32 is the table-driven
-    variant of the materialised Gram kernel (table: GVI_EXP2_TABLE in csrc/gram.cu).  Their bodies are plain IEEE-754
+    variant of the materialised Gram kernel (table: GVI_EXP2_TABLE in csrc/common.cuh).  Their bodies are plain IEEE-754
     double arithmetic (fma, add, compare, an integer add into the exponent field), so the DEVICE SOURCE itself is
     compiled for the host here (tests/csrc/gvi_exp_host.c supplies the three bit-cast intrinsics) and swept over 8e6
     arguments of the range the kernels use: <= 1 ulp against expl(), exact 1 at 0, exact 0 below -708 (and at -inf),
@@ -226,11 +226,10 @@ def test_device_exp_source_evaluated_on_the_host(tmp_path, variant):
         body = re.search(r"__device__ __forceinline__ double gvi_exp_neg_t32\(double s, const double2\* tab.*?\n\}\n", src,
                          flags=re.S)
         assert body, "gvi_exp_neg_t32 not found in common.cuh"
-        gram = open(os.path.join(root, "gvi_gaussian_process_b200", "csrc", "gram.cu")).read()
-        table = re.search(r"__device__ const double2 GVI_EXP2_TABLE\[32\] = \{.*?\};", gram, flags=re.S)
-        assert table, "GVI_EXP2_TABLE not found in gram.cu"
+        table = re.search(r"static __device__ const double2 GVI_EXP2_TABLE\[32\] = \{.*?\};", src, flags=re.S)
+        assert table, "GVI_EXP2_TABLE not found in common.cuh"
         text = ("typedef struct { double x, y; } double2;\n"
-                + table.group(0).replace("__device__ const", "static const") + "\n#define CHECKED 1\n" + body.group(0)
+                + table.group(0).replace("static __device__ const", "static const") + "\n#define CHECKED 1\n" + body.group(0)
                 + "static inline double gvi_exp(double x) { return gvi_exp_neg_t32(-x, GVI_EXP2_TABLE, 1); }\n")
     (tmp_path / "gvi_exp_body.inc").write_text(text)
     gcc = shutil.which("gcc")
