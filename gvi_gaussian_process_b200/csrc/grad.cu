@@ -472,7 +472,7 @@ extern "C" size_t gvi_fused_step_grad_workspace_bytes(int64_t N, int M, int D) {
   if (N < 1 || M < 1 || D < 1) return 0;
   size_t total = 0;
   carve_grad(nullptr, N, M, D, &total);
-  if (D > 32) {
+  if (D > 32 || gvi_step_tile_points(factor_layout(M, D).Mp, D, true) == 0) {  // the GEMM route (grad_wide.cu)
     const size_t wide = gvi_gp_predict_grad_wide_workspace_bytes(N, M, D);
     if (wide > total) total = wide;
   }
@@ -528,7 +528,9 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
   cudaStream_t st = (cudaStream_t)stream;
   const FactorLayout f = factor_layout(M, D);
   const double* Fq = (const double*)factor;
-  if (D > 32)  // wide inputs: the contraction with dK/dlog_ls runs as GEMMs over all d at once (grad_wide.cu)
+  // wide inputs (D > 32) and inducing sets whose b tile does not fit shared memory (M > 3456): the contraction with
+  // dK/dlog_ls runs as GEMMs over all d at once (grad_wide.cu) - any D, any M
+  if (D > 32 || gvi_step_tile_points(f.Mp, D, true) == 0)
     return gvi_gp_predict_grad_wide(Fq, M, D, X, N, g_var, frozen_cholesky, out, workspace, st);
   GradWs w = carve_grad(workspace, N, M, D, nullptr);
   StepParams P{};

@@ -189,9 +189,15 @@ class GeneralisedVariationalInference:
         grads = {"log_scaling": out[3] / n, "log_lengthscales": dll.reshape(ll_shape), "mean_output": dm / n}
         return (out[0] + out[1]) / n, grads
 
+    # the gradient tile kernel keeps the b tile of T >= 8 points in shared memory: M <= 3456; larger inducing sets are
+    # differentiated term by term (variance VJP on the GEMM route of csrc/grad_wide.cu)
+    FUSED_GRADIENT_MAX_M = 3456
+
     def _calculate_loss(self, parameters, x, y):
         if self._fusable():
             wants = torch.is_grad_enabled() and self._wants_grad(parameters)
+            if wants and self._empirical_risk.gp.kernel.inducing_points.shape[0] > self.FUSED_GRADIENT_MAX_M:
+                return self._calculate_loss_term_by_term(parameters, x, y)
             if not wants:
                 out3 = self.loss_sums(parameters, x, y)
                 return (out3[0] + out3[1]) / out3[2]
@@ -199,6 +205,9 @@ class GeneralisedVariationalInference:
                 return _FusedLoss.apply(self, parameters, x, y, *self._grad_leaves(parameters))
             # LogSVGPKernel (dense El): trained through the general path below (dLoss/dSigma from the weighted-Gram
             # kernel, the M x M parameterisation differentiated by the host framework)
+        return self._calculate_loss_term_by_term(parameters, x, y)
+
+    def _calculate_loss_term_by_term(self, parameters, x, y):
         gp = self._empirical_risk.gp
         parameters = gp._to_parameters(parameters)
         x = as_device(x)  # one device copy, so both terms see the same tensor

@@ -317,3 +317,51 @@ def test_in_tree_dgemm_triangular_and_symmetric_modes(S):
     S._lib.check(lib.gvi_test_dgemv_f64(0, nr, mp, aa.data_ptr(), mp, y0.data_ptr(), 0.0, y2.data_ptr(),
                                         S._lib.current_stream()), "gemv N")
     assert float((y2 - aa @ y0).abs().max()) <= 1e-12 * float((aa @ y0).abs().max())
+
+
+def test_training_gradients_beyond_3456_inducing_points():
+    """r01 limit lifted: with M > 3456 the b tile of the gradient tile kernel no longer fits shared memory; the objective
+    is then differentiated term by term and the variance VJP takes the GEMM route (csrc/grad_wide.cu on csrc/dgemm.cu),
+    which has no size limit - BASELINE configs[4] reaches M = 4096.  loss.backward() against the torch-f64 twin (1e-8)."""
+    from gvi_gaussian_process_b200.src.empirical_risks import NegativeLogLikelihood
+    from gvi_gaussian_process_b200.src.generalised_variational_inference import GeneralisedVariationalInference
+    from gvi_gaussian_process_b200.src.gps import ApproximateGPRegression, GPRegression
+    from gvi_gaussian_process_b200.src.kernels.approximate import SparsePosteriorKernel
+    from gvi_gaussian_process_b200.src.kernels.standard import ARDKernel
+    from gvi_gaussian_process_b200.src.means import ConstantMean, CustomMean
+    from gvi_gaussian_process_b200.src.regularisations.projected import ProjectedKLRegularisation
+    from oracle import torch_twin as TT
+
+    rng = np.random.default_rng(12)
+    n, m, d = 300, 3600, 4
+    x, z = rng.standard_normal((n, d)), 2.0 * rng.standard_normal((m, d))
+    y, yz = rng.standard_normal(n), rng.standard_normal(m)
+    ls0, ll0 = 0.1, rng.normal(1.0, 0.1, d)  # short lengthscales: a well-conditioned 3600 x 3600 Gram
+    kernel = ARDKernel(number_of_dimensions=d)
+    ls = torch.tensor(ls0, dtype=torch.float64, device="cuda", requires_grad=True)
+    ll = torch.tensor(ll0, dtype=torch.float64, device="cuda", requires_grad=True)
+    mq = (0.3 * torch.randn(n, dtype=torch.float64, device="cuda")).requires_grad_(True)
+    amean = CustomMean(mean_function=lambda p, xx: p[: xx.shape[0]])
+    sparse = SparsePosteriorKernel(base_kernel=kernel, inducing_points=z, diagonal_regularisation=1e-5)
+    approx = ApproximateGPRegression(mean=amean, kernel=sparse)
+    ap = approx.Parameters.construct(mean=amean.Parameters.construct(custom=mq),
+                                     kernel=sparse.Parameters.construct(
+                                         base_kernel=kernel.Parameters.construct(log_scaling=ls, log_lengthscales=ll)))
+    mean0 = ConstantMean()
+    exact = GPRegression(mean=mean0, kernel=kernel, x=z, y=yz)
+    ep = exact.Parameters.construct(log_observation_noise=0.0, mean=mean0.Parameters.construct(constant=0.0),
+                                    kernel=kernel.Parameters.construct(log_scaling=-0.2, log_lengthscales=ll0 + 0.05))
+    gvi = GeneralisedVariationalInference(
+        regularisation=ProjectedKLRegularisation(gp=approx, regulariser=exact, regulariser_parameters=ep, mode="posterior"),
+        empirical_risk=NegativeLogLikelihood(gp=approx))
+    assert gvi._fusable()
+    loss = gvi.calculate_loss(ap, dev(x), dev(y))
+    loss.backward()
+    gp_ = lambda a, b: O.ard_gram(-0.2, ll0 + 0.05, a, b)
+    dp_ = lambda a: O.ard_gram_diag(-0.2, ll0 + 0.05, a)
+    m_p, v_p = O.exact_gp_posterior(gp_, dp_, np.zeros(n), z, yz, 0.0, x)
+    ref_loss, g_ls, g_ll, g_m = TT.gvi_loss_and_grads(x, y, z, host(mq), ls0, ll0, m_p, v_p, "kl", 0.5, 1e-5, False)
+    assert abs(float(loss.detach()) - ref_loss) <= 1e-10 * abs(ref_loss)
+    assert abs(float(ls.grad) - g_ls) <= 1e-8 * max(abs(g_ls), 1e-3)
+    assert np.max(np.abs(host(ll.grad) - g_ll)) <= 1e-8 * max(np.max(np.abs(g_ll)), 1e-3)
+    assert np.max(np.abs(host(mq.grad) - g_m)) <= 1e-8 * max(np.max(np.abs(g_m)), 1e-3)
