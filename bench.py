@@ -385,7 +385,7 @@ def run_gpu(args):
     # ---- configs[4]: scaling sweep, inducing selection + predictive variance over the global N sharded by rank ------------
     try:
         config5 = bench_config5(torch, comm, L, distributed, dev, to_d, theta, rank, world, barrier, max_over_ranks,
-                                hbm_peak, fp64_peak, quick=args.quick)
+                                hbm_peak, fp64_peak, quick=args.quick or args.short)
     except Exception as e:  # pragma: no cover
         config5 = {"error": f"{type(e).__name__}: {e}"}
 
@@ -801,6 +801,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="profiling runs: skip the widened rows, shorten the config5 sweep")
+    ap.add_argument("--short", action="store_true", help="launch-list runs: shorten the config5 sweep, keep the widened rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     result = run_reference(args) if args.impl == "reference" else run_gpu(args)
