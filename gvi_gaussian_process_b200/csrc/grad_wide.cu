@@ -21,7 +21,9 @@ int gvi_launch_wide_gram_zz(const double* F, const FactorLayout& f, double* out,
 size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D);
 
 namespace {
-constexpr int WCHUNK = 2048;
+// rows of X per pass: 37 x 128, so that a chunk x M = 2048 product is 16 x 37 = 592 = 4 x 148 output tiles of the in-tree GEMM -
+// whole waves of CTAs (2048 rows gave 256 tiles: 1.73 waves)
+constexpr int WCHUNK = 4736;
 
 // out[i][d] = rows[i][d] * (sqrtw ? sqrtw[d] : 1) - shift[d]  (d < D),  out[i][D] = 1;  leading dimension Da = D + 1
 __global__ void __launch_bounds__(256) shift_aug_kernel(const double* __restrict__ rows, int64_t nr, int D,
