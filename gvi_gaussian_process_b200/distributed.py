@@ -117,9 +117,16 @@ def calculate_gram_row_sharded(kernel, parameters, x1_local, x2, comm: Optional[
     src/kernels/standard/base.py:95-103 builds the whole [m1, m2] array on one device).  Returns this rank's row block
     [m1_local, m2]; with gather=True (equal slice sizes on every rank) the replicated [m1, m2] Gram."""
     block = kernel.calculate_gram(parameters, x1_local, x2)
-    if not gather or comm is None or comm.world == 1:
+    if not gather:
         return block
-    return comm.allgather(block.contiguous()).reshape(-1, block.shape[-1])
+    if comm is not None:
+        return block if comm.world == 1 else comm.allgather(block.contiguous()).reshape(-1, block.shape[-1])
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:  # host-logic tests over gloo
+        block = block.contiguous()
+        out = torch.empty((dist.get_world_size() * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block)
+        return out
+    return block
 
 
 def resolve_records(records: torch.Tensor, first: bool) -> int:

@@ -132,3 +132,37 @@ def test_sharded_selector_protocol_matches_single_process(n, m_sel, ones_kernel)
     ref = O.conditional_variance_select(x, m_sel, lambda a, b: O.ard_gram(ls, ll, a, b),
                                         lambda a: O.ard_gram_diag(ls, ll, a))
     assert ret[0] == ret[1] == ref.tolist()
+
+
+class _OracleArdKernel:
+    """Stands in for the CUDA ARDKernel in the CPU test: same `calculate_gram(parameters, x1, x2)` signature."""
+
+    def calculate_gram(self, parameters, x1, x2):
+        return torch.tensor(O.ard_gram(parameters["log_scaling"], parameters["log_lengthscales"], np.asarray(x1), np.asarray(x2)))
+
+
+def _worker_gram(rank, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    x, z, _, _, _, ls, ll = _problem()
+    x = x[:1000]  # equal slices on both ranks (the gathered form needs them)
+    lo, hi = distributed.shard_bounds(x.shape[0], rank, WORLD)
+    params = {"log_scaling": ls, "log_lengthscales": ll}
+    block = distributed.calculate_gram_row_sharded(_OracleArdKernel(), params, x[lo:hi], z)
+    full = distributed.calculate_gram_row_sharded(_OracleArdKernel(), params, x[lo:hi], z, gather=True)
+    ret[rank] = (block.numpy(), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_row_sharded_gram_blocks_tile_the_full_gram():
+    """`calculate_gram` with the rows of x1 sharded by rank - every rank's block is its rows of the
+    full Gram, and the gathered form is the full Gram on every rank."""
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_gram, args=(port, ret), nprocs=WORLD, join=True)
+    x, z, _, _, _, ls, ll = _problem()
+    ref = O.ard_gram(ls, ll, x[:1000], z)
+    for rank in range(WORLD):
+        lo, hi = distributed.shard_bounds(1000, rank, WORLD)
+        block, full = ret[rank]
+        assert np.array_equal(block, ref[lo:hi]) and np.array_equal(full, ref)
