@@ -41,6 +41,7 @@ SIGNATURES = {
     "gvi_risk_grad_f64": (c_int, [c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "gvi_fused_step_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "gvi_fused_step_workspace_bytes_d": (c_size_t, [c_int64, c_int, c_int]),
     "gvi_fused_step_f64": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),

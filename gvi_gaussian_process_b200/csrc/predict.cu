@@ -912,6 +912,15 @@ int gvi_fill_step_params(StepParams& P, const void* factor_q, const void* factor
   return GVI_OK;
 }
 
+// D > 32 adds the two K-row rings (q and p) and the Gram kernel's workspace; equal to the call above for D <= 32
+extern "C" size_t gvi_fused_step_workspace_bytes_d(int64_t N, int M, int D) {
+  size_t bytes = gvi_fused_step_workspace_bytes(N, M);
+  if (bytes == 0 || D <= 32) return bytes;
+  const int Mp = (M + 31) / 32 * 32;
+  const int64_t rows = wide_chunk_rows(Mp);
+  return bytes + ((size_t)2 * rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D)) * sizeof(double);
+}
+
 extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                                   const double* y, const double* m_q, const double* prior_mean_p,
                                   const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind,
@@ -927,6 +936,42 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
   P.partials = (double*)workspace + STEP_COUNTER_DOUBLES;
   P.tile_partials = P.partials + fused_records_doubles();
   P.acc_scratch = P.tile_partials + fused_tile_doubles(N);
+  if (D > 32) {
+    // wide inputs: the K rows of q and p are built chunk by chunk by the tensor-pipe Gram kernel into two rings that stay
+    // L2 resident; the tile kernel consumes both and runs the risk epilogue - still no N x M array in HBM and one ABI
+    // call, with 2-3 launches per chunk of <= 3552 points (workspace: gvi_fused_step_workspace_bytes_d)
+    const FactorLayout f = factor_layout(M, D);
+    const int64_t rows = wide_chunk_rows(f.Mp);  // a multiple of 24: the chunks' tile records are contiguous
+    double* ring_q = P.acc_scratch + gvi_step_scratch_doubles(f.Mp);
+    double* ring_p = ring_q + (size_t)rows * f.Mp;
+    double* gws = ring_p + (size_t)rows * f.Mp;
+    const StepParams P0 = P;
+    for (int64_t r0 = 0; r0 < N; r0 += rows) {
+      const int64_t nr = N - r0 < rows ? N - r0 : rows;
+      StepParams C = P0;
+      auto off = [r0](const double* p) { return p ? p + r0 : nullptr; };
+      auto offw = [r0](double* p) { return p ? p + r0 : nullptr; };
+      for (int ps = 0; ps < C.npass; ps++) {
+        PassDesc& pd = C.pass[ps];
+        double* ring = ps == 0 ? ring_q : ring_p;
+        rc = gvi_launch_wide_gram(pd.F, f, X + r0 * D, nr, ring, gws, st);
+        if (rc) return rc;
+        pd.prior_mean = off(pd.prior_mean);
+        pd.mean_out = offw(pd.mean_out);
+        pd.var_out = offw(pd.var_out);
+        pd.Kpre = ring;
+        pd.ldk = f.Mp;
+      }
+      C.X = nullptr; C.N = nr;
+      C.y = off(C.y); C.m_q = off(C.m_q); C.m_p_in = off(C.m_p_in); C.v_p_in = off(C.v_p_in);
+      C.tile_partials = P0.tile_partials + (r0 / 24) * 2;
+      int g = gvi_launch_step(C, st);
+      if (g < 0) return g;
+    }
+    int nrec_w = gvi_launch_tile_reduce(P.tile_partials, (N + 23) / 24, 0, P.partials, st);
+    if (nrec_w < 0) return nrec_w;
+    return gvi_launch_finish(P.partials, nrec_w, N, 0, D, (const double*)factor_q, out3, st);
+  }
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   // forward launches use 24-point tiles; per-tile records -> fixed-order reduction -> out3

@@ -257,7 +257,7 @@ def fused_step(factor_q: GpFactor, factor_p, x, y, m_q, prior_mean_p, m_p_in, v_
     n = x.shape[0]
     if out3 is None:
         out3 = empty(3)
-    ws = _workspace("step", _L().gvi_fused_step_workspace_bytes(n, factor_q.m))
+    ws = _workspace("step", _L().gvi_fused_step_workspace_bytes_d(n, factor_q.m, factor_q.d))
     rc = _L().gvi_fused_step_f64(_lib.ptr(factor_q.buf), _lib.ptr(factor_p.buf) if factor_p is not None else None,
                                  factor_q.m, factor_q.d, _lib.ptr(x), _lib.ptr(y), _lib.ptr(m_q),
                                  _lib.ptr(prior_mean_p), _lib.ptr(m_p_in), _lib.ptr(v_p_in), n, int(reg_kind),

@@ -77,9 +77,8 @@ class GeneralisedVariationalInference:
             return False  # the wrapper kernel's own preprocess_function is applied by calculate_gram on the general path
         if rg.mode == RegularisationMode.posterior:
             reg = rg.regulariser
-            return (isinstance(reg, GPRegression) and reg._ard and reg.x.shape == gp.kernel.inducing_points.shape
-                    and reg.x.shape[1] <= 32)
-        return gp.kernel.inducing_points.shape[1] <= 32
+            return isinstance(reg, GPRegression) and reg._ard and reg.x.shape == gp.kernel.inducing_points.shape
+        return True
 
     def loss_sums(self, parameters, x, y, refactor_regulariser: bool = True):
         """Shard-local sums [sum NLL_i, sum D0_i, N] of the fused step (device tensor, no host sync).
@@ -192,11 +191,15 @@ class GeneralisedVariationalInference:
     # the gradient tile kernel keeps the b tile of T >= 8 points in shared memory: M <= 3456; larger inducing sets are
     # differentiated term by term (variance VJP on the GEMM route of csrc/grad_wide.cu)
     FUSED_GRADIENT_MAX_M = 3456
+    # ... and evaluates the kernel inside the tile: D <= 32 (wider inputs: K rows from the tensor-pipe Gram kernel; the
+    # forward objective stays one call - gvi_fused_step_f64 walks L2-sized chunks - the gradient goes term by term)
+    FUSED_GRADIENT_MAX_D = 32
 
     def _calculate_loss(self, parameters, x, y):
         if self._fusable():
             wants = torch.is_grad_enabled() and self._wants_grad(parameters)
-            if wants and self._empirical_risk.gp.kernel.inducing_points.shape[0] > self.FUSED_GRADIENT_MAX_M:
+            z_shape = self._empirical_risk.gp.kernel.inducing_points.shape
+            if wants and (z_shape[0] > self.FUSED_GRADIENT_MAX_M or z_shape[1] > self.FUSED_GRADIENT_MAX_D):
                 return self._calculate_loss_term_by_term(parameters, x, y)
             if not wants:
                 out3 = self.loss_sums(parameters, x, y)

@@ -157,6 +157,10 @@ int gvi_risk_grad_f64(int reg_kind, double renyi_alpha, const double* y, const d
  * factor_p may be NULL with reg_kind == GVI_REG_NONE.  prior-mode regulariser: pass factor_p = NULL and
  * m_p/v_p arrays instead.  out3 as in gvi_risk_f64.  var_q_out/mean_p_out/var_p_out optional (may be NULL). */
 size_t gvi_fused_step_workspace_bytes(int64_t N, int M);
+/* D > 32: the K rows of q and p are built <= 3552 points at a time by the tensor-pipe Gram kernel into two L2-resident
+ * rings which the tile kernel consumes (2-3 launches per chunk inside the one call; no N x M array in HBM).  Such calls
+ * need the larger workspace of gvi_fused_step_workspace_bytes_d (== the call above for D <= 32).                    */
+size_t gvi_fused_step_workspace_bytes_d(int64_t N, int M, int D);
 int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
                        const double* y, const double* m_q, const double* prior_mean_p,
                        const double* m_p_in, const double* v_p_in, int64_t N, int reg_kind, double renyi_alpha,

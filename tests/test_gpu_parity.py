@@ -227,15 +227,27 @@ def test_predictive_parity_wide_inputs(S, n, m, d):
     p = exact_gp.predict_probability(exact_params, x_dev)
     assert rel_norm(host(q.covariance), v_q_ref) <= TOL
     assert rel_norm(host(p.mean).reshape(-1), m_p_ref) <= TOL and rel_norm(host(p.covariance), v_p_ref) <= TOL
-    # the objective falls back to predict + risk kernels (the single-launch fused step needs D <= 32)
+    # the objective is ONE call of gvi_fused_step_f64 for wide inputs too (r02): K rows of q and p from the tensor-pipe
+    # Gram kernel through two L2-sized rings, <= 3552 points per chunk (n = 5000: two chunks, the second ragged)
     risk = S.NegativeLogLikelihood(gp=approx_gp)
     reg = S.projected.ProjectedKLRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
                                                 mode="posterior")
     gvi = S.GeneralisedVariationalInference(regularisation=reg, empirical_risk=risk)
-    assert not gvi._fusable()
+    assert gvi._fusable()
     ref = O.gaussian_nll(pr["y"], pr["m_q"], v_q_ref) + O.projected_regularisation("kl", m_p_ref, v_p_ref, pr["m_q"],
                                                                                   v_q_ref)
-    assert abs(float(gvi.calculate_loss(approx_params, x_dev, dev(pr["y"]))) - ref) <= TOL * abs(ref)
+    fused = float(gvi.calculate_loss(approx_params, x_dev, dev(pr["y"])))
+    assert abs(fused - ref) <= TOL * abs(ref)
+    unfused = float(gvi._calculate_loss_term_by_term(approx_params, x_dev, dev(pr["y"])))
+    assert abs(fused - unfused) <= 1e-12 * abs(ref)
+    # prior-mode regulariser (no second pass: m_p, v_p arrays) through the same wide route
+    reg_prior = S.projected.ProjectedKLRegularisation(gp=approx_gp, regulariser=exact_gp,
+                                                      regulariser_parameters=exact_params, mode="prior")
+    gvi_prior = S.GeneralisedVariationalInference(regularisation=reg_prior, empirical_risk=risk)
+    assert gvi_prior._fusable()
+    a = float(gvi_prior.calculate_loss(approx_params, x_dev, dev(pr["y"])))
+    b = float(gvi_prior._calculate_loss_term_by_term(approx_params, x_dev, dev(pr["y"])))
+    assert abs(a - b) <= 1e-12 * abs(b)
 
 
 def test_sparse_posterior_full_gram_and_identity_golden(S):
