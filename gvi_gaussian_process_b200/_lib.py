@@ -33,6 +33,7 @@ SIGNATURES = {
                                          c_double, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gvi_gp_factor_set_extra_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p]),
     "gvi_gp_predict_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gvi_gp_predict_workspace_bytes_n": (c_size_t, [c_int, c_int, c_int64]),
     "gvi_gp_predict_f64": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "gvi_risk_workspace_bytes": (c_size_t, [c_int64]),

@@ -795,24 +795,36 @@ int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int
 int gvi_launch_wide_gram(const double* F, const FactorLayout& f, const double* x, int64_t nr, double* out,
                          double* workspace, cudaStream_t st);
 
-// wide inputs (D > 32): K(x_chunk, Z) is built CHUNK rows at a time by the tensor-pipe Gram kernel into a ring that
-// stays L2 resident, and the tile kernel consumes it (one 24-point tile per CTA and launch)
+// wide inputs (D > 32): K(x_chunk, Z) is built CHUNK rows at a time by the tensor-pipe Gram kernel into a ring and the
+// tile kernel consumes it.  The ring need not stay in L2: 16 B per K entry written + read against ~M flop of tensor
+// work on it (M = 2048: 5 ns of HBM time per point against 250 ns of arithmetic).  What matters is that both kernels
+// run whole waves: a chunk is k x (148 x 24) rows, k <= 8 tiles per CTA of the tile kernel (dynamic tile order), and
+// for k = 8 or 4 (with Mp a multiple of 256) also a whole number of waves of the Gram kernel's 128 x 128 tiles
+// (28 416 rows = 222 row tiles; r02 first version: 3552-row chunks = 448 Gram tiles = 3.03 waves, 25 % of the Gram
+// kernel idle, and one exposed K-tile transposition per launch).  Ring <= 512 MB.
 constexpr int64_t WIDE_CHUNK = (int64_t)GVI_NUM_SMS * 24;
-static int64_t wide_chunk_rows(int Mp) {
-  int64_t rows = (96LL << 20) / ((int64_t)Mp * 8) / 24 * 24;  // <= 96 MB of K rows
-  if (rows > WIDE_CHUNK) rows = WIDE_CHUNK;
-  return rows < 24 ? 24 : rows;
+static int64_t wide_chunk_rows(int Mp, int64_t N) {
+  int64_t k = (512LL << 20) / (WIDE_CHUNK * (int64_t)Mp * 8);
+  k = k < 1 ? 1 : (k >= 8 ? 8 : (k >= 4 ? 4 : k));
+  int64_t rows = k * WIDE_CHUNK;
+  const int64_t need = (N + 23) / 24 * 24;
+  return need < rows ? (need < 24 ? 24 : need) : rows;
+}
+static size_t wide_ring_doubles(int M, int Mp, int D, int64_t N, int nrings) {
+  const int64_t rows = wide_chunk_rows(Mp, N);
+  return (size_t)nrings * rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D);
 }
 
-extern "C" size_t gvi_gp_predict_workspace_bytes(int M, int D) {
-  if (M < 1 || D < 1) return 0;
+extern "C" size_t gvi_gp_predict_workspace_bytes_n(int M, int D, int64_t N) {
+  if (M < 1 || D < 1 || N < 0) return 0;
   const int Mp = (M + 31) / 32 * 32;
   size_t doubles = STEP_COUNTER_DOUBLES + gvi_step_scratch_doubles(Mp);
-  if (D > 32) {
-    const int64_t rows = wide_chunk_rows(Mp);
-    doubles += (size_t)rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D);
-  }
+  if (D > 32) doubles += wide_ring_doubles(M, Mp, D, N, 1);
   return doubles * sizeof(double);
+}
+// enough for any N (D > 32: the full-sized ring)
+extern "C" size_t gvi_gp_predict_workspace_bytes(int M, int D) {
+  return gvi_gp_predict_workspace_bytes_n(M, D, INT64_MAX / 2);
 }
 
 extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
@@ -838,7 +850,7 @@ extern "C" int gvi_gp_predict_f64(const void* factor, int M, int D, const double
   }
   GVI_CHECK_ARG(workspace, "D > 32 needs a workspace of gvi_gp_predict_workspace_bytes(M, D)");
   const double* F = (const double*)factor;
-  const int64_t rows = wide_chunk_rows(f.Mp);
+  const int64_t rows = wide_chunk_rows(f.Mp, N);
   double* ring = (double*)workspace + STEP_COUNTER_DOUBLES + gvi_step_scratch_doubles(f.Mp);
   double* gws = ring + (size_t)rows * f.Mp;
   // the factor buffer carries sqrt(w), the pre-scaled inducing points and amp^2: everything the Gram needs
@@ -917,8 +929,7 @@ extern "C" size_t gvi_fused_step_workspace_bytes_d(int64_t N, int M, int D) {
   size_t bytes = gvi_fused_step_workspace_bytes(N, M);
   if (bytes == 0 || D <= 32) return bytes;
   const int Mp = (M + 31) / 32 * 32;
-  const int64_t rows = wide_chunk_rows(Mp);
-  return bytes + ((size_t)2 * rows * Mp + gvi_gram_dmma_workspace_doubles(rows, M, D)) * sizeof(double);
+  return bytes + wide_ring_doubles(M, Mp, D, N, 2) * sizeof(double);
 }
 
 extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,
@@ -939,9 +950,9 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
   if (D > 32) {
     // wide inputs: the K rows of q and p are built chunk by chunk by the tensor-pipe Gram kernel into two rings that stay
     // L2 resident; the tile kernel consumes both and runs the risk epilogue - still no N x M array in HBM and one ABI
-    // call, with 2-3 launches per chunk of <= 3552 points (workspace: gvi_fused_step_workspace_bytes_d)
+    // call, with 2-3 launches per chunk of <= 28 416 points (workspace: gvi_fused_step_workspace_bytes_d)
     const FactorLayout f = factor_layout(M, D);
-    const int64_t rows = wide_chunk_rows(f.Mp);  // a multiple of 24: the chunks' tile records are contiguous
+    const int64_t rows = wide_chunk_rows(f.Mp, N);  // a multiple of 24: the chunks' tile records are contiguous
     double* ring_q = P.acc_scratch + gvi_step_scratch_doubles(f.Mp);
     double* ring_p = ring_q + (size_t)rows * f.Mp;
     double* gws = ring_p + (size_t)rows * f.Mp;

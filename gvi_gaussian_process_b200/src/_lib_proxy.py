@@ -125,7 +125,7 @@ def gp_predict(factor: GpFactor, x, prior_mean=None, log_noise_add=None, want_me
     n = x.shape[0]
     mean = empty(n) if want_mean else None
     var = empty(n)
-    nbytes = _L().gvi_gp_predict_workspace_bytes(factor.m, factor.d)
+    nbytes = _L().gvi_gp_predict_workspace_bytes_n(factor.m, factor.d, n)
     ws = _workspace("predict", nbytes) if nbytes else None
     rc = _L().gvi_gp_predict_f64(_lib.ptr(factor.buf), factor.m, factor.d, _lib.ptr(x), n, _lib.ptr(prior_mean),
                                  _lib.ptr(log_noise_add), _lib.ptr(mean), _lib.ptr(var), _lib.ptr(ws),

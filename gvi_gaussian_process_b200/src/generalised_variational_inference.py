@@ -192,7 +192,7 @@ class GeneralisedVariationalInference:
     # differentiated term by term (variance VJP on the GEMM route of csrc/grad_wide.cu)
     FUSED_GRADIENT_MAX_M = 3456
     # ... and evaluates the kernel inside the tile: D <= 32 (wider inputs: K rows from the tensor-pipe Gram kernel; the
-    # forward objective stays one call - gvi_fused_step_f64 walks L2-sized chunks - the gradient goes term by term)
+    # forward objective stays one call - gvi_fused_step_f64 walks chunks of <= 28 416 points - the gradient goes term by term)
     FUSED_GRADIENT_MAX_D = 32
 
     def _calculate_loss(self, parameters, x, y):

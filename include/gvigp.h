@@ -109,9 +109,12 @@ int gvi_gp_factor_set_extra_f64(void* factor, int M, int D, const double* E, int
  * mean_out / prior_mean / log_noise_add may be NULL; workspace may be NULL when its size query returns 0.
  * Any M: for M > 1152 the K tile is swept in 1024-column panels and the partial triangular products are parked
  * in the (L2-resident) workspace between sweeps - still no N x M array in HBM.  Any D: for D > 32 the rows
- * K(x_chunk, Z) are produced 3552 points at a time by the tensor-pipe Gram kernel into an L2-sized ring inside the
- * workspace and consumed by the tile kernel (the fused step / gradient entry points support D <= 32).          */
-size_t gvi_gp_predict_workspace_bytes(int M, int D);   /* 0 unless M > 1152 (1024-column K panels) or D > 32 */
+ * K(x_chunk, Z) are produced <= 28 416 points at a time (whole waves of both kernels) by the tensor-pipe Gram kernel
+ * into a ring inside the workspace (<= 512 MB) and consumed by the tile kernel; gvi_fused_step_f64 does the same
+ * with two rings, the gradient entry points take the GEMM route of grad_wide.cu for D > 32.
+ * gvi_gp_predict_workspace_bytes(M, D) is enough for any N; the _n variant sizes the ring for one call's N.    */
+size_t gvi_gp_predict_workspace_bytes(int M, int D);
+size_t gvi_gp_predict_workspace_bytes_n(int M, int D, int64_t N);
 int gvi_gp_predict_f64(const void* factor, int M, int D, const double* X, int64_t N,
                        const double* prior_mean, const double* log_noise_add,
                        double* mean_out, double* var_out, void* workspace, void* stream);
@@ -157,8 +160,8 @@ int gvi_risk_grad_f64(int reg_kind, double renyi_alpha, const double* y, const d
  * factor_p may be NULL with reg_kind == GVI_REG_NONE.  prior-mode regulariser: pass factor_p = NULL and
  * m_p/v_p arrays instead.  out3 as in gvi_risk_f64.  var_q_out/mean_p_out/var_p_out optional (may be NULL). */
 size_t gvi_fused_step_workspace_bytes(int64_t N, int M);
-/* D > 32: the K rows of q and p are built <= 3552 points at a time by the tensor-pipe Gram kernel into two L2-resident
- * rings which the tile kernel consumes (2-3 launches per chunk inside the one call; no N x M array in HBM).  Such calls
+/* D > 32: the K rows of q and p are built <= 28 416 points at a time by the tensor-pipe Gram kernel into two rings
+ * which the tile kernel consumes (2-3 launches per chunk inside the one call; no N x M array in HBM).  Such calls
  * need the larger workspace of gvi_fused_step_workspace_bytes_d (== the call above for D <= 32).                    */
 size_t gvi_fused_step_workspace_bytes_d(int64_t N, int M, int D);
 int gvi_fused_step_f64(const void* factor_q, const void* factor_p, int M, int D, const double* X,

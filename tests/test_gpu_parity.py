@@ -213,9 +213,10 @@ def test_predictive_parity(S, n, m, d):
     assert np.all(host(q.covariance) > -1e-12) and np.all(host(p.covariance) > 0)
 
 
-@pytest.mark.parametrize("n,m,d", [(5000, 300, 33), (700, 1300, 784)])
+@pytest.mark.parametrize("n,m,d", [(5000, 300, 33), (700, 1300, 784), (30000, 64, 40)])
 def test_predictive_parity_wide_inputs(S, n, m, d):
-    """D > 32 (config #4's MNIST-like width): K(x,Z) rows come from the tensor-pipe Gram kernel in L2-sized chunks."""
+    """D > 32 (config #4's MNIST-like width): K(x,Z) rows come from the tensor-pipe Gram kernel in chunks of <= 28 416
+    points (n = 30 000: two chunks, the second ragged)."""
     rng = np.random.default_rng(d)
     x, z = rng.uniform(0, 1, (n, d)), rng.uniform(0, 1, (m, d))
     pr = dict(x=x, z=z, y=rng.standard_normal(n), yz=rng.standard_normal(m), ls_q=0.1,
@@ -228,7 +229,7 @@ def test_predictive_parity_wide_inputs(S, n, m, d):
     assert rel_norm(host(q.covariance), v_q_ref) <= TOL
     assert rel_norm(host(p.mean).reshape(-1), m_p_ref) <= TOL and rel_norm(host(p.covariance), v_p_ref) <= TOL
     # the objective is ONE call of gvi_fused_step_f64 for wide inputs too (r02): K rows of q and p from the tensor-pipe
-    # Gram kernel through two L2-sized rings, <= 3552 points per chunk (n = 5000: two chunks, the second ragged)
+    # Gram kernel through two rings, <= 28 416 points per chunk
     risk = S.NegativeLogLikelihood(gp=approx_gp)
     reg = S.projected.ProjectedKLRegularisation(gp=approx_gp, regulariser=exact_gp, regulariser_parameters=exact_params,
                                                 mode="posterior")
