@@ -15,11 +15,19 @@
 #include "dgemm.cuh"
 
 namespace {
-constexpr int BM = 128, BN = 128, BK = 16, GT = 512, PER = BM * BK / GT;  // PER staged elements per thread and operand
-constexpr int LDK = BK + 4;    // row stride of a [row][k] stage
-constexpr int LDR = BM + 4;    // row stride of a [k][row] stage (BM == BN)
-constexpr int STAGE_A = BM * LDK > BK * LDR ? BM * LDK : BK * LDR;  // doubles per operand stage, either orientation
-constexpr int STAGE = 2 * STAGE_A;                                   // A + B
+constexpr int BK = 16, GT = 512;
+// WT = edge of a warp's output tile: 32 -> 128 x 128 per CTA (the throughput shape), 16 -> 64 x 64 per CTA, two CTAs per
+// SM (small products: M^3-shaped work at M ~ 1024 has only 64 tiles of 128 x 128 - 43 % of the SMs, each bound by its own
+// tensor pipe - against 256 tiles of 64 x 64)
+template <int WT>
+struct Tile {
+  static constexpr int BM = 4 * WT, BN = 4 * WT, NF = WT / 8;  // NF x NF DMMA tiles per warp
+  static constexpr int PER = BM * BK / GT;                     // staged elements per thread and operand
+  static constexpr int LDK = BK + 4;                           // row stride of a [row][k] stage
+  static constexpr int LDR = BM + 4;                           // row stride of a [k][row] stage (BM == BN)
+  static constexpr int STAGE_A = BM * LDK > BK * LDR ? BM * LDK : BK * LDR;  // doubles per operand stage, either orientation
+  static constexpr int STAGE = 2 * STAGE_A;                                   // A + B
+};
 
 struct GemmParams {
   int m, n, k;
@@ -35,12 +43,13 @@ struct GemmParams {
 };
 
 // element (r, kk) of op(X) for a tile starting at (r0, k0): TX = false -> X[r][k] (k contiguous), true -> X[k][r]
-template <bool TX>
+template <int WT, bool TX>
 __device__ __forceinline__ void load_stage_regs(const double* __restrict__ X, int64_t ldx, int r0, int rmax, int k0,
-                                                int kmax, double (&v)[PER]) {
+                                                int kmax, double (&v)[Tile<WT>::PER]) {
+  constexpr int BM = Tile<WT>::BM;
   const int t = threadIdx.x;
 #pragma unroll
-  for (int e = 0; e < PER; e++) {
+  for (int e = 0; e < Tile<WT>::PER; e++) {
     const int idx = t + GT * e;
     int r, kk;
     if (!TX) {
@@ -56,81 +65,84 @@ __device__ __forceinline__ void load_stage_regs(const double* __restrict__ X, in
     v[e] = val;
   }
 }
-template <bool TX>
-__device__ __forceinline__ void store_stage(double* __restrict__ S, const double (&v)[PER]) {
+template <int WT, bool TX>
+__device__ __forceinline__ void store_stage(double* __restrict__ S, const double (&v)[Tile<WT>::PER]) {
+  constexpr int BM = Tile<WT>::BM, LDK = Tile<WT>::LDK, LDR = Tile<WT>::LDR;
   const int t = threadIdx.x;
 #pragma unroll
-  for (int e = 0; e < PER; e++) {
+  for (int e = 0; e < Tile<WT>::PER; e++) {
     const int idx = t + GT * e;
     if (!TX) S[(idx / BK) * LDK + idx % BK] = v[e];
     else S[(idx / BM) * LDR + idx % BM] = v[e];
   }
 }
 // fragment element op(X)[row][kk] from a stage
-template <bool TX>
+template <int WT, bool TX>
 __device__ __forceinline__ double frag(const double* __restrict__ S, int row, int kk) {
-  return TX ? S[kk * LDR + row] : S[row * LDK + kk];
+  return TX ? S[kk * Tile<WT>::LDR + row] : S[row * Tile<WT>::LDK + kk];
 }
 
 // TA: op(A) = A^T (A stored [k][m]);  TB: op(B) = B^T (B stored [n][k])
-template <bool TA, bool TB>
-__global__ void __launch_bounds__(GT, 1) dgemm_kernel(const GemmParams p) {
+template <int WT, bool TA, bool TB>
+__global__ void __launch_bounds__(GT, WT == 32 ? 1 : 2) dgemm_kernel(const GemmParams p) {
+  using TL = Tile<WT>;
+  constexpr int BM = TL::BM, BN = TL::BN, NF = TL::NF, PER = TL::PER, STAGE = TL::STAGE, STAGE_A = TL::STAGE_A;
   extern __shared__ __align__(16) double gemm_smem[];
   // tiles with the longest k range first (K_UPTO_N: the rightmost column tiles), so the tail of the grid is cheap
   const int bx = p.kmode == GVI_GEMM_K_UPTO_N ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
   const int m0 = blockIdx.y * BM, n0 = bx * BN;
   if (p.symm && m0 + BM <= n0) return;  // strictly above the diagonal: written as the mirror of its transpose
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps, warp tile 32 x 32
+  const int wm = warp >> 2, wn = warp & 3;  // 4 x 4 warps, warp tile WT x WT
   const int fr = lane >> 2, fk = lane & 3;
   // k range of this output tile
   int kbeg = 0, kend = p.k;
   if (p.kmode == GVI_GEMM_K_UPTO_N) kend = min(p.k, n0 + BN);          // op(B)[k][n] = 0 for k > n
   else if (p.kmode == GVI_GEMM_K_FROM_N) kbeg = (n0 / BK) * BK;        // op(B)[k][n] = 0 for k < n
-  double acc[4][4][2];
+  double acc[NF][NF][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++)
+  for (int mt = 0; mt < NF; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    for (int nt = 0; nt < NF; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
   // op(A) stage: TA means stored [k][m] -> "TX" orientation; op(B): stored [n][k] when TB (the [row][k] orientation)
   constexpr bool AX = TA, BX = !TB;
   double ra[PER], rb[PER];
   const int nchunk = (kend - kbeg + BK - 1) / BK;
   if (nchunk > 0) {
-    load_stage_regs<AX>(p.A, p.lda, m0, p.m, kbeg, kend, ra);
-    load_stage_regs<BX>(p.B, p.ldb, n0, p.n, kbeg, kend, rb);
+    load_stage_regs<WT, AX>(p.A, p.lda, m0, p.m, kbeg, kend, ra);
+    load_stage_regs<WT, BX>(p.B, p.ldb, n0, p.n, kbeg, kend, rb);
   }
   for (int c = 0; c < nchunk; c++) {
     double* Sa = gemm_smem + (c & 1) * STAGE;
     double* Sb = Sa + STAGE_A;
-    store_stage<AX>(Sa, ra);
-    store_stage<BX>(Sb, rb);
+    store_stage<WT, AX>(Sa, ra);
+    store_stage<WT, BX>(Sb, rb);
     __syncthreads();
     if (c + 1 < nchunk) {  // the next chunk travels while this one is multiplied
-      load_stage_regs<AX>(p.A, p.lda, m0, p.m, kbeg + (c + 1) * BK, kend, ra);
-      load_stage_regs<BX>(p.B, p.ldb, n0, p.n, kbeg + (c + 1) * BK, kend, rb);
+      load_stage_regs<WT, AX>(p.A, p.lda, m0, p.m, kbeg + (c + 1) * BK, kend, ra);
+      load_stage_regs<WT, BX>(p.B, p.ldb, n0, p.n, kbeg + (c + 1) * BK, kend, rb);
     }
 #pragma unroll
     for (int k0 = 0; k0 < BK; k0 += 4) {
-      double a[4], b[4];
+      double a[NF], b[NF];
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++) a[mt] = frag<AX>(Sa, 32 * wm + 8 * mt + fr, k0 + fk);
+      for (int mt = 0; mt < NF; mt++) a[mt] = frag<WT, AX>(Sa, WT * wm + 8 * mt + fr, k0 + fk);
 #pragma unroll
-      for (int nt = 0; nt < 4; nt++) b[nt] = frag<BX>(Sb, 32 * wn + 8 * nt + fr, k0 + fk);
+      for (int nt = 0; nt < NF; nt++) b[nt] = frag<WT, BX>(Sb, WT * wn + 8 * nt + fr, k0 + fk);
 #pragma unroll
-      for (int mt = 0; mt < 4; mt++)
+      for (int mt = 0; mt < NF; mt++)
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+        for (int nt = 0; nt < NF; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
     }
     // the stage written two iterations from now is this one: one barrier per chunk suffices with two buffers, because
     // the next store_stage goes to the other buffer and the one after that is separated from these reads by that barrier
   }
   // epilogue
 #pragma unroll
-  for (int mt = 0; mt < 4; mt++)
+  for (int mt = 0; mt < NF; mt++)
 #pragma unroll
-    for (int nt = 0; nt < 4; nt++) {
-      const int r = m0 + 32 * wm + 8 * mt + fr, c = n0 + 32 * wn + 8 * nt + 2 * fk;
+    for (int nt = 0; nt < NF; nt++) {
+      const int r = m0 + WT * wm + 8 * mt + fr, c = n0 + WT * wn + 8 * nt + 2 * fk;
       if (r >= p.m) continue;
 #pragma unroll
       for (int e = 0; e < 2; e++) {
@@ -150,16 +162,26 @@ __global__ void __launch_bounds__(GT, 1) dgemm_kernel(const GemmParams p) {
     }
 }
 
-template <bool TA, bool TB>
-int launch(const GemmParams& p, cudaStream_t st) {
+template <int WT, bool TA, bool TB>
+int launch_wt(const GemmParams& p, cudaStream_t st) {
   static std::atomic<unsigned long long> configured{0};
-  const size_t smem = (size_t)2 * STAGE * sizeof(double);
+  constexpr int BM = Tile<WT>::BM, BN = Tile<WT>::BN;
+  const size_t smem = (size_t)2 * Tile<WT>::STAGE * sizeof(double);
   if (gvi_first_use_on_this_device(configured))
-    GVI_CUDA(cudaFuncSetAttribute(dgemm_kernel<TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GVI_CUDA(cudaFuncSetAttribute(dgemm_kernel<WT, TA, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((p.n + BN - 1) / BN), (unsigned)((p.m + BM - 1) / BM));
-  dgemm_kernel<TA, TB><<<grid, GT, smem, st>>>(p);
+  dgemm_kernel<WT, TA, TB><<<grid, GT, smem, st>>>(p);
   GVI_CHECK_LAUNCH("dgemm_kernel");
   return GVI_OK;
+}
+template <bool TA, bool TB>
+int launch(const GemmParams& p, cudaStream_t st) {
+  // tiles of 128 x 128 that do work (a symmetric result computes the lower triangle only): below ~3/4 of a wave the
+  // product is bound by the tensor pipes of the few SMs that hold a tile -> quarter-size tiles, two CTAs per SM
+  const int64_t tn = (p.n + 127) / 128, tm = (p.m + 127) / 128;
+  const int64_t tiles = p.symm ? tn * (tn + 1) / 2 : tn * tm;
+  if (tiles * 4 < (int64_t)GVI_NUM_SMS * 3) return launch_wt<16, TA, TB>(p, st);
+  return launch_wt<32, TA, TB>(p, st);
 }
 }  // namespace
 

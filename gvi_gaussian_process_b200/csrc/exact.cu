@@ -10,8 +10,8 @@
 //   dLoss/dtheta = <G1, dK_xZ/dtheta> + <G2, dK_ZZ/dtheta> + sum_i g_i dk_ii/dtheta,   dLoss/dlog s2 = s2 tr(G2)
 // Unlike the approximate GP the mean depends on the hyper-parameters (through alpha and k_i), and the work is O(M^3)
 // on at most a few thousand points (the inducing set itself), so this is the DENSE route: K(x_chunk, Z) is
-// materialised chunk by chunk, the M^3-shaped products are plain library GEMMs (cuBLAS) against the dense L^-1 kept
-// in the factor state, and hand-written kernels do the Gram chunk, the elementwise cotangents and the contractions
+// materialised chunk by chunk, the M^3-shaped products run on the in-tree tensor-pipe GEMM (dgemm.cu) against the dense
+// L^-1 kept in the factor state, and hand-written kernels do the Gram chunk, the elementwise cotangents and the contractions
 // with dK/dtheta (recomputing k_ij on the fly, fixed-order reductions).
 #include "dgemm.cuh"
 
@@ -120,33 +120,49 @@ __global__ void __launch_bounds__(256) ard_contract_kernel(const double* __restr
   }
 }
 
-// acc[d] (+)= sum_r rowpart[r][d] in a fixed order; slot 32 is the <G, K> sum
-__global__ void contract_finish_kernel(const double* __restrict__ rowpart, int R, int D, int first,
-                                       double* __restrict__ acc) {
-  const int d = threadIdx.x;
-  if (d > 32 || (d >= D && d < 32)) return;
+// fixed-order block sum (256 threads): thread t adds its strided share, then a shared-memory tree
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (tid < s) red[tid] += red[tid + s];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+
+// acc[d] (+)= sum_r rowpart[r][d] in a fixed order; slot 32 is the <G, K> sum.  One CTA per slot d (33 CTAs).
+__global__ void __launch_bounds__(256) contract_finish_kernel(const double* __restrict__ rowpart, int R, int D, int first,
+                                                              double* __restrict__ acc) {
+  __shared__ double red[256];
+  const int d = blockIdx.x;
+  if (d >= D && d < 32) return;
   double a = 0.0;
-  for (int r = 0; r < R; r++) a += rowpart[(size_t)r * 33 + d];
-  acc[d] = first ? a : acc[d] + a;
+  for (int r = threadIdx.x; r < R; r += 256) a += rowpart[(size_t)r * 33 + d];
+  a = block_sum_256(a, red);
+  if (threadIdx.x == 0) acc[d] = first ? a : acc[d] + a;
 }
 
 // out[0..2] = {0, 0, N}; out[3] = 2 (<G1,K> + <G2,K_ZZ> + sum g k_ii); out[4+d] = both contractions;
 // out[4+D] = s2 tr(G2)
-__global__ void exact_finish_kernel(const double* __restrict__ acc1, const double* __restrict__ acc2,
-                                    const double* __restrict__ G2, int M, int Mp, int D, int64_t N,
-                                    const double* __restrict__ log_noise, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) exact_finish_kernel(const double* __restrict__ acc1, const double* __restrict__ acc2,
+                                                           const double* __restrict__ G2, int M, int Mp, int D, int64_t N,
+                                                           const double* __restrict__ log_noise, double* __restrict__ out) {
+  __shared__ double red[256];
   const int tid = threadIdx.x;
+  double tr = 0.0;
+  for (int j = tid; j < M; j += 256) tr += G2[(size_t)j * Mp + j];
+  tr = block_sum_256(tr, red);
   if (tid < D) out[4 + tid] = acc1[tid] + acc2[tid];
   if (tid == 32) {
     out[0] = out[1] = 0.0;
     out[2] = (double)N;
     out[3] = 2.0 * (acc1[32] + acc2[32]);
   }
-  if (tid == 33) {
-    double tr = 0.0;
-    for (int j = 0; j < M; j++) tr += G2[(size_t)j * Mp + j];
-    out[4 + D] = log_noise ? exp(log_noise[0]) * tr : 0.0;
-  }
+  if (tid == 33) out[4 + D] = log_noise ? exp(log_noise[0]) * tr : 0.0;
 }
 
 struct ExactWs {
@@ -222,16 +238,16 @@ extern "C" int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, c
     if (h_mean && (rc = gvi_dgemv_rm(true, Mp, nr, w.Aa, Mp, h_mean + r0, 1.0, w.w, st))) return rc;
     ard_contract_kernel<<<nr, 256, 0, st>>>(w.K, Mp, M, X + r0 * D, 1, F, f, g_var + r0, w.rowpart);
     GVI_CHECK_LAUNCH("ard_contract_kernel");
-    contract_finish_kernel<<<1, 64, 0, st>>>(w.rowpart, nr, D, first, w.acc1);
+    contract_finish_kernel<<<33, 256, 0, st>>>(w.rowpart, nr, D, first, w.acc1);
     GVI_CHECK_LAUNCH("contract_finish_kernel");
   }
   rank1_sub_kernel<<<GVI_NUM_SMS * 4, 256, 0, st>>>(w.G2, w.w, alpha, Mp);
   GVI_CHECK_LAUNCH("rank1_sub_kernel");
   ard_contract_kernel<<<M, 256, 0, st>>>(w.G2, Mp, M, F + f.zs_off, 0, F, f, nullptr, w.rowpart);
   GVI_CHECK_LAUNCH("ard_contract_kernel");
-  contract_finish_kernel<<<1, 64, 0, st>>>(w.rowpart, M, D, 1, w.acc2);
+  contract_finish_kernel<<<33, 256, 0, st>>>(w.rowpart, M, D, 1, w.acc2);
   GVI_CHECK_LAUNCH("contract_finish_kernel");
-  exact_finish_kernel<<<1, 64, 0, st>>>(w.acc1, w.acc2, w.G2, M, Mp, D, N, log_noise, out);
+  exact_finish_kernel<<<1, 256, 0, st>>>(w.acc1, w.acc2, w.G2, M, Mp, D, N, log_noise, out);
   GVI_CHECK_LAUNCH("exact_finish_kernel");
   return GVI_OK;
 }

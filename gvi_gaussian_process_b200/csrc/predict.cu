@@ -688,6 +688,20 @@ int gvi_step_tile_points(int Mp, int D, bool grad) {
   if (step_smem_bytes_d<1>(Mp, Mp, D, grad, 16, true) <= SMEM_LIMIT) return 8;
   return 0;
 }
+// points per tile of a forward launch over N points
+// (small launches are bound by the tile-pass latency of the SMs that hold a tile: measured at M = 1024, D = 8 a pass over
+// T points takes about 12 + 5.6 T us, and a launch ceil(tiles / 148) of them - tools/small_time.py)
+int gvi_step_forward_tile_points(int64_t N) {
+  if (N >= (int64_t)GVI_NUM_SMS * 24 * 4) return 24;
+  int best = 24;
+  double best_cost = 0.0;
+  for (int T = 24; T >= 8; T -= 8) {
+    const int64_t tiles = (N + T - 1) / T;
+    const double cost = (double)((tiles + GVI_NUM_SMS - 1) / GVI_NUM_SMS) * (12.0 + 5.6 * T);
+    if (T == 24 || cost < best_cost) best = T, best_cost = cost;
+  }
+  return best;
+}
 // scratch (doubles) for launches that sweep the K tile in panels: parked accumulators + per-group norms, per CTA
 size_t gvi_step_scratch_doubles(int Mp) {
   return (size_t)2 * GVI_NUM_SMS * ((size_t)Mp * 24 + (size_t)(Mp / GVI_GROUP_ROWS) * 24);
@@ -758,6 +772,12 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
     // profiling aid (env GVI_DEBUG_GRID): cap the grid, e.g. 148 in the two-CTA shape = one 8-warp CTA per SM
     static const int debug_grid = gvi_debug_env("GVI_DEBUG_GRID");
     if (debug_grid > 0) return launch_step_nt<3>(P, debug_grid, st);
+    // small launches: 16- or 8-point tiles spread the points over more SMs (a tile-pass is bound by one SM's tensor
+    // pipe; N = 1024: 43 tiles of 24 points against 128 tiles of 8, 182 -> 59 us)
+    const int T = P.tile_points ? P.tile_points : gvi_step_forward_tile_points(P.N);
+    if (T != 24) P.two_cta = 0;  // the two-CTA shape exists for 24-point tiles only; Pc / reds_in_smem stay valid (less smem)
+    if (T == 8) return launch_step_nt<1>(P, GVI_NUM_SMS, st);
+    if (T == 16) return launch_step_nt<2>(P, GVI_NUM_SMS, st);
     return launch_step_nt<3>(P, P.two_cta ? 2 * GVI_NUM_SMS : GVI_NUM_SMS, st);
   }
   // gradient mode keeps the whole b tile in shared memory
@@ -893,7 +913,10 @@ static size_t fused_records_doubles() {
   const size_t n = (size_t)(2 * GVI_NUM_SMS > STEP_REDUCE_BLOCKS ? 2 * GVI_NUM_SMS : STEP_REDUCE_BLOCKS);
   return n * STEP_PARTIAL_STRIDE;
 }
-static size_t fused_tile_doubles(int64_t N) { return (size_t)((N + 23) / 24) * 2 + 2; }
+static size_t fused_tile_doubles(int64_t N) {
+  const int T = gvi_step_forward_tile_points(N);
+  return (size_t)((N + T - 1) / T) * 2 + 2;
+}
 extern "C" size_t gvi_fused_step_workspace_bytes(int64_t N, int M) {
   if (N < 1 || M < 1) return 0;
   const int Mp = (M + 31) / 32 * 32;
@@ -976,6 +999,7 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
       C.X = nullptr; C.N = nr;
       C.y = off(C.y); C.m_q = off(C.m_q); C.m_p_in = off(C.m_p_in); C.v_p_in = off(C.v_p_in);
       C.tile_partials = P0.tile_partials + (r0 / 24) * 2;
+      C.tile_points = 24;  // also for a short last chunk: one record per 24 points throughout
       int g = gvi_launch_step(C, st);
       if (g < 0) return g;
     }
@@ -986,7 +1010,8 @@ extern "C" int gvi_fused_step_f64(const void* factor_q, const void* factor_p, in
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   // forward launches use 24-point tiles; per-tile records -> fixed-order reduction -> out3
-  int nrec = gvi_launch_tile_reduce(P.tile_partials, (N + 23) / 24, 0, P.partials, st);
+  const int T = gvi_step_forward_tile_points(N);
+  int nrec = gvi_launch_tile_reduce(P.tile_partials, (N + T - 1) / T, 0, P.partials, st);
   if (nrec < 0) return nrec;
   return gvi_launch_finish(P.partials, nrec, N, 0, D, (const double*)factor_q, out3, st);
 }

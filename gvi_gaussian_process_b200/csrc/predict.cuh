@@ -55,6 +55,7 @@ struct StepParams {
   double* reds_scratch; // [gridDim.x][G*T]   (when the per-group norms do not fit in shared memory)
   int reds_in_smem;     // set by the launcher
   int two_cta;          // set by the launcher: 8-warp CTAs, two per SM
+  int tile_points;      // forward launches: 0 = chosen from N (gvi_step_forward_tile_points), else 24 / 16 / 8
   int has_extra;        // the q factor carries an extra matrix E (SVGP): single panel required
   // gradient mode: a_i = A^-1 k_i of every tile is also written to a ring in the operand order of the weighted-Gram
   // (SYRK) kernel of grad.cu, together with g_i, so that S = sum_i g_i a_i a_i^T is accumulated from the a_i directly
@@ -77,6 +78,7 @@ __host__ __device__ __forceinline__ int syrk_frag_index(int c, int i) {
 }
 
 int gvi_step_tile_points(int Mp, int D, bool grad);
+int gvi_step_forward_tile_points(int64_t N);  // 24, or 16 / 8 for launches of a few waves at most
 // forward-only launches use column panels when the whole K tile does not fit: returns Pc (== Mp: single panel)
 size_t gvi_step_scratch_doubles(int Mp);  // per-launch scratch for the panel path
 int gvi_launch_step(const StepParams& P, cudaStream_t st);
