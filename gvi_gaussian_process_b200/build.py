@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gram.cu", "gram_dmma.cu", "chol.cu", "chol_coop.cu", "dgemm.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu", "diag.cu"]
+SOURCES = ["gram.cu", "gram_mma.cu", "gram_dmma.cu", "chol.cu", "chol_coop.cu", "dgemm.cu", "predict.cu", "grad.cu", "risk.cu", "select.cu", "classify.cu", "exact.cu", "optim.cu", "grad_wide.cu", "comm.cu", "prng.cu", "diag.cu"]
 LIB_PATH = os.path.join(HERE, "libgvigp.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

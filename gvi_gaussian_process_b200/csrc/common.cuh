@@ -233,6 +233,14 @@ __device__ __forceinline__ double gvi_exp_neg_t32(double s, const double2* tab, 
   return tiny ? 0.0 : scaled;
 }
 
+// guard of the tensor-pipe Gram for small D (gram_mma.cu): guard[0], guard[1] = bit patterns of R1^2 = max_i |u_i|^2 and
+// R2^2 = max_j |v_j|^2 (scaled, centred inputs).  True = the expanded form |u|^2 + |v|^2 - 2 u.v is accurate to
+// ~1e-11 relative in k for every pair; false (also for NaN / inf norms) = direct differences.
+__device__ __forceinline__ bool gvi_gram_fast_ok(const unsigned long long* __restrict__ guard) {
+  const double r1 = __longlong_as_double((long long)guard[0]), r2 = __longlong_as_double((long long)guard[1]);
+  return r1 + r2 + 2.0 * sqrt(r1 * r2) <= 4096.0;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,10 +11,12 @@ __global__ void __launch_bounds__(TC) ard_gram_kernel(const double* __restrict__
                                                       const double* __restrict__ x2, int64_t m2, int D,
                                                       const double* __restrict__ log_scaling,
                                                       const double* __restrict__ log_ls, int ls_len,
-                                                      double* __restrict__ out, int64_t ld) {
+                                                      double* __restrict__ out, int64_t ld,
+                                                      const unsigned long long* __restrict__ guard) {
   __shared__ double xs[TR][DC];
   __shared__ double zs[DC][TC + 1];
   __shared__ double w[DC];
+  if (guard && gvi_gram_fast_ok(guard)) return;  // the tensor-pipe kernel (gram_mma.cu) produced this Gram
   const int tid = threadIdx.x;
   const int64_t col0 = (int64_t)blockIdx.x * TC;
   const int64_t row0 = (int64_t)blockIdx.y * TR;
@@ -77,7 +79,9 @@ __global__ void __launch_bounds__(256, GRAM_MIN_CTAS) ard_gram_tile_kernel(const
                                                                const double* __restrict__ x2, int64_t m2, int D,
                                                                const double* __restrict__ log_scaling,
                                                                const double* __restrict__ log_ls, int ls_len,
-                                                               double* __restrict__ out, int64_t ld) {
+                                                               double* __restrict__ out, int64_t ld,
+                                                               const unsigned long long* __restrict__ guard) {
+  if (guard && gvi_gram_fast_ok(guard)) return;  // the tensor-pipe kernel (gram_mma.cu) produced this Gram
   constexpr int RB = GRAM_RB;  // rows of x1 per staged block
   constexpr int RT = DP <= 8 ? 8 : 4;  // rows per inner step (lab: tools/lab/gram_lab.cu - 8 x 2 chains per thread at 3 CTAs/SM was best)
   __shared__ __align__(16) double xs[RB][DP];
@@ -181,7 +185,8 @@ __global__ void __launch_bounds__(256, GRAM_MIN_CTAS) ard_gram_tile_kernel(const
 
 template <int DP, int CT>
 int launch_ard_gram_tile(const double* x1, int64_t m1, const double* x2, int64_t m2, int D, const double* log_scaling,
-                         const double* log_ls, int ls_len, double* out, int64_t ld, cudaStream_t st) {
+                         const double* log_ls, int ls_len, double* out, int64_t ld, const unsigned long long* guard,
+                         cudaStream_t st) {
   const int64_t gx = (m2 + 256 * CT - 1) / (256 * CT);
   constexpr int64_t rows_per_cta = (int64_t)GRAM_RB * GRAM_RBLOCKS;
   const int64_t gy = (m1 + rows_per_cta - 1) / rows_per_cta;
@@ -190,7 +195,7 @@ int launch_ard_gram_tile(const double* x1, int64_t m1, const double* x2, int64_t
     const int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
     ard_gram_tile_kernel<DP, CT><<<dim3((unsigned)gx, (unsigned)ny), 256, 0, st>>>(
         x1 + y0 * rows_per_cta * D, m1 - y0 * rows_per_cta, x2, m2, D, log_scaling, log_ls, ls_len,
-        out + y0 * rows_per_cta * ld, ld);
+        out + y0 * rows_per_cta * ld, ld, guard);
     GVI_CHECK_LAUNCH("ard_gram_tile_kernel");
   }
   return GVI_OK;
@@ -319,14 +324,14 @@ extern "C" int gvi_kernel_pairs_f64(int kind, const double* x1, const double* x2
   return GVI_OK;
 }
 
-int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
-                        const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
-                        cudaStream_t st) {
-  if (m1 == 0 || m2 == 0) return GVI_OK;
-  if (D <= 2) return launch_ard_gram_tile<2, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
-  if (D <= 4) return launch_ard_gram_tile<4, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
-  if (D <= 8) return launch_ard_gram_tile<8, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
-  if (D <= 16) return launch_ard_gram_tile<16, 1>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, st);
+// guard != null: the tensor-pipe kernel of gram_mma.cu was launched ahead; these kernels exit at once if it ran
+static int launch_ard_gram_direct(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                                  const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                                  const unsigned long long* guard, cudaStream_t st) {
+  if (D <= 2) return launch_ard_gram_tile<2, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, guard, st);
+  if (D <= 4) return launch_ard_gram_tile<4, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, guard, st);
+  if (D <= 8) return launch_ard_gram_tile<8, 2>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, guard, st);
+  if (D <= 16) return launch_ard_gram_tile<16, 1>(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, guard, st);
   // 16 < D < 24 (or no workspace for the tensor-pipe kernel): one column per thread, features staged 16 at a time
   int64_t gy = (m1 + TR - 1) / TR;
   int64_t gx = (m2 + TC - 1) / TC;
@@ -336,11 +341,27 @@ int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t 
     int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
     dim3 grid((unsigned)gx, (unsigned)ny);
     ard_gram_kernel<<<grid, TC, 0, st>>>(x1 + y0 * TR * D, m1 - y0 * TR, x2, m2, D, log_scaling, log_ls, ls_len,
-                                         out + y0 * TR * ld, ld);
+                                         out + y0 * TR * ld, ld, guard);
     GVI_CHECK_LAUNCH("ard_gram_kernel");
   }
   return GVI_OK;
 }
+
+int gvi_launch_ard_gram(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                        const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                        cudaStream_t st) {
+  if (m1 == 0 || m2 == 0) return GVI_OK;
+  return launch_ard_gram_direct(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld, nullptr, st);
+}
+
+size_t gvi_gram_mma_workspace_bytes();
+int gvi_launch_ard_gram_mma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
+                            const double* log_scaling, const double* log_ls, int ls_len, double* out, int64_t ld,
+                            unsigned long long* guard, cudaStream_t st);
+// 5 <= D < 24 and an output large enough to pay for three extra launches: guarded tensor-pipe kernel, then the
+// direct-difference kernel as its fall-back (exactly one of the two does the work; decided on the device)
+constexpr int GVI_GRAM_MMA_MIN_D = 5;
+constexpr int64_t GVI_GRAM_MMA_MIN_ELEMS = 1 << 18;
 
 size_t gvi_gram_dmma_workspace_doubles(int64_t m1, int64_t m2, int D);
 int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
@@ -348,11 +369,16 @@ int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int
                              double* workspace, cudaStream_t st);
 
 // wide inputs go through the tensor-pipe contraction (gram_dmma.cu) when the caller supplies the workspace
-constexpr int GVI_GRAM_DMMA_MIN_D = 24;
+#ifndef GVI_GRAM_DMMA_MIN_D_VALUE
+#define GVI_GRAM_DMMA_MIN_D_VALUE 24
+#endif
+constexpr int GVI_GRAM_DMMA_MIN_D = GVI_GRAM_DMMA_MIN_D_VALUE;
 
 extern "C" size_t gvi_ard_gram_workspace_bytes(int64_t m1, int64_t m2, int D) {
-  if (m1 < 1 || m2 < 1 || D < GVI_GRAM_DMMA_MIN_D) return 0;
-  return gvi_gram_dmma_workspace_doubles(m1, m2, D) * sizeof(double);
+  if (m1 < 1 || m2 < 1) return 0;
+  if (D >= GVI_GRAM_DMMA_MIN_D) return gvi_gram_dmma_workspace_doubles(m1, m2, D) * sizeof(double);
+  if (D >= GVI_GRAM_MMA_MIN_D && m1 * m2 >= GVI_GRAM_MMA_MIN_ELEMS) return gvi_gram_mma_workspace_bytes();
+  return 0;
 }
 
 extern "C" int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
@@ -366,6 +392,15 @@ extern "C" int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, 
   if (D >= GVI_GRAM_DMMA_MIN_D && workspace)
     return gvi_launch_ard_gram_dmma(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out,
                                     (double*)workspace, (cudaStream_t)stream);
+  if (workspace && D >= GVI_GRAM_MMA_MIN_D && D < GVI_GRAM_DMMA_MIN_D && m1 * m2 >= GVI_GRAM_MMA_MIN_ELEMS &&
+      (reinterpret_cast<uintptr_t>(workspace) & 7) == 0) {
+    unsigned long long* guard = (unsigned long long*)workspace;
+    int rc = gvi_launch_ard_gram_mma(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out, guard,
+                                     (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_ard_gram_direct(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out, guard,
+                                  (cudaStream_t)stream);
+  }
   return gvi_launch_ard_gram(x1, m1, x2, m2, D, log_scaling, log_ls, ls_len, out, ld_out, (cudaStream_t)stream);
 }
 

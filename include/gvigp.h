@@ -46,7 +46,11 @@ int64_t gvi_launch_count(void);
  * out[i*ld_out + j] = exp(log_scaling)^2 * exp(-0.5 * sum_d exp(log_ls[d]) * (x1[i,d]-x2[j,d])^2).
  * ls_len is D, or 1 (a scalar lengthscale broadcast over D, README.md:92-94). */
 /* D >= 24 with a workspace: the x1.x2^T contraction runs on the FP64 tensor pipe (DMMA) with the squared-distance,
- * lengthscale and exp epilogue fused; otherwise (workspace NULL or small D) direct differences.                  */
+ * lengthscale and exp epilogue fused; otherwise (workspace NULL or small D) direct differences.
+ * 5 <= D < 24 with a workspace (256 bytes; the size query returns 0 for outputs too small to pay for it): the same
+ * expansion on the tensor pipe BEHIND A DEVICE-SIDE GUARD - a pass over the inputs bounds (max |u| + max |v|)^2 of the
+ * scaled, centred rows; within 4096 (error of k <= 1.2e-11 relative) the tensor-pipe kernel writes the result, else
+ * (short lengthscales, far-apart clusters, inf / NaN inputs) the direct-difference kernel does; no host sync.       */
 size_t gvi_ard_gram_workspace_bytes(int64_t m1, int64_t m2, int D);
 int gvi_ard_gram_f64(const double* x1, int64_t m1, const double* x2, int64_t m2, int D,
                      const double* log_scaling, const double* log_ls, int ls_len,

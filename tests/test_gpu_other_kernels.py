@@ -235,7 +235,10 @@ def test_generic_gram_entry_points_equal_the_ard_path(S):
         v_fused = host(sparse.calculate_gram(sparse.Parameters.construct(base_kernel=kp), x, full_covariance=False))
         f = L.GpFactor(m, 1).factor_from_gram(ard.calculate_gram(kp, z, z).contiguous(), 1e-5, False)
         _, v_gram = L.gp_predict_any_kernel(f, ard, kp, dev(z), dev(x), want_mean=False)
-        assert rel_norm(host(v_gram), v_fused) <= 1e-12
+        # (900 x 1300 at D = 8 takes the guarded tensor-pipe Gram of csrc/gram_mma.cu: entries within ~10 ulp of the
+        # direct differences, amplified by cond(A) in v = k(x,x) - k^T A^-1 k: 1.6e-12 measured, 3.5e-14 with the
+        # direct-difference Gram, tools/lab/gram_guard_dev.py)
+        assert rel_norm(host(v_gram), v_fused) <= (1e-12 if n * m < (1 << 18) else 2e-11)
 
 
 def test_svgp_mean_golden(S):

@@ -113,6 +113,47 @@ def test_ard_gram_tensor_pipe_contraction(S, m1, m2, d, offset):
     assert rel_elem(host(out), ref) <= TOL
 
 
+@pytest.mark.parametrize("m1,m2,d", [(2051, 517, 8), (1000, 300, 5), (1500, 1030, 13), (777, 600, 20)])
+def test_ard_gram_guarded_tensor_pipe_small_d(S, m1, m2, d):
+    """5 <= D < 24 (csrc/gram_mma.cu): the x.z part of the exponent runs on the tensor pipe when the guard
+    (R1 + R2)^2 <= 4096 over the scaled, centred inputs holds, else the direct-difference kernel does the work -
+    decided on the device.  Checked here: the fast path against the oracle (<= 1e-10 elementwise, inputs far from the
+    origin included: the centring removes a common offset), the tripped guard (short lengthscales: the result must be
+    the direct kernel's, bit for bit), ragged sizes, an odd leading dimension, and a NaN input (-> NaN row)."""
+    rng = np.random.default_rng(m1 + d)
+    ls = 0.3
+    k = S.ARDKernel(number_of_dimensions=d)
+    for offset, log_ls, fast in ((0.0, np.log(1.0 / d), True), (1000.0, np.log(1.0 / d), True), (0.0, 9.0, False)):
+        x1, x2 = offset + rng.standard_normal((m1, d)), offset + rng.standard_normal((m2, d))
+        ll = log_ls + 0.3 * rng.standard_normal(d)
+        ref = O.ard_gram(ls, ll, x1, x2)
+        g = host(k.calculate_gram(k.Parameters.construct(log_scaling=ls, log_lengthscales=ll), x1, x2))
+        assert rel_elem(g, ref) <= TOL, (offset, log_ls)
+        direct = torch.empty(m1, m2, dtype=torch.float64, device="cuda")
+        S._lib_proxy.ard_gram(dev(x1), dev(x2), dev([ls]), dev(ll), direct, tensor_pipe=False)
+        assert rel_elem(host(direct), ref) <= TOL
+        same_bits = np.array_equal(g, host(direct))
+        assert same_bits == (not fast), "the guard decides which kernel writes the result"
+        if fast:  # the bound the guard promises (1.2e-11) against the direct kernel
+            assert np.max(np.abs(g - host(direct)) / np.maximum(np.abs(host(direct)), 1e-300)) <= 2e-11
+    # odd leading dimension (scalar stores) and a NaN coordinate: its row is NaN, the others are untouched
+    x1, x2 = rng.standard_normal((m1, d)), rng.standard_normal((m2, d))
+    ll = np.full(d, np.log(1.0 / d))
+    out = torch.full((m1, m2 + 1), -7.0, dtype=torch.float64, device="cuda")
+    lib = S._lib.load()
+    ws = torch.zeros(lib.gvi_ard_gram_workspace_bytes(m1, m2, d) // 8, dtype=torch.float64, device="cuda")
+    assert ws.numel() > 0
+    a1, a2, als, all_ = dev(x1), dev(x2), dev([ls]), dev(ll)
+    rc = lib.gvi_ard_gram_f64(a1.data_ptr(), m1, a2.data_ptr(), m2, d, als.data_ptr(), all_.data_ptr(), d, out.data_ptr(),
+                              m2 + 1, ws.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    o = host(out)
+    assert rel_elem(o[:, :m2], O.ard_gram(ls, ll, x1, x2)) <= TOL and np.all(o[:, m2] == -7.0)
+    x1[3, d - 1] = np.nan
+    g = host(k.calculate_gram(k.Parameters.construct(log_scaling=ls, log_lengthscales=ll), x1, x2))
+    assert np.all(np.isnan(g[3])) and not np.any(np.isnan(np.delete(g, 3, axis=0)))
+
+
 def test_gram_shape_asserts(S):
     k = S.ARDKernel(number_of_dimensions=3)
     p = k.Parameters.construct(log_scaling=0.0, log_lengthscales=np.zeros(3))

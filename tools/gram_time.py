@@ -16,7 +16,7 @@ shapes = [(400000, 1024, 8)] if quick else [(400000, 1024, 8), (1000000, 512, 8)
 for N, M, D in shapes:
     X = T(rng.standard_normal((N, D))); Z = T(rng.standard_normal((M, D))); ls = T([0.0]); ll = T(np.full(D, np.log(1.0/D)))
     out = torch.empty(N, M, dtype=torch.float64, device=dev)
-    for tp in ((True, False) if D >= 24 else (False,)):
+    for tp in ((True, False) if D >= int(os.environ.get("GRAM_TP_MIN_D", 5)) else (False,)):
         for _ in range(2): L.ard_gram(X, Z, ls, ll, out, tensor_pipe=tp)
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
