@@ -23,19 +23,51 @@ __global__ void __launch_bounds__(RTHREADS) risk_kernel(int kind, double alpha, 
   const bool aligned = (((uintptr_t)mq | (uintptr_t)vq | (uintptr_t)(y ? y : mq) | (uintptr_t)(has_reg ? mp : mq) |
                          (uintptr_t)(has_reg ? vp : mq)) & 15) == 0;
   if (aligned) {
-    for (int64_t p = (int64_t)blockIdx.x * RTHREADS + tid; p < npairs; p += (int64_t)gridDim.x * RTHREADS) {
-      double2 m2 = reinterpret_cast<const double2*>(mq)[p];
-      double2 v2 = reinterpret_cast<const double2*>(vq)[p];
+    // two pairs (four points) per thread and trip: ten 16-byte loads in flight before the first dependent FP64
+    // instruction, four independent log / divide chains per term; the sums keep a fixed order (a: pair p then p + stride)
+    const int64_t stride = (int64_t)gridDim.x * RTHREADS;
+    const double2 zero2 = make_double2(0.0, 0.0), one2 = make_double2(1.0, 1.0);
+    for (int64_t p = (int64_t)blockIdx.x * RTHREADS + tid; p < npairs; p += 2 * stride) {
+      const int64_t p1 = p + stride;
+      const bool two = p1 < npairs;
+      const double2 m2a = reinterpret_cast<const double2*>(mq)[p];
+      const double2 v2a = reinterpret_cast<const double2*>(vq)[p];
+      const double2 m2b = two ? reinterpret_cast<const double2*>(mq)[p1] : zero2;
+      const double2 v2b = two ? reinterpret_cast<const double2*>(vq)[p1] : one2;
+      double2 y2a = zero2, y2b = zero2, pma = zero2, pva = one2, pmb = zero2, pvb = one2;
       if (y) {
-        double2 y2 = reinterpret_cast<const double2*>(y)[p];
-        a += gvi_nll_term(y2.x, m2.x, v2.x);
-        a += gvi_nll_term(y2.y, m2.y, v2.y);
+        y2a = reinterpret_cast<const double2*>(y)[p];
+        if (two) y2b = reinterpret_cast<const double2*>(y)[p1];
       }
       if (has_reg) {
-        double2 pm = reinterpret_cast<const double2*>(mp)[p];
-        double2 pv = reinterpret_cast<const double2*>(vp)[p];
-        b += gvi_reg_term(kind, alpha, pm.x, pv.x, m2.x, v2.x);
-        b += gvi_reg_term(kind, alpha, pm.y, pv.y, m2.y, v2.y);
+        pma = reinterpret_cast<const double2*>(mp)[p];
+        pva = reinterpret_cast<const double2*>(vp)[p];
+        if (two) {
+          pmb = reinterpret_cast<const double2*>(mp)[p1];
+          pvb = reinterpret_cast<const double2*>(vp)[p1];
+        }
+      }
+      if (y) {
+        const double t0 = gvi_nll_term(y2a.x, m2a.x, v2a.x), t1 = gvi_nll_term(y2a.y, m2a.y, v2a.y);
+        const double t2 = gvi_nll_term(y2b.x, m2b.x, v2b.x), t3 = gvi_nll_term(y2b.y, m2b.y, v2b.y);
+        a += t0;
+        a += t1;
+        if (two) {
+          a += t2;
+          a += t3;
+        }
+      }
+      if (has_reg) {
+        const double t0 = gvi_reg_term(kind, alpha, pma.x, pva.x, m2a.x, v2a.x);
+        const double t1 = gvi_reg_term(kind, alpha, pma.y, pva.y, m2a.y, v2a.y);
+        const double t2 = gvi_reg_term(kind, alpha, pmb.x, pvb.x, m2b.x, v2b.x);
+        const double t3 = gvi_reg_term(kind, alpha, pmb.y, pvb.y, m2b.y, v2b.y);
+        b += t0;
+        b += t1;
+        if (two) {
+          b += t2;
+          b += t3;
+        }
       }
     }
   }
@@ -102,8 +134,19 @@ extern "C" int gvi_risk_f64(int reg_kind, double renyi_alpha, const double* y, c
   GVI_CHECK_ARG(reg_kind >= GVI_REG_NONE && reg_kind <= GVI_REG_SQUARED_DIFFERENCE, "reg_kind");
   GVI_CHECK_ARG(reg_kind == GVI_REG_NONE || (m_p && v_p), "regulariser needs m_p and v_p");
   cudaStream_t st = (cudaStream_t)stream;
-  int64_t want = (N / 2 + RTHREADS - 1) / RTHREADS;
-  int blocks = (int)(want < 1 ? 1 : (want > RBLOCKS ? RBLOCKS : want));
+  // grid = the CTAs that are resident at once (a whole number per SM): with a fixed 4 per SM and 76 registers only 3
+  // fit, and the 148 left-over CTAs ran as a second, quarter-full wave (1.75 -> 1.18 ms at N = 1e8 came from the
+  // cheaper terms, the rest of the way to the HBM roofline from this)
+  static std::atomic<int> per_sm_cached{0};
+  int per_sm = per_sm_cached.load();
+  if (per_sm == 0) {
+    GVI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, risk_kernel, RTHREADS, 0));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    per_sm_cached.store(per_sm);
+  }
+  const int resident = GVI_NUM_SMS * per_sm;
+  int64_t want = (N / 4 + RTHREADS - 1) / RTHREADS;  // four points per thread and trip
+  int blocks = (int)(want < 1 ? 1 : (want > resident ? resident : want));
   risk_kernel<<<blocks, RTHREADS, 0, st>>>(reg_kind, renyi_alpha, y, m_q, v_q, m_p, v_p, N, (double*)workspace);
   GVI_CHECK_LAUNCH("risk_kernel");
   risk_finish_kernel<<<1, 256, 0, st>>>((const double*)workspace, blocks, N, out3);

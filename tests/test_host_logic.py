@@ -246,6 +246,37 @@ def test_device_exp_source_evaluated_on_the_host(tmp_path, variant):
         assert fields[flag].strip() == "1", out
 
 
+def test_device_log_source_evaluated_on_the_host(tmp_path):
+    """gvi_log (csrc/common.cuh) is the logarithm of the Gaussian NLL and of the KL / Renyi / Bhattacharyya terms in the
+    risk kernel and the fused epilogue: table + function text compiled for the host and swept over 1e7 arguments (every
+    binade, [0.5, 2] densely, 1 +- 2^-k, the table's interval boundaries): <= 2 ulp against logl() (1.84 next to the
+    interval around 1, where log c and r cancel by one bit), log(1) = +0 exactly,
+    log(0) = -inf, negative -> NaN (a negative predictive variance must surface as a NaN loss like the reference's
+    jnp.log), inf, NaN and subnormal arguments through the library branch."""
+    import re
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "gvi_gaussian_process_b200", "csrc", "common.cuh")).read()
+    body = re.search(r"static __device__ const double GVI_LOG_TABLE\[128\]\[3\] = \{.*?__device__ __forceinline__ double gvi_log\(double x\) \{.*?\n\}\n",
+                     src, flags=re.S)
+    assert body, "gvi_log not found in common.cuh"
+    (tmp_path / "gvi_log_body.inc").write_text(body.group(0).replace("static __device__ const", "static const"))
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    exe = tmp_path / "gvi_log_host"
+    build = subprocess.run([gcc, "-O2", "-ffp-contract=off", "-I", str(tmp_path),
+                            os.path.join(root, "tests", "csrc", "gvi_log_host.c"), "-o", str(exe), "-lm"],
+                           capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300).stdout
+    fields = dict(line.split(None, 1) for line in out.strip().splitlines())
+    assert float(fields["max_ulp"].split()[0]) <= 2.0, out
+    for flag in ("one", "zero", "negative", "inf", "nan", "subnormal"):
+        assert fields[flag].strip() == "1", out
+
+
 def _pointwise_host(tmp_path):
     """Compile the device source of the pointwise loss terms (csrc/common.cuh) for the host; returns a callable
     rows[kind, alpha, y, mp, cp, mq, cq] -> array [n, 6] = (nll, dnll/dm, dnll/dv, D0, dD0/dmq, dD0/dcq)."""
@@ -255,10 +286,10 @@ def _pointwise_host(tmp_path):
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = open(os.path.join(root, "gvi_gaussian_process_b200", "csrc", "common.cuh")).read()
-    body = re.search(r"__device__ __forceinline__ double gvi_nll_term\(.*?__device__ __forceinline__ double gvi_reg_term\(.*?\n\}\n",
+    body = re.search(r"static __device__ const double GVI_LOG_TABLE\[128\]\[3\] = \{.*?__device__ __forceinline__ double gvi_reg_term\(.*?\n\}\n",
                      src, flags=re.S)
     assert body, "pointwise loss terms not found in common.cuh"
-    for name in ("gvi_nll_term", "gvi_nll_grad", "gvi_reg_grad", "gvi_reg_term"):
+    for name in ("gvi_log", "gvi_nll_term", "gvi_nll_grad", "gvi_reg_grad", "gvi_reg_term"):
         assert name in body.group(0)
     (tmp_path / "pointwise_body.inc").write_text(body.group(0))
     gxx = shutil.which("g++")
