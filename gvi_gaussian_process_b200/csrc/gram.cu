@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TC) ard_gram_kernel(const double* __restrict__
 }
 
 constexpr int GRAM_RB = 64;      // rows of x1 staged per block of the tile kernel
-constexpr int GRAM_RBLOCKS = 4;  // row blocks per CTA
+constexpr int GRAM_RBLOCKS = 4;  // row blocks per CTA (large Grams; small ones take fewer so that the grid covers the SMs)
 
 // Materialised Gram for D <= 16 - the API call ARDKernel.calculate_gram (src/kernels/standard/base.py:95-103,
 // ard_kernel.py:58-66).  The output is written once (8 B per element: the HBM store roofline), so the kernel is shaped
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(256, GRAM_MIN_CTAS) ard_gram_tile_kernel(const
                                                                const double* __restrict__ log_scaling,
                                                                const double* __restrict__ log_ls, int ls_len,
                                                                double* __restrict__ out, int64_t ld,
-                                                               const unsigned long long* __restrict__ guard) {
+                                                               const unsigned long long* __restrict__ guard,
+                                                               int rblocks) {
   if (guard && gvi_gram_fast_ok(guard)) return;  // the tensor-pipe kernel (gram_mma.cu) produced this Gram
   constexpr int RB = GRAM_RB;  // rows of x1 per staged block
   constexpr int RT = DP <= 8 ? 8 : 4;  // rows per inner step (lab: tools/lab/gram_lab.cu - 8 x 2 chains per thread at 3 CTAs/SM was best)
@@ -103,8 +104,8 @@ __global__ void __launch_bounds__(256, GRAM_MIN_CTAS) ard_gram_tile_kernel(const
   const double acc0 = -2.0 * log_scaling[0];  // exp(-(acc0 + s)) = exp(log_scaling)^2 exp(-s)
   const double2* tb = &tab[0][tid & 7];
   const bool vec2 = CT == 2 && ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && (col0 + 1 < m2);
-  for (int blk = 0; blk < GRAM_RBLOCKS; blk++) {
-    const int64_t row0 = ((int64_t)blockIdx.y * GRAM_RBLOCKS + blk) * RB;
+  for (int blk = 0; blk < rblocks; blk++) {
+    const int64_t row0 = ((int64_t)blockIdx.y * rblocks + blk) * RB;
     if (row0 >= m1) break;
     __syncthreads();  // the previous block's readers are done with xs
     for (int idx = tid; idx < RB * DP; idx += 256) {
@@ -188,14 +189,18 @@ int launch_ard_gram_tile(const double* x1, int64_t m1, const double* x2, int64_t
                          const double* log_ls, int ls_len, double* out, int64_t ld, const unsigned long long* guard,
                          cudaStream_t st) {
   const int64_t gx = (m2 + 256 * CT - 1) / (256 * CT);
-  constexpr int64_t rows_per_cta = (int64_t)GRAM_RB * GRAM_RBLOCKS;
+  // K_ZZ of a factorisation (1024 x 1024: 2 column blocks) ran on 8 CTAs with four row blocks each - 74 us of every
+  // factor chain; one row block per CTA until the grid reaches two CTAs per SM
+  int rblocks = GRAM_RBLOCKS;
+  while (rblocks > 1 && gx * ((m1 + (int64_t)GRAM_RB * rblocks - 1) / ((int64_t)GRAM_RB * rblocks)) < 2 * GVI_NUM_SMS) rblocks /= 2;
+  const int64_t rows_per_cta = (int64_t)GRAM_RB * rblocks;
   const int64_t gy = (m1 + rows_per_cta - 1) / rows_per_cta;
   const int64_t max_gy = 65535;  // grid.y limit: loop over row super-blocks
   for (int64_t y0 = 0; y0 < gy; y0 += max_gy) {
     const int64_t ny = gy - y0 < max_gy ? gy - y0 : max_gy;
     ard_gram_tile_kernel<DP, CT><<<dim3((unsigned)gx, (unsigned)ny), 256, 0, st>>>(
         x1 + y0 * rows_per_cta * D, m1 - y0 * rows_per_cta, x2, m2, D, log_scaling, log_ls, ls_len,
-        out + y0 * rows_per_cta * ld, ld, guard);
+        out + y0 * rows_per_cta * ld, ld, guard, rblocks);
     GVI_CHECK_LAUNCH("ard_gram_tile_kernel");
   }
   return GVI_OK;
