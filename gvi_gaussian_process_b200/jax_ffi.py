@@ -114,7 +114,7 @@ def gp_factor(z, log_scaling, log_lengthscales, diagonal_regularisation=1e-5, is
 def gp_predict(factor, m, x, prior_mean=None):
     jax, jnp, ffi = _jax()
     n, d = x.shape
-    ws = _sizes().gvi_gp_predict_workspace_bytes(m, d) // 8
+    ws = _sizes().gvi_gp_predict_workspace_bytes_n(m, d, n) // 8
     has_prior = prior_mean is not None
     mean, var, _ = ffi.ffi_call("gvi_gp_predict", (jax.ShapeDtypeStruct((n,), jnp.float64),) * 2
                                 + (jax.ShapeDtypeStruct((ws,), jnp.float64),))(
@@ -144,7 +144,7 @@ def fused_loss(m, reg_kind, alpha=0.5, diagonal_regularisation=1e-5):
     @jax.custom_vjp
     def loss(log_scaling, log_lengthscales, m_q, z, factor_p, prior_mean_p, x, y):
         factor_q = gp_factor(z, log_scaling, log_lengthscales, diagonal_regularisation)
-        ws = lib.gvi_fused_step_workspace_bytes(x.shape[0], m) // 8
+        ws = lib.gvi_fused_step_workspace_bytes_d(x.shape[0], m, x.shape[1]) // 8
         out3, _ = ffi.ffi_call("gvi_fused_step", (jax.ShapeDtypeStruct((3,), jnp.float64),
                                                   jax.ShapeDtypeStruct((ws,), jnp.float64)))(
             factor_q, factor_p, x, y, m_q, prior_mean_p, m=int(m), reg_kind=int(reg_kind), alpha=float(alpha))

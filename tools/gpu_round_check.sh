@@ -47,10 +47,21 @@ if [ -s "${OUT}/profile_plain.log" ]; then
     -k regex:"chol_inverse_coop_kernel|dgemm_kernel|select_update_sharded_kernel|select_finalize_sharded_kernel" -c 12 \
     -o "${OUT}/prof_round2" -f python tools/profile_round2.py
 fi
+# 5b. kernels of the last session: guarded tensor-pipe Gram, risk reduction at N = 1e8, quarter-tile GEMM, 8-point forward
+#     tiles, and a fresh capture of the gradient-mode tile kernel + SYRK
+step profile2b_plain 600 python tools/profile_round2b.py
+if [ -s "${OUT}/profile2b_plain.log" ]; then
+  step ncu_round2b 1200 ncu --set full --clock-control none --import-source on \
+    -k regex:"ard_gram_mma_kernel|gram_guard_kernel|risk_kernel|dgemm_kernel|gp_step_kernel|syrk_kernel" -c 26 \
+    -o "${OUT}/prof_round2b" -f python tools/profile_round2b.py
+fi
 step selector_time 600 python tools/selector_time.py
 step factor_time 600 python tools/factor_only.py
 step gram_time 600 python tools/gram_time.py
 step dgemm_time 600 python tools/dgemm_time.py
+step risk_time 600 python tools/risk_time.py
+step small_time 600 python tools/small_time.py
+step widened 900 python tools/widened_launches.py
 
 echo "overall fail=${fail}" | tee -a "${OUT}/steps.log"
 exit "${fail}"
