@@ -292,6 +292,32 @@ __global__ void factor_header_kernel(double* __restrict__ F, FactorLayout f, con
   }
 }
 
+// F[7] = max_j |z~_j - z~_0|^2: the inducing points' half of the guard of the tile kernel's tensor-pipe phase 1
+// (predict.cu).  One CTA, after the header kernel.
+__global__ void __launch_bounds__(256) zs_radius_kernel(double* __restrict__ F, FactorLayout f) {
+  __shared__ double red[256];
+  const double* __restrict__ Zs = F + f.zs_off;
+  double best = 0.0;
+  for (int j = threadIdx.x; j < f.M; j += 256) {
+    double s = 0.0;
+    for (int d = 0; d < f.D; d++) {
+      const double v = Zs[(int64_t)j * f.D + d] - Zs[d];
+      s = fma(v, v, s);
+    }
+    best = (s > best || s != s) ? s : best;  // a NaN radius fails the guard
+  }
+  red[threadIdx.x] = best;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+      const double o = red[threadIdx.x + st];
+      if (o > red[threadIdx.x] || o != o) red[threadIdx.x] = o;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) F[7] = red[0];
+}
+
 // header of a state built from a caller-supplied Gram: no kernel parameters (k(x,x) arrives per point)
 __global__ void factor_header_gram_kernel(double* __restrict__ F, FactorLayout f, double abs_jitter) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -586,6 +612,8 @@ static int factor_impl(const double* Z, int M, int D, const double* log_scaling,
     factor_header_kernel<<<64, 256, 0, st>>>(F, f, Z, log_scaling, log_ls, ls_len, is_abs ? reg : 0.0,
                                              chol_log_scaling != nullptr);
     GVI_CHECK_LAUNCH("factor_header_kernel");
+    zs_radius_kernel<<<1, 256, 0, st>>>(F, f);
+    GVI_CHECK_LAUNCH("zs_radius_kernel");
   }
   // K_ZZ of the Cholesky: the caller's Gram, the kernel's own parameters, or the frozen (regulariser) parameters
   // Wide inputs (D >= 24): the x.z^T contraction on the tensor pipe (gram_dmma.cu), its operand staging placed in the

@@ -67,7 +67,8 @@ constexpr int gvi_debug_env(const char*) { return 0; }
 // [0] amp2 = exp(log_scaling)^2   [1] k(x,x)   [2] jitter actually added   [3] chol info (as double)
 // [4] absolute jitter (0 when the regulariser is trace-relative; used by d var / d log_scaling)
 // [5] 1 when the Cholesky factor was built from OTHER (frozen) kernel parameters than the K-tile parameters
-// [6] 1 when the extra packed matrix E is set: var += ||E k||^2 (SVGP family)   [7] rsvd
+// [6] 1 when the extra packed matrix E is set: var += ||E k||^2 (SVGP family)
+// [7] max_j |z~_j - z~_0|^2 (guard of the tile kernel's tensor-pipe phase 1)
 // [8, 8+D)            sqrtw[d] = sqrt(exp(log_ls[d]))
 // [zs_off, +Mp*D)     Z pre-scaled by sqrtw (rows >= M are zero)
 // [alpha_off, +Mp)    alpha = A^-1 y_Z (zero padded)

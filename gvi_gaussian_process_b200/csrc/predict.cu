@@ -32,6 +32,13 @@ constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 #define GVI_PB 4
 #endif
 constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phase 1 (independent exp chains)
+#ifndef GVI_P1_MMA
+#define GVI_P1_MMA 1
+#endif
+#ifndef GVI_P1_TABLE
+#define GVI_P1_TABLE 1
+#endif
+constexpr double GVI_P1_BOUND = 512.0;  // guard of the tensor-pipe phase 1: (|u|max + |v|max)^2 in scaled units
 
 // One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
 // acc[mt][nt] += sum_{kp in [kp0, kp0+nkp)} A(group rows 8mt.., cols 8kp..) * Ktile(cols 8kp.., points 8nt..).
@@ -146,7 +153,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
   double* redm = xs + T * DR;                                     // [WARPS][T]
   double* res = redm + WARPS * T;                                 // [2 GPs][T][2] (mean, var)
   double* gs = res + 2 * T * 2;                                   // [T] g_i = dR/dv_q,i of the tile
-  double* tail = gs + T;
+  const double2* etab = reinterpret_cast<const double2*>(gs + T);  // [32] 2^(j/32) hi / lo (tensor-pipe phase 1)
+  double* tail = gs + T + (GVI_P1_TABLE ? 64 : 0);
   const bool multi = P.Pc < P.Mp;
   // [G][T] squared norms per row group: shared memory when it fits, L2 scratch otherwise
   double* reds = P.reds_in_smem ? tail : P.reds_scratch + (size_t)blockIdx.x * P.G * T;
@@ -163,6 +171,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
   // the kernel (37 of its 64 FP64 instructions per entry; the FP64 pipe shares its datapath with the DMMAs)
   double* kscr = GRAD ? P.bscratch + ((size_t)GVI_NUM_SMS + blockIdx.x) * P.Mp * T : nullptr;
 
+  if (GVI_P1_TABLE && threadIdx.x < 32)
+    const_cast<double2*>(etab)[threadIdx.x] = GVI_EXP2_TABLE[threadIdx.x];  // visible after the first barrier of the loop
   long long& s_tile = *reinterpret_cast<long long*>(counter + 2);  // inside the 16 spare bytes after the group counter
   constexpr int TILE_STRIDE = GRAD ? STEP_PARTIAL_STRIDE : 2;
   for (int64_t tile = blockIdx.x;; tile += gridDim.x) {
@@ -199,7 +209,105 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         if (tid == 0) *counter = 0;
       }
       // ---- phase 1: K panel (T x Pc) into shared memory in B-fragment order; mean partials ------------------
-      if (!(P.debug_skip & 1)) {
+      bool p1_done = false;
+      if constexpr (GVI_P1_MMA && DR >= 8 && DR <= 16) {  // DR = 32: the 24 A-fragment values spill at the 128-register cap
+        // Tensor-pipe form of the exponent (5 <= D): s_ij = |u_i|^2/2 + |v_j|^2/2 - u_i.v_j with u = x~ - c~, v = z~ - c~
+        // (c~ = z~_0), the dot product as DMMA m8n8k4 (A = -u for the tile's T points, B = v for 8 columns), the
+        // accumulator started at |u_i|^2/2 + |v_j|^2/2 - log amp^2: D + 1 datapath slots per kernel evaluation instead of
+        // 2 D + 4, in warp tiles of T x 8 with 2 NT independent exp chains per lane.  The expansion cancels, so it runs
+        // only while (|u|max + |v|max)^2 <= GVI_P1_BOUND (error of k <= (D + 3) eps bound / 2 ~ 3e-13 relative at D = 8;
+        // |v|max^2 = F[7] from the factorisation); every warp evaluates the same guard from the same values, a tile
+        // that fails it (short lengthscales, outliers) takes the direct-difference code below.
+        constexpr int KS = DR / 4;
+        const int q = lane & 3, r = lane >> 2;
+        const double* __restrict__ Zs = F + f.zs_off;
+        const double* __restrict__ alpha = F + f.alpha_off;
+        double cz[KS], a[NT][KS], hnu[NT];
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) cz[ks] = (q + 4 * ks < P.D) ? Zs[q + 4 * ks] : 0.0;
+        double numax = 0.0;
+#pragma unroll
+        for (int mt = 0; mt < NT; mt++) {
+          const bool live = row0 + 8 * mt + r < P.N;
+          double part = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            const double u = live ? xs[(8 * mt + r) * DR + q + 4 * ks] - cz[ks] : 0.0;
+            a[mt][ks] = -u;
+            part = fma(u, u, part);
+          }
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          hnu[mt] = 0.5 * part;
+          numax = part > numax ? part : numax;
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          const double other = __shfl_xor_sync(0xffffffffu, numax, o);
+          numax = other > numax ? other : numax;
+        }
+        const double r2 = F[7];
+        if (!pd.Kpre && !(P.debug_skip & 1) && numax + r2 + 2.0 * sqrt(numax * r2) <= GVI_P1_BOUND) {
+          p1_done = true;
+          const double lamp = log(amp2);
+          double mf[NT];
+#pragma unroll
+          for (int mt = 0; mt < NT; mt++) mf[mt] = 0.0;
+          for (int ct = warp; ct < (c_hi - c_lo) / 8; ct += WARPS) {
+            const int j0 = c_lo + 8 * ct;
+            double b[KS], part = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) {
+              const int k = q + 4 * ks;
+              const double v = (k < P.D) ? Zs[(int64_t)(j0 + r) * P.D + k] - cz[ks] : 0.0;
+              b[ks] = v;
+              part = fma(v, v, part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);  // |v|^2 of column j0 + r in the four lanes of row r
+            double init[2], aj[2];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              const double hv = 0.5 * __shfl_sync(0xffffffffu, part, (2 * q + e) * 4);
+              const int j = j0 + 2 * q + e;
+              init[e] = (j < P.M) ? hv - lamp : 1e300;  // padding columns: exp(-1e300) = 0
+              aj[e] = alpha[j];
+            }
+            double acc[NT][2];
+#pragma unroll
+            for (int mt = 0; mt < NT; mt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) acc[mt][e] = hnu[mt] + init[e];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+              for (int mt = 0; mt < NT; mt++) dmma884(acc[mt][0], acc[mt][1], a[mt][ks], b[ks]);
+#pragma unroll
+            for (int mt = 0; mt < NT; mt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++)
+                acc[mt][e] = GVI_P1_TABLE ? gvi_exp_neg_t32<true>(acc[mt][e], etab, 1) : gvi_exp(-acc[mt][e]);
+            // K tile entry (point i = 8 mt + r, column jl = 8 ct + 2 q + e) in the B-fragment order of phase 2
+            double* __restrict__ kbase = Ksm + (size_t)ct * (NT * 64) + r * 8;
+#pragma unroll
+            for (int mt = 0; mt < NT; mt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const int c = 2 * q + e;
+                kbase[mt * 64 + (c >> 2) + 2 * (c & 3)] = acc[mt][e];
+                mf[mt] = fma(acc[mt][e], aj[e], mf[mt]);
+              }
+          }
+#pragma unroll
+          for (int mt = 0; mt < NT; mt++) {
+            double v = mf[mt];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (q == 0) redm[warp * T + 8 * mt + r] = (c_lo == 0) ? v : redm[warp * T + 8 * mt + r] + v;
+          }
+        }
+      }
+      if (!p1_done && !(P.debug_skip & 1)) {
         double macc[T];
 #pragma unroll
         for (int i = 0; i < T; i++) macc[i] = 0.0;
@@ -623,7 +731,7 @@ template <int NT, int DR>
 size_t step_smem_bytes(int Mp, int Pc, bool grad, int warps, bool reds_in_smem) {
   constexpr int T = 8 * NT;
   const size_t G = Mp / GVI_GROUP_ROWS;
-  size_t doubles = (size_t)Pc * T + T * DR + (size_t)warps * T + 4 * T + T;
+  size_t doubles = (size_t)Pc * T + T * DR + (size_t)warps * T + 4 * T + T + (GVI_P1_TABLE ? 64 : 0);
   if (reds_in_smem) doubles += G * T;
   if (grad) doubles += G * (DR + 1);
   return doubles * sizeof(double) + 16;

@@ -34,7 +34,7 @@ step bench 900 python bench.py
 #    up there apart from the host framework's mean network) - only after the plain run exited 0
 step bench_short 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --short
 if [ -s "${OUT}/bench_short.log" ]; then
-  step ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv \
+  step ncu_launches 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv \
     --log-file "${OUT}/launches.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline --short
   # 4. one --set full capture of the dominant kernel (fused forward step)
   step ncu_step 900 ncu --set full --clock-control none --import-source on -k regex:gp_step_kernel -s 3 -c 1 \
@@ -43,7 +43,7 @@ fi
 # 5. the round-2 kernels: factorisation, GEMM, Gram tile kernel, sharded selector
 step profile_plain 600 python tools/profile_round2.py
 if [ -s "${OUT}/profile_plain.log" ]; then
-  step ncu_round2 900 ncu --set full --clock-control none --import-source on \
+  step ncu_round2 900 ncu --set full --clock-control none \
     -k regex:"chol_inverse_coop_kernel|dgemm_kernel|select_update_sharded_kernel|select_finalize_sharded_kernel" -c 12 \
     -o "${OUT}/prof_round2" -f python tools/profile_round2.py
 fi
@@ -51,7 +51,7 @@ fi
 #     tiles, and a fresh capture of the gradient-mode tile kernel + SYRK
 step profile2b_plain 600 python tools/profile_round2b.py
 if [ -s "${OUT}/profile2b_plain.log" ]; then
-  step ncu_round2b 1200 ncu --set full --clock-control none --import-source on \
+  step ncu_round2b 1200 ncu --set full --clock-control none \
     -k regex:"ard_gram_mma_kernel|gram_guard_kernel|risk_kernel|dgemm_kernel|gp_step_kernel|syrk_kernel" -c 26 \
     -o "${OUT}/prof_round2b" -f python tools/profile_round2b.py
 fi
@@ -63,5 +63,13 @@ step risk_time 600 python tools/risk_time.py
 step small_time 600 python tools/small_time.py
 step widened 900 python tools/widened_launches.py
 
+# gpurun copies gpurun_out/ back only below 64 MiB: keep the raw-metric CSV of every capture, drop the big reports
+for rep in "${OUT}"/*.ncu-rep; do
+  [ -f "${rep}" ] || continue
+  ncu -i "${rep}" --page raw --csv > "${rep%.ncu-rep}_raw.csv" 2>/dev/null
+  size=$(stat -c %s "${rep}")
+  if [ "${size}" -gt 12000000 ]; then rm -f "${rep}"; fi
+done
+du -sh "${OUT}" | tee -a "${OUT}/steps.log"
 echo "overall fail=${fail}" | tee -a "${OUT}/steps.log"
 exit "${fail}"
