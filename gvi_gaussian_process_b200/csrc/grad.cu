@@ -433,6 +433,8 @@ static int gvi_grad_launch_accumulate_S(const StepParams& P0, const GradWs& w, i
       if (!Pp.pass[0].var_out) Pp.pass[0].var_out = w.vp;
       Pp.M = P0.M; Pp.Mp = P0.Mp; Pp.D = P0.D; Pp.G = P0.G;
       Pp.X = P.X; Pp.N = n;
+      Pp.tile_points = 24;  // every chunk in the same launch shape (a short last chunk would otherwise take 8-point tiles
+                            // on 16 warps, whose mean partial sums are grouped differently): chunking stays bit-invisible
       Pp.tile_counter = P0.tile_counter;
       Pp.acc_scratch = w.pscratch;
       const int gp = gvi_launch_step(Pp, st);

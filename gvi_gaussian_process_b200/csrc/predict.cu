@@ -210,68 +210,85 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
       }
       // ---- phase 1: K panel (T x Pc) into shared memory in B-fragment order; mean partials ------------------
       bool p1_done = false;
-      if constexpr (GVI_P1_MMA && DR >= 8 && DR <= 16) {  // DR = 32: the 24 A-fragment values spill at the 128-register cap
+      if constexpr (GVI_P1_MMA && DR >= 4) {  // DR = 32: the 24 A-fragment values spill at the 128-register cap
         // Tensor-pipe form of the exponent (5 <= D): s_ij = |u_i|^2/2 + |v_j|^2/2 - u_i.v_j with u = x~ - c~, v = z~ - c~
         // (c~ = z~_0), the dot product as DMMA m8n8k4 (A = -u for the tile's T points, B = v for 8 columns), the
         // accumulator started at |u_i|^2/2 + |v_j|^2/2 - log amp^2: D + 1 datapath slots per kernel evaluation instead of
-        // 2 D + 4, in warp tiles of T x 8 with 2 NT independent exp chains per lane.  The expansion cancels, so it runs
-        // only while (|u|max + |v|max)^2 <= GVI_P1_BOUND (error of k <= (D + 3) eps bound / 2 ~ 3e-13 relative at D = 8;
-        // |v|max^2 = F[7] from the factorisation); every warp evaluates the same guard from the same values, a tile
-        // that fails it (short lengthscales, outliers) takes the direct-difference code below.
+        // 2 D + 4, in warp tiles of T x 8 with 2 NT independent exp chains per lane.  The expansion cancels, so a point
+        // takes it only while (|u_i| + |v|max)^2 <= GVI_P1_BOUND (error of k <= (D + 3) eps bound / 2 ~ 3e-13 relative at
+        // D = 8; |v|max^2 = F[7] from the factorisation); every warp evaluates the same guards from the same values.
+        // Points that fail (outliers) are re-evaluated by direct differences; a tile without a passing point (short
+        // lengthscales) takes the direct-difference code below as a whole.
         constexpr int KS = DR / 4;
+        constexpr bool A_REGS = KS <= 4;  // D > 16: the 3 x 8 A values per lane would spill - re-read from the x tile
         const int q = lane & 3, r = lane >> 2;
         const double* __restrict__ Zs = F + f.zs_off;
         const double* __restrict__ alpha = F + f.alpha_off;
-        double cz[KS], a[NT][KS], hnu[NT];
+        double cz[KS], a[NT][A_REGS ? KS : 1], hnu[NT];
+        bool live_mt[NT];
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) cz[ks] = (q + 4 * ks < P.D) ? Zs[q + 4 * ks] : 0.0;
-        double numax = 0.0;
+        const double r2 = F[7];
+        bool flag[NT];  // point 8 mt + r fails its guard: evaluated by direct differences (fix-up below)
+        unsigned fast_live = 0u, slow_live = 0u;
 #pragma unroll
         for (int mt = 0; mt < NT; mt++) {
           const bool live = row0 + 8 * mt + r < P.N;
+          live_mt[mt] = live;
           double part = 0.0;
 #pragma unroll
           for (int ks = 0; ks < KS; ks++) {
             const double u = live ? xs[(8 * mt + r) * DR + q + 4 * ks] - cz[ks] : 0.0;
-            a[mt][ks] = -u;
+            if (A_REGS) a[mt][ks] = -u;
             part = fma(u, u, part);
           }
           part += __shfl_xor_sync(0xffffffffu, part, 1);
           part += __shfl_xor_sync(0xffffffffu, part, 2);
           hnu[mt] = 0.5 * part;
-          numax = part > numax ? part : numax;
+          // PER POINT (not per tile): which arithmetic a point gets must not depend on the tile it falls into, so that
+          // chunked / sharded / differently tiled launches stay bit identical
+          flag[mt] = !(part + r2 + 2.0 * sqrt(part * r2) <= GVI_P1_BOUND);
+          fast_live |= __ballot_sync(0xffffffffu, live && !flag[mt]);
+          slow_live |= __ballot_sync(0xffffffffu, live && flag[mt]);
         }
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          const double other = __shfl_xor_sync(0xffffffffu, numax, o);
-          numax = other > numax ? other : numax;
-        }
-        const double r2 = F[7];
-        if (!pd.Kpre && !(P.debug_skip & 1) && numax + r2 + 2.0 * sqrt(numax * r2) <= GVI_P1_BOUND) {
+        // no point of the tile passes (short lengthscales): the whole tile takes the direct-difference code below
+        if (!pd.Kpre && !(P.debug_skip & 1) && fast_live != 0u) {
           p1_done = true;
           const double lamp = log(amp2);
           double mf[NT];
 #pragma unroll
           for (int mt = 0; mt < NT; mt++) mf[mt] = 0.0;
-          for (int ct = warp; ct < (c_hi - c_lo) / 8; ct += WARPS) {
+          // the next column tile's inducing-point coordinates and alpha travel while this one is evaluated
+          const int nct = (c_hi - c_lo) / 8;
+          double zr[KS], ar[2];
+          auto fetch = [&](int ct) {
+            const int j0 = c_lo + 8 * ct;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+              zr[ks] = (q + 4 * ks < P.D) ? Zs[(int64_t)(j0 + r) * P.D + q + 4 * ks] : 0.0;  // cz is 0 there as well
+#pragma unroll
+            for (int e = 0; e < 2; e++) ar[e] = alpha[j0 + 2 * q + e];
+          };
+          if (warp < nct) fetch(warp);
+          for (int ct = warp; ct < nct; ct += WARPS) {
             const int j0 = c_lo + 8 * ct;
             double b[KS], part = 0.0;
 #pragma unroll
             for (int ks = 0; ks < KS; ks++) {
-              const int k = q + 4 * ks;
-              const double v = (k < P.D) ? Zs[(int64_t)(j0 + r) * P.D + k] - cz[ks] : 0.0;
+              const double v = zr[ks] - cz[ks];
               b[ks] = v;
               part = fma(v, v, part);
             }
+            const double aj[2] = {ar[0], ar[1]};
+            if (ct + WARPS < nct) fetch(ct + WARPS);
             part += __shfl_xor_sync(0xffffffffu, part, 1);
             part += __shfl_xor_sync(0xffffffffu, part, 2);  // |v|^2 of column j0 + r in the four lanes of row r
-            double init[2], aj[2];
+            double init[2];
 #pragma unroll
             for (int e = 0; e < 2; e++) {
               const double hv = 0.5 * __shfl_sync(0xffffffffu, part, (2 * q + e) * 4);
               const int j = j0 + 2 * q + e;
               init[e] = (j < P.M) ? hv - lamp : 1e300;  // padding columns: exp(-1e300) = 0
-              aj[e] = alpha[j];
             }
             double acc[NT][2];
 #pragma unroll
@@ -281,7 +298,12 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
 #pragma unroll
             for (int ks = 0; ks < KS; ks++)
 #pragma unroll
-              for (int mt = 0; mt < NT; mt++) dmma884(acc[mt][0], acc[mt][1], a[mt][ks], b[ks]);
+              for (int mt = 0; mt < NT; mt++) {
+                double am;
+                if constexpr (A_REGS) am = a[mt][ks];
+                else am = live_mt[mt] ? cz[ks] - xs[(8 * mt + r) * DR + q + 4 * ks] : 0.0;
+                dmma884(acc[mt][0], acc[mt][1], am, b[ks]);
+              }
 #pragma unroll
             for (int mt = 0; mt < NT; mt++)
 #pragma unroll
@@ -303,7 +325,40 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
             double v = mf[mt];
             v += __shfl_xor_sync(0xffffffffu, v, 1);
             v += __shfl_xor_sync(0xffffffffu, v, 2);
-            if (q == 0) redm[warp * T + 8 * mt + r] = (c_lo == 0) ? v : redm[warp * T + 8 * mt + r] + v;
+            if (q == 0 && !(flag[mt] && live_mt[mt]))
+              redm[warp * T + 8 * mt + r] = (c_lo == 0) ? v : redm[warp * T + 8 * mt + r] + v;
+          }
+          if (slow_live != 0u) {
+            // fix-up of the points that failed their guard (outliers; rare): the direct-difference arithmetic of the code
+            // below, bit for bit, over the column tiles THIS warp wrote above (same-warp ordering of the K-tile stores)
+            __syncwarp();
+#pragma unroll 1
+            for (int mt = 0; mt < NT; mt++) {
+              const unsigned fm = __ballot_sync(0xffffffffu, flag[mt] && live_mt[mt]);
+#pragma unroll 1
+              for (int rr = 0; rr < 8; rr++) {
+                if (!((fm >> (4 * rr)) & 1u)) continue;
+                const int i = 8 * mt + rr;
+                double msum = 0.0;
+                for (int ct = warp + WARPS * (lane >> 3); ct < nct; ct += 4 * WARPS) {
+                  const int jl = 8 * ct + (lane & 7), j = c_lo + jl;
+                  double sa = 0.0, sb = 0.0;
+#pragma unroll
+                  for (int d = 0; d < DR; d += 2) {
+                    const double z0 = (d < P.D) ? Zs[(int64_t)j * P.D + d] : 0.0;
+                    const double z1 = (d + 1 < P.D) ? Zs[(int64_t)j * P.D + d + 1] : 0.0;
+                    const double d0 = xs[i * DR + d] - z0, d1 = xs[i * DR + d + 1] - z1;
+                    sa = fma(d0, d0, sa);
+                    sb = fma(d1, d1, sb);
+                  }
+                  const double kk = ((j < P.M) ? amp2 : 0.0) * gvi_exp(-0.5 * (sa + sb));
+                  Ksm[(size_t)(jl >> 3) * (NT * 64) + ((jl >> 2) & 1) + 2 * (jl & 3) + (i >> 3) * 64 + (i & 7) * 8] = kk;
+                  msum = fma(kk, alpha[j], msum);
+                }
+                msum = warp_sum(msum);
+                if (lane == 0) redm[warp * T + i] = (c_lo == 0) ? msum : redm[warp * T + i] + msum;
+              }
+            }
           }
         }
       }

@@ -254,6 +254,37 @@ def test_predictive_parity(S, n, m, d):
     assert np.all(host(q.covariance) > -1e-12) and np.all(host(p.covariance) > 0)
 
 
+@pytest.mark.parametrize("n,m,d,ll_shift", [(4001, 200, 8, 0.0), (3000, 1100, 5, 0.0), (2500, 96, 16, 0.0), (1500, 64, 27, 0.0),
+                                           (2000, 150, 8, 7.0)])
+def test_tile_kernel_guarded_tensor_pipe_kernel_evaluations(S, n, m, d, ll_shift):
+    """Phase 1 of the tile kernel evaluates k(x_i, z_j) through |u|^2/2 + |v|^2/2 - u.v on the tensor pipe for every point
+    whose guard (|u_i| + |v|max)^2 <= 512 holds and by direct differences for the others (csrc/predict.cu).  Checked:
+    parity with the oracle for a data set with OUTLIERS (some points 40 lengthscales away: mixed tiles, the fix-up path),
+    for short lengthscales (ll_shift = 7: no point passes, whole tiles take the direct code), and that the value a point
+    gets does not depend on the tile it falls into - the same points predicted in a different order / batch give the
+    same bits."""
+    rng = np.random.default_rng(n + d)
+    pr = make_problem(n, m, d, seed=n + m)
+    out_rows = rng.choice(n, size=37, replace=False)
+    pr["x"][out_rows] *= 40.0
+    pr["ll_q"] = pr["ll_q"] + ll_shift
+    pr["ll_p"] = pr["ll_p"] + ll_shift
+    v_q_ref, m_p_ref, v_p_ref = oracle_predictions(pr)
+    approx_gp, approx_params, exact_gp, exact_params, x_dev = build_models(S, pr)
+    q = approx_gp.predict_probability(approx_params, x_dev)
+    p = exact_gp.predict_probability(exact_params, x_dev)
+    assert rel_norm(host(q.covariance), v_q_ref) <= TOL
+    assert rel_norm(host(p.mean).reshape(-1), m_p_ref) <= TOL and rel_norm(host(p.covariance), v_p_ref) <= TOL
+    # tile independence: reversed order and a 1000-point slice (8- / 16-point tiles) reproduce the same bits per point
+    rev = torch.flip(x_dev, dims=[0]).contiguous()
+    p_rev = exact_gp.predict_probability(exact_params, rev)
+    assert np.array_equal(host(p_rev.covariance)[::-1], host(p.covariance))
+    assert np.array_equal(host(p_rev.mean).reshape(-1)[::-1], host(p.mean).reshape(-1))
+    sl = x_dev[777:1777].contiguous()
+    p_sl = exact_gp.predict_probability(exact_params, sl)
+    assert np.array_equal(host(p_sl.covariance), host(p.covariance)[777:1777])
+
+
 @pytest.mark.parametrize("n,m,d", [(5000, 300, 33), (700, 1300, 784), (30000, 64, 40)])
 def test_predictive_parity_wide_inputs(S, n, m, d):
     """D > 32 (config #4's MNIST-like width): K(x,Z) rows come from the tensor-pipe Gram kernel in chunks of <= 28 416
