@@ -318,7 +318,7 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
     w.tile_partials = take((size_t)w.ntiles * STEP_PARTIAL_STRIDE * 8);
   }
   w.g = take((size_t)N * 8);
-  w.bscratch = take((size_t)2 * GVI_NUM_SMS * f.Mp * T * 8);  // per CTA: the b tile and q's parked K tile
+  w.bscratch = take((size_t)4 * GVI_NUM_SMS * f.Mp * T * 8);  // per CTA (up to two per SM): the b tile and q's parked K tile
   w.Cpart = take((size_t)w.nsplit * f.Mp * f.Mp * 8);
   w.C = take((size_t)f.Mp * f.Mp * 8);
   w.rowpart = take((size_t)f.Mp * 32 * 8);
@@ -335,7 +335,7 @@ GradWs carve_grad(void* ws, int64_t N, int M, int D, size_t* total) {
   // a chunk is a whole number of 148 x 24-point waves (3552 = 32 x 111 points: a multiple of every tile height).
   const int64_t wave = (int64_t)GVI_NUM_SMS * 24;
   const int64_t wave_bytes = wave / PC * Gc * BLK * 8;
-  int64_t nw = (1LL << 30) / wave_bytes;
+  int64_t nw = (1LL << 30) / wave_bytes;  // (2 and 4 GB rings measured: no difference, 141.4 - 141.8 ms per step)
   if (g_chunk_waves_cap > 0 && nw > g_chunk_waves_cap) nw = g_chunk_waves_cap;
   const int64_t need_w = (N + wave - 1) / wave;
   if (nw > need_w) nw = need_w;
@@ -503,6 +503,7 @@ extern "C" int gvi_fused_step_grad_f64(const void* factor_q, const void* factor_
   P.g_out = w.g;
   P.dm_out = dm_out;
   P.bscratch = w.bscratch;
+  P.acc_scratch = w.pscratch;  // panel scratch of the two-CTA gradient shape (the p launch of a chunk is done with it)
   int grid;
   if (frozen_cholesky) {  // A does not depend on the trained parameters: no <dK_ZZ, S> term, one launch
     if ((grid = gvi_launch_step(P, st)) < 0) return grid;
@@ -547,6 +548,7 @@ extern "C" int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const d
   P.grad = 1;
   P.g_in = g_var;
   P.bscratch = w.bscratch;
+  P.acc_scratch = w.pscratch;  // panel scratch of the two-CTA gradient shape (the p launch of a chunk is done with it)
   int grid, rc;
   if (frozen_cholesky) {
     if ((grid = gvi_launch_step(P, st)) < 0) return grid;
@@ -625,6 +627,7 @@ extern "C" int gvi_svgp_step_grad_f64(const void* factor_q, const void* factor_p
   P.g_out = w.g;
   P.dm_out = dm_out;
   P.bscratch = w.bscratch;
+  P.acc_scratch = w.pscratch;  // panel scratch of the two-CTA gradient shape (the p launch of a chunk is done with it)
   int grid = gvi_launch_step(P, st);
   if (grid < 0) return grid;
   if ((grid = gvi_launch_tile_reduce(w.tile_partials, w.ntiles, 1, w.partials, st)) < 0) return grid;

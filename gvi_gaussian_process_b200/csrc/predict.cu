@@ -38,6 +38,9 @@ constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phas
 #ifndef GVI_P1_TABLE
 #define GVI_P1_TABLE 1
 #endif
+#ifndef GVI_GRAD_TWO_CTA
+#define GVI_GRAD_TWO_CTA 1
+#endif
 constexpr double GVI_P1_BOUND = 512.0;  // guard of the tensor-pipe phase 1: (|u|max + |v|max)^2 in scaled units
 
 // One GVI_GROUP_ROWS-row group of a packed triangular matrix times the T-point tile held in shared memory (fragment order):
@@ -166,10 +169,10 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t ntiles = (P.N + T - 1) / T;
   const FactorLayout f = factor_layout(P.M, P.D);
-  double* bscr = GRAD ? P.bscratch + (size_t)blockIdx.x * P.Mp * T : nullptr;
+  double* bscr = GRAD ? P.bscratch + (size_t)2 * blockIdx.x * P.Mp * T : nullptr;
   // q's K tile is parked next to it (L2 resident): the T2 epilogue of phase 3 reads k_ij back instead of re-evaluating
   // the kernel (37 of its 64 FP64 instructions per entry; the FP64 pipe shares its datapath with the DMMAs)
-  double* kscr = GRAD ? P.bscratch + ((size_t)GVI_NUM_SMS + blockIdx.x) * P.Mp * T : nullptr;
+  double* kscr = GRAD ? P.bscratch + ((size_t)2 * blockIdx.x + 1) * P.Mp * T : nullptr;
 
   if (GVI_P1_TABLE && threadIdx.x < 32)
     const_cast<double2*>(etab)[threadIdx.x] = GVI_EXP2_TABLE[threadIdx.x];  // visible after the first barrier of the loop
@@ -437,8 +440,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
       __syncthreads();
       if (keep_b) {  // park q's K tile for phase 3 (the warps go on to phase 2 as soon as their share is on its way)
         const double2* Ks2r = reinterpret_cast<const double2*>(Ksm);
-        double2* kscr2 = reinterpret_cast<double2*>(kscr);
-        for (int idx = tid; idx < P.Mp * T / 2; idx += THREADS) __stcg(kscr2 + idx, Ks2r[idx]);
+        double2* kscr2 = reinterpret_cast<double2*>(kscr) + (size_t)c_lo * T / 2;  // this panel's columns
+        for (int idx = tid; idx < (c_hi - c_lo) * T / 2; idx += THREADS) __stcg(kscr2 + idx, Ks2r[idx]);
       }
       // ---- phase 2: b = L^-1 k on the tensor pipe, accumulate ||b||^2 ----------------------------------
       auto run_groups = [&](const double* __restrict__ W, const bool store_b) {
@@ -623,11 +626,6 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
     // ---- gradient phase 3: a = L^-T b for q, then sum_i g_i a_ij k_ij (x~_id - z~_jd)^2 and sum_i g_i |a_i|^2 ----
     if (GRAD && !P.grad_pointwise_only) {
       const double* __restrict__ F = P.pass[0].F;
-      double2* Ks2w = reinterpret_cast<double2*>(Ksm);
-      const double2* scr2 = reinterpret_cast<const double2*>(bscr);
-      for (int idx = tid; idx < P.Mp * T / 2; idx += THREADS) Ks2w[idx] = __ldcg(scr2 + idx);  // b tile replaces K tile
-      if (tid == 0) *counter = 0;
-      __syncthreads();
       if (P.a_ring && tid < T) {  // the weights g_i ride at the end of every column block of the point's group
         const int64_t p = row0 + tid;
         for (int cb = 0; cb * SYRK_CB < P.Mp; cb++)
@@ -636,19 +634,55 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
       const double2* __restrict__ Ks2 = reinterpret_cast<const double2*>(Ksm);
       const double* __restrict__ WT = F + f.wpackT_off;
       const double* __restrict__ Zs = F + f.zs_off;
+      // a_j = sum_{c >= j} L^-1[c][j] b_c: group g needs the b rows from 16 g up.  The b tile comes back from the scratch
+      // in panels of Pc rows (one panel when the whole tile fits: the 16-warp shape), the TOP panel first - every group
+      // starts there - and groups that reach below a panel park their accumulators like phase 2 does.
+      for (int c_hi = P.Mp; c_hi > 0;) {
+      const int c_lo = (c_hi - 1) / P.Pc * P.Pc;
+      __syncthreads();  // the previous panel's (or the passes') readers are done with the tile
+      {
+        double2* Ks2w = reinterpret_cast<double2*>(Ksm);
+        const double2* scr2 = reinterpret_cast<const double2*>(bscr) + (size_t)c_lo * T / 2;
+        for (int idx = tid; idx < (c_hi - c_lo) * T / 2; idx += THREADS) Ks2w[idx] = __ldcg(scr2 + idx);  // b panel replaces K
+      }
+      if (tid == 0) *counter = 0;
+      __syncthreads();
+      const int ng = c_hi / GVI_GROUP_ROWS;  // groups 0 .. ng - 1 reach into this panel
       while (true) {
         int g = 0;
         if (lane == 0) g = atomicAdd(counter, 1);
         g = __shfl_sync(0xffffffffu, g, 0);  // ascending g = largest k-range first
-        if (g >= P.G) break;
+        if (g >= ng) break;
         double acc[MT][NT][2];
+        if (c_hi == P.Mp) {
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++)
+          for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-          for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        const int kp0 = GVI_GROUP_ROWS * g / 8;
-        group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) + lane, kp0, P.Mp / 8 - kp0,
-                      Ks2, lane, acc);
+            for (int nt = 0; nt < NT; nt++) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        } else {  // partial sums parked by the panel above
+          const double* src = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) acc[mt][nt][e] = __ldcg(src + ((mt * NT + nt) * 2 + e) * 32);
+        }
+        const int kp0 = GVI_GROUP_ROWS * g / 8;                  // first k-pair of the group (absolute)
+        const int kp_beg = max(kp0, c_lo / 8), kp_end = c_hi / 8;  // its k-pairs inside this panel
+        group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(WT + wpackT_group_off(g, P.G)) +
+                                       (size_t)(kp_beg - kp0) * MT * 32 + lane,
+                                   kp_beg - c_lo / 8, kp_end - kp_beg, Ks2, lane, acc);
+        if (GVI_GROUP_ROWS * g < c_lo) {  // the group continues in the panel below
+          double* dst = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
+#pragma unroll
+          for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+              for (int e = 0; e < 2; e++) __stcg(dst + ((mt * NT + nt) * 2 + e) * 32, acc[mt][nt][e]);
+          continue;
+        }
         if (P.a_ring) {
           // a_ij of this group -> operand blocks of the S = sum_i g_i a_i a_i^T accumulation (grad.cu): per (mt, nt)
           // the warp covers 8 columns x 8 points = 512 contiguous bytes of the block
@@ -718,6 +752,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
         na2 = warp_sum(na2);
         if (lane == 0) gpart[g * (DR + 1) + DR] = na2;
       }
+      c_hi = c_lo;
+      }  // b panels
       __syncthreads();
       {
         double* rec = P.tile_partials + (size_t)tile * TILE_STRIDE;
@@ -819,6 +855,9 @@ int launch_step_inst2(const StepParams& P, int grid_cap, cudaStream_t st) {
 }
 template <int NT, int DR>
 int launch_step_inst(const StepParams& P, int grid_cap, cudaStream_t st) {
+  if constexpr (NT == 3) {
+    if (P.grad && P.two_cta) return launch_step_inst2<NT, DR, true, 8>(P, grid_cap, st);
+  }
   if (P.grad) return launch_step_inst2<NT, DR, true, 16>(P, grid_cap, st);
   if constexpr (NT == 3) {
     if (P.two_cta) return launch_step_inst2<NT, DR, false, 8>(P, grid_cap, st);
@@ -871,22 +910,28 @@ size_t gvi_step_scratch_doubles(int Mp) {
 }
 
 // forward launches: pick the panel width and the launch shape.  Returns false if nothing fits.
-static bool plan_forward(StepParams& P, bool allow_two_cta) {
+static bool plan_forward(StepParams& P, bool allow_two_cta, bool grad = false) {
   const int D = P.pass[0].Kpre ? 1 : P.D;
   if (allow_two_cta) {
-    // two CTAs per SM: the widest panel (multiple of 64 columns) that leaves room for two CTAs
+    // two CTAs per SM: the widest panel (multiple of 64 columns) that leaves room for two CTAs; the per-group norms
+    // move to the L2 scratch when that saves a panel (gradient mode at M = 1024: 512 instead of 448 columns)
+    int best_pc = 0, best_reds = 1;
     for (int reds_smem = 1; reds_smem >= 0; reds_smem--) {
       int pc = P.Mp;  // whole tile if it fits, else the widest multiple of 64 columns
-      if (step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) > SMEM_LIMIT_2CTA) {
+      if (step_smem_bytes_d<3>(P.Mp, pc, D, grad, 8, reds_smem) > SMEM_LIMIT_2CTA) {
         pc = P.Mp / 64 * 64;
-        while (pc > 64 && step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) > SMEM_LIMIT_2CTA) pc -= 64;
+        while (pc > 64 && step_smem_bytes_d<3>(P.Mp, pc, D, grad, 8, reds_smem) > SMEM_LIMIT_2CTA) pc -= 64;
       }
-      if (step_smem_bytes_d<3>(P.Mp, pc, D, false, 8, reds_smem) <= SMEM_LIMIT_2CTA && (pc == P.Mp || pc >= 256)) {
-        P.two_cta = 1;
-        P.Pc = pc;
-        P.reds_in_smem = reds_smem;
-        return true;
+      if (step_smem_bytes_d<3>(P.Mp, pc, D, grad, 8, reds_smem) <= SMEM_LIMIT_2CTA && (pc == P.Mp || pc >= 256)) {
+        const int panels = (P.Mp + pc - 1) / pc;
+        if (best_pc == 0 || panels < (P.Mp + best_pc - 1) / best_pc) best_pc = pc, best_reds = reds_smem;
       }
+    }
+    if (best_pc > 0) {
+      P.two_cta = 1;
+      P.Pc = best_pc;
+      P.reds_in_smem = best_reds;
+      return true;
     }
   }
   P.two_cta = 0;
@@ -943,7 +988,14 @@ int gvi_launch_step(const StepParams& P_in, cudaStream_t st) {
     if (T == 16) return launch_step_nt<2>(P, GVI_NUM_SMS, st);
     return launch_step_nt<3>(P, P.two_cta ? 2 * GVI_NUM_SMS : GVI_NUM_SMS, st);
   }
-  // gradient mode keeps the whole b tile in shared memory
+  // gradient mode, M <= 1024 with a panel scratch: the forward launch shape - two 8-warp CTAs per SM, K and b tiles in
+  // panels (phase 1 and the T2 epilogue of one CTA hide under the other's DMMAs instead of being exposed)
+  if (GVI_GRAD_TWO_CTA && !one_cta && !P.has_extra && P.acc_scratch && P.Mp <= 1024 && !P.grad_pointwise_only &&
+      gvi_step_tile_points(P.Mp, P.D, true) == 24 && plan_forward(P, true, true) && P.two_cta) {
+    P.reds_scratch = P.acc_scratch + (size_t)2 * GVI_NUM_SMS * P.Mp * 24;
+    return launch_step_nt<3>(P, 2 * GVI_NUM_SMS, st);
+  }
+  // otherwise the whole b tile stays in shared memory (one 16-warp CTA per SM)
   P.Pc = P.Mp;
   P.two_cta = 0;
   P.reds_in_smem = 1;
