@@ -375,7 +375,7 @@ int gvi_launch_ard_gram_dmma(const double* x1, int64_t m1, const double* x2, int
 
 // wide inputs go through the tensor-pipe contraction (gram_dmma.cu) when the caller supplies the workspace
 #ifndef GVI_GRAM_DMMA_MIN_D_VALUE
-#define GVI_GRAM_DMMA_MIN_D_VALUE 24
+#define GVI_GRAM_DMMA_MIN_D_VALUE 24  // (A/B switch: at D = 8 / 16 / 20 that kernel runs at 27 / 25 / 22 % of the store roofline)
 #endif
 constexpr int GVI_GRAM_DMMA_MIN_D = GVI_GRAM_DMMA_MIN_D_VALUE;
 

@@ -32,14 +32,15 @@ constexpr int MT = GVI_MT;    // 8-row m-tiles per group
 #define GVI_PB 4
 #endif
 constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phase 1 (independent exp chains)
+// A/B switches of tools/ab_build.py (profiles/ncu_final_r02.md has the measurements); the defaults are the product:
 #ifndef GVI_P1_MMA
-#define GVI_P1_MMA 1
+#define GVI_P1_MMA 1        // phase 1 on the tensor pipe behind the per-point guard (0: direct differences only)
 #endif
 #ifndef GVI_P1_TABLE
-#define GVI_P1_TABLE 1
+#define GVI_P1_TABLE 1      // its exp: table-driven, 12 FP64 instructions (0: gvi_exp, 20)
 #endif
 #ifndef GVI_GRAD_TWO_CTA
-#define GVI_GRAD_TWO_CTA 1
+#define GVI_GRAD_TWO_CTA 1  // gradient mode in the two-CTA panel shape for M <= 1024 (0: one 16-warp CTA per SM)
 #endif
 constexpr double GVI_P1_BOUND = 512.0;  // guard of the tensor-pipe phase 1: (|u|max + |v|max)^2 in scaled units
 
