@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# One gpurun call that re-establishes every judged number of a round on a fresh B200 (about 6-8 GPU-minutes):
+# One gpurun call that re-establishes every judged number of a round on a fresh B200 (about 11 GPU-minutes):
 #   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_round_check.sh r02'
 # Order follows the profiling recipe: each command first exits 0 WITHOUT ncu, then runs under ncu; numbers printed
 # under ncu are never bench values.  Everything lands in gpurun_out/<tag>/ ; copy what is to be judged into profiles/.
