@@ -39,6 +39,9 @@ constexpr int PB = GVI_PB;    // kernel evaluations in flight per thread in phas
 #ifndef GVI_P1_TABLE
 #define GVI_P1_TABLE 1      // its exp: table-driven, 12 FP64 instructions (0: gvi_exp, 20)
 #endif
+#ifndef GVI_SKIP_ZERO
+#define GVI_SKIP_ZERO 1     // skip the zero m-tile of a group's last k-pair in phase 2 (two-CTA shape)
+#endif
 #ifndef GVI_GRAD_TWO_CTA
 #define GVI_GRAD_TWO_CTA 1  // gradient mode in the two-CTA panel shape for M <= 1024 (0: one 16-warp CTA per SM)
 #endif
@@ -54,9 +57,13 @@ constexpr double GVI_P1_BOUND = 512.0;  // guard of the tensor-pipe phase 1: (|u
 #ifndef GVI_DEEP_A
 #define GVI_DEEP_A 1
 #endif
+// `kskip`: index of a k-pair whose m-tile 0 is known to be zero and is not multiplied (-1: none).  The last k-pair of a
+// group of a packed LOWER-triangular matrix covers the columns 16 g + 8 .. 16 g + 15, strictly above the rows of m-tile 0:
+// 6 of the group's 24 (g + 1) DMMAs, 0.8 % of phase 2 at M = 1024 and 1.5 % at M = 512.
 template <int NT, bool PREFETCH_B>
 __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp0, int nkp,
-                                          const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2]) {
+                                          const double2* __restrict__ Ks2, int lane, double (&acc)[MT][NT][2],
+                                          int kskip = -1) {
   if constexpr (!PREFETCH_B && GVI_DEEP_A) {
     // A fragments fetched TWO k-pairs ahead through three rotating register buffers (+8 registers): with two CTAs per
     // SM a CTA is alone on the tensor pipe while its neighbour generates a K tile, i.e. two warps per sub-partition -
@@ -80,10 +87,24 @@ __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
     };
+    auto tail_step = [&](const double2 (&a)[MT], int k) {  // the group's last k-pair: m-tile 0 is zero there
+      double2 b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) b[nt] = Ks2[((kp0 + k) * NT + nt) * 32 + lane];
+#pragma unroll
+      for (int mt = 1; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].x, b[nt].x);
+#pragma unroll
+      for (int mt = 1; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt].y, b[nt].y);
+    };
     lda(a0, 0);
     lda(a1, 1);
+    const int n1 = kskip >= 0 ? nkp - 1 : nkp;  // full steps (the skipped m-tile can only be in the last k-pair)
     int k = 0;
-    for (; k + 3 <= nkp; k += 3) {
+    for (; k + 3 <= n1; k += 3) {
       lda(a2, k + 2);
       step(a0, k);
       lda(a0, k + 3);
@@ -91,8 +112,20 @@ __device__ __forceinline__ void group_mma(const double2* __restrict__ Ag, int kp
       lda(a1, k + 4);
       step(a2, k + 2);
     }
-    if (k < nkp) step(a0, k);
-    if (k + 1 < nkp) step(a1, k + 1);
+    if (kskip < 0) {
+      if (k < nkp) step(a0, k);
+      if (k + 1 < nkp) step(a1, k + 1);
+    } else if (n1 - k == 0) {
+      tail_step(a0, k);
+    } else if (n1 - k == 1) {
+      step(a0, k);
+      tail_step(a1, k + 1);
+    } else {
+      lda(a2, k + 2);
+      step(a0, k);
+      step(a1, k + 1);
+      tail_step(a2, k + 2);
+    }
     return;
   }
   if constexpr (!PREFETCH_B) {
@@ -473,7 +506,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 8 ? 2 : 1) gp_step_kernel
                 for (int e = 0; e < 2; e++) acc[mt][nt][e] = __ldcg(src + ((mt * NT + nt) * 2 + e) * 32);
           }
           group_mma<NT, WARPS == 16>(reinterpret_cast<const double2*>(W + wpack_group_off(g)) + (size_t)kp_lo * MT * 32 + lane, 0,
-                        kp_end - kp_lo, Ks2, lane, acc);
+                        kp_end - kp_lo, Ks2, lane, acc, GVI_SKIP_ZERO && kp_end == nkp_g ? kp_end - kp_lo - 1 : -1);
           if (kp_end < nkp_g) {  // the group continues in the next panel
             double* dst = ascr + (size_t)g * (GVI_GROUP_ROWS * T) + lane;
 #pragma unroll
