@@ -213,7 +213,7 @@ int gvi_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, i
  * h_mean[i] = dLoss/dmean_i (NULL = 0):  out[0] = out[1] = 0, out[2] = N, out[3] = dLoss/dlog_scaling,
  * out[4+d] = dLoss/dlog_lengthscales[d], out[4+D] = dLoss/dlog_observation_noise (5 + D doubles).  The gradient
  * w.r.t. the prior-mean parameters is the host framework's (dLoss/dm(x_i) = h_mean[i]).  Dense route: K(x,Z) in
- * row chunks, M^3-shaped products by cuBLAS, hand-written contraction kernels (D <= 32) or the GEMM formulation of
+ * row chunks, M^3-shaped products on the in-tree tensor-pipe GEMM (dgemm.cu), hand-written contraction kernels (D <= 32) or the GEMM formulation of
  * the contraction for wider inputs (grad_wide.cu).                                                               */
 size_t gvi_exact_gp_predict_grad_workspace_bytes(int64_t N, int M, int D);
 int gvi_exact_gp_predict_grad_f64(const void* factor, int M, int D, const double* X, int64_t N, const double* g_var,
